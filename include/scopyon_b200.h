@@ -1,0 +1,237 @@
+/*
+ * scopyon_b200 -- C ABI of the B200-native image-formation hot path.
+ *
+ * The reference (ecell/scopyon) is pure Python and has no FFI; the seam this
+ * library plugs into is `_EPIFMSimulator.output_frame / generate_frames`
+ * (/root/reference/src/scopyon/_epifm.py:1017-1049,1121-1225) and
+ * `sample_inputs / sample` (sampling.py:121-162, sampling2.py:70-149).
+ * Each entry point below names the reference code it replaces.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no exceptions cross the boundary.
+ *   - every pointer named d_* is DEVICE memory owned by the caller.
+ *   - every call takes the CUDA stream to enqueue on (a cudaStream_t passed as
+ *     void*); calls are asynchronous with respect to the host.
+ *   - return value: 0 = ok, <0 = invalid argument (SCB_E_*), >0 = cudaError_t.
+ *     scb_last_error() returns a human-readable message for the calling thread.
+ *   - no global state; thread-safe as long as streams and buffers differ.
+ *   - image axis 0 ("w", rows) is the particle's x, axis 1 ("h", columns,
+ *     contiguous in memory) is y  (_epifm.py:225-231).
+ */
+#ifndef SCOPYON_B200_H
+#define SCOPYON_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCB_VERSION 100
+
+#define SCB_E_INVALID   (-1)   /* bad argument value                          */
+#define SCB_E_NULL      (-2)   /* required pointer is NULL                    */
+#define SCB_E_WORKSPACE (-3)   /* workspace too small                         */
+#define SCB_E_UNSUPPORTED (-4)
+
+/* PSF model, fluorophore.type (_epifm.py:62-74) */
+#define SCB_PSF_BORN_WOLF 0
+#define SCB_PSF_GAUSSIAN  1
+
+/* detector.type (_epifm.py:1445-1461) */
+#define SCB_DET_CMOS  0
+#define SCB_DET_EMCCD 1
+#define SCB_DET_CCD   2
+
+/* analog_to_digital_converter.type (_epifm.py:941-954) */
+#define SCB_FPN_NONE   0
+#define SCB_FPN_PIXEL  1
+#define SCB_FPN_COLUMN 2
+
+/* element type of image buffers */
+#define SCB_F32 0
+#define SCB_F64 1
+
+/* Camera grid + PSF-table geometry (_epifm.py:1175-1176, 57-60, 226-231). */
+typedef struct scb_geometry {
+    int32_t n_w, n_h;        /* detector.image_size                                   */
+    int32_t n_radial;        /* radial samples: len(arange(0, radial_cutoff, 1 nm))   */
+    int32_t n_depth_keys;    /* integer-nm depth keys 0..n_depth_keys-1; the frozen   */
+                             /* beyond-cutoff table ("key -1") is key n_depth_keys    */
+    double pixel_length;     /* detector.pixel_length / magnification  [m]            */
+    double resolution;       /* table sample pitch, 1e-9 m                            */
+    double depth_cutoff;     /* fluorophore.depth_cutoff [m]                          */
+    double focal[3];         /* detector.focal_point as (depth, x, y) [m]             */
+} scb_geometry;
+
+/* Photophysics scalars (_epifm.py:1281-1315, 1343-1360, 1486-1491); all config-only
+ * values are evaluated once on the host in the reference's operation order. */
+typedef struct scb_photophysics {
+    double amplitude0;         /* snells_law() amplitude at depth 0                    */
+    double penetration_depth;  /* snells_law() depth; +inf for epi-illumination        */
+    double x_sec;              /* ln10 * abs_coeff * 0.1 / N_A                         */
+    double quantum_yield;
+    double absorb_frac;        /* 1 - 10^(-A)                                          */
+    double norm_scale;         /* sum(fluoem_norm) * psf_normalization                 */
+    double budget_scale;       /* half_life / ln2 * N_emit0; <=0: photobleaching off   */
+} scb_photophysics;
+
+/* Detector + ADC scalars (_epifm.py:1430-1484, 926-963). */
+typedef struct scb_detector {
+    int32_t type;              /* SCB_DET_*                                            */
+    int32_t fpn_type;          /* SCB_FPN_*                                            */
+    int32_t bit;               /* ADC bit depth                                        */
+    int32_t background_on;
+    double qe;                 /* detector.QE                                          */
+    double background;         /* effects.background.mean [photons/pixel]              */
+    double readout_noise;      /* e-, Gaussian sigma (EMCCD, CCD)                      */
+    double emgain;             /* EMCCD multiplication gain                            */
+    double fullwell;           /* e-                                                   */
+    double adc_offset;         /* ADC0 [counts]                                        */
+    double fpn_count;          /* fixed-pattern-noise sigma [counts]                   */
+} scb_detector;
+
+/* CMOS read-noise table as a Walker alias table (replaces the per-pixel
+ * rng.choice over catalog/detector/RNDist_F40.csv, _epifm.py:332-345). */
+typedef struct scb_alias_entry {
+    float value;        /* electrons if the coin lands below `threshold`   */
+    float alias_value;  /* electrons otherwise                             */
+    float threshold;    /* in [0,1]                                        */
+    float pad;
+} scb_alias_entry;
+
+int scb_version(void);
+const char *scb_last_error(void);
+
+/* ---- PSF tables -------------------------------------------------------------- */
+
+/* Radial PSF profile psf(r, z) on r = 0,1,..,n_radial-1 nm for each table depth.
+ * Replaces PointSpreadingFunction.get_distribution:
+ *   Born-Wolf  _epifm.py:181-213 (NA = 1.4, 100-term rho sum), Gaussian _epifm.py:133-134.
+ * d_depths[n_keys] (m) -> d_radial[n_keys][n_radial] (1/m^2). */
+int scb_psf_radial_build(int psf_type, double wave_length, double radial_width,
+                         int n_radial, int n_keys, const double *d_depths,
+                         double *d_radial, void *stream);
+
+/* Bytes of scratch scb_psf_sat_build needs. */
+size_t scb_psf_sat_workspace_bytes(int n_radial, int n_keys);
+
+/* Fixed-point summed-area tables of the Cartesian PSF table.
+ * Replaces radial_to_cartesian (_epifm.py:98-126) and turns the per-pixel slice sums
+ * of overlay_signal_ (_epifm.py:277-282) into four table reads:
+ *   T[a][b]  = lerp(radial, min(sqrt((a-c)^2+(b-c)^2), c)),  c = n_radial-1, a,b in [0, 2c]
+ *   Q[a][b]  = llrint(T[a][b] * scale_k),  scale_k a power of two chosen per table
+ *   S[a][b]  = sum_{a'<a, b'<b} Q[a'][b']                     a,b in [0, 2c+1]
+ * d_sat[n_keys][2c+2][2c+2] (int64), d_inv_scale[n_keys] = 1/scale_k. */
+int scb_psf_sat_build(const double *d_radial, int n_radial, int n_keys,
+                      int64_t *d_sat, double *d_inv_scale,
+                      void *d_workspace, size_t workspace_bytes, void *stream);
+
+/* ---- particles --------------------------------------------------------------- */
+
+/* Brownian displacement, replaces move_points (sampling.py:88-119) and
+ * sampling2.__move_points (sampling2.py:33-50):  x[d] += N(0, sigma[d]) for n_steps
+ * consecutive steps, sigma[d] = sqrt(2 D[d] dt).  Normals come from Philox4x32-10
+ * keyed (seed; particle, step) so any shard of particles / steps reproduces the same
+ * trajectory.  d_x/d_y/d_z: SoA coordinates (NULL for an absent axis), updated in place
+ * unless d_out_* are given.  d_state + d_sigma_state[n_states]: per-state isotropic
+ * sigma (sampling2); otherwise sigma_axis[3].  periodic != 0 wraps into [lower, upper)
+ * per axis after each step (sampling2.py:43-49). */
+int scb_diffuse(uint64_t seed, uint64_t first_step, int n_steps, int64_t n, int64_t first_particle,
+                const double *d_x, const double *d_y, const double *d_z,
+                double *d_out_x, double *d_out_y, double *d_out_z,
+                const double sigma_axis[3],
+                const int32_t *d_state, const double *d_sigma_state, int n_states,
+                int periodic, const double lower[3], const double upper[3],
+                void *stream);
+
+/* State transitions of sampling2.__transition_states (sampling2.py:52-68, with the
+ * intended side='left'): next = searchsorted(cumsum(P[state]), u).  d_pacc is the
+ * row-wise cumulative transition matrix [n_states][n_states]. */
+int scb_transition_states(uint64_t seed, uint64_t step, int64_t n, int64_t first_particle,
+                          int32_t *d_state, const double *d_pacc, int n_states, void *stream);
+
+/* Uniform initial placement, replaces sample_points (sampling.py:78-83):
+ * coord[d] = lower[d] + u * (upper[d]-lower[d]),  u from Philox keyed (seed; particle). */
+int scb_place_uniform(uint64_t seed, int64_t n, int64_t first_particle,
+                      double *d_x, double *d_y, double *d_z,
+                      const double lower[3], const double upper[3], void *stream);
+
+/* Photon emission, photobleaching budget and per-spot PSF weight for one snapshot.
+ * Replaces the scalar part of __overlay_molecule_plane (_epifm.py:1281-1315,1321-1333):
+ *   amplitude = amplitude0 * exp(-|depth - focal[0]| / penetration_depth)
+ *   N_emit    = QY * (amplitude * x_sec * unit_time) * absorb_frac
+ *   budget    : first sight -> Exp(1) * budget_scale (Philox keyed (seed; molecule id));
+ *               budget -= N_emit; if <= 0: budget = 0, p_state = 0
+ *   weight    = norm_scale * (p_state * N_emit / 4 pi)
+ * d_budget may be NULL (no bleaching: form_image).  d_mol_slot maps a particle row to its
+ * slot in d_budget / d_true_data (NULL: identity); d_mol_id is the id used as RNG key
+ * (NULL: identity).  d_true_data[n_slots][8] accumulates the reference's per-molecule
+ * vector (_epifm.py:1324-1333) when non-NULL. */
+int scb_emit_bleach(uint64_t seed, int64_t n,
+                    const double *d_depth, const double *d_x, const double *d_y,
+                    const double *d_p_state,
+                    const int32_t *d_mol_slot, const int64_t *d_mol_id,
+                    double unit_time, double focal_depth, const scb_photophysics *phys,
+                    double *d_budget, double *d_weight, double *d_true_data,
+                    void *stream);
+
+/* ---- rendering --------------------------------------------------------------- */
+
+/* Upper bound of scratch bytes scb_render_expected needs for n_spots spots. */
+size_t scb_render_workspace_bytes(const scb_geometry *geom, int64_t n_spots);
+
+/* Expected (pre-noise) photon image of one frame.  Replaces get_molecule_plane +
+ * PointSpreadingFunction.overlay_signal_ (_epifm.py:1262-1264, 224-282) with identical
+ * pixel-edge index arithmetic (IEEE fp64, same operation order):
+ *   out[i][j] (+)= sum_spots  weight * 1e-18 * box_sum(T_key; left_i..left_{i+1}, top_j..top_{j+1})
+ * Spots are binned to 16x16-pixel screen tiles by a counting sort; one CTA renders one
+ * tile, gathers summed-area-table corners into shared memory and accumulates in
+ * registers (no atomics on the image).  d_slot_of_key[n_depth_keys+1] maps a depth key
+ * to its table index in d_sat (-1: table absent -> the spot is counted in *d_errors).
+ * out_type: SCB_F32 / SCB_F64; accumulate != 0 adds to the existing image. */
+int scb_render_expected(const scb_geometry *geom, int64_t n_spots,
+                        const double *d_depth, const double *d_x, const double *d_y,
+                        const double *d_weight,
+                        const int64_t *d_sat, const double *d_inv_scale,
+                        const int32_t *d_slot_of_key,
+                        void *d_out, int out_type, int accumulate,
+                        void *d_workspace, size_t workspace_bytes,
+                        int32_t *d_errors, void *stream);
+
+/* ---- detector ---------------------------------------------------------------- */
+
+/* ADC offset map with fixed-pattern noise, replaces
+ * calculate_analog_to_digital_converter_gain (_epifm.py:926-963):
+ * offset = rint(N(ADC0, fpn_count)) per pixel (SCB_FPN_PIXEL, n = n_w*n_h) or per
+ * axis-1 index (SCB_FPN_COLUMN, n = n_h); Philox keyed (seed; index). */
+int scb_adc_offsets(uint64_t seed, int64_t n, double adc0, double fpn_count,
+                    void *d_offset, int elem_type, void *stream);
+
+/* Fused detector pass: background + QE, shot noise (Poisson; EMCCD: Poisson -> Gamma
+ * multiplication register, truncated like EMCCD.probability_distribution), readout
+ * noise (Gaussian, or CMOS alias table), full-well clip, ADC gain/offset, clip to
+ * [0, 2^bit - 1].  Replaces __detector_output + CMOS/EMCCD/CCD + ADC
+ * (_epifm.py:1430-1484, 329-433).  One pass over the frame: reads d_photons once,
+ * writes d_adc once.  Philox keyed (seed; frame, pixel).
+ *   d_photons      expected photons per pixel (render output), elem_type
+ *   d_offset       NULL (SCB_FPN_NONE), [n_h] (COLUMN) or [n_w*n_h] (PIXEL), elem_type
+ *   d_cmos_alias   alias table [n_alias] (CMOS only)
+ *   d_expectation  optional out: QE*(photons+background)          (camera[:,:,0])
+ *   d_in_signal / d_in_noise  optional injected draws (bit-exact ADC tests)
+ *   d_out_signal / d_out_noise optional taps of the drawn signal / noise (statistics tests)
+ */
+int scb_detector_adc(uint64_t seed, uint64_t frame, const scb_detector *det,
+                     int32_t n_w, int32_t n_h, int elem_type,
+                     const void *d_photons, const void *d_offset,
+                     const scb_alias_entry *d_cmos_alias, int n_alias,
+                     void *d_adc, void *d_expectation,
+                     const void *d_in_signal, const void *d_in_noise,
+                     void *d_out_signal, void *d_out_noise,
+                     void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCOPYON_B200_H */

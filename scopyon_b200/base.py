@@ -1,0 +1,166 @@
+"""Public facade: the same call signatures as the reference's ``scopyon.base``
+(``/root/reference/src/scopyon/base.py:20-294``), with the frame formation handed to
+the GPU engine.
+"""
+import collections.abc
+import numbers
+import warnings
+from logging import getLogger
+
+import numpy
+
+from . import _epifm
+from .config import Configuration
+from .image import Image
+
+_log = getLogger(__name__)
+
+__all__ = [
+    "EnvironSettings", "EPIFMSimulator",
+    "form_image", "generate_images", "create_simulator"
+    ]
+
+
+class EnvironSettings:
+
+    def __init__(self, config):
+        self.initialize(config)
+
+    def initialize(self, config):
+        # multiprocessing.Pool workers of the reference (base.py:20-26); one GPU does the
+        # work here, the value is kept for interface compatibility only
+        self.processes = config.processes
+
+
+def _project(points, pre):
+    """3-D world coordinates -> (depth, x, y) in the camera frame (base.py:76-91)."""
+    data = points * pre.scale - numpy.array(pre.origin)
+    unit_z = numpy.cross(pre.unit_x, pre.unit_y)
+    return numpy.stack((numpy.dot(data, unit_z), numpy.dot(data, pre.unit_x), numpy.dot(data, pre.unit_y)), axis=1)
+
+
+class EPIFMSimulator(object):
+
+    def __init__(self, config=None, method=None, rng=None):
+        """
+        Args:
+            config (Configuration or str, optional): configuration or a YAML file name.
+            method (str, optional): name of the configuration section used
+                (defaults to ``config.default``).
+            rng (numpy.RandomState, optional): seeds the device random streams.
+        """
+        if config is None:
+            config = Configuration()
+        elif isinstance(config, str):
+            config = Configuration(filename=config)
+        elif not isinstance(config, Configuration):
+            raise TypeError("Configuration or str must be given [{}].".format(type(config)))
+        if rng is None:
+            warnings.warn('A random number generator is not given.')
+            rng = numpy.random.RandomState()
+        self.__config = config
+        # (the reference evaluates `config.default.lower()` here, which cannot work on a
+        # sub-tree; fall back to the `method` key like create_simulator does)
+        self.__method = method or str(config.get('method', 'default')).lower()
+        self.__rng = rng
+
+    def base(self):
+        return _epifm._EPIFMSimulator(
+            configs=_epifm.EPIFMConfigs(self.__config[self.__method], rng=self.__rng),
+            environ=EnvironSettings(self.__config.environ))
+
+    def __format_data(self, inputs):
+        """Normalise one point array to ``(N, 5)`` rows ``[depth, x, y, molecule id, p_state]``
+        (base.py:61-110)."""
+        assert isinstance(inputs, numpy.ndarray)
+        if inputs.ndim != 2:
+            raise ValueError("The given 'inputs' has wrong dimension.")
+        pre = self.__config.preprocessing
+        n, width = inputs.shape
+        data = numpy.zeros((n, 5))
+        if width in (2, 4):     # points on the focal plane
+            data[:, 1:3] = inputs[:, :2] * pre.scale
+        elif width in (3, 5):
+            data[:, 0:3] = _project(inputs[:, :3], pre)
+        else:
+            raise ValueError("The given 'inputs' has wrong shape.")
+        if width in (2, 3):
+            data[:, 3] = numpy.arange(n)    # molecule id
+            data[:, 4] = 1.0                # photon state
+        else:
+            data[:, 3:5] = inputs[:, width - 2:]
+        return data
+
+    def __format_inputs(self, inputs):
+        if isinstance(inputs, numpy.ndarray):
+            return ((0.0, self.__format_data(inputs)), )
+        if isinstance(inputs, collections.abc.Iterable):
+            data = []
+            for elem in inputs:
+                if not (isinstance(elem, (tuple, list)) and len(elem) == 2
+                        and isinstance(elem[0], numbers.Real) and isinstance(elem[1], numpy.ndarray)):
+                    raise ValueError("The given 'inputs' has wrong type.")
+                data.append((elem[0], self.__format_data(elem[1])))
+            return data
+        raise TypeError(
+            "Invalid argument was given [{}]."
+            " A ndarray is expected.".format(type(inputs)))
+
+    def form_image(self, inputs, start_time=0.0, exposure_time=None, full_output=False):
+        """Form one image.
+
+        Returns:
+            Image, or ``(Image, dict)`` when ``full_output``: ``'expectation'`` is the
+            expected photoelectron image, ``'true_data'`` maps a molecule id to
+            ``[exposure, photon state, X px, Y px, X m, Y m, depth*t, normalization]``.
+        """
+        data = self.__format_inputs(inputs)
+        base = self.base()
+        camera, infodict = base.output_frame(
+            data, start_time=start_time, exposure_time=exposure_time, rng=self.__rng,
+            _full_output=full_output)
+        img = Image(camera[:, :, 1])
+        if full_output:
+            infodict.update(dict(expectation=camera[:, :, 0]))
+            return img, infodict
+        return img
+
+    def generate_images(self, inputs, num_frames, start_time=0.0, exposure_time=None, full_output=False):
+        """Generate ``num_frames`` images (a generator), photobleaching carried across frames."""
+        data = self.__format_inputs(inputs)
+        base = self.base()
+        for (camera, infodict) in base.generate_frames(
+                data, num_frames, start_time=start_time, exposure_time=exposure_time, rng=self.__rng,
+                full_output=full_output):
+            img = Image(camera[:, :, 1])
+            if full_output:
+                infodict.update(dict(expectation=camera[:, :, 0]))
+                yield img, infodict
+            else:
+                yield img
+
+
+def create_simulator(config=None, method=None, rng=None):
+    """Return a simulator for ``config[method]`` (base.py:203-225)."""
+    if method is None:
+        method = config.get('method', 'default').lower()
+    simulator_type = config[method].type.lower()
+    if simulator_type == 'epifm':
+        return EPIFMSimulator(config=config, method=method, rng=rng)
+    raise ValueError(f"An unknown type [{simulator_type}] was given.")
+
+
+def form_image(
+        inputs, start_time=0.0, exposure_time=None, *,
+        method=None, config=None, rng=None, full_output=False):
+    """Form one image from points ``(N, 2|3|4|5)`` or ``[(time, points), ...]`` (base.py:227-258)."""
+    sim = create_simulator(config, method=method, rng=rng)
+    return sim.form_image(inputs, start_time, exposure_time, full_output=full_output)
+
+
+def generate_images(
+        inputs, num_frames, start_time=0.0, exposure_time=None, *,
+        method=None, config=None, rng=None, full_output=False):
+    """Generate a movie (generator of images), base.py:260-294."""
+    sim = create_simulator(config, method=method, rng=rng)
+    return sim.generate_images(inputs, num_frames, start_time, exposure_time, full_output=full_output)

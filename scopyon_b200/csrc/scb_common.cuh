@@ -1,0 +1,112 @@
+// Shared device helpers: error plumbing, Philox4x32-10, uniform/normal transforms.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <math.h>
+#include "../../include/scopyon_b200.h"
+
+#define SCB_SM_COUNT 148  // B200: 2 dies x 74 SMs
+
+void scb_set_error(const char *fmt, ...);
+
+#define SCB_REQUIRE(cond, code, ...)            \
+    do {                                        \
+        if (!(cond)) {                          \
+            scb_set_error(__VA_ARGS__);         \
+            return (code);                      \
+        }                                       \
+    } while (0)
+
+#define SCB_CUDA_LAUNCH_CHECK(what)                                          \
+    do {                                                                     \
+        cudaError_t e__ = cudaGetLastError();                                \
+        if (e__ != cudaSuccess) {                                            \
+            scb_set_error("%s: %s", what, cudaGetErrorString(e__));          \
+            return (int)e__;                                                 \
+        }                                                                    \
+    } while (0)
+
+#define SCB_CUDA(call)                                                       \
+    do {                                                                     \
+        cudaError_t e__ = (call);                                            \
+        if (e__ != cudaSuccess) {                                            \
+            scb_set_error("%s: %s", #call, cudaGetErrorString(e__));         \
+            return (int)e__;                                                 \
+        }                                                                    \
+    } while (0)
+
+// Random-stream tags: the 4th counter word.  One tag per consumer keeps every
+// (seed, entity, step) stream independent of how the work is sharded.
+enum : uint32_t {
+    SCB_TAG_DIFFUSE = 0x44494646u,  // 'DIFF'
+    SCB_TAG_PLACE   = 0x504c4143u,  // 'PLAC'
+    SCB_TAG_BUDGET  = 0x42554447u,  // 'BUDG'
+    SCB_TAG_TRANS   = 0x5452414eu,  // 'TRAN'
+    SCB_TAG_FPN     = 0x46504e20u,  // 'FPN '
+    SCB_TAG_SHOT    = 0x53484f54u,  // 'SHOT' first draw of a pixel quad
+    SCB_TAG_READ    = 0x52454144u,  // 'READ' readout-noise draw of a pixel quad
+    SCB_TAG_EXTRA   = 0x58545241u,  // 'XTRA' per-pixel overflow stream (rejection loops)
+};
+
+struct Philox4 {
+    uint32_t x, y, z, w;
+};
+
+// Philox4x32-10 (Salmon et al., SC'11).  counter = (c0,c1,c2,c3), key = (k0,k1).
+__host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2,
+                                                          uint32_t c3, uint32_t k0, uint32_t k1) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+    const uint32_t W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p0 = (uint64_t)M0 * c0;
+        uint64_t p1 = (uint64_t)M1 * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        c1 = (uint32_t)p1;
+        c3 = (uint32_t)p0;
+        c0 = n0;
+        c2 = n2;
+        k0 += W0;
+        k1 += W1;
+    }
+    Philox4 out = {c0, c1, c2, c3};
+    return out;
+}
+
+__host__ __device__ __forceinline__ Philox4 philox_at(uint64_t seed, uint64_t entity, uint32_t step,
+                                                      uint32_t tag) {
+    return philox4x32_10((uint32_t)entity, (uint32_t)(entity >> 32), step, tag, (uint32_t)seed,
+                         (uint32_t)(seed >> 32));
+}
+
+// (0,1] and [0,1) uniforms from 32 random bits; both avoid the value that would break
+// the transform they feed (log(0), or an index equal to the table size).
+__device__ __forceinline__ float u01_open_low(uint32_t r) {  // (0, 1]
+    return ((float)(r >> 8) + 1.0f) * 5.9604644775390625e-08f;  // 2^-24
+}
+__device__ __forceinline__ float u01_half_open(uint32_t r) {  // [0, 1)
+    return (float)(r >> 8) * 5.9604644775390625e-08f;
+}
+__host__ __device__ __forceinline__ double u01_open_low_53(uint32_t hi, uint32_t lo) {  // (0,1]
+    uint64_t v = (((uint64_t)hi << 32) | lo) >> 11;  // 53 bits
+    return ((double)v + 1.0) * 1.1102230246251565e-16;  // 2^-53
+}
+
+// Box-Muller in fp32 on two 32-bit words: two independent N(0,1).  The radius uses all
+// 32 bits of r0 (tail out to 6.66 sigma); sincospif keeps the angle exact at octants.
+__device__ __forceinline__ void box_muller(uint32_t r0, uint32_t r1, float &n0, float &n1) {
+    float u = ((float)r0 + 1.0f) * 2.3283064365386963e-10f;  // (0, 1]; small values keep full precision
+    float radius = sqrtf(-2.0f * logf(u));
+    float s, c;
+    sincospif((float)r1 * 4.656612873077393e-10f, &s, &c);  // angle = 2 pi r1 / 2^32
+    n0 = radius * c;
+    n1 = radius * s;
+}
+
+static inline unsigned int scb_grid_for(int64_t n, int block, int per_thread = 1) {
+    int64_t work = (n + (int64_t)block * per_thread - 1) / ((int64_t)block * per_thread);
+    if (work < 1) work = 1;
+    return (unsigned int)work;
+}

@@ -1,0 +1,338 @@
+"""Device engine: owns the GPU-resident state of one simulator (PSF summed-area tables,
+read-noise alias table, ADC offset map, scratch) and runs one frame through the
+C-ABI kernels.  PyTorch is used for device memory, streams and host<->device copies only.
+"""
+import ctypes
+
+import numpy
+
+from . import _native
+from ._epifm import RESOLUTION, catalog_tables, depth_keys_of
+
+try:
+    import torch
+except ImportError as exc:   # pragma: no cover
+    raise ImportError("scopyon_b200 needs PyTorch for device memory management") from exc
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError(
+            "scopyon_b200 needs a CUDA device (built for NVIDIA B200, sm_100a); there is no CPU fallback")
+
+
+def walker_alias(values, weights):
+    """Walker/Vose alias table of a categorical distribution -> (n, 4) float32 rows
+    (value, alias_value, threshold, 0): the layout of ``scb_alias_entry``."""
+    values = numpy.asarray(values, dtype=numpy.float64)
+    p = numpy.asarray(weights, dtype=numpy.float64)
+    n = len(p)
+    scaled = p / p.sum() * n
+    threshold = numpy.ones(n)
+    alias = numpy.arange(n)
+    small = [i for i in range(n) if scaled[i] < 1.0]
+    large = [i for i in range(n) if scaled[i] >= 1.0]
+    while small and large:
+        s, l = small.pop(), large.pop()
+        threshold[s] = scaled[s]
+        alias[s] = l
+        scaled[l] = (scaled[l] + scaled[s]) - 1.0
+        (small if scaled[l] < 1.0 else large).append(l)
+    table = numpy.zeros((n, 4), dtype=numpy.float32)
+    table[:, 0] = values
+    table[:, 1] = values[alias]
+    table[:, 2] = threshold
+    return table
+
+
+class DeviceBudgetState:
+    """Photon budgets per molecule on the device (the reference's ``fluorescence_states``
+    dict, ``_epifm.py:1039-1041, 1294-1306``).  NaN marks a molecule not seen yet."""
+
+    def __init__(self, ids, seed, device, initial=None):
+        ids = numpy.asarray(ids, dtype=numpy.int64)
+        if initial:
+            ids = numpy.concatenate([ids, numpy.fromiter(initial.keys(), dtype=numpy.int64, count=len(initial))])
+        self.ids = numpy.unique(ids)
+        self.seed = int(seed)
+        host = numpy.full(len(self.ids), numpy.nan)
+        if initial:
+            keys = numpy.fromiter(initial.keys(), dtype=numpy.int64, count=len(initial))
+            host[numpy.searchsorted(self.ids, keys)] = numpy.fromiter(
+                initial.values(), dtype=numpy.float64, count=len(initial))
+        self.budget = torch.from_numpy(host).to(device)
+
+    def slots_of(self, ids):
+        ids = numpy.asarray(ids, dtype=numpy.int64)
+        slots = numpy.searchsorted(self.ids, ids)
+        slots = numpy.minimum(slots, len(self.ids) - 1)
+        if len(ids) and not numpy.array_equal(self.ids[slots], ids):
+            raise ValueError("a molecule id absent from the input data was given")
+        return slots.astype(numpy.int32)
+
+    def as_dict(self, only_seen=True):
+        host = self.budget.cpu().numpy()
+        keep = ~numpy.isnan(host) if only_seen else numpy.ones(len(host), dtype=bool)
+        return {int(i): float(b) for i, b in zip(self.ids[keep], host[keep])}
+
+
+class DeviceEngine:
+
+    def __init__(self, configs, device=None, precision=None):
+        require_cuda()
+        self.lib = _native.load()
+        self.configs = configs
+        self.device = torch.device(device if device is not None else "cuda:{}".format(torch.cuda.current_device()))
+        self.precision = precision or "f32"
+        if self.precision not in ("f32", "f64"):
+            raise ValueError("precision must be 'f32' or 'f64'")
+        self.elem_type = _native.F32 if self.precision == "f32" else _native.F64
+        self.dtype = torch.float32 if self.precision == "f32" else torch.float64
+        self.geom = configs.geometry()
+        self.phys = configs.photophysics()
+        self.det = configs.detector_struct()
+        self.psf_type = _native.PSF_GAUSSIAN if configs.fluorophore_type == 'Gaussian' else _native.PSF_BORN_WOLF
+        if self.psf_type == _native.PSF_GAUSSIAN and configs.psf_radial_width is None:
+            raise ValueError('fluorophore.radial_width must be given for Gaussian type fluorophore.')
+        self.n_w, self.n_h = int(self.geom.n_w), int(self.geom.n_h)
+        self.pitch = 2 * (self.geom.n_radial - 1) + 2
+
+        # PSF summed-area tables, grown on demand
+        self.sat = None
+        self.inv_scale = None
+        self.n_tables = 0
+        self.slot_host = numpy.full(self.geom.n_depth_keys + 1, -1, dtype=numpy.int32)
+        self.slot_of_key = torch.from_numpy(self.slot_host.copy()).to(self.device)
+        self.errors = torch.zeros(1, dtype=torch.int32, device=self.device)
+
+        # detector-side constants
+        self.alias = None
+        if configs.detector_type == "CMOS":
+            rn = catalog_tables()["cmos_readout"]
+            self.alias = torch.from_numpy(walker_alias(rn["electrons"], rn["weight"])).to(self.device)
+        self.offset = None
+        fpn = configs.ADConverter_fpn_type
+        if fpn != 'none':
+            n = self.n_w * self.n_h if fpn == 'pixel' else self.n_h
+            self.offset = torch.empty(n, dtype=self.dtype, device=self.device)
+            self._call("scb_adc_offsets", configs.fpn_seed, n, float(configs.ADConverter_offset0),
+                       float(configs.ADConverter_fpn_count), _native.ptr(self.offset), self.elem_type,
+                       self._stream())
+        self._workspace = None
+        self._expected = torch.zeros((self.n_w, self.n_h), dtype=self.dtype, device=self.device)
+
+    # ------------------------------------------------------------------ plumbing
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _call(self, name, *args):
+        _native.check(getattr(self.lib, name)(*args), name)
+
+    def _to_device(self, array, dtype=None):
+        host = torch.from_numpy(numpy.ascontiguousarray(array))
+        if dtype is not None:
+            host = host.to(dtype)
+        return host.pin_memory().to(self.device, non_blocking=True)
+
+    def _render_workspace(self, n_spots):
+        need = self.lib.scb_render_workspace_bytes(ctypes.byref(self.geom), n_spots)
+        if need == 0:
+            raise _native.NativeError("scb_render_workspace_bytes: " + self.lib.scb_last_error().decode())
+        if self._workspace is None or self._workspace.numel() < need:
+            self._workspace = torch.empty(int(need * 1.25) + 256, dtype=torch.uint8, device=self.device)
+        return self._workspace
+
+    # ------------------------------------------------------------------ PSF tables
+    def table_depth(self, key):
+        """Depth a table is evaluated at (``_epifm.py:80-84``)."""
+        return float(key) * RESOLUTION if key < self.geom.n_depth_keys else float(self.configs.depth_cutoff)
+
+    def ensure_tables(self, keys):
+        """Build the summed-area tables of depth keys not resident yet."""
+        keys = numpy.unique(numpy.asarray(keys, dtype=numpy.int64))
+        if self.psf_type == _native.PSF_GAUSSIAN:
+            # depth independent (_epifm.py:133-134): one table serves every key
+            if self.n_tables == 0:
+                self._build_tables([0])
+                self.slot_host[:] = 0
+                self.slot_of_key.copy_(torch.from_numpy(self.slot_host))
+            return
+        missing = [int(k) for k in keys if self.slot_host[k] < 0]
+        if not missing:
+            return
+        first = self._build_tables(missing)
+        for i, k in enumerate(missing):
+            self.slot_host[k] = first + i
+        self.slot_of_key.copy_(torch.from_numpy(self.slot_host))
+
+    def ensure_all_tables(self):
+        self.ensure_tables(numpy.arange(self.geom.n_depth_keys + 1))
+
+    def _build_tables(self, keys, radial=None):
+        n_new = len(keys)
+        need = self.n_tables + n_new
+        capacity = 0 if self.sat is None else self.sat.shape[0]
+        if need > capacity:
+            new_cap = min(max(need, 2 * capacity, 1), self.geom.n_depth_keys + 1)
+            new_cap = max(new_cap, need)
+            sat = torch.empty((new_cap, self.pitch, self.pitch), dtype=torch.int64, device=self.device)
+            inv = torch.zeros(new_cap, dtype=torch.float64, device=self.device)
+            if self.n_tables:
+                sat[:self.n_tables].copy_(self.sat[:self.n_tables])
+                inv[:self.n_tables].copy_(self.inv_scale[:self.n_tables])
+            self.sat, self.inv_scale = sat, inv
+        n_radial = self.geom.n_radial
+        if radial is None:
+            depths = self._to_device(numpy.array([self.table_depth(k) for k in keys], dtype=numpy.float64))
+            radial = torch.empty((n_new, n_radial), dtype=torch.float64, device=self.device)
+            self._call("scb_psf_radial_build", self.psf_type, float(self.configs.psf_wavelength),
+                       float(self.configs.psf_radial_width or 0.0), n_radial, n_new,
+                       _native.ptr(depths), _native.ptr(radial), self._stream())
+        work_bytes = self.lib.scb_psf_sat_workspace_bytes(n_radial, n_new)
+        work = torch.empty(work_bytes, dtype=torch.uint8, device=self.device)
+        first = self.n_tables
+        self._call("scb_psf_sat_build", _native.ptr(radial), n_radial, n_new,
+                   ctypes.c_void_p(self.sat[first].data_ptr()), ctypes.c_void_p(self.inv_scale[first:].data_ptr()),
+                   _native.ptr(work), work_bytes, self._stream())
+        self.n_tables = need
+        self.last_radial = radial
+        return first
+
+    # ------------------------------------------------------------------ states
+    def new_budget_state(self, input_data, seed, initial=None):
+        ids = numpy.concatenate([numpy.asarray(p[:, 3], dtype=numpy.int64) for _, p in input_data]) \
+            if len(input_data) else numpy.zeros(0, dtype=numpy.int64)
+        return DeviceBudgetState(ids, seed, self.device, initial=initial)
+
+    # ------------------------------------------------------------------ one frame
+    def render_expected(self, snapshots, states=None, want_true_data=False, out=None, exposure_time=None):
+        """Expected photon image (device tensor) of the given ``[(unit_time, particles(N,5))]``
+        plus the post-processed ``true_data`` dict (or None)."""
+        cfg = self.configs
+        out = self._expected if out is None else out
+        sizes = [len(p) for _, p in snapshots]
+        total = int(sum(sizes))
+        stream = self._stream()
+        focal = cfg.detector_focal_point
+        true_dev, true_ids = None, None
+        if total == 0:
+            out.zero_()
+            return out, ({} if want_true_data else None)
+
+        soa = torch.empty((4, total), dtype=torch.float64, device=self.device)     # depth, x, y, p_state
+        weight = torch.empty(total, dtype=torch.float64, device=self.device)
+        all_ids = numpy.concatenate([numpy.asarray(p[:, 3], dtype=numpy.int64) for _, p in snapshots])
+        if states is not None:
+            table_ids = states.ids
+        elif want_true_data:
+            table_ids = numpy.unique(all_ids)
+        else:
+            table_ids = None
+        if want_true_data:
+            true_ids = table_ids
+            true_dev = torch.zeros((len(table_ids), 8), dtype=torch.float64, device=self.device)
+
+        keys = []
+        offset = 0
+        for (unit_time, particles), n in zip(snapshots, sizes):
+            if n == 0:
+                continue
+            particles = numpy.asarray(particles, dtype=numpy.float64)
+            ids = all_ids[offset: offset + n]
+            order = None
+            rounds = [(0, n)]
+            if table_ids is not None:
+                uniq, counts = numpy.unique(ids, return_counts=True)
+                if len(uniq) < n:
+                    # a molecule id repeated inside one snapshot: the reference updates its
+                    # budget row by row, so launch occurrence k only after occurrence k-1
+                    order = numpy.argsort(ids, kind='stable')
+                    rank = numpy.empty(n, dtype=numpy.int64)
+                    starts = numpy.concatenate([[0], numpy.cumsum(counts)[:-1]])
+                    rank[order] = numpy.arange(n) - numpy.repeat(starts, counts)
+                    order = numpy.argsort(rank, kind='stable')
+                    level_sizes = numpy.bincount(rank)
+                    bounds = numpy.concatenate([[0], numpy.cumsum(level_sizes)])
+                    rounds = [(int(bounds[i]), int(bounds[i + 1])) for i in range(len(level_sizes))]
+                    particles, ids = particles[order], ids[order]
+            seg = soa[:, offset: offset + n]
+            cols = numpy.ascontiguousarray(particles[:, [0, 1, 2, 4]].T)
+            seg.copy_(torch.from_numpy(cols).pin_memory(), non_blocking=True)
+            slots_dev = ids_dev = None
+            if table_ids is not None:
+                slots = numpy.searchsorted(table_ids, ids).astype(numpy.int32)
+                slots_dev = self._to_device(slots)
+                ids_dev = self._to_device(ids)
+            keys.append(depth_keys_of(particles[:, 0] - focal[0], cfg.depth_cutoff, self.geom.n_depth_keys))
+            for lo, hi in rounds:
+                sl = slice(offset + lo, offset + hi)
+                self._call(
+                    "scb_emit_bleach", states.seed if states is not None else 0, hi - lo,
+                    _native.ptr(soa[0, sl]), _native.ptr(soa[1, sl]), _native.ptr(soa[2, sl]),
+                    _native.ptr(soa[3, sl]),
+                    None if slots_dev is None else _native.ptr(slots_dev[lo:hi]),
+                    None if ids_dev is None else _native.ptr(ids_dev[lo:hi]),
+                    float(unit_time), float(focal[0]), ctypes.byref(self.phys),
+                    None if states is None else _native.ptr(states.budget),
+                    _native.ptr(weight[sl]), None if true_dev is None else _native.ptr(true_dev), stream)
+            offset += n
+
+        self.ensure_tables(numpy.concatenate(keys))
+        work = self._render_workspace(total)
+        self._call(
+            "scb_render_expected", ctypes.byref(self.geom), total,
+            _native.ptr(soa[0]), _native.ptr(soa[1]), _native.ptr(soa[2]), _native.ptr(weight),
+            _native.ptr(self.sat), _native.ptr(self.inv_scale), _native.ptr(self.slot_of_key),
+            _native.ptr(out), _native.F32 if out.dtype == torch.float32 else _native.F64, 0,
+            _native.ptr(work), work.numel(), _native.ptr(self.errors), stream)
+
+        true_data = None
+        if want_true_data:
+            true_data = self._finish_true_data(true_dev.cpu().numpy(), true_ids, exposure_time)
+        return out, true_data
+
+    def _finish_true_data(self, acc, ids, exposure_time):
+        """Time averages and pixel coordinates of the per-molecule vector (``_epifm.py:1207-1216``)."""
+        cfg = self.configs
+        p_0 = cfg.detector_focal_point
+        pl = cfg.pixel_length
+        seen = acc[:, 0] > 0
+        acc, ids = acc[seen], ids[seen]
+        acc[:, 1] /= exposure_time
+        acc[:, 2:6] /= acc[:, 0:1]
+        acc[:, 2] = (acc[:, 2] - p_0[1]) / pl + (self.n_w - 1) * 0.5
+        acc[:, 3] = (acc[:, 3] - p_0[2]) / pl + (self.n_h - 1) * 0.5
+        return {int(i): row.copy() for i, row in zip(ids, acc)}
+
+    def detect(self, photons, frame_index, noise_seed, adc=None, expectation=None,
+               in_signal=None, in_noise=None, out_signal=None, out_noise=None):
+        """Detector + ADC pass on a device image (``_epifm.py:1430-1470``)."""
+        if adc is None:
+            adc = torch.empty_like(photons)
+        elem = _native.F32 if photons.dtype == torch.float32 else _native.F64
+        offset = self.offset
+        if offset is not None and offset.dtype != photons.dtype:
+            offset = offset.to(photons.dtype)
+        self._call(
+            "scb_detector_adc", int(noise_seed), int(frame_index), ctypes.byref(self.det),
+            self.n_w, self.n_h, elem, _native.ptr(photons), _native.ptr(offset),
+            _native.ptr(self.alias), 0 if self.alias is None else int(self.alias.shape[0]),
+            _native.ptr(adc), _native.ptr(expectation), _native.ptr(in_signal), _native.ptr(in_noise),
+            _native.ptr(out_signal), _native.ptr(out_noise), self._stream())
+        return adc
+
+    def form_frame(self, snapshots, frame_index, noise_seed, states, exposure_time, want_true_data):
+        """``(camera (Nw, Nh, 2) float64 on the host, true_data)`` for one frame."""
+        photons, true_data = self.render_expected(
+            snapshots, states=states, want_true_data=want_true_data, exposure_time=exposure_time)
+        pair = torch.empty((2, self.n_w, self.n_h), dtype=self.dtype, device=self.device)
+        self.detect(photons, frame_index, noise_seed, adc=pair[1], expectation=pair[0])
+        host = pair.cpu()   # synchronises the stream
+        n_err = int(self.errors.item())
+        if n_err:
+            self.errors.zero_()
+            raise _native.NativeError("{} spots referenced a PSF table that was not built".format(n_err))
+        camera = numpy.empty((self.n_w, self.n_h, 2), dtype=numpy.float64)
+        camera[:, :, 0] = host[0].numpy()
+        camera[:, :, 1] = host[1].numpy()
+        return camera, true_data
