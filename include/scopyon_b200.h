@@ -177,6 +177,19 @@ int scb_emit_bleach(uint64_t seed, int64_t n,
                     double *d_budget, double *d_weight, double *d_true_data,
                     void *stream);
 
+/* Advance a device-resident movie by n_frames WITHOUT rendering: per frame, photon
+ * emission + budget depletion at the current position (as scb_emit_bleach, unit_time =
+ * exposure), then one Brownian step (as scb_diffuse, step index = frame index).  This is
+ * the trajectory/budget prefix a rank replays before its own block of frames when a
+ * movie is partitioned by frame blocks across GPUs (generate_frames is strictly
+ * sequential in the reference, _epifm.py:1045-1049; the counter-based RNG removes that
+ * dependency).  d_depth/d_x/d_y and d_budget are updated in place. */
+int scb_replay_frames(uint64_t diffuse_seed, uint64_t budget_seed, uint64_t first_frame, int64_t n_frames,
+                      int64_t n, int64_t first_particle,
+                      double *d_depth, double *d_x, double *d_y,
+                      const double sigma_dxy[3], double unit_time, double focal_depth,
+                      const scb_photophysics *phys, double *d_budget, void *stream);
+
 /* ---- rendering --------------------------------------------------------------- */
 
 /* Upper bound of scratch bytes scb_render_expected needs for n_spots spots. */
@@ -199,6 +212,14 @@ int scb_render_expected(const scb_geometry *geom, int64_t n_spots,
                         void *d_out, int out_type, int accumulate,
                         void *d_workspace, size_t workspace_bytes,
                         int32_t *d_errors, void *stream);
+
+/* Measurement hook (bench.py): between scb_profile_begin and scb_profile_end every
+ * scb_render_expected brackets its tile-render kernel with CUDA events on the stream it
+ * was given; scb_profile_end synchronises those events and returns the summed device time
+ * and the number of bracketed launches.  Process-wide, not thread-safe; never enabled
+ * on the product path. */
+int scb_profile_begin(int max_launches);
+int scb_profile_end(double *total_ms, int64_t *launches);
 
 /* ---- detector ---------------------------------------------------------------- */
 

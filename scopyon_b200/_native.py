@@ -77,10 +77,16 @@ SIGNATURES = {
     "scb_emit_bleach": (ctypes.c_int, [
         ctypes.c_uint64, ctypes.c_int64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
         ctypes.c_double, ctypes.c_double, ctypes.POINTER(Photophysics), c_ptr, c_ptr, c_ptr, c_ptr]),
+    "scb_replay_frames": (ctypes.c_int, [
+        ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+        c_ptr, c_ptr, c_ptr, ctypes.POINTER(ctypes.c_double), ctypes.c_double, ctypes.c_double,
+        ctypes.POINTER(Photophysics), c_ptr, c_ptr]),
     "scb_render_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(Geometry), ctypes.c_int64]),
     "scb_render_expected": (ctypes.c_int, [
         ctypes.POINTER(Geometry), ctypes.c_int64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
         c_ptr, ctypes.c_int, ctypes.c_int, c_ptr, ctypes.c_size_t, c_ptr, c_ptr]),
+    "scb_profile_begin": (ctypes.c_int, [ctypes.c_int]),
+    "scb_profile_end": (ctypes.c_int, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64)]),
     "scb_adc_offsets": (ctypes.c_int, [
         ctypes.c_uint64, ctypes.c_int64, ctypes.c_double, ctypes.c_double, c_ptr, ctypes.c_int, c_ptr]),
     "scb_detector_adc": (ctypes.c_int, [

@@ -311,7 +311,45 @@ int check_geometry(const scb_geometry *geom) {
     return 0;
 }
 
+// ---- measurement hook -----------------------------------------------------------
+struct ProfilePool {
+    cudaEvent_t *start = nullptr, *stop = nullptr;
+    int capacity = 0, used = 0;
+    bool enabled = false;
+} g_profile;
+
 }  // namespace
+
+extern "C" int scb_profile_begin(int max_launches) {
+    SCB_REQUIRE(max_launches > 0 && max_launches <= (1 << 20), SCB_E_INVALID, "scb_profile_begin: max_launches=%d", max_launches);
+    if (g_profile.capacity < max_launches) {
+        for (int i = 0; i < g_profile.capacity; ++i) { cudaEventDestroy(g_profile.start[i]); cudaEventDestroy(g_profile.stop[i]); }
+        free(g_profile.start); free(g_profile.stop);
+        g_profile.start = (cudaEvent_t *)malloc(sizeof(cudaEvent_t) * max_launches);
+        g_profile.stop = (cudaEvent_t *)malloc(sizeof(cudaEvent_t) * max_launches);
+        for (int i = 0; i < max_launches; ++i) { SCB_CUDA(cudaEventCreate(&g_profile.start[i])); SCB_CUDA(cudaEventCreate(&g_profile.stop[i])); }
+        g_profile.capacity = max_launches;
+    }
+    g_profile.used = 0;
+    g_profile.enabled = true;
+    return 0;
+}
+
+extern "C" int scb_profile_end(double *total_ms, int64_t *launches) {
+    SCB_REQUIRE(total_ms && launches, SCB_E_NULL, "scb_profile_end: NULL pointer");
+    g_profile.enabled = false;
+    double sum = 0.0;
+    for (int i = 0; i < g_profile.used; ++i) {
+        float ms = 0.f;
+        SCB_CUDA(cudaEventSynchronize(g_profile.stop[i]));
+        SCB_CUDA(cudaEventElapsedTime(&ms, g_profile.start[i], g_profile.stop[i]));
+        sum += ms;
+    }
+    *total_ms = sum;
+    *launches = g_profile.used;
+    g_profile.used = 0;
+    return 0;
+}
 
 extern "C" size_t scb_render_workspace_bytes(const scb_geometry *geom, int64_t n_spots) {
     if (check_geometry(geom) != 0 || n_spots < 0) return 0;
@@ -349,12 +387,15 @@ extern "C" int scb_render_expected(const scb_geometry *geom, int64_t n_spots, co
         tile_fill_kernel<<<scb_grid_for(n_spots, 256), 256, 0, s>>>(g, n_spots, w.spots, w.tile_start,
                                                                    w.tile_cursor, w.pair_spot);
     }
+    const bool timed = g_profile.enabled && g_profile.used < g_profile.capacity;
+    if (timed) cudaEventRecord(g_profile.start[g_profile.used], s);
     if (out_type == SCB_F32)
         render_tiles_kernel<float><<<n_tiles, kThreads, 0, s>>>(g, w.spots, w.tile_start, w.pair_spot, d_sat,
                                                                (float *)d_out, accumulate);
     else
         render_tiles_kernel<double><<<n_tiles, kThreads, 0, s>>>(g, w.spots, w.tile_start, w.pair_spot, d_sat,
                                                                 (double *)d_out, accumulate);
+    if (timed) cudaEventRecord(g_profile.stop[g_profile.used++], s);
     SCB_CUDA_LAUNCH_CHECK("scb_render_expected");
     return 0;
 }

@@ -1,0 +1,170 @@
+"""Device-resident movies, partitioned by frame blocks across GPUs.
+
+The reference makes a movie by materialising the whole trajectory on the host
+(``sample_inputs``, ``sampling.py:154-162``) and rendering frames strictly in sequence
+(``generate_frames``, ``_epifm.py:1045-1049``).  Here particles live on the GPU: frame
+``f`` = [emission + photobleaching at the current positions -> tile-binned PSF render ->
+detector/ADC] followed by one Brownian step.  Every random draw is keyed by
+(seed; particle|pixel, frame), so rank ``r`` of ``G`` reproduces frames
+``[r F/G, (r+1) F/G)`` exactly as a single GPU would: it replays the trajectory and the
+photon budgets of the frames before its block with ``scb_replay_frames`` (no rendering)
+and then renders its own block.  No collective sits inside the per-frame compute; NCCL is
+only used to gather finished frames (``gather_frames``).
+"""
+import ctypes
+
+import numpy
+
+from . import _native
+from ._epifm import EPIFMConfigs, draw_seed
+from .engine import DeviceEngine, torch
+
+
+def frame_block(num_frames, rank, world_size):
+    """Contiguous block ``[first, last)`` of frames owned by ``rank``."""
+    base, extra = divmod(int(num_frames), int(world_size))
+    first = rank * base + min(rank, extra)
+    return first, first + base + (1 if rank < extra else 0)
+
+
+class DeviceMovie:
+    """N molecules diffusing in a box, imaged frame by frame on one GPU.
+
+    Args:
+        config (Configuration): scopyon configuration (``config[method]`` is used).
+        n_molecules, lower, upper: uniform initial placement in camera coordinates
+            ``(x, y, depth)`` [m] (``sample_points``, ``sampling.py:78-83``).
+        D: diffusion constant(s) [m^2/s], scalar or per axis ``(x, y, depth)``.
+        seed (int): seeds every Philox stream of the movie.
+    """
+
+    def __init__(self, config, n_molecules, lower, upper, D, seed, method="default", device=None,
+                 precision="f32", exposure_time=None):
+        rng = numpy.random.RandomState(seed % (2 ** 32))
+        self.configs = EPIFMConfigs(config[method], rng=rng)
+        self.engine = DeviceEngine(self.configs, device=device, precision=precision)
+        eng = self.engine
+        self.n = int(n_molecules)
+        self.exposure = float(exposure_time or self.configs.detector_exposure_time)
+        self.place_seed = draw_seed(rng)
+        self.diffuse_seed = draw_seed(rng)
+        self.budget_seed = draw_seed(rng)
+        self.noise_seed = draw_seed(rng)
+        D = numpy.ones(3) * D if numpy.isscalar(D) else numpy.asarray(D, dtype=float)
+        self.sigma_xyd = numpy.sqrt(2 * D * self.exposure)                 # sampling.py:118
+        self.lower = numpy.asarray(lower, dtype=float)
+        self.upper = numpy.asarray(upper, dtype=float)
+        self.is_3d = bool(self.upper[2] > self.lower[2] or self.lower[2] != self.configs.detector_focal_point[0]
+                          or self.sigma_xyd[2] > 0)
+        # coords rows: x, y, depth (the order scb_diffuse / scb_place_uniform use)
+        self.coords = torch.zeros((3, self.n), dtype=torch.float64, device=eng.device)
+        self.weight = torch.empty(self.n, dtype=torch.float64, device=eng.device)
+        self.bleaching = self.configs.effects.photobleaching_switch
+        self.budget = torch.full((self.n,), float("nan"), dtype=torch.float64, device=eng.device) \
+            if self.bleaching else None
+        self.frame = 0
+        self.photons = torch.empty((eng.n_w, eng.n_h), dtype=eng.dtype, device=eng.device)
+        self.work = eng._render_workspace(self.n)
+        if self.is_3d:
+            eng.ensure_all_tables()
+        else:
+            eng.ensure_tables([0])
+        self.reset()
+
+    # ------------------------------------------------------------------ state
+    def _p(self, row):
+        return ctypes.c_void_p(self.coords[row].data_ptr())
+
+    def reset(self, first_frame=0):
+        """Place the molecules and replay to ``first_frame`` (frames before it are not rendered)."""
+        eng = self.engine
+        _native.check(eng.lib.scb_place_uniform(
+            self.place_seed, self.n, 0, self._p(0), self._p(1), self._p(2),
+            _native.vec3(self.lower), _native.vec3(self.upper), eng._stream()), "scb_place_uniform")
+        if self.budget is not None:
+            self.budget.fill_(float("nan"))
+        self.frame = 0
+        if first_frame > 0:
+            sigma_dxy = _native.vec3([self.sigma_xyd[2], self.sigma_xyd[0], self.sigma_xyd[1]])
+            _native.check(eng.lib.scb_replay_frames(
+                self.diffuse_seed, self.budget_seed, 0, int(first_frame), self.n, 0,
+                self._p(2), self._p(0), self._p(1), sigma_dxy, self.exposure,
+                float(self.configs.detector_focal_point[0]), ctypes.byref(eng.phys),
+                _native.ptr(self.budget), eng._stream()), "scb_replay_frames")
+            self.frame = int(first_frame)
+
+    # ------------------------------------------------------------------ one frame
+    def render_next(self, adc_out, expectation_out=None):
+        """Render frame ``self.frame`` into ``adc_out`` (device tensor (Nw, Nh)) and advance."""
+        eng = self.engine
+        stream = eng._stream()
+        focal = self.configs.detector_focal_point
+        _native.check(eng.lib.scb_emit_bleach(
+            self.budget_seed, self.n, self._p(2), self._p(0), self._p(1), None, None, None,
+            self.exposure, float(focal[0]), ctypes.byref(eng.phys), _native.ptr(self.budget),
+            _native.ptr(self.weight), None, stream), "scb_emit_bleach")
+        _native.check(eng.lib.scb_render_expected(
+            ctypes.byref(eng.geom), self.n, self._p(2), self._p(0), self._p(1), _native.ptr(self.weight),
+            _native.ptr(eng.sat), _native.ptr(eng.inv_scale), _native.ptr(eng.slot_of_key),
+            _native.ptr(self.photons), eng.elem_type, 0, _native.ptr(self.work), self.work.numel(),
+            _native.ptr(eng.errors), stream), "scb_render_expected")
+        eng.detect(self.photons, self.frame, self.noise_seed, adc=adc_out, expectation=expectation_out)
+        _native.check(eng.lib.scb_diffuse(
+            self.diffuse_seed, self.frame, 1, self.n, 0, self._p(0), self._p(1), self._p(2),
+            None, None, None, _native.vec3(self.sigma_xyd), None, None, 0, 0, None, None, stream), "scb_diffuse")
+        self.frame += 1
+
+    def render_block(self, out):
+        """Fill ``out`` (device tensor (B, Nw, Nh)) with the next B frames."""
+        for k in range(out.shape[0]):
+            self.render_next(out[k])
+        return out
+
+    def positions(self):
+        """Current ``(N, 5)`` rows ``[depth, x, y, id, p_state]`` on the host (for parity checks)."""
+        xyd = self.coords.cpu().numpy()
+        data = numpy.zeros((self.n, 5))
+        data[:, 0], data[:, 1], data[:, 2] = xyd[2], xyd[0], xyd[1]
+        data[:, 3] = numpy.arange(self.n)
+        data[:, 4] = 1.0
+        return data
+
+
+def gather_frames(local_frames, num_frames, group=None, dst=None):
+    """Assemble the frame stack from per-rank blocks (``frame_block`` partition).
+
+    ``local_frames``: tensor ``(frames of this rank, Nw, Nh)``.  Uses
+    ``torch.distributed`` (NCCL over NVLink for device tensors, gloo for host tensors):
+    ``all_gather`` of equally padded blocks, or ``gather`` to ``dst``.  Returns the full
+    ``(num_frames, Nw, Nh)`` tensor (on ``dst`` only when given, else on every rank).
+    """
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    longest = max(frame_block(num_frames, r, world)[1] - frame_block(num_frames, r, world)[0] for r in range(world))
+    shape = (longest,) + tuple(local_frames.shape[1:])
+    padded = local_frames.new_zeros(shape)
+    padded[: local_frames.shape[0]].copy_(local_frames)
+    if dst is None:
+        blocks = [torch.empty_like(padded) for _ in range(world)]
+        dist.all_gather(blocks, padded, group=group)
+    else:
+        blocks = [torch.empty_like(padded) for _ in range(world)] if rank == dst else None
+        dist.gather(padded, blocks, dst=dst, group=group)
+        if rank != dst:
+            return None
+    parts = []
+    for r in range(world):
+        first, last = frame_block(num_frames, r, world)
+        parts.append(blocks[r][: last - first])
+    return torch.cat(parts, dim=0)
+
+
+def assemble_channels(channel, group=None):
+    """Two-colour assembly (``examples/twocolor.py:14-16``, ``image.py:38-68``): every rank
+    renders one channel; all ranks receive the ``(Nw, Nh, world)`` stack."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    planes = [torch.empty_like(channel) for _ in range(world)]
+    dist.all_gather(planes, channel.contiguous(), group=group)
+    return torch.stack(planes, dim=-1)

@@ -1,0 +1,156 @@
+"""The drop-in public API on the GPU: form_image / generate_images / output_frame with the
+reference's signatures, checked against the golden vectors and the oracle."""
+import warnings
+
+import numpy
+import pytest
+
+import epifm_oracle as orc
+import scopyon_b200
+from conftest import format_inputs, golden, make_configs
+
+pytestmark = pytest.mark.gpu
+
+
+def tirf_config():
+    config = scopyon_b200.DefaultConfiguration()
+    config.default.detector.exposure_time = 33.0e-3
+    return config
+
+
+def test_form_image_tirf_example(known_answers):
+    """examples/tirf.py / detection.py verbatim (BASELINE config 1)."""
+    g = golden("tirf_c1.npz")
+    config = tirf_config()
+    rng = numpy.random.RandomState(123)
+    pixel_length = config.default.detector.pixel_length / config.default.magnification
+    L_2 = config.default.detector.image_size[0] * pixel_length * 0.5
+    inputs = rng.uniform(-L_2, +L_2, size=(100, 2))
+    assert numpy.array_equal(inputs, g["inputs"])
+    img, info = scopyon_b200.form_image(inputs, config=config, rng=rng, full_output=True)
+    assert isinstance(img, scopyon_b200.Image) and img.shape == (512, 512) and img.dtype == numpy.float64
+    want = 0.92 * (g["photons"] + 0.01)
+    got = info["expectation"]
+    assert abs(got - want).max() / want.max() < 1e-6           # fp32 frame storage
+    assert abs(got.sum() - known_answers["tirf_c1"]["expectation_sum"]) / got.sum() < 1e-6
+    # true_data: [t, state, X px, Y px, X m, Y m, depth*t, normalization]  
+    t0 = info["true_data"][0]
+    assert numpy.allclose(t0, [0.033, 1, 356.092223, 146.003339, 6.67832186e-06, -7.26948783e-06, 0, 112.385481],
+                          rtol=1e-8)
+    assert len(info["true_data"]) == 100 and "fluorescence_states" not in info
+    # EMCCD frame statistics: offset 2000 counts, gain 12.59 e-/count, readout 100 e-, EM gain 300
+    adc = img.as_array()
+    dark = want < 0.0093
+    assert abs(adc[dark].mean() - (2000 + 0.0092 * 300 / 12.591286829513976)) < 0.2
+    assert abs(adc[dark].std() - numpy.sqrt(100 ** 2 + 2 * 0.0092 * 300 ** 2) / 12.591286829513976) < 0.3
+    bright = want > 4
+    assert adc[bright].mean() > 2000 + 0.8 * want[bright].mean() * 300 / 12.59
+    # plain call returns just the image; a seeded rng reproduces it
+    again = scopyon_b200.form_image(inputs, config=config, rng=restart(123, 200))
+    assert numpy.array_equal(again.as_array(), adc)
+    other = scopyon_b200.form_image(inputs, config=config, rng=numpy.random.RandomState(5))
+    assert not numpy.array_equal(other.as_array(), adc)
+
+
+def restart(seed, n_uniform):
+    rng = numpy.random.RandomState(seed)
+    rng.uniform(size=n_uniform)
+    return rng
+
+
+def test_twocolor_example():
+    """examples/twocolor.py (BASELINE config 2): two channels from one rng, stacked as RGB."""
+    config = scopyon_b200.DefaultConfiguration()
+    config.update("default: {detector: {type: CCD, image_size: [128, 128]}}")
+    pixel_length = config.default.detector.pixel_length / config.default.magnification
+    L_2 = 128 * pixel_length * 0.5
+    rng = numpy.random.RandomState(123)
+    inputs = rng.uniform(-L_2, +L_2, size=(250, 2))
+    img1 = scopyon_b200.form_image(inputs[: 200], config=config, rng=rng)
+    img2 = scopyon_b200.form_image(inputs[150:], config=config, rng=rng)
+    img = scopyon_b200.Image.RGB(red=img1, green=img2)
+    assert img.shape == (128, 128, 3) and (img.as_array()[:, :, 2] == 0).all()
+    assert numpy.array_equal(img.as_array()[:, :, 0], img1.as_array())
+    assert img.as_8bit().dtype == numpy.uint8
+
+
+def test_output_frame_with_state_dict_against_oracle():
+    """Motion blur + photobleaching through the reference's seam (_epifm.py:1121-1225):
+    budgets handed in as a dict, updated in place, expectation / true_data / states equal
+    the oracle's frame by frame."""
+    g = golden("movie_ccd.npz")
+    config, configs, params = make_configs(str(g["yaml"]))
+    inputs = [(float(t), p) for t, p in zip(g["times"], g["points"])]
+    data = format_inputs(config, inputs)
+    from scopyon_b200._epifm import _EPIFMSimulator
+    from scopyon_b200.engine import DeviceEngine
+    sim = _EPIFMSimulator(configs)
+    sim._engine = DeviceEngine(configs, precision="f64")
+    rng = numpy.random.RandomState(0)
+    ids = g["true_ids"]
+    budgets = {int(i): float(b) for i, b in zip(ids, numpy.linspace(0.05, 2.5, len(ids)))}   # some bleach mid-movie
+    mine, theirs = dict(budgets), dict(budgets)
+    psf = orc.PsfTables(params)
+    for f in range(4):
+        camera, info = sim.output_frame(data, frame_index=f, fluorescence_states=mine, rng=rng)
+        photons, true_data = orc.expected_frame(data, params, frame_index=f, fluorescence_states=theirs, psf=psf)
+        want = orc.detector_expectation(photons, params)
+        assert abs(camera[:, :, 0] - want).max() / want.max() < 1e-9
+        assert set(info["true_data"]) == set(true_data)
+        for m in true_data:
+            assert numpy.allclose(info["true_data"][m], true_data[m], rtol=1e-12, atol=0)
+        assert set(mine) == set(theirs)
+        assert all(abs(mine[m] - theirs[m]) <= 1e-12 * max(theirs[m], 1e-30) for m in theirs)
+        assert info["fluorescence_states"] == mine
+    assert sum(1 for b in mine.values() if b == 0) >= 2        # some molecules did bleach
+
+
+def test_generate_images_movie_and_bleaching_decay():
+    """examples/bleaching.py shape (BASELINE config 3), shortened: N=300, 12 frames."""
+    config = scopyon_b200.DefaultConfiguration()
+    config.update("""
+default:
+    magnification: 360
+    detector: {exposure_time: 0.033, image_size: [256, 256], type: CCD}
+    effects: {photo_bleaching: {switch: true, half_life: 0.1}}
+""")
+    pixel_length = config.default.detector.pixel_length / config.default.magnification
+    L_2 = 256 * pixel_length * 0.5
+    rng = numpy.random.RandomState(123)
+    num_frames, dt = 12, 0.033
+    t = numpy.arange(0, (num_frames + 1) * dt, dt)
+    inputs = scopyon_b200.sample_inputs(t, N=300, lower=-L_2, upper=+L_2, ndim=2, D=0.1e-12, rng=rng)
+    gen = scopyon_b200.generate_images(inputs, num_frames=num_frames, config=config, rng=rng, full_output=True)
+    assert hasattr(gen, "__next__")                            # a generator like the reference's
+    frames = list(gen)
+    assert len(frames) == num_frames
+    totals = [info["expectation"].sum() - 0.92 * 0.01 * 256 * 256 for _, info in frames]
+    alive = [sum(1 for b in info["fluorescence_states"].values() if b > 0) for _, info in frames]
+    assert all(a >= b for a, b in zip(alive, alive[1:])) and alive[-1] < 0.35 * 300 < alive[0]
+    assert totals[-1] < 0.4 * totals[0]
+    # survival follows the half-life: after k frames exp(-ln2 * k dt / T) of the molecules emit
+    want = 300 * numpy.exp(-numpy.log(2) * num_frames * dt / 0.1)
+    assert abs(alive[-1] - want) < 5 * numpy.sqrt(want) + 5
+    imgs = list(scopyon_b200.generate_images(inputs, num_frames=3, config=config, rng=numpy.random.RandomState(1)))
+    assert all(isinstance(i, scopyon_b200.Image) for i in imgs)
+
+
+def test_cmos_3d_epi_movie_against_oracle_expectation():
+    """Scaled-down BASELINE config 4: EPI 3-D, CMOS, column FPN; bleaching off so the
+    expectation is deterministic and comparable to the golden reference frames."""
+    g = golden("movie_cmos3d.npz")
+    yaml = str(g["yaml"]) + "    effects: {photo_bleaching: {switch: false}}\n"
+    config = scopyon_b200.DefaultConfiguration()
+    config.update(yaml)
+    inputs = [(float(t), p) for t, p in zip(g["times"], g["points"])]
+    frames = list(scopyon_b200.generate_images(inputs, num_frames=2, config=config, rng=numpy.random.RandomState(3),
+                                               full_output=True))
+    _, _, params = make_configs(yaml)
+    data = format_inputs(config, inputs)
+    for f, (img, info) in enumerate(frames):
+        photons, _ = orc.expected_frame(data, params, frame_index=f)
+        want = orc.detector_expectation(photons, params)
+        assert abs(info["expectation"] - want).max() / want.max() < 1e-6
+        assert "fluorescence_states" not in info
+        adc = img.as_array()
+        assert adc.min() >= 0 and abs(adc.mean() - (100 + (want.mean() + 1.9) / (30000 / (65536 - 100)))) < 3

@@ -1,0 +1,171 @@
+"""Detector + ADC pass on the GPU (C ABI: scb_detector_adc, scb_adc_offsets).
+
+ADC arithmetic is checked bit for bit with injected draws; the samplers are checked
+statistically against the reference's distributions (moments, KS / chi-square at the
+stated sample sizes)."""
+import numpy
+import pytest
+import scipy.stats
+import torch
+
+import epifm_oracle as orc
+from conftest import cmos_table, golden, gpu_engine
+
+pytestmark = pytest.mark.gpu
+
+CCD = "default: {detector: {type: CCD, image_size: [256, 192], readout_noise: 3.0}}"
+
+
+def run_detector(engine, photons, frame=0, seed=1234, taps=True, **inject):
+    dev = photons.device
+    adc = torch.empty_like(photons)
+    expectation = torch.empty_like(photons)
+    sig = torch.empty_like(photons) if taps else None
+    noi = torch.empty_like(photons) if taps else None
+    engine.detect(photons, frame, seed, adc=adc, expectation=expectation, out_signal=sig, out_noise=noi, **inject)
+    torch.cuda.synchronize()
+    f = lambda t: None if t is None else t.cpu().numpy()
+    return f(adc), f(expectation), f(sig), f(noi)
+
+
+@pytest.mark.parametrize("fpn", ["none", "column", "pixel"])
+def test_adc_bit_exact_with_injected_draws(fpn):
+    yaml = """
+default:
+    detector: {type: CCD, image_size: [60, 44], readout_noise: 3.0}
+    analog_to_digital_converter: {type: %s, count: 3.0, offset: 100, fullwell: 30000}
+""" % fpn
+    _, configs, params, engine = gpu_engine(yaml, precision="f64")
+    rng = numpy.random.RandomState(3)
+    shape = (60, 44)
+    photons = rng.uniform(0, 50, shape)
+    signal = rng.poisson(40.0, shape).astype(float)
+    signal[0, :5] = [0, 1e6, 29999.5, 30000.5, 123.4]
+    noise = rng.normal(0, 80, shape)                       # large: drives some pixels negative / above full well
+    to = lambda a: torch.from_numpy(a).to(engine.device)
+    adc, expectation, _, _ = run_detector(engine, to(photons), in_signal=to(signal), in_noise=to(noise))
+    if fpn == "none":
+        offset, gain = orc.adc_params(params)
+    else:
+        dev_offset = engine.offset.cpu().numpy()
+        assert (dev_offset == numpy.rint(dev_offset)).all()
+        normals = dev_offset            # already rint-ed; rint is idempotent
+        offset, gain = orc.adc_params(params, normals)
+    want = orc.adc_counts(signal + noise, params["adc_fullwell"], gain, offset, params["adc_bit"])
+    assert numpy.array_equal(adc, want)                                    # bit for bit
+    assert numpy.array_equal(expectation, orc.detector_expectation(photons, params))
+    assert adc.min() >= 0 and adc.max() <= 2 ** 16 - 1
+
+
+def test_adc_known_answers(known_answers):
+    _, configs, params, engine = gpu_engine("default: {detector: {type: CCD, image_size: [1, 8]}}", precision="f64")
+    pe = numpy.array(known_answers["adc"]["pe"] + [0.0])
+    to = lambda a: torch.from_numpy(a.reshape(1, 8)).to(engine.device)
+    adc, _, _, _ = run_detector(engine, to(numpy.zeros(8)), in_signal=to(pe), in_noise=to(numpy.zeros(8)))
+    assert adc.ravel()[:7].tolist() == known_answers["adc"]["counts"]
+
+
+def test_fpn_offsets_distribution():
+    yaml = """
+default:
+    detector: {type: CMOS, image_size: [512, 512]}
+    analog_to_digital_converter: {type: pixel, count: 2.0, offset: 100}
+"""
+    _, _, _, engine = gpu_engine(yaml, precision="f32")
+    off = engine.offset.cpu().numpy().astype(float)
+    assert (off == numpy.rint(off)).all()
+    assert abs(off.mean() - 100) < 0.02 and abs(off.std() - numpy.sqrt(4 + 1 / 12.0)) < 0.02
+    _, _, _, again = gpu_engine(yaml, precision="f32")
+    assert numpy.array_equal(off, again.offset.cpu().numpy())               # same rng seed -> same map
+
+
+@pytest.mark.parametrize("lam", [0.0092, 0.7, 5.0, 11.9, 12.1, 80.0, 2500.0])
+def test_poisson_shot_noise(lam):
+    """CCD/CMOS signal ~ Poisson(E) (_epifm.py:352,432): moments + KS on 49 152 pixels."""
+    _, _, params, engine = gpu_engine(CCD, precision="f32")
+    qe, bg = params["QE"], params["background_mean"]
+    photons = torch.full((256, 192), lam / qe - bg, dtype=torch.float32, device=engine.device)
+    _, expectation, sig, _ = run_detector(engine, photons)
+    lam_eff = float(expectation.astype(float).mean())
+    n = sig.size
+    assert (sig == numpy.rint(sig)).all() and sig.min() >= 0
+    assert abs(sig.mean() - lam_eff) < 5 * numpy.sqrt(lam_eff / n)
+    assert abs(sig.var() / lam_eff - 1) < 5 * numpy.sqrt(2.0 / n) + 3 / (lam_eff * n) ** 0.5
+    # discrete KS: compare empirical cdf to the Poisson cdf on the integers
+    ks = numpy.arange(0, int(sig.max()) + 2)
+    ecdf = numpy.searchsorted(numpy.sort(sig.ravel()), ks, side="right") / n
+    assert abs(ecdf - scipy.stats.poisson.cdf(ks, lam_eff)).max() < 1.63 / numpy.sqrt(n)   # alpha = 0.01
+
+
+def test_gaussian_readout_noise_and_determinism():
+    _, _, params, engine = gpu_engine(CCD, precision="f32")
+    photons = torch.zeros((256, 192), dtype=torch.float32, device=engine.device)
+    adc, _, sig, noi = run_detector(engine, photons, frame=3)
+    n = noi.size
+    assert abs(noi.mean()) < 5 * 3.0 / numpy.sqrt(n) and abs(noi.std() / 3.0 - 1) < 5 / numpy.sqrt(2 * n)
+    assert scipy.stats.kstest(noi.ravel() / 3.0, "norm").pvalue > 1e-3
+    assert abs(numpy.corrcoef(noi[:, :-1].ravel(), noi[:, 1:].ravel())[0, 1]) < 5 / numpy.sqrt(n)
+    again, _, _, _ = run_detector(engine, photons, frame=3)
+    other, _, _, _ = run_detector(engine, photons, frame=4)
+    assert numpy.array_equal(adc, again) and not numpy.array_equal(adc, other)
+    # counter-based: a crop of the frame draws the same numbers as the full frame's head
+    head = torch.zeros((64, 192), dtype=torch.float32, device=engine.device)
+    yaml = "default: {detector: {type: CCD, image_size: [64, 192], readout_noise: 3.0}}"
+    _, _, _, small = gpu_engine(yaml, precision="f32")
+    crop, _, _, _ = run_detector(small, head, frame=3)
+    assert numpy.array_equal(crop, adc[:64])
+
+
+def test_cmos_readout_noise_matches_table():
+    """CMOS noise is a categorical draw from RNDist_F40 (_epifm.py:334-345): chi-square."""
+    _, _, params, engine = gpu_engine("default: {detector: {type: CMOS, image_size: [1024, 1024]}}", precision="f32")
+    photons = torch.zeros((1024, 1024), dtype=torch.float32, device=engine.device)
+    _, _, sig, noi = run_detector(engine, photons)
+    values, p = orc.cmos_readout_pmf(cmos_table())
+    idx = numpy.rint((noi.ravel().astype(float) - values[0]) / 0.1).astype(int)
+    assert idx.min() >= 0 and idx.max() < len(values)
+    assert numpy.allclose(values[idx], noi.ravel(), atol=1e-5)
+    counts = numpy.bincount(idx, minlength=len(values)).astype(float)
+    n = noi.size
+    keep = p * n >= 10
+    chi2 = ((counts[keep] - p[keep] * n) ** 2 / (p[keep] * n)).sum()
+    assert chi2 < scipy.stats.chi2.ppf(0.999, keep.sum() - 1)
+    assert counts[~keep].sum() <= max(20.0, 5 * p[~keep].sum() * n)
+    assert abs(noi.mean() - (values * p).sum()) < 5 * numpy.sqrt(((values ** 2 * p).sum()) / n)
+
+
+@pytest.mark.parametrize("case", [0, 1, 2, 3])
+def test_emccd_signal_matches_reference_pmf(case):
+    """EMCCD.get_signal draws from the pmf of _epifm.py:365-391.  The golden file holds the
+    reference's own cdf for E = 0.0092 (background level), 0.5, 5 and 50 at gain 300."""
+    g = golden("emccd_pmf.npz")
+    E = float(g["E{}".format(case)])
+    _, _, params, engine = gpu_engine("default: {detector: {image_size: [512, 512]}}", precision="f32")
+    qe, bg = params["QE"], params["background_mean"]
+    photons = torch.full((512, 512), E / qe - bg, dtype=torch.float32, device=engine.device)
+    _, expectation, sig, _ = run_detector(engine, photons)
+    sig = sig.ravel().astype(float)
+    n = sig.size
+    lo, hi = g["support{}".format(case)]
+    assert sig.min() >= lo and sig.max() <= hi and (sig == numpy.rint(sig)).all()
+    S, cdf = g["S{}".format(case)].astype(float), g["cdf{}".format(case)]
+    ecdf = numpy.searchsorted(numpy.sort(sig), S, side="right") / n
+    assert abs(ecdf - cdf).max() < 1.63 / numpy.sqrt(n) + 2e-3             # KS, alpha = 0.01 (+ grid thinning)
+    mean, var = float(g["mean{}".format(case)]), float(g["var{}".format(case)])
+    assert abs(sig.mean() - mean) < 5 * numpy.sqrt(var / n) + 1e-3 * mean
+    assert abs(sig.var() / var - 1) < 0.05
+    if lo == 0:
+        p0 = float(g["p0_{}".format(case)])
+        assert abs((sig == 0).mean() - p0) < 5 * numpy.sqrt(p0 * (1 - p0) / n) + 1e-4
+
+
+def test_f32_and_f64_paths_agree_on_adc():
+    yaml = "default: {detector: {type: CCD, image_size: [64, 64], readout_noise: 2.0}}"
+    _, _, _, e32 = gpu_engine(yaml, precision="f32")
+    _, _, _, e64 = gpu_engine(yaml, precision="f64")
+    rng = numpy.random.RandomState(0)
+    photons = rng.uniform(0, 30, (64, 64))
+    a32, _, s32, n32 = run_detector(e32, torch.from_numpy(photons.astype(numpy.float32)).to(e32.device))
+    a64, _, s64, n64 = run_detector(e64, torch.from_numpy(photons).to(e64.device))
+    assert (s32 == s64).mean() > 0.999 and numpy.allclose(n32, n64, rtol=1e-6, atol=1e-6)
+    assert numpy.allclose(a32, a64, rtol=2e-6, atol=1e-3)

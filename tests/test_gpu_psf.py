@@ -1,0 +1,57 @@
+"""PSF tables on the GPU against the oracle (C ABI: scb_psf_radial_build, scb_psf_sat_build)."""
+import numpy
+import pytest
+
+import c_oracle
+import epifm_oracle as orc
+from conftest import golden, gpu_engine, oracle_tables
+
+pytestmark = pytest.mark.gpu
+
+
+def test_born_wolf_radial_profile_matches_reference():
+    g = golden("radial_profiles.npz")
+    _, _, params, engine = gpu_engine()
+    keys = [0, 1, 100, 289, 500, 800, 1000, engine.geom.n_depth_keys]   # last = frozen at the cutoff
+    engine.ensure_tables(keys)
+    got = engine.last_radial.cpu().numpy()
+    want = g["born_wolf"]
+    # tolerance: CUDA j0/sincos vs cephes/glibc, 100-term sum -> a few ulp of the peak
+    assert abs(got - want).max() / want.max() < 1e-13
+    rel = abs(got - want) / want.max()
+    assert rel.max() < 1e-13 and (got >= 0).all()
+
+
+def test_gaussian_radial_profile():
+    _, _, params, engine = gpu_engine("""
+default:
+    fluorophore: {type: Gaussian, radial_width: {value: 100.0e-9, units: m}, wave_length: {value: 600.0e-9, units: m}}
+""")
+    engine.ensure_tables([0, 5, 700])
+    assert engine.n_tables == 1 and (engine.slot_host == 0).all()      # depth independent
+    got = engine.last_radial.cpu().numpy()[0]
+    want = orc.gaussian_radial(orc.radial_grid(1000e-9), 100e-9)
+    assert abs(got - want).max() / want.max() < 1e-14
+
+
+def test_sat_bit_exact_against_c_oracle():
+    _, _, params, engine = gpu_engine()
+    sats, inv, _ = oracle_tables(params, engine, [0, 800, engine.geom.n_depth_keys])
+    got = engine.sat[:3].cpu().numpy()
+    assert numpy.array_equal(engine.inv_scale[:3].cpu().numpy(), inv)
+    assert numpy.array_equal(got, sats)                                # int64, bit for bit
+    # and the table integral equals the reference's (known answer 0.9788254597277128)
+    total = got[0][-1, -1] * inv[0] * 1e-18
+    assert abs(total - 0.9788254597277128) < 1e-12
+
+
+def test_sat_from_device_profile_close_to_reference_table():
+    _, _, params, engine = gpu_engine()
+    engine.ensure_tables([100])
+    S = engine.sat[0].cpu().numpy().astype(numpy.float64) * float(engine.inv_scale[0])
+    # key 100 is the table at 100 * 1 nm; note int(100e-9 / 1e-9) == 99 in fp64 (_epifm.py:80)
+    key, table = orc.PsfTables(params).get(engine.table_depth(100))
+    assert key == 100
+    want = numpy.zeros_like(S)
+    want[1:, 1:] = table.cumsum(0).cumsum(1)
+    assert abs(S - want).max() / want.max() < 1e-12

@@ -1,0 +1,60 @@
+"""The C-ABI library loads without a GPU and exports every symbol the header declares."""
+import ctypes
+import os
+import re
+
+from conftest import ROOT
+from scopyon_b200 import _native, build
+
+
+def header_functions():
+    text = open(os.path.join(ROOT, "include", "scopyon_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(scb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_builds_and_exports_header_symbols():
+    build.build_library()
+    lib = _native.load()
+    names = header_functions()
+    assert len(names) >= 13
+    for name in names:
+        assert hasattr(lib, name), "{} is declared in the header but not exported".format(name)
+    assert sorted(_native.SIGNATURES) == names     # the ctypes prototypes cover the whole header
+    assert lib.scb_version() == 100
+
+
+def test_struct_layouts_match_header():
+    # sizes implied by the header's field lists (natural alignment)
+    assert ctypes.sizeof(_native.Geometry) == 4 * 4 + 3 * 8 + 3 * 8
+    assert ctypes.sizeof(_native.Photophysics) == 7 * 8
+    assert ctypes.sizeof(_native.Detector) == 4 * 4 + 7 * 8
+
+
+def test_argument_validation_without_gpu():
+    lib = _native.load()
+    geom = _native.Geometry(n_w=0, n_h=16, n_radial=1000, n_depth_keys=1002, pixel_length=1e-7, resolution=1e-9,
+                            depth_cutoff=1e-6)
+    assert lib.scb_render_workspace_bytes(ctypes.byref(geom), 10) == 0
+    assert b"image_size" in lib.scb_last_error()
+    geom.n_w = 512
+    geom.n_h = 512
+    assert lib.scb_render_workspace_bytes(ctypes.byref(geom), 100000) > 100000 * 48
+    assert lib.scb_psf_sat_workspace_bytes(1000, 3) == (3 * 1999 + 3) * 8
+    rc = lib.scb_psf_radial_build(7, 5e-7, 0.0, 1000, 1, None, None, None)
+    assert rc == -2    # SCB_E_NULL, reported before any device work
+
+
+def test_philox_known_answers():
+    """Philox4x32-10 test vectors of Random123 (kat_vectors)."""
+    lib = _native.load()
+    cases = [
+        ((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+        ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+        ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+         (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1)),
+    ]
+    for ctr, key, want in cases:
+        out = (ctypes.c_uint32 * 4)()
+        lib.scb_philox4x32_10((ctypes.c_uint32 * 4)(*ctr), (ctypes.c_uint32 * 2)(*key), out)
+        assert tuple(out) == want
