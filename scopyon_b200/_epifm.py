@@ -344,17 +344,19 @@ class _EPIFMSimulator:
             yield self.output_frame(
                 input_data, frame_index=frame_index, start_time=start_time, exposure_time=exposure_time,
                 fluorescence_states=states, rng=rng, processes=processes,
-                _noise_seed=noise_seed, _full_output=full_output)
+                _noise_seed=noise_seed, _full_output=full_output, _planes=not full_output)
 
     def output_frame(
             self, input_data, frame_index=0, start_time=0.0, exposure_time=None,
-            fluorescence_states=None, rng=None, processes=None, _noise_seed=None, _full_output=True):
+            fluorescence_states=None, rng=None, processes=None, _noise_seed=None, _full_output=True,
+            _planes=False):
         """One camera frame, ``(camera (Nw, Nh, 2) float64, infodict)`` (``_epifm.py:1121-1225``).
 
         ``camera[:, :, 0]`` is the expected photoelectron image, ``camera[:, :, 1]`` the ADC
         counts.  ``fluorescence_states`` may be ``None`` (no bleaching), a ``dict`` of
         molecule id -> remaining budget (updated in place like the reference's), or the
-        device-resident state ``generate_frames`` creates.
+        device-resident state ``generate_frames`` creates.  (``_planes=True`` is the facade's
+        fast path: ``camera`` is then the bare ``(Nw, Nh)`` ADC image.)
         """
         exposure_time = exposure_time or self.configs.detector_exposure_time
         if rng is None:
@@ -374,9 +376,15 @@ class _EPIFMSimulator:
 
         noise_seed = draw_seed(rng) if _noise_seed is None else _noise_seed
         snapshots = [(unit_time, input_data[k][1]) for k, unit_time in windows]
-        camera, true_data = engine.form_frame(
+        adc, expectation, true_data = engine.form_frame(
             snapshots, frame_index=frame_index, noise_seed=noise_seed, states=states,
-            exposure_time=exposure_time, want_true_data=_full_output)
+            exposure_time=exposure_time, want_true_data=_full_output, want_expectation=not _planes)
+        if _planes:
+            camera = adc
+        else:
+            camera = numpy.empty(adc.shape + (2,), dtype=numpy.float64)   # _epifm.py:1177
+            camera[:, :, 0] = expectation
+            camera[:, :, 1] = adc
 
         infodict = dict(true_data=true_data if true_data is not None else {})
         if fluorescence_states is not None:

@@ -118,7 +118,9 @@ class EPIFMSimulator(object):
         base = self.base()
         camera, infodict = base.output_frame(
             data, start_time=start_time, exposure_time=exposure_time, rng=self.__rng,
-            _full_output=full_output)
+            _full_output=full_output, _planes=not full_output)
+        if not full_output:
+            return Image(camera)
         img = Image(camera[:, :, 1])
         if full_output:
             infodict.update(dict(expectation=camera[:, :, 0]))
@@ -132,12 +134,11 @@ class EPIFMSimulator(object):
         for (camera, infodict) in base.generate_frames(
                 data, num_frames, start_time=start_time, exposure_time=exposure_time, rng=self.__rng,
                 full_output=full_output):
-            img = Image(camera[:, :, 1])
             if full_output:
                 infodict.update(dict(expectation=camera[:, :, 0]))
-                yield img, infodict
+                yield Image(camera[:, :, 1]), infodict
             else:
-                yield img
+                yield Image(camera)     # the bare ADC plane (fast path, no expectation copy)
 
 
 def create_simulator(config=None, method=None, rng=None):

@@ -76,6 +76,104 @@ class DeviceBudgetState:
         return {int(i): float(b) for i, b in zip(self.ids[keep], host[keep])}
 
 
+class SatStore:
+    """Device-resident PSF summed-area tables of one PSF model, grown on demand.
+
+    ``sat[slot]`` is the int64 table of one depth key (``scb_psf_sat_build``),
+    ``slot_of_key`` maps depth keys to slots (-1: not built).  All depth keys of the
+    default configuration take 1003 x 32 MB = 32 GB of the B200's 180 GB."""
+
+    _shared = {}
+
+    @classmethod
+    def shared(cls, engine):
+        cfg = engine.configs
+        key = (str(engine.device), engine.psf_type, float(cfg.psf_wavelength), cfg.psf_radial_width,
+               engine.geom.n_radial, engine.geom.n_depth_keys, float(cfg.depth_cutoff))
+        store = cls._shared.get(key)
+        if store is None:
+            store = cls._shared[key] = cls(engine)
+        return store
+
+    @classmethod
+    def clear_shared(cls):
+        cls._shared.clear()
+
+    def __init__(self, engine):
+        cfg = engine.configs
+        self.lib = engine.lib
+        self.device = engine.device
+        self.psf_type = engine.psf_type
+        self.wavelength = float(cfg.psf_wavelength)
+        self.radial_width = float(cfg.psf_radial_width or 0.0)
+        self.depth_cutoff = float(cfg.depth_cutoff)
+        self.n_radial = int(engine.geom.n_radial)
+        self.n_depth_keys = int(engine.geom.n_depth_keys)
+        self.pitch = 2 * (self.n_radial - 1) + 2
+        self.sat = None
+        self.inv_scale = None
+        self.n_tables = 0
+        self.last_radial = None
+        self.slot_host = numpy.full(self.n_depth_keys + 1, -1, dtype=numpy.int32)
+        self.slot_of_key = torch.from_numpy(self.slot_host.copy()).to(self.device)
+
+    def table_depth(self, key):
+        """Depth a table is evaluated at (``_epifm.py:80-84``)."""
+        return float(key) * RESOLUTION if key < self.n_depth_keys else self.depth_cutoff
+
+    def all_resident(self):
+        return self.n_tables > 0 and bool((self.slot_host >= 0).all())
+
+    def ensure(self, keys, stream):
+        """Build the tables of depth keys not resident yet."""
+        keys = numpy.unique(numpy.asarray(keys, dtype=numpy.int64))
+        if self.psf_type == _native.PSF_GAUSSIAN:
+            # depth independent (_epifm.py:133-134): one table serves every key
+            if self.n_tables == 0:
+                self.build([0], stream)
+                self.slot_host[:] = 0
+                self.slot_of_key.copy_(torch.from_numpy(self.slot_host))
+            return
+        missing = [int(k) for k in keys if self.slot_host[k] < 0]
+        if not missing:
+            return
+        first = self.build(missing, stream)
+        for i, k in enumerate(missing):
+            self.slot_host[k] = first + i
+        self.slot_of_key.copy_(torch.from_numpy(self.slot_host))
+
+    def build(self, keys, stream, radial=None):
+        """Append tables for ``keys``; returns the first new slot.  ``radial`` (n, n_radial)
+        overrides the device-computed radial profiles (parity tests feed the oracle's)."""
+        n_new = len(keys)
+        need = self.n_tables + n_new
+        capacity = 0 if self.sat is None else self.sat.shape[0]
+        if need > capacity:
+            new_cap = max(min(max(need, 2 * capacity, 1), self.n_depth_keys + 1), need)
+            sat = torch.empty((new_cap, self.pitch, self.pitch), dtype=torch.int64, device=self.device)
+            inv = torch.zeros(new_cap, dtype=torch.float64, device=self.device)
+            if self.n_tables:
+                sat[:self.n_tables].copy_(self.sat[:self.n_tables])
+                inv[:self.n_tables].copy_(self.inv_scale[:self.n_tables])
+            self.sat, self.inv_scale = sat, inv
+        if radial is None:
+            depths = torch.tensor([self.table_depth(k) for k in keys], dtype=torch.float64).to(self.device)
+            radial = torch.empty((n_new, self.n_radial), dtype=torch.float64, device=self.device)
+            _native.check(self.lib.scb_psf_radial_build(
+                self.psf_type, self.wavelength, self.radial_width, self.n_radial, n_new,
+                _native.ptr(depths), _native.ptr(radial), stream), "scb_psf_radial_build")
+        work_bytes = self.lib.scb_psf_sat_workspace_bytes(self.n_radial, n_new)
+        work = torch.empty(work_bytes, dtype=torch.uint8, device=self.device)
+        first = self.n_tables
+        _native.check(self.lib.scb_psf_sat_build(
+            _native.ptr(radial), self.n_radial, n_new, ctypes.c_void_p(self.sat[first].data_ptr()),
+            ctypes.c_void_p(self.inv_scale[first:].data_ptr()), _native.ptr(work), work_bytes, stream),
+            "scb_psf_sat_build")
+        self.n_tables = need
+        self.last_radial = radial
+        return first
+
+
 class DeviceEngine:
 
     def __init__(self, configs, device=None, precision=None):
@@ -97,12 +195,9 @@ class DeviceEngine:
         self.n_w, self.n_h = int(self.geom.n_w), int(self.geom.n_h)
         self.pitch = 2 * (self.geom.n_radial - 1) + 2
 
-        # PSF summed-area tables, grown on demand
-        self.sat = None
-        self.inv_scale = None
-        self.n_tables = 0
-        self.slot_host = numpy.full(self.geom.n_depth_keys + 1, -1, dtype=numpy.int32)
-        self.slot_of_key = torch.from_numpy(self.slot_host.copy()).to(self.device)
+        # PSF summed-area tables: shared by every engine of this process with the same PSF
+        # (the reference rebuilds its table cache on each form_image call, base.py:56-59)
+        self.tables = SatStore.shared(self)
         self.errors = torch.zeros(1, dtype=torch.int32, device=self.device)
 
         # detector-side constants
@@ -143,60 +238,24 @@ class DeviceEngine:
         return self._workspace
 
     # ------------------------------------------------------------------ PSF tables
+    sat = property(lambda self: self.tables.sat)
+    inv_scale = property(lambda self: self.tables.inv_scale)
+    slot_of_key = property(lambda self: self.tables.slot_of_key)
+    slot_host = property(lambda self: self.tables.slot_host)
+    n_tables = property(lambda self: self.tables.n_tables)
+    last_radial = property(lambda self: self.tables.last_radial)
+
     def table_depth(self, key):
-        """Depth a table is evaluated at (``_epifm.py:80-84``)."""
-        return float(key) * RESOLUTION if key < self.geom.n_depth_keys else float(self.configs.depth_cutoff)
+        return self.tables.table_depth(key)
 
     def ensure_tables(self, keys):
-        """Build the summed-area tables of depth keys not resident yet."""
-        keys = numpy.unique(numpy.asarray(keys, dtype=numpy.int64))
-        if self.psf_type == _native.PSF_GAUSSIAN:
-            # depth independent (_epifm.py:133-134): one table serves every key
-            if self.n_tables == 0:
-                self._build_tables([0])
-                self.slot_host[:] = 0
-                self.slot_of_key.copy_(torch.from_numpy(self.slot_host))
-            return
-        missing = [int(k) for k in keys if self.slot_host[k] < 0]
-        if not missing:
-            return
-        first = self._build_tables(missing)
-        for i, k in enumerate(missing):
-            self.slot_host[k] = first + i
-        self.slot_of_key.copy_(torch.from_numpy(self.slot_host))
+        self.tables.ensure(keys, self._stream())
 
     def ensure_all_tables(self):
-        self.ensure_tables(numpy.arange(self.geom.n_depth_keys + 1))
+        self.tables.ensure(numpy.arange(self.geom.n_depth_keys + 1), self._stream())
 
     def _build_tables(self, keys, radial=None):
-        n_new = len(keys)
-        need = self.n_tables + n_new
-        capacity = 0 if self.sat is None else self.sat.shape[0]
-        if need > capacity:
-            new_cap = min(max(need, 2 * capacity, 1), self.geom.n_depth_keys + 1)
-            new_cap = max(new_cap, need)
-            sat = torch.empty((new_cap, self.pitch, self.pitch), dtype=torch.int64, device=self.device)
-            inv = torch.zeros(new_cap, dtype=torch.float64, device=self.device)
-            if self.n_tables:
-                sat[:self.n_tables].copy_(self.sat[:self.n_tables])
-                inv[:self.n_tables].copy_(self.inv_scale[:self.n_tables])
-            self.sat, self.inv_scale = sat, inv
-        n_radial = self.geom.n_radial
-        if radial is None:
-            depths = self._to_device(numpy.array([self.table_depth(k) for k in keys], dtype=numpy.float64))
-            radial = torch.empty((n_new, n_radial), dtype=torch.float64, device=self.device)
-            self._call("scb_psf_radial_build", self.psf_type, float(self.configs.psf_wavelength),
-                       float(self.configs.psf_radial_width or 0.0), n_radial, n_new,
-                       _native.ptr(depths), _native.ptr(radial), self._stream())
-        work_bytes = self.lib.scb_psf_sat_workspace_bytes(n_radial, n_new)
-        work = torch.empty(work_bytes, dtype=torch.uint8, device=self.device)
-        first = self.n_tables
-        self._call("scb_psf_sat_build", _native.ptr(radial), n_radial, n_new,
-                   ctypes.c_void_p(self.sat[first].data_ptr()), ctypes.c_void_p(self.inv_scale[first:].data_ptr()),
-                   _native.ptr(work), work_bytes, self._stream())
-        self.n_tables = need
-        self.last_radial = radial
-        return first
+        return self.tables.build(keys, self._stream(), radial=radial)
 
     # ------------------------------------------------------------------ states
     def new_budget_state(self, input_data, seed, initial=None):
@@ -234,36 +293,22 @@ class DeviceEngine:
 
         keys = []
         offset = 0
+        all_resident = self.tables.all_resident()
         for (unit_time, particles), n in zip(snapshots, sizes):
             if n == 0:
                 continue
             particles = numpy.asarray(particles, dtype=numpy.float64)
             ids = all_ids[offset: offset + n]
-            order = None
-            rounds = [(0, n)]
+            order, rounds, slots_dev, ids_dev = None, [(0, n)], None, None
             if table_ids is not None:
-                uniq, counts = numpy.unique(ids, return_counts=True)
-                if len(uniq) < n:
-                    # a molecule id repeated inside one snapshot: the reference updates its
-                    # budget row by row, so launch occurrence k only after occurrence k-1
-                    order = numpy.argsort(ids, kind='stable')
-                    rank = numpy.empty(n, dtype=numpy.int64)
-                    starts = numpy.concatenate([[0], numpy.cumsum(counts)[:-1]])
-                    rank[order] = numpy.arange(n) - numpy.repeat(starts, counts)
-                    order = numpy.argsort(rank, kind='stable')
-                    level_sizes = numpy.bincount(rank)
-                    bounds = numpy.concatenate([[0], numpy.cumsum(level_sizes)])
-                    rounds = [(int(bounds[i]), int(bounds[i + 1])) for i in range(len(level_sizes))]
-                    particles, ids = particles[order], ids[order]
+                order, rounds, slots_dev, ids_dev = self._molecule_slots(table_ids, ids)
+                if order is not None:
+                    particles = particles[order]
             seg = soa[:, offset: offset + n]
             cols = numpy.ascontiguousarray(particles[:, [0, 1, 2, 4]].T)
             seg.copy_(torch.from_numpy(cols).pin_memory(), non_blocking=True)
-            slots_dev = ids_dev = None
-            if table_ids is not None:
-                slots = numpy.searchsorted(table_ids, ids).astype(numpy.int32)
-                slots_dev = self._to_device(slots)
-                ids_dev = self._to_device(ids)
-            keys.append(depth_keys_of(particles[:, 0] - focal[0], cfg.depth_cutoff, self.geom.n_depth_keys))
+            if not all_resident:
+                keys.append(depth_keys_of(particles[:, 0] - focal[0], cfg.depth_cutoff, self.geom.n_depth_keys))
             for lo, hi in rounds:
                 sl = slice(offset + lo, offset + hi)
                 self._call(
@@ -277,7 +322,13 @@ class DeviceEngine:
                     _native.ptr(weight[sl]), None if true_dev is None else _native.ptr(true_dev), stream)
             offset += n
 
-        self.ensure_tables(numpy.concatenate(keys))
+        if keys:
+            needed = numpy.unique(numpy.concatenate(keys))
+            # a 3-D scene that touches many depth keys will touch all of them soon: build the lot
+            if self.psf_type != _native.PSF_GAUSSIAN and (self.slot_host[needed] < 0).sum() > 128:
+                self.ensure_all_tables()
+            else:
+                self.ensure_tables(needed)
         work = self._render_workspace(total)
         self._call(
             "scb_render_expected", ctypes.byref(self.geom), total,
@@ -290,6 +341,32 @@ class DeviceEngine:
         if want_true_data:
             true_data = self._finish_true_data(true_dev.cpu().numpy(), true_ids, exposure_time)
         return out, true_data
+
+    def _molecule_slots(self, table_ids, ids):
+        """Device copies of (budget/true_data slot, molecule id) per particle row, cached while
+        consecutive snapshots carry the same id column (the usual case).  When an id repeats
+        inside one snapshot the reference updates its budget row by row, so the rows are
+        reordered into rounds (occurrence k launched after occurrence k-1)."""
+        cache = getattr(self, "_slot_cache", None)
+        if cache is not None and cache[0] is table_ids and cache[1].shape == ids.shape \
+                and numpy.array_equal(cache[1], ids):
+            return cache[2]
+        n = len(ids)
+        order, rounds = None, [(0, n)]
+        uniq, counts = numpy.unique(ids, return_counts=True)
+        if len(uniq) < n:
+            by_id = numpy.argsort(ids, kind='stable')
+            rank = numpy.empty(n, dtype=numpy.int64)
+            starts = numpy.concatenate([[0], numpy.cumsum(counts)[:-1]])
+            rank[by_id] = numpy.arange(n) - numpy.repeat(starts, counts)
+            order = numpy.argsort(rank, kind='stable')
+            bounds = numpy.concatenate([[0], numpy.cumsum(numpy.bincount(rank))])
+            rounds = [(int(bounds[i]), int(bounds[i + 1])) for i in range(len(bounds) - 1)]
+        ordered = ids if order is None else ids[order]
+        slots = numpy.searchsorted(table_ids, ordered).astype(numpy.int32)
+        result = (order, rounds, self._to_device(slots), self._to_device(ordered))
+        self._slot_cache = (table_ids, ids.copy(), result)
+        return result
 
     def _finish_true_data(self, acc, ids, exposure_time):
         """Time averages and pixel coordinates of the per-molecule vector (``_epifm.py:1207-1216``)."""
@@ -321,18 +398,25 @@ class DeviceEngine:
             _native.ptr(out_signal), _native.ptr(out_noise), self._stream())
         return adc
 
-    def form_frame(self, snapshots, frame_index, noise_seed, states, exposure_time, want_true_data):
-        """``(camera (Nw, Nh, 2) float64 on the host, true_data)`` for one frame."""
+    def form_frame(self, snapshots, frame_index, noise_seed, states, exposure_time, want_true_data,
+                   want_expectation=True):
+        """One frame on the host: ``(adc (Nw, Nh) float64, expectation (Nw, Nh) float64 or None,
+        true_data)``.  The planes are widened to float64 on the device and come back through a
+        pinned staging buffer, so the host only does one memcpy per plane."""
         photons, true_data = self.render_expected(
             snapshots, states=states, want_true_data=want_true_data, exposure_time=exposure_time)
+        planes = 2 if want_expectation else 1
         pair = torch.empty((2, self.n_w, self.n_h), dtype=self.dtype, device=self.device)
-        self.detect(photons, frame_index, noise_seed, adc=pair[1], expectation=pair[0])
-        host = pair.cpu()   # synchronises the stream
+        self.detect(photons, frame_index, noise_seed, adc=pair[0], expectation=pair[1] if want_expectation else None)
+        if getattr(self, "_staging", None) is None:
+            self._staging = torch.empty((2, self.n_w, self.n_h), dtype=torch.float64).pin_memory()
+        self._staging[:planes].copy_(pair[:planes], non_blocking=True)   # widening copy, device -> pinned host
+        torch.cuda.current_stream(self.device).synchronize()
         n_err = int(self.errors.item())
         if n_err:
             self.errors.zero_()
             raise _native.NativeError("{} spots referenced a PSF table that was not built".format(n_err))
-        camera = numpy.empty((self.n_w, self.n_h, 2), dtype=numpy.float64)
-        camera[:, :, 0] = host[0].numpy()
-        camera[:, :, 1] = host[1].numpy()
-        return camera, true_data
+        host = self._staging.numpy()
+        adc = numpy.array(host[0])
+        expectation = numpy.array(host[1]) if want_expectation else None
+        return adc, expectation, true_data

@@ -70,8 +70,9 @@ def cmos_table():
 
 def gpu_engine(yaml_update=None, precision="f64", seed=0):
     """(config, configs, oracle params, DeviceEngine) on cuda:0."""
-    from scopyon_b200.engine import DeviceEngine
+    from scopyon_b200.engine import DeviceEngine, SatStore
     config, configs, params = make_configs(yaml_update, seed=seed)
+    SatStore.clear_shared()     # every test starts from an empty table store
     return config, configs, params, DeviceEngine(configs, precision=precision)
 
 

@@ -1,0 +1,134 @@
+"""Per-kernel microbenchmarks on one GPU (CUDA events, L2 flushed between launches).
+
+  python tools/microbench.py [detector] [diffuse] [render] [tables]
+
+Prints one JSON object per measurement: achieved GB/s against the algorithmic bytes of
+SURVEY.md section 8(d) (8 B per pixel-frame for noise+ADC, 48 B per particle-step fp64
+diffusion, 8.5 B per spot-pixel eval for the SAT render)."""
+import ctypes
+import json
+import os
+import sys
+import time
+
+import numpy
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import scopyon_b200  # noqa: E402
+from scopyon_b200 import _epifm, _native  # noqa: E402
+from scopyon_b200.engine import DeviceEngine  # noqa: E402
+from scopyon_b200.sampling import DeviceParticles  # noqa: E402
+
+PEAK = 6545.6
+if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")):
+    PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+FLUSH = None
+
+
+def flush_l2():
+    global FLUSH
+    if FLUSH is None:
+        FLUSH = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    FLUSH.fill_(1)
+
+
+def timed(fn, iters=10, warm=3, flush=True):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    times = []
+    for _ in range(iters):
+        if flush:
+            flush_l2()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        times.append(a.elapsed_time(b))
+    return float(numpy.median(times)), float(min(times))
+
+
+def engine_for(yaml, precision="f32"):
+    import warnings
+    config = scopyon_b200.DefaultConfiguration()
+    config.update(yaml)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        configs = _epifm.EPIFMConfigs(config.default, rng=numpy.random.RandomState(0))
+    return configs, DeviceEngine(configs, precision=precision)
+
+
+def bench_detector():
+    for det, extra in (("CMOS", "analog_to_digital_converter: {type: column, count: 2.0, offset: 100, fullwell: 30000}"),
+                       ("CMOS", "analog_to_digital_converter: {type: none, offset: 100, fullwell: 30000}"),
+                       ("CCD", "analog_to_digital_converter: {type: none}"),
+                       ("EMCCD", "analog_to_digital_converter: {type: none}")):
+        for size in (2048, 4096):
+            yaml = "default:\n    detector: {type: %s, image_size: [%d, %d], QE: 0.73}\n    %s\n" % (det, size, size, extra)
+            configs, eng = engine_for(yaml)
+            for level, label in ((0.0, "background only"), (0.6, "C4-like 0.6 photons/px"), (20.0, "bright 20 photons/px")):
+                photons = torch.full((size, size), level, dtype=torch.float32, device="cuda")
+                adc = torch.empty_like(photons)
+                ms, best = timed(lambda: eng.detect(photons, 1, 42, adc=adc))
+                gbs = size * size * 8 / (ms * 1e-3) / 1e9
+                print(json.dumps({"kernel": "detector_kernel<float,%s>" % det, "fpn": configs.ADConverter_fpn_type,
+                                  "size": size, "signal": label, "ms": ms, "ms_best": best, "GB/s": gbs,
+                                  "frac_of_measured_hbm": gbs / PEAK, "frames/s": 1e3 / ms}))
+
+
+def bench_diffuse():
+    for n in (100000, 10000000, 50000000):
+        parts = DeviceParticles(n, 3)
+        ms, best = timed(lambda: parts.step(1, 0, [1e-8, 1e-8, 1e-8]))
+        gbs = n * 48 / (ms * 1e-3) / 1e9
+        print(json.dumps({"kernel": "diffuse_kernel", "particles": n, "ms": ms, "ms_best": best, "GB/s": gbs,
+                          "frac_of_measured_hbm": gbs / PEAK, "particle_steps/s": n / (ms * 1e-3)}))
+
+
+def bench_render():
+    sys.path.insert(0, ROOT)
+    from bench import C4_YAML, count_spot_pixel_evals
+    for size, n, three_d in ((2048, 100000, False), (2048, 100000, True), (512, 1000, False)):
+        configs, eng = engine_for(C4_YAML % (size, size))
+        pl = configs.pixel_length
+        rng = numpy.random.RandomState(1)
+        data = numpy.zeros((n, 5))
+        data[:, 1:3] = rng.uniform(-size * pl / 2, size * pl / 2, (n, 2))
+        if three_d:
+            data[:, 0] = rng.uniform(0, 1.5e-6, n)
+        data[:, 3] = numpy.arange(n)
+        data[:, 4] = 1
+        t0 = time.time()
+        eng.ensure_all_tables() if three_d else eng.ensure_tables([0])
+        torch.cuda.synchronize()
+        build_s = time.time() - t0
+        soa = torch.from_numpy(numpy.ascontiguousarray(data[:, [0, 1, 2, 4]].T)).cuda()
+        w = torch.full((n,), 30.0, dtype=torch.float64, device="cuda")
+        out = torch.empty((size, size), dtype=torch.float32, device="cuda")
+        work = eng._render_workspace(n)
+
+        def go():
+            eng._call("scb_render_expected", ctypes.byref(eng.geom), n, _native.ptr(soa[0]), _native.ptr(soa[1]),
+                      _native.ptr(soa[2]), _native.ptr(w), _native.ptr(eng.sat), _native.ptr(eng.inv_scale),
+                      _native.ptr(eng.slot_of_key), _native.ptr(out), _native.F32, 0, _native.ptr(work), work.numel(),
+                      _native.ptr(eng.errors), eng._stream())
+        ms, best = timed(go)
+        evals = count_spot_pixel_evals(data, size, pl)
+        print(json.dumps({"kernel": "scb_render_expected (prepare+scan+fill+render)", "size": size, "spots": n,
+                          "3d": three_d, "ms": ms, "ms_best": best, "evals": evals, "evals/s": evals / (ms * 1e-3),
+                          "GB/s_algorithmic": evals * 8.5 / (ms * 1e-3) / 1e9, "tables": eng.n_tables,
+                          "table_build_s": build_s, "errors": int(eng.errors.item())}))
+
+
+if __name__ == "__main__":
+    what = sys.argv[1:] or ["detector", "diffuse", "render"]
+    print(json.dumps({"gpu": torch.cuda.get_device_name(0), "hbm_peak_gbs": PEAK}))
+    if "detector" in what:
+        bench_detector()
+    if "diffuse" in what:
+        bench_diffuse()
+    if "render" in what:
+        bench_render()
