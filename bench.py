@@ -177,17 +177,20 @@ def cpu_sample(args, n_threads):
     t_table = t_render = 0.0
     expected = numpy.zeros((args.size, args.size))
     slot = numpy.full(geom.n_depth_keys + 1, -1, dtype=numpy.int32)
-    for key in numpy.unique(keys):
-        sel = keys == key
-        depth = key * 1e-9 if key < geom.n_depth_keys else params["depth_cutoff"]
+    uniq = numpy.unique(keys)
+    batch = 8                      # tables resident at once (8 x 32 MB); the reference caches them all
+    for b0 in range(0, len(uniq), batch):
+        group = uniq[b0: b0 + batch]
         t0 = time.perf_counter()
-        table = c_oracle.table_from_radial(orc.radial_profile(params, depth))
+        tables = numpy.stack([c_oracle.table_from_radial(orc.radial_profile(
+            params, key * 1e-9 if key < geom.n_depth_keys else params["depth_cutoff"])) for key in group])
         t_table += time.perf_counter() - t0
         slot[:] = -1
-        slot[key] = 0
+        slot[group] = numpy.arange(len(group))
+        sel = numpy.isin(keys, group)
         t0 = time.perf_counter()
         expected += c_oracle.render_bruteforce(geom, pts[sel, 2], pts[sel, 0], pts[sel, 1], weight[sel],
-                                               table[None], slot, n_threads=n_threads)
+                                               tables, slot, n_threads=n_threads)
         t_render += time.perf_counter() - t0
     rn = _epifm.catalog_tables()["cmos_readout"]
     t0 = time.perf_counter()

@@ -161,13 +161,13 @@ int orc_render_sat(const orc_geometry *g, int64_t n_spots, const double *depth, 
 }
 
 /* ---- reference algorithm: direct slice sums over the fp64 table ------------------- */
-/* tables: [n_slots][side][side] fp64.  Threads split the spot list (like the reference's
- * Pool.map over array_split(particles), _epifm.py:1250-1260) and reduce their images. */
+/* tables: [n_slots][side][side] fp64.  Threads take spots dynamically (the reference's
+ * Pool.map over array_split(particles), _epifm.py:1250-1260, in spirit); each spot's
+ * footprint is summed into a private buffer and then added to the shared image. */
 int orc_render_bruteforce(const orc_geometry *g, int64_t n_spots, const double *depth, const double *x,
                           const double *y, const double *weight, const double *tables,
                           const int32_t *slot_of_key, double *expected, int n_threads) {
     const int side = 2 * (g->n_radial - 1) + 1;
-    const size_t n_pix = (size_t)g->n_w * g->n_h;
     const double unit_area = g->resolution * g->resolution;
     int missing = 0;
 #ifdef _OPENMP
@@ -175,16 +175,11 @@ int orc_render_bruteforce(const orc_geometry *g, int64_t n_spots, const double *
 #endif
 #pragma omp parallel reduction(+ : missing)
     {
-        int tid = 0, nt = 1;
-#ifdef _OPENMP
-        tid = omp_get_thread_num();
-        nt = omp_get_num_threads();
-#endif
-        double *img = (nt == 1) ? expected : (double *)calloc(n_pix, sizeof(double));
         int *left = (int *)malloc(sizeof(int) * ORC_MAX_EDGES * 2), *top = left + ORC_MAX_EDGES;
-        const int64_t chunk = (n_spots + nt - 1) / nt;
-        const int64_t s0 = tid * chunk, s1 = (s0 + chunk < n_spots) ? s0 + chunk : n_spots;
-        for (int64_t s = s0; s < s1; ++s) {
+        size_t cap = 64 * 64;
+        double *foot = (double *)malloc(sizeof(double) * cap);
+#pragma omp for schedule(dynamic, 1)
+        for (int64_t s = 0; s < n_spots; ++s) {
             const double w = weight[s];
             if (!(w > 0.0)) continue;
             const double xi = x[s] - g->focal[1], yi = y[s] - g->focal[2], dz = depth[s] - g->focal[0];
@@ -194,6 +189,8 @@ int orc_render_bruteforce(const orc_geometry *g, int64_t n_spots, const double *
             const int ni = edges_of(xi, g->n_w, g->pixel_length, side, g->resolution, &i0, left, ORC_MAX_EDGES);
             const int nj = edges_of(yi, g->n_h, g->pixel_length, side, g->resolution, &j0, top, ORC_MAX_EDGES);
             if (ni < 2 || nj < 2) continue;
+            const size_t need = (size_t)(ni - 1) * (nj - 1);
+            if (need > cap) { cap = need; foot = (double *)realloc(foot, sizeof(double) * cap); }
             const double *T = tables + (size_t)slot * side * side;
             for (int a = 0; a + 1 < ni; ++a)
                 for (int b = 0; b + 1 < nj; ++b) {
@@ -205,15 +202,15 @@ int orc_render_bruteforce(const orc_geometry *g, int64_t n_spots, const double *
                         sum += rs;
                     }
                     const double photons = sum * unit_area;
-                    if (photons > 0) img[(size_t)(i0 + a) * g->n_h + (j0 + b)] += photons * w;
+                    foot[(size_t)a * (nj - 1) + b] = photons > 0 ? photons * w : 0.0;
                 }
+#pragma omp critical
+            for (int a = 0; a + 1 < ni; ++a)
+                for (int b = 0; b + 1 < nj; ++b)
+                    expected[(size_t)(i0 + a) * g->n_h + (j0 + b)] += foot[(size_t)a * (nj - 1) + b];
         }
         free(left);
-        if (nt > 1) {
-#pragma omp critical
-            for (size_t i = 0; i < n_pix; ++i) expected[i] += img[i];
-            free(img);
-        }
+        free(foot);
     }
     return missing;
 }
