@@ -242,7 +242,12 @@ int scb_adc_offsets(uint64_t seed, int64_t n, double adc0, double fpn_count,
  *   d_expectation  optional out: QE*(photons+background)          (camera[:,:,0])
  *   d_in_signal / d_in_noise  optional injected draws (bit-exact ADC tests)
  *   d_out_signal / d_out_noise optional taps of the drawn signal / noise (statistics tests)
+ *   d_workspace    scratch of scb_detector_workspace_bytes(): the streaming pass finishes
+ *                  every pixel whose expectation is < 12 e- (and, for EMCCD, drew no
+ *                  electron) and lists the others; a second pass runs the general
+ *                  samplers on that list with the same per-pixel random streams.
  */
+size_t scb_detector_workspace_bytes(int32_t n_w, int32_t n_h);
 int scb_detector_adc(uint64_t seed, uint64_t frame, const scb_detector *det,
                      int32_t n_w, int32_t n_h, int elem_type,
                      const void *d_photons, const void *d_offset,
@@ -250,6 +255,7 @@ int scb_detector_adc(uint64_t seed, uint64_t frame, const scb_detector *det,
                      void *d_adc, void *d_expectation,
                      const void *d_in_signal, const void *d_in_noise,
                      void *d_out_signal, void *d_out_noise,
+                     void *d_workspace, size_t workspace_bytes,
                      void *stream);
 
 #ifdef __cplusplus

@@ -21,7 +21,7 @@
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kMaxAlias = 1024;
+constexpr int kMaxAlias = 256;
 
 // Per-pixel overflow stream for rejection loops: Philox keyed (seed; pixel, frame), tag
 // EXTRA, block counter in the low bits of the tag word.
@@ -45,18 +45,29 @@ struct PixelRng {
     }
 };
 
-// Poisson by inversion (sequential search), lambda < 12.
+// Poisson by inversion for lambda < 12, on one 32-bit random word.  The word is compared
+// (as a float) against the cumulative probabilities scaled by 2^32; the first four terms
+// are unrolled and branch free, so a warp only diverges when a lane draws k >= 4.
+constexpr float kSmallLambda = 12.0f;
+
 __device__ __forceinline__ float poisson_small(float lambda, uint32_t r) {
-    const float u = u01_open_low(r);
-    float p = __expf(-lambda);
+    const float rf = (float)r;                                              // [0, 2^32]
+    float p = exp2f(fmaf(lambda, -1.4426950408889634f, 32.0f));             // 2^32 * exp(-lambda)
     float s = p;
-    int k = 0;
-    while (u > s && k < 128) {
-        ++k;
-        p *= __fdividef(lambda, (float)k);
-        s += p;
+    int k = rf >= s;
+    p *= lambda;             s += p; k += rf >= s;
+    p *= lambda * 0.5f;      s += p; k += rf >= s;
+    p *= lambda * (1.0f / 3.0f); s += p; k += rf >= s;
+    if (k == 4) {
+#pragma unroll 1
+        while (k < 160) {
+            p *= __fdividef(lambda, (float)k);
+            s += p;
+            if (rf < s) break;
+            ++k;
+        }
     }
-    return (float)k;
+    return lambda > 0.0f ? (float)k : 0.0f;
 }
 
 // PTRS, W. Hoermann, "The transformed rejection method for generating Poisson random
@@ -82,7 +93,7 @@ __device__ __noinline__ double poisson_ptrs(double lambda, PixelRng &rng) {
 
 __device__ __forceinline__ double poisson_any(double lambda, uint32_t r, PixelRng &rng) {
     if (!(lambda > 0.0)) return 0.0;      // E <= 0 (or NaN): no signal, _epifm.py:395-396
-    if (lambda < 12.0) return (double)poisson_small((float)lambda, r);
+    if (lambda < (double)kSmallLambda) return (double)poisson_small((float)lambda, r);
     return poisson_ptrs(lambda, rng);
 }
 
@@ -124,28 +135,6 @@ __device__ __noinline__ double emccd_signal(double E, double gain, uint32_t r, P
     return fmin(fmax(rint(gain * E), s_min), s_max - 1.0);
 }
 
-template <typename T>
-__device__ __forceinline__ void load4(const T *p, T v[4]) {
-    if constexpr (sizeof(T) == 4) {
-        float4 q = __ldcs(reinterpret_cast<const float4 *>(p));
-        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
-    } else {
-        double2 a = __ldcs(reinterpret_cast<const double2 *>(p));
-        double2 b = __ldcs(reinterpret_cast<const double2 *>(p) + 1);
-        v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
-    }
-}
-
-template <typename T>
-__device__ __forceinline__ void store4(T *p, const T v[4]) {
-    if constexpr (sizeof(T) == 4) {
-        __stcs(reinterpret_cast<float4 *>(p), make_float4(v[0], v[1], v[2], v[3]));
-    } else {
-        __stcs(reinterpret_cast<double2 *>(p), make_double2(v[0], v[1]));
-        __stcs(reinterpret_cast<double2 *>(p) + 1, make_double2(v[2], v[3]));
-    }
-}
-
 struct DetArgs {
     uint64_t seed, frame;
     scb_detector det;
@@ -153,11 +142,14 @@ struct DetArgs {
     int32_t n_h;
     int n_alias;
     double adc_max, pow2bit;
+    float inv_fullwell, inv_nh;
     const void *photons, *offset;
     const scb_alias_entry *alias;
     void *adc, *expectation;
     const void *in_signal, *in_noise;
     void *out_signal, *out_noise;
+    uint32_t *slow_list;       // pixels that left the fast path (bright, or EMCCD with electrons)
+    uint32_t *slow_count;
 };
 
 // ADC, _epifm.py:1472-1484 with gain = fullwell / (2^bit - offset), _epifm.py:958.
@@ -171,117 +163,207 @@ __device__ __forceinline__ double adc_convert(double pe, double offset, const De
 }
 __device__ __forceinline__ float adc_convert(float pe, float offset, const DetArgs &a) {
     pe = fminf(pe, (float)a.det.fullwell);
-    const float inv_gain = __fdividef((float)a.pow2bit - offset, (float)a.det.fullwell);
-    float v = fmaf(pe, inv_gain, offset);
-    return fminf(fmaxf(v, 0.0f), (float)a.adc_max);
+    const float inv_gain = ((float)a.pow2bit - offset) * a.inv_fullwell;
+    return fminf(fmaxf(fmaf(pe, inv_gain, offset), 0.0f), (float)a.adc_max);
+}
+
+// column (axis-1 index) of flat pixel p0 without a 64-bit division
+__device__ __forceinline__ int column_of(int64_t p0, const DetArgs &a) {
+    if (p0 >= ((int64_t)1 << 24)) return (int)(p0 % a.n_h);
+    const int row = (int)__fmul_rz((float)(int)p0, a.inv_nh);
+    int j = (int)p0 - row * a.n_h;
+    if (j < 0) j += a.n_h;
+    if (j >= a.n_h) j -= a.n_h;
+    return j;
+}
+
+template <typename T>
+struct PixelOut {
+    T adc, ex, sig, noi;
+};
+
+// One pixel: expectation -> shot noise (+EM gain) -> readout noise -> ADC.
+// Scalars only (no local arrays), so everything stays in registers.
+template <typename T, int DET>
+__device__ __forceinline__ PixelOut<T> detect_pixel(const DetArgs &a, const scb_alias_entry *s_alias, int64_t pix,
+                                                    bool valid, T photons, T offset, uint32_t r_shot,
+                                                    uint32_t r_read, float normal, T qe, T bg) {
+    PixelOut<T> o;
+    o.ex = qe * (photons + bg);                                           // _epifm.py:1438-1441
+    if (a.in_signal) {
+        o.sig = valid ? ((const T *)a.in_signal)[pix] : (T)0;
+    } else {
+        const float lam = (float)o.ex;
+        // fast path: small expectation; an EMCCD pixel with zero photoelectrons stays zero
+        // (S = 0 lies inside the reference's support whenever E < 12)
+        const float n_small = poisson_small(fminf(lam, kSmallLambda), r_shot);
+        o.sig = (T)n_small;
+        if (valid && (!(lam < kSmallLambda) || (DET == SCB_DET_EMCCD && n_small != 0.0f)))
+            a.slow_list[atomicAdd(a.slow_count, 1u)] = (uint32_t)pix;   // finished by detector_slow_kernel
+    }
+    if (a.in_noise) {
+        o.noi = valid ? ((const T *)a.in_noise)[pix] : (T)0;
+    } else if (DET == SCB_DET_CMOS) {
+        const uint64_t prod = (uint64_t)r_read * (uint32_t)a.n_alias;
+        const scb_alias_entry e = s_alias[(uint32_t)(prod >> 32)];
+        const float frac = (float)(uint32_t)prod * 2.3283064365386963e-10f;
+        o.noi = (T)(frac < e.threshold ? e.value : e.alias_value);
+    } else {
+        o.noi = (T)a.det.readout_noise * (T)normal;                       // _epifm.py:360-362
+    }
+    o.adc = adc_convert(o.sig + o.noi, offset, a);                        // _epifm.py:1464-1469
+    return o;
+}
+
+template <typename T>
+__device__ __forceinline__ void store_quad(void *base, int64_t p0, int64_t n_pix, bool full, T v0, T v1, T v2, T v3) {
+    T *p = (T *)base + p0;
+    if (full) {
+        if constexpr (sizeof(T) == 4) {
+            __stcs(reinterpret_cast<float4 *>(p), make_float4(v0, v1, v2, v3));
+        } else {
+            __stcs(reinterpret_cast<double2 *>(p), make_double2(v0, v1));
+            __stcs(reinterpret_cast<double2 *>(p) + 1, make_double2(v2, v3));
+        }
+    } else {
+        if (p0 + 0 < n_pix) p[0] = v0;
+        if (p0 + 1 < n_pix) p[1] = v1;
+        if (p0 + 2 < n_pix) p[2] = v2;
+        if (p0 + 3 < n_pix) p[3] = v3;
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ void load_quad(const void *base, int64_t p0, int64_t n_pix, bool full, bool streaming,
+                                          T &v0, T &v1, T &v2, T &v3) {
+    const T *p = (const T *)base + p0;
+    if (full) {
+        if constexpr (sizeof(T) == 4) {
+            const float4 q = streaming ? __ldcs(reinterpret_cast<const float4 *>(p))
+                                       : __ldg(reinterpret_cast<const float4 *>(p));
+            v0 = q.x; v1 = q.y; v2 = q.z; v3 = q.w;
+        } else {
+            const double2 lo = streaming ? __ldcs(reinterpret_cast<const double2 *>(p))
+                                         : __ldg(reinterpret_cast<const double2 *>(p));
+            const double2 hi = streaming ? __ldcs(reinterpret_cast<const double2 *>(p) + 1)
+                                         : __ldg(reinterpret_cast<const double2 *>(p) + 1);
+            v0 = lo.x; v1 = lo.y; v2 = hi.x; v3 = hi.y;
+        }
+    } else {
+        v0 = (p0 + 0 < n_pix) ? p[0] : (T)0;
+        v1 = (p0 + 1 < n_pix) ? p[1] : (T)0;
+        v2 = (p0 + 2 < n_pix) ? p[2] : (T)0;
+        v3 = (p0 + 3 < n_pix) ? p[3] : (T)0;
+    }
 }
 
 template <typename T, int DET>
-__global__ void __launch_bounds__(kThreads)
-detector_kernel(DetArgs a) {
+__global__ void __launch_bounds__(kThreads, 4)
+detector_kernel(const __grid_constant__ DetArgs a) {
     __shared__ scb_alias_entry s_alias[DET == SCB_DET_CMOS ? kMaxAlias : 1];
     if (DET == SCB_DET_CMOS) {
         for (int i = threadIdx.x; i < a.n_alias; i += kThreads) s_alias[i] = a.alias[i];
         __syncthreads();
     }
-    const T *photons = (const T *)a.photons;
-    const T *offset = (const T *)a.offset;
-    T *adc = (T *)a.adc;
     const int64_t n_quads = (a.n_pix + 3) >> 2;
     const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
     const uint32_t f_lo = (uint32_t)a.frame, f_hi = (uint32_t)(a.frame >> 32);
     const T qe = (T)a.det.qe;
     const T bg = a.det.background_on ? (T)a.det.background : (T)0;
+    const bool row_aligned = (a.n_h & 3) == 0;
+    const bool gaussian_readout = DET != SCB_DET_CMOS && a.in_noise == nullptr && a.det.readout_noise > 0.0;
 
     for (int64_t q = (int64_t)blockIdx.x * kThreads + threadIdx.x; q < n_quads; q += (int64_t)gridDim.x * kThreads) {
         const int64_t p0 = q << 2;
         const bool full = p0 + 4 <= a.n_pix;
-        T ph[4], off[4], sig[4], noi[4], out[4], ex[4];
-        if (full) {
-            load4(photons + p0, ph);
-        } else {
-            for (int i = 0; i < 4; ++i) ph[i] = (p0 + i < a.n_pix) ? photons[p0 + i] : (T)0;
-        }
+        T ph0, ph1, ph2, ph3;
+        load_quad<T>(a.photons, p0, a.n_pix, full, true, ph0, ph1, ph2, ph3);
         // ADC offset: scalar, per column (axis-1 index), or per pixel  (_epifm.py:941-952)
+        T of0, of1, of2, of3;
         if (a.det.fpn_type == SCB_FPN_NONE) {
-            for (int i = 0; i < 4; ++i) off[i] = (T)a.det.adc_offset;
+            of0 = of1 = of2 = of3 = (T)a.det.adc_offset;
         } else if (a.det.fpn_type == SCB_FPN_PIXEL) {
-            if (full) load4(offset + p0, off);
-            else for (int i = 0; i < 4; ++i) off[i] = (p0 + i < a.n_pix) ? offset[p0 + i] : (T)0;
+            load_quad<T>(a.offset, p0, a.n_pix, full, true, of0, of1, of2, of3);
         } else {
-            const int j0 = (int)(p0 % a.n_h);
-            if ((a.n_h & 3) == 0 && full) {   // the quad stays inside one image row
-                for (int i = 0; i < 4; ++i) off[i] = offset[j0 + i];
+            const int j0 = column_of(p0, a);
+            if (row_aligned) {                 // the quad stays inside one image row
+                load_quad<T>(a.offset, j0, a.n_h, true, false, of0, of1, of2, of3);
             } else {
-                for (int i = 0; i < 4; ++i) off[i] = offset[(j0 + i) % a.n_h];
+                const T *o = (const T *)a.offset;
+                of0 = o[j0];
+                of1 = o[j0 + 1 < a.n_h ? j0 + 1 : j0 + 1 - a.n_h];
+                of2 = o[j0 + 2 < a.n_h ? j0 + 2 : j0 + 2 - a.n_h];
+                of3 = o[j0 + 3 < a.n_h ? j0 + 3 : j0 + 3 - a.n_h];
             }
         }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) ex[i] = qe * (ph[i] + bg);    // _epifm.py:1438-1441
+        Philox4 rs = {0u, 0u, 0u, 0u}, rr = {0u, 0u, 0u, 0u};
+        if (a.in_signal == nullptr)
+            rs = philox4x32_10((uint32_t)q, (uint32_t)(q >> 32), f_lo, SCB_TAG_SHOT ^ f_hi, k0, k1);
+        if (a.in_noise == nullptr && (DET == SCB_DET_CMOS || gaussian_readout))
+            rr = philox4x32_10((uint32_t)q, (uint32_t)(q >> 32), f_lo, SCB_TAG_READ ^ f_hi, k0, k1);
+        float n0 = 0.f, n1 = 0.f, n2 = 0.f, n3 = 0.f;
+        if (gaussian_readout) {
+            box_muller(rr.x, rr.y, n0, n1);
+            box_muller(rr.z, rr.w, n2, n3);
+        }
+        const PixelOut<T> o0 = detect_pixel<T, DET>(a, s_alias, p0 + 0, p0 + 0 < a.n_pix, ph0, of0, rs.x, rr.x, n0, qe, bg);
+        const PixelOut<T> o1 = detect_pixel<T, DET>(a, s_alias, p0 + 1, p0 + 1 < a.n_pix, ph1, of1, rs.y, rr.y, n1, qe, bg);
+        const PixelOut<T> o2 = detect_pixel<T, DET>(a, s_alias, p0 + 2, p0 + 2 < a.n_pix, ph2, of2, rs.z, rr.z, n2, qe, bg);
+        const PixelOut<T> o3 = detect_pixel<T, DET>(a, s_alias, p0 + 3, p0 + 3 < a.n_pix, ph3, of3, rs.w, rr.w, n3, qe, bg);
 
-        // ---- shot noise (+ EM gain)
-        if (a.in_signal) {
-            const T *in = (const T *)a.in_signal;
-            for (int i = 0; i < 4; ++i) sig[i] = (p0 + i < a.n_pix) ? in[p0 + i] : (T)0;
-        } else {
-            const Philox4 r = philox4x32_10((uint32_t)q, (uint32_t)(q >> 32), f_lo, SCB_TAG_SHOT ^ f_hi, k0, k1);
-            const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float lam = (float)ex[i];
-                // fast path: small expectation; an EMCCD pixel with zero photoelectrons
-                // stays zero (S = 0 lies inside the reference's support whenever E < 12)
-                const float n_small = (lam > 0.0f && lam < 12.0f) ? poisson_small(lam, rw[i]) : 0.0f;
-                if (lam < 12.0f && (DET != SCB_DET_EMCCD || n_small == 0.0f)) {
-                    sig[i] = (T)n_small;
-                } else {
-                    PixelRng rng(a.seed, (uint64_t)(p0 + i), a.frame);
-                    if (DET == SCB_DET_EMCCD) sig[i] = (T)emccd_signal((double)ex[i], a.det.emgain, rw[i], rng);
-                    else sig[i] = (T)poisson_any((double)ex[i], rw[i], rng);
-                }
-            }
-        }
-        // ---- readout noise
+        store_quad<T>(a.adc, p0, a.n_pix, full, o0.adc, o1.adc, o2.adc, o3.adc);
+        if (a.expectation) store_quad<T>(a.expectation, p0, a.n_pix, full, o0.ex, o1.ex, o2.ex, o3.ex);
+        if (a.out_signal) store_quad<T>(a.out_signal, p0, a.n_pix, full, o0.sig, o1.sig, o2.sig, o3.sig);
+        if (a.out_noise) store_quad<T>(a.out_noise, p0, a.n_pix, full, o0.noi, o1.noi, o2.noi, o3.noi);
+    }
+}
+
+// Second pass over the (usually short) list of pixels that need the general samplers:
+// PTRS Poisson for E >= 12, Poisson -> Gamma multiplication register for EMCCD.  Draws are
+// keyed by pixel and frame exactly as in the streaming kernel, so the readout noise added
+// here is the one the streaming kernel drew.
+template <typename T, int DET>
+__global__ void __launch_bounds__(kThreads)
+detector_slow_kernel(const __grid_constant__ DetArgs a) {
+    const uint32_t n = *a.slow_count;
+    const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
+    const uint32_t f_lo = (uint32_t)a.frame, f_hi = (uint32_t)(a.frame >> 32);
+    for (uint32_t t = blockIdx.x * kThreads + threadIdx.x; t < n; t += gridDim.x * kThreads) {
+        const int64_t pix = a.slow_list[t];
+        const int64_t q = pix >> 2;
+        const int w = (int)(pix & 3);
+        const T qe = (T)a.det.qe;
+        const T bg = a.det.background_on ? (T)a.det.background : (T)0;
+        const T ex = qe * (((const T *)a.photons)[pix] + bg);
+        T offset = (T)a.det.adc_offset;
+        if (a.det.fpn_type == SCB_FPN_PIXEL) offset = ((const T *)a.offset)[pix];
+        else if (a.det.fpn_type == SCB_FPN_COLUMN) offset = ((const T *)a.offset)[pix % a.n_h];
+        const Philox4 rs = philox4x32_10((uint32_t)q, (uint32_t)(q >> 32), f_lo, SCB_TAG_SHOT ^ f_hi, k0, k1);
+        const uint32_t r_shot = w == 0 ? rs.x : w == 1 ? rs.y : w == 2 ? rs.z : rs.w;
+        PixelRng rng(a.seed, (uint64_t)pix, a.frame);
+        double sig;
+        if (DET == SCB_DET_EMCCD) sig = emccd_signal((double)ex, a.det.emgain, r_shot, rng);
+        else sig = poisson_any((double)ex, r_shot, rng);
+        T noi = (T)0;
         if (a.in_noise) {
-            const T *in = (const T *)a.in_noise;
-            for (int i = 0; i < 4; ++i) noi[i] = (p0 + i < a.n_pix) ? in[p0 + i] : (T)0;
+            noi = ((const T *)a.in_noise)[pix];
         } else {
-            const Philox4 r = philox4x32_10((uint32_t)q, (uint32_t)(q >> 32), f_lo, SCB_TAG_READ ^ f_hi, k0, k1);
+            const Philox4 rr = philox4x32_10((uint32_t)q, (uint32_t)(q >> 32), f_lo, SCB_TAG_READ ^ f_hi, k0, k1);
             if (DET == SCB_DET_CMOS) {
-                const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const uint64_t prod = (uint64_t)rw[i] * (uint32_t)a.n_alias;
-                    const scb_alias_entry e = s_alias[(uint32_t)(prod >> 32)];
-                    const float frac = (float)(uint32_t)prod * 2.3283064365386963e-10f;
-                    noi[i] = (T)(frac < e.threshold ? e.value : e.alias_value);
-                }
-            } else if (a.det.readout_noise > 0.0) {   // _epifm.py:360-362
-                float n0, n1, n2, n3;
-                box_muller(r.x, r.y, n0, n1);
-                box_muller(r.z, r.w, n2, n3);
-                const T rn = (T)a.det.readout_noise;
-                noi[0] = rn * (T)n0; noi[1] = rn * (T)n1; noi[2] = rn * (T)n2; noi[3] = rn * (T)n3;
-            } else {
-                noi[0] = noi[1] = noi[2] = noi[3] = (T)0;
+                const uint32_t r_read = w == 0 ? rr.x : w == 1 ? rr.y : w == 2 ? rr.z : rr.w;
+                const uint64_t prod = (uint64_t)r_read * (uint32_t)a.n_alias;
+                const scb_alias_entry e = a.alias[(uint32_t)(prod >> 32)];
+                const float frac = (float)(uint32_t)prod * 2.3283064365386963e-10f;
+                noi = (T)(frac < e.threshold ? e.value : e.alias_value);
+            } else if (a.det.readout_noise > 0.0) {
+                float n0, n1;
+                if (w < 2) box_muller(rr.x, rr.y, n0, n1);
+                else box_muller(rr.z, rr.w, n0, n1);
+                noi = (T)a.det.readout_noise * (T)((w & 1) ? n1 : n0);
             }
         }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) out[i] = adc_convert(sig[i] + noi[i], off[i], a);   // _epifm.py:1464-1469
-
-        if (full) {
-            store4(adc + p0, out);
-            if (a.expectation) store4((T *)a.expectation + p0, ex);
-            if (a.out_signal) store4((T *)a.out_signal + p0, sig);
-            if (a.out_noise) store4((T *)a.out_noise + p0, noi);
-        } else {
-            for (int i = 0; i < 4 && p0 + i < a.n_pix; ++i) {
-                adc[p0 + i] = out[i];
-                if (a.expectation) ((T *)a.expectation)[p0 + i] = ex[i];
-                if (a.out_signal) ((T *)a.out_signal)[p0 + i] = sig[i];
-                if (a.out_noise) ((T *)a.out_noise)[p0 + i] = noi[i];
-            }
-        }
+        ((T *)a.adc)[pix] = adc_convert((T)sig + noi, offset, a);
+        if (a.out_signal) ((T *)a.out_signal)[pix] = (T)sig;
     }
 }
 
@@ -300,10 +382,12 @@ template <typename T, int DET>
 void launch_detector(const DetArgs &a, cudaStream_t s) {
     const int64_t n_quads = (a.n_pix + 3) >> 2;
     int64_t blocks = (n_quads + kThreads - 1) / kThreads;
-    const int64_t cap = (int64_t)SCB_SM_COUNT * 8;   // 8 resident CTAs of 256 threads per SM
+    const int64_t cap = (int64_t)SCB_SM_COUNT * 4;   // one wave: 4 resident CTAs of 256 threads per SM
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
+    cudaMemsetAsync(a.slow_count, 0, sizeof(uint32_t), s);
     detector_kernel<T, DET><<<(unsigned)blocks, kThreads, 0, s>>>(a);
+    if (a.in_signal == nullptr) detector_slow_kernel<T, DET><<<SCB_SM_COUNT * 2, kThreads, 0, s>>>(a);
 }
 
 }  // namespace
@@ -323,11 +407,17 @@ extern "C" int scb_adc_offsets(uint64_t seed, int64_t n, double adc0, double fpn
     return 0;
 }
 
+extern "C" size_t scb_detector_workspace_bytes(int32_t n_w, int32_t n_h) {
+    if (n_w <= 0 || n_h <= 0) return 0;
+    return 256 + (size_t)n_w * n_h * sizeof(uint32_t);   // counter + worst-case pixel list
+}
+
 extern "C" int scb_detector_adc(uint64_t seed, uint64_t frame, const scb_detector *det, int32_t n_w, int32_t n_h,
                                 int elem_type, const void *d_photons, const void *d_offset,
                                 const scb_alias_entry *d_cmos_alias, int n_alias, void *d_adc,
                                 void *d_expectation, const void *d_in_signal, const void *d_in_noise,
-                                void *d_out_signal, void *d_out_noise, void *stream) {
+                                void *d_out_signal, void *d_out_noise, void *d_workspace,
+                                size_t workspace_bytes, void *stream) {
     SCB_REQUIRE(det && d_photons && d_adc, SCB_E_NULL, "scb_detector_adc: NULL pointer");
     SCB_REQUIRE(n_w > 0 && n_h > 0, SCB_E_INVALID, "scb_detector_adc: image %d x %d", n_w, n_h);
     SCB_REQUIRE(elem_type == SCB_F32 || elem_type == SCB_F64, SCB_E_INVALID, "elem_type=%d", elem_type);
@@ -344,11 +434,18 @@ extern "C" int scb_detector_adc(uint64_t seed, uint64_t frame, const scb_detecto
     const size_t align = elem_type == SCB_F32 ? 16 : 16;
     SCB_REQUIRE(((uintptr_t)d_photons % align) == 0 && ((uintptr_t)d_adc % align) == 0, SCB_E_INVALID,
                 "scb_detector_adc: image buffers must be 16-byte aligned");
+    SCB_REQUIRE((int64_t)n_w * n_h < ((int64_t)1 << 32), SCB_E_INVALID, "scb_detector_adc: image too large");
+    SCB_REQUIRE(d_workspace && workspace_bytes >= scb_detector_workspace_bytes(n_w, n_h), SCB_E_WORKSPACE,
+                "scb_detector_adc: workspace %zu < %zu", workspace_bytes, scb_detector_workspace_bytes(n_w, n_h));
     DetArgs a;
+    a.slow_count = (uint32_t *)d_workspace;
+    a.slow_list = (uint32_t *)((char *)d_workspace + 256);
     a.seed = seed; a.frame = frame; a.det = *det;
     a.n_pix = (int64_t)n_w * n_h; a.n_h = n_h;
     a.n_alias = need_alias ? n_alias : 0;
     a.pow2bit = ldexp(1.0, det->bit);
+    a.inv_fullwell = (float)(1.0 / det->fullwell);
+    a.inv_nh = (float)(1.0 / (double)n_h);
     a.adc_max = a.pow2bit - 1.0;
     a.photons = d_photons; a.offset = d_offset; a.alias = d_cmos_alias;
     a.adc = d_adc; a.expectation = d_expectation;

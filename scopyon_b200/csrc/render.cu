@@ -58,8 +58,8 @@ __global__ void __launch_bounds__(256)
 spot_prepare_kernel(Geo g, int64_t n, const double *__restrict__ depth, const double *__restrict__ x,
                     const double *__restrict__ y, const double *__restrict__ weight,
                     const double *__restrict__ inv_scale, const int32_t *__restrict__ slot_of_key,
-                    SpotRec *__restrict__ spots, int *__restrict__ tile_count,
-                    int32_t *__restrict__ errors) {
+                    SpotRec *__restrict__ spots, uint16_t *__restrict__ edges, int edge_cap,
+                    int *__restrict__ tile_count, int32_t *__restrict__ errors) {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
     SpotRec rec;
@@ -101,6 +101,13 @@ spot_prepare_kernel(Geo g, int64_t n, const double *__restrict__ depth, const do
                 const int u0 = rec.jmin / kTile, u1 = (rec.jmax - 1) / kTile;
                 for (int ti = t0; ti <= t1; ++ti)
                     for (int tj = u0; tj <= u1; ++tj) atomicAdd(&tile_count[ti * g.ntj + tj], 1);
+                // table sample index of every pixel edge the footprint touches (_epifm.py:236-253):
+                // rows first, then columns; the render kernel only looks them up
+                uint16_t *e = edges + (size_t)s * 2 * edge_cap;
+                for (int i = rec.imin; i <= rec.imax; ++i)
+                    e[i - rec.imin] = (uint16_t)edge_index(i, rec.imin, rec.imax, rec.ox, g);
+                for (int j = rec.jmin; j <= rec.jmax; ++j)
+                    e[edge_cap + j - rec.jmin] = (uint16_t)edge_index(j, rec.jmin, rec.jmax, rec.oy, g);
             }
         }
     }
@@ -162,14 +169,21 @@ struct __align__(16) StageMeta {
     double pad;
 };
 
+constexpr int kCornersPerLane = (kEdge * kEdge + 31) / 32;   // 10
+
+// SAT corner gather: L2-only (.cg).  With the default .ca policy an L1 miss pulls the
+// whole 128-byte line for an 8-byte corner (measured: 3.2 L2 sectors per gather).
+__device__ __forceinline__ long long load_corner(const int64_t *p) {
+    return __ldcg(reinterpret_cast<const long long *>(p));
+}
+
 template <typename OutT>
 __global__ void __launch_bounds__(kThreads)
-render_tiles_kernel(Geo g, const SpotRec *__restrict__ spots, const int *__restrict__ tile_start,
-                    const int *__restrict__ pair_spot, const int64_t *__restrict__ sat,
-                    OutT *__restrict__ out, int accumulate) {
+render_tiles_kernel(Geo g, const SpotRec *__restrict__ spots, const uint16_t *__restrict__ edges,
+                    int edge_cap, const int *__restrict__ tile_start, const int *__restrict__ pair_spot,
+                    const int64_t *__restrict__ sat, OutT *__restrict__ out, int accumulate) {
     __shared__ long long corners[kBatch][kEdge * kEdge];
     __shared__ StageMeta meta[kBatch];
-    __shared__ int s_left[kBatch][kEdge], s_top[kBatch][kEdge];
     __shared__ int ids_raw[kSortCap], ids[kSortCap];
 
     const int tile = blockIdx.x;
@@ -185,6 +199,7 @@ render_tiles_kernel(Geo g, const SpotRec *__restrict__ spots, const int *__restr
     for (int chunk = seg_begin; chunk < seg_end; chunk += kSortCap) {
         const int n_chunk = min(kSortCap, seg_end - chunk);
         // ---- order the chunk by spot index (rank sort; indices are distinct)
+        __syncthreads();
         for (int t = threadIdx.x; t < n_chunk; t += kThreads) ids_raw[t] = pair_spot[chunk + t];
         __syncthreads();
         for (int t = threadIdx.x; t < n_chunk; t += kThreads) {
@@ -195,39 +210,75 @@ render_tiles_kernel(Geo g, const SpotRec *__restrict__ spots, const int *__restr
         }
         __syncthreads();
 
-        for (int base = 0; base < n_chunk; base += kBatch) {
-            // ---- stage: warp b prepares spot base+b (edges, then SAT corners)
-            const int b = warp;
-            if (base + b < n_chunk) {
-                const SpotRec rec = spots[ids[base + b]];
+        // Software pipeline: the SAT corners of round r+1 are in flight (registers) while
+        // round r is accumulated from shared memory.
+        long long v[kCornersPerLane];
+        StageMeta m_next;
+        int ncl_next = 1;
+
+        auto issue = [&](int base) {
+            // warp b gathers the corners of spot base+b into registers
+            m_next.nrow = 0; m_next.ncol = 0; m_next.r0 = 0; m_next.c0 = 0; m_next.w = 0.0; m_next.pad = 0.0;
+            ncl_next = 1;
+            if (base + warp < n_chunk) {
+                const int sid = ids[base + warp];
+                const SpotRec rec = spots[sid];
                 const int r_lo = max(rec.imin, row0), r_hi = min(rec.imax, row0 + kTile);
                 const int c_lo = max(rec.jmin, col0), c_hi = min(rec.jmax, col0 + kTile);
                 const int nrow = r_hi - r_lo, ncol = c_hi - c_lo;
-                for (int e = lane; e < nrow + ncol + 2; e += 32) {
-                    if (e <= nrow) s_left[b][e] = edge_index(r_lo + e, rec.imin, rec.imax, rec.ox, g);
-                    else s_top[b][e - nrow - 1] = edge_index(c_lo + e - nrow - 1, rec.jmin, rec.jmax, rec.oy, g);
-                }
-                __syncwarp();
+                // lane e < 17 holds row edge e, lane 17 + l holds column edge l (l < 15); the last
+                // two column edges ride in a second register of lanes 0 and 1
+                const uint16_t *e = edges + (size_t)sid * 2 * edge_cap;
+                int edge_a = 0, edge_b = 0;
+                if (lane <= nrow) edge_a = e[r_lo - rec.imin + lane];
+                else if (lane >= kEdge && lane - kEdge <= ncol) edge_a = e[edge_cap + c_lo - rec.jmin + lane - kEdge];
+                if (lane < 2 && 15 + lane <= ncol) edge_b = e[edge_cap + c_lo - rec.jmin + 15 + lane];
                 const int64_t *S = sat + (size_t)rec.slot * pitch * pitch;
                 const int ncl = ncol + 1;
                 const int n_corner = (nrow + 1) * ncl;
                 const float inv = 1.0f / (float)ncl;
-                for (int idx = lane; idx < n_corner; idx += 32) {
-                    const int k = (int)(((float)idx + 0.5f) * inv);
-                    const int l = idx - k * ncl;
-                    corners[b][k * kEdge + l] = S[(size_t)s_left[b][k] * pitch + s_top[b][l]];
+#pragma unroll
+                for (int t = 0; t < kCornersPerLane; ++t) {
+                    const int idx = lane + 32 * t;
+                    const int cid = min(idx, n_corner - 1);
+                    const int k = (int)(((float)cid + 0.5f) * inv);
+                    const int l = cid - k * ncl;
+                    const int a = __shfl_sync(0xffffffffu, edge_a, k);
+                    const int b_lo = __shfl_sync(0xffffffffu, edge_a, min(kEdge + l, 31));
+                    const int b_hi = __shfl_sync(0xffffffffu, edge_b, max(l - 15, 0));
+                    const int b = l < 15 ? b_lo : b_hi;
+                    v[t] = 0;
+                    if (idx < n_corner) v[t] = load_corner(S + (size_t)a * pitch + b);
                 }
-                if (lane == 0) {
-                    StageMeta m;
-                    m.r0 = r_lo - row0; m.nrow = nrow; m.c0 = c_lo - col0; m.ncol = ncol;
-                    m.w = rec.w; m.pad = 0.0;
-                    meta[b] = m;
-                }
-            } else if (lane == 0) {
-                meta[b].nrow = 0;
-                meta[b].ncol = 0;
+                m_next.r0 = r_lo - row0; m_next.nrow = nrow; m_next.c0 = c_lo - col0; m_next.ncol = ncol;
+                m_next.w = rec.w;
+                ncl_next = ncl;
             }
-            __syncthreads();
+        };
+        auto commit = [&]() {
+            // registers -> shared memory (waits for the gathers)
+            const int n_corner = (m_next.nrow + 1) * ncl_next;
+            const float inv = 1.0f / (float)ncl_next;
+            if (m_next.nrow > 0) {
+#pragma unroll
+                for (int t = 0; t < kCornersPerLane; ++t) {
+                    const int idx = lane + 32 * t;
+                    if (idx < n_corner) {
+                        const int k = (int)(((float)idx + 0.5f) * inv);
+                        const int l = idx - k * ncl_next;
+                        corners[warp][k * kEdge + l] = v[t];
+                    }
+                }
+            }
+            if (lane == 0) meta[warp] = m_next;
+        };
+
+        issue(0);
+        commit();
+        __syncthreads();
+        for (int base = 0; base < n_chunk; base += kBatch) {
+            const bool more = base + kBatch < n_chunk;
+            if (more) issue(base + kBatch);
             // ---- accumulate: thread (py, px) owns one pixel
 #pragma unroll
             for (int q = 0; q < kBatch; ++q) {
@@ -240,6 +291,10 @@ render_tiles_kernel(Geo g, const SpotRec *__restrict__ spots, const int *__restr
                 }
             }
             __syncthreads();
+            if (more) {
+                commit();
+                __syncthreads();
+            }
         }
     }
 
@@ -253,6 +308,8 @@ render_tiles_kernel(Geo g, const SpotRec *__restrict__ spots, const int *__restr
 
 struct Workspace {
     SpotRec *spots;
+    uint16_t *edges;
+    int edge_cap;            // edge slots per axis per spot
     int *tile_count, *tile_cursor, *tile_start, *pair_spot;
     size_t bytes;
     int64_t pair_capacity;
@@ -292,6 +349,15 @@ Workspace carve(const Geo &g, int64_t n, void *base) {
     char *p = (char *)base;
     size_t off = 0;
     w.spots = (SpotRec *)(p + off); off += align_up((size_t)(n > 0 ? n : 1) * sizeof(SpotRec));
+    // pixel edges per axis: footprint rows <= ceil(sw/pl) + 1, plus one closing edge, rounded up to 8
+    {
+        double rows = ceil(g.sw / g.pl) + 3.0;
+        int64_t cap = (int64_t)rows;
+        const int64_t most = (g.n_w > g.n_h ? g.n_w : g.n_h) + 1;
+        if (cap > most) cap = most;
+        w.edge_cap = (int)((cap + 7) & ~(int64_t)7);
+    }
+    w.edges = (uint16_t *)(p + off); off += align_up((size_t)(n > 0 ? n : 1) * 2 * w.edge_cap * sizeof(uint16_t));
     w.tile_count = (int *)(p + off); off += align_up(n_tiles * sizeof(int));
     w.tile_cursor = (int *)(p + off); off += align_up(n_tiles * sizeof(int));
     w.tile_start = (int *)(p + off); off += align_up((n_tiles + 1) * sizeof(int));
@@ -380,7 +446,8 @@ extern "C" int scb_render_expected(const scb_geometry *geom, int64_t n_spots, co
     SCB_CUDA(cudaMemsetAsync(w.tile_count, 0, (size_t)((char *)w.tile_start - (char *)w.tile_count), s));
     if (n_spots > 0) {
         spot_prepare_kernel<<<scb_grid_for(n_spots, 256), 256, 0, s>>>(
-            g, n_spots, d_depth, d_x, d_y, d_weight, d_inv_scale, d_slot_of_key, w.spots, w.tile_count, d_errors);
+            g, n_spots, d_depth, d_x, d_y, d_weight, d_inv_scale, d_slot_of_key, w.spots, w.edges, w.edge_cap,
+            w.tile_count, d_errors);
     }
     tile_scan_kernel<<<1, 1024, 0, s>>>(n_tiles, w.tile_count, w.tile_start);
     if (n_spots > 0) {
@@ -390,11 +457,11 @@ extern "C" int scb_render_expected(const scb_geometry *geom, int64_t n_spots, co
     const bool timed = g_profile.enabled && g_profile.used < g_profile.capacity;
     if (timed) cudaEventRecord(g_profile.start[g_profile.used], s);
     if (out_type == SCB_F32)
-        render_tiles_kernel<float><<<n_tiles, kThreads, 0, s>>>(g, w.spots, w.tile_start, w.pair_spot, d_sat,
-                                                               (float *)d_out, accumulate);
+        render_tiles_kernel<float><<<n_tiles, kThreads, 0, s>>>(g, w.spots, w.edges, w.edge_cap, w.tile_start,
+                                                               w.pair_spot, d_sat, (float *)d_out, accumulate);
     else
-        render_tiles_kernel<double><<<n_tiles, kThreads, 0, s>>>(g, w.spots, w.tile_start, w.pair_spot, d_sat,
-                                                                (double *)d_out, accumulate);
+        render_tiles_kernel<double><<<n_tiles, kThreads, 0, s>>>(g, w.spots, w.edges, w.edge_cap, w.tile_start,
+                                                                w.pair_spot, d_sat, (double *)d_out, accumulate);
     if (timed) cudaEventRecord(g_profile.stop[g_profile.used++], s);
     SCB_CUDA_LAUNCH_CHECK("scb_render_expected");
     return 0;

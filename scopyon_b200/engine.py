@@ -214,6 +214,8 @@ class DeviceEngine:
                        float(configs.ADConverter_fpn_count), _native.ptr(self.offset), self.elem_type,
                        self._stream())
         self._workspace = None
+        self._det_work = torch.empty(self.lib.scb_detector_workspace_bytes(self.n_w, self.n_h), dtype=torch.uint8,
+                                     device=self.device)
         self._expected = torch.zeros((self.n_w, self.n_h), dtype=self.dtype, device=self.device)
 
     # ------------------------------------------------------------------ plumbing
@@ -395,7 +397,8 @@ class DeviceEngine:
             self.n_w, self.n_h, elem, _native.ptr(photons), _native.ptr(offset),
             _native.ptr(self.alias), 0 if self.alias is None else int(self.alias.shape[0]),
             _native.ptr(adc), _native.ptr(expectation), _native.ptr(in_signal), _native.ptr(in_noise),
-            _native.ptr(out_signal), _native.ptr(out_noise), self._stream())
+            _native.ptr(out_signal), _native.ptr(out_noise), _native.ptr(self._det_work), self._det_work.numel(),
+            self._stream())
         return adc
 
     def form_frame(self, snapshots, frame_index, noise_seed, states, exposure_time, want_true_data,
