@@ -273,11 +273,19 @@ detector_kernel(const __grid_constant__ DetArgs a) {
     const bool row_aligned = (a.n_h & 3) == 0;
     const bool gaussian_readout = DET != SCB_DET_CMOS && a.in_noise == nullptr && a.det.readout_noise > 0.0;
 
-    for (int64_t q = (int64_t)blockIdx.x * kThreads + threadIdx.x; q < n_quads; q += (int64_t)gridDim.x * kThreads) {
+    // software pipeline: the next quad's photons are in flight while this one is processed
+    const int64_t stride = (int64_t)gridDim.x * kThreads;
+    int64_t q = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    T nx0 = (T)0, nx1 = (T)0, nx2 = (T)0, nx3 = (T)0;
+    if (q < n_quads) load_quad<T>(a.photons, q << 2, a.n_pix, (q << 2) + 4 <= a.n_pix, true, nx0, nx1, nx2, nx3);
+    for (; q < n_quads; q += stride) {
         const int64_t p0 = q << 2;
         const bool full = p0 + 4 <= a.n_pix;
-        T ph0, ph1, ph2, ph3;
-        load_quad<T>(a.photons, p0, a.n_pix, full, true, ph0, ph1, ph2, ph3);
+        const T ph0 = nx0, ph1 = nx1, ph2 = nx2, ph3 = nx3;
+        if (q + stride < n_quads) {
+            const int64_t pn = (q + stride) << 2;
+            load_quad<T>(a.photons, pn, a.n_pix, pn + 4 <= a.n_pix, true, nx0, nx1, nx2, nx3);
+        }
         // ADC offset: scalar, per column (axis-1 index), or per pixel  (_epifm.py:941-952)
         T of0, of1, of2, of3;
         if (a.det.fpn_type == SCB_FPN_NONE) {
@@ -315,6 +323,91 @@ detector_kernel(const __grid_constant__ DetArgs a) {
         if (a.expectation) store_quad<T>(a.expectation, p0, a.n_pix, full, o0.ex, o1.ex, o2.ex, o3.ex);
         if (a.out_signal) store_quad<T>(a.out_signal, p0, a.n_pix, full, o0.sig, o1.sig, o2.sig, o3.sig);
         if (a.out_noise) store_quad<T>(a.out_noise, p0, a.n_pix, full, o0.noi, o1.noi, o2.noi, o3.noi);
+    }
+}
+
+// Streaming kernel specialised for the production configuration: fp32 frames, no injected
+// draws, no taps, n_pix a multiple of 4 and < 2^31.  Same arithmetic and the same random
+// streams as detector_kernel<float, DET> (checked against it in tests), but 32-bit
+// indexing, no per-pixel validity or tap branches, and the column index advanced
+// incrementally -- the pass is instruction bound by the two Philox4x32-10 blocks per quad.
+template <int DET, int FPN>
+__global__ void __launch_bounds__(kThreads, 4)
+detector_fast_kernel(const __grid_constant__ DetArgs a) {
+    __shared__ scb_alias_entry s_alias[DET == SCB_DET_CMOS ? kMaxAlias : 1];
+    if (DET == SCB_DET_CMOS) {
+        for (int i = threadIdx.x; i < a.n_alias; i += kThreads) s_alias[i] = a.alias[i];
+        __syncthreads();
+    }
+    const uint32_t n_quads = (uint32_t)(a.n_pix >> 2);
+    const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
+    const uint32_t f_lo = (uint32_t)a.frame, t_shot = SCB_TAG_SHOT ^ (uint32_t)(a.frame >> 32),
+                   t_read = SCB_TAG_READ ^ (uint32_t)(a.frame >> 32);
+    const float qe = (float)a.det.qe;
+    const float qe_bg = a.det.background_on ? (float)(a.det.qe * a.det.background) : 0.0f;
+    const float fullwell = (float)a.det.fullwell, pow2bit = (float)a.pow2bit, adc_max = (float)a.adc_max;
+    const float inv_fullwell = a.inv_fullwell, emgain_unused = 0.f; (void)emgain_unused;
+    const float rn = (float)a.det.readout_noise;
+    const float4 *photons = reinterpret_cast<const float4 *>(a.photons);
+    float4 *adc = reinterpret_cast<float4 *>(a.adc);
+    const float *offset = (const float *)a.offset;
+    const uint32_t n_alias = (uint32_t)a.n_alias;
+
+    const PhiloxKeys keys = philox_round_keys(k0, k1);
+    const uint32_t stride = gridDim.x * kThreads;
+    uint32_t q = blockIdx.x * kThreads + threadIdx.x;
+    // column of the quad's first pixel, advanced by (4*stride) mod n_h per iteration
+    uint32_t j0 = 0, j_step = 0;
+    if (FPN == SCB_FPN_COLUMN) {
+        j0 = (uint32_t)(((uint64_t)q << 2) % (uint32_t)a.n_h);
+        j_step = (uint32_t)(((uint64_t)stride << 2) % (uint32_t)a.n_h);
+    }
+    float4 next = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q < n_quads) next = __ldcs(photons + q);
+    for (; q < n_quads; q += stride) {
+        const float4 ph = next;
+        if (q + stride < n_quads) next = __ldcs(photons + q + stride);
+        float4 off;
+        if (FPN == SCB_FPN_NONE) {
+            off.x = off.y = off.z = off.w = (float)a.det.adc_offset;
+        } else if (FPN == SCB_FPN_PIXEL) {
+            off = __ldcs(reinterpret_cast<const float4 *>(offset) + q);
+        } else {
+            off = __ldg(reinterpret_cast<const float4 *>(offset + j0));
+            j0 += j_step;
+            if (j0 >= (uint32_t)a.n_h) j0 -= (uint32_t)a.n_h;
+        }
+        const Philox4 rs = philox4x32_10(q, 0u, f_lo, t_shot, keys);
+        Philox4 rr = {0u, 0u, 0u, 0u};
+        if (DET == SCB_DET_CMOS || rn > 0.0f) rr = philox4x32_10(q, 0u, f_lo, t_read, keys);
+        float n0 = 0.f, n1 = 0.f, n2 = 0.f, n3 = 0.f;
+        if (DET != SCB_DET_CMOS && rn > 0.0f) {
+            box_muller(rr.x, rr.y, n0, n1);
+            box_muller(rr.z, rr.w, n2, n3);
+        }
+        auto pixel = [&](float photon, float off_i, uint32_t r_shot, uint32_t r_read, float normal,
+                         uint32_t pix) -> float {
+            const float lam = fmaf(qe, photon, qe_bg);
+            const float sig = poisson_small(fminf(lam, kSmallLambda), r_shot);
+            if (!(lam < kSmallLambda) || (DET == SCB_DET_EMCCD && sig != 0.0f))
+                a.slow_list[atomicAdd(a.slow_count, 1u)] = pix;
+            float noi;
+            if (DET == SCB_DET_CMOS) {
+                const uint64_t prod = (uint64_t)r_read * n_alias;
+                const scb_alias_entry e = s_alias[(uint32_t)(prod >> 32)];
+                noi = ((float)(uint32_t)prod * 2.3283064365386963e-10f) < e.threshold ? e.value : e.alias_value;
+            } else {
+                noi = rn * normal;
+            }
+            const float pe = fminf(sig + noi, fullwell);
+            return fminf(fmaxf(fmaf(pe, (pow2bit - off_i) * inv_fullwell, off_i), 0.0f), adc_max);
+        };
+        float4 out;
+        out.x = pixel(ph.x, off.x, rs.x, rr.x, n0, (q << 2) + 0);
+        out.y = pixel(ph.y, off.y, rs.y, rr.y, n1, (q << 2) + 1);
+        out.z = pixel(ph.z, off.z, rs.z, rr.z, n2, (q << 2) + 2);
+        out.w = pixel(ph.w, off.w, rs.w, rr.w, n3, (q << 2) + 3);
+        __stcs(adc + q, out);
     }
 }
 
@@ -382,11 +475,20 @@ template <typename T, int DET>
 void launch_detector(const DetArgs &a, cudaStream_t s) {
     const int64_t n_quads = (a.n_pix + 3) >> 2;
     int64_t blocks = (n_quads + kThreads - 1) / kThreads;
-    const int64_t cap = (int64_t)SCB_SM_COUNT * 4;   // one wave: 4 resident CTAs of 256 threads per SM
+    const int64_t cap = (int64_t)SCB_SM_COUNT * 4 * 2;   // two waves of 4 resident CTAs (256 threads) per SM
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     cudaMemsetAsync(a.slow_count, 0, sizeof(uint32_t), s);
-    detector_kernel<T, DET><<<(unsigned)blocks, kThreads, 0, s>>>(a);
+    const bool fast = sizeof(T) == 4 && !a.in_signal && !a.in_noise && !a.out_signal && !a.out_noise &&
+                      !a.expectation && (a.n_pix & 3) == 0 && a.n_pix < ((int64_t)1 << 31) &&
+                      (a.det.fpn_type != SCB_FPN_COLUMN || (a.n_h & 3) == 0);
+    if (fast) {
+        if (a.det.fpn_type == SCB_FPN_NONE) detector_fast_kernel<DET, SCB_FPN_NONE><<<(unsigned)blocks, kThreads, 0, s>>>(a);
+        else if (a.det.fpn_type == SCB_FPN_PIXEL) detector_fast_kernel<DET, SCB_FPN_PIXEL><<<(unsigned)blocks, kThreads, 0, s>>>(a);
+        else detector_fast_kernel<DET, SCB_FPN_COLUMN><<<(unsigned)blocks, kThreads, 0, s>>>(a);
+    } else {
+        detector_kernel<T, DET><<<(unsigned)blocks, kThreads, 0, s>>>(a);
+    }
     if (a.in_signal == nullptr) detector_slow_kernel<T, DET><<<SCB_SM_COUNT * 2, kThreads, 0, s>>>(a);
 }
 

@@ -19,7 +19,7 @@ constexpr int kTile = 16;             // pixels per tile edge
 constexpr int kEdge = kTile + 1;      // pixel edges per tile edge
 constexpr int kBatch = 8;             // spots staged per round = warps per CTA
 constexpr int kThreads = kTile * kTile;
-constexpr int kSortCap = 2048;        // spots per tile ordered in shared memory per chunk
+constexpr int kSortCap = 1024;        // spots per tile ordered in shared memory per chunk
 
 struct __align__(16) SpotRec {
     double ox, oy;      // table origin in camera coordinates: W/2 + x - sw/2   (_epifm.py:233,236)
@@ -169,21 +169,22 @@ struct __align__(16) StageMeta {
     double pad;
 };
 
-constexpr int kCornersPerLane = (kEdge * kEdge + 31) / 32;   // 10
-
-// SAT corner gather: L2-only (.cg).  With the default .ca policy an L1 miss pulls the
-// whole 128-byte line for an 8-byte corner (measured: 3.2 L2 sectors per gather).
-__device__ __forceinline__ long long load_corner(const int64_t *p) {
-    return __ldcg(reinterpret_cast<const long long *>(p));
+// 8-byte asynchronous global -> shared copy (LDGSTS): the SAT corner gathers of a whole
+// round are in flight at once and need no registers.
+__device__ __forceinline__ void cp_async_8(void *smem, const void *gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem));
 }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
 template <typename OutT>
 __global__ void __launch_bounds__(kThreads)
 render_tiles_kernel(Geo g, const SpotRec *__restrict__ spots, const uint16_t *__restrict__ edges,
                     int edge_cap, const int *__restrict__ tile_start, const int *__restrict__ pair_spot,
                     const int64_t *__restrict__ sat, OutT *__restrict__ out, int accumulate) {
-    __shared__ long long corners[kBatch][kEdge * kEdge];
-    __shared__ StageMeta meta[kBatch];
+    __shared__ long long corners[2][kBatch][kEdge * kEdge];
+    __shared__ StageMeta meta[2][kBatch];
     __shared__ int ids_raw[kSortCap], ids[kSortCap];
 
     const int tile = blockIdx.x;
@@ -210,91 +211,57 @@ render_tiles_kernel(Geo g, const SpotRec *__restrict__ spots, const uint16_t *__
         }
         __syncthreads();
 
-        // Software pipeline: the SAT corners of round r+1 are in flight (registers) while
-        // round r is accumulated from shared memory.
-        long long v[kCornersPerLane];
-        StageMeta m_next;
-        int ncl_next = 1;
-
-        auto issue = [&](int base) {
-            // warp b gathers the corners of spot base+b into registers
-            m_next.nrow = 0; m_next.ncol = 0; m_next.r0 = 0; m_next.c0 = 0; m_next.w = 0.0; m_next.pad = 0.0;
-            ncl_next = 1;
+        // Warp b stages spot base+b of a round: lane l owns column edge l, the row edge of
+        // each footprint row is broadcast, and lane l copies corner (row k, col l) straight
+        // into shared memory with cp.async.
+        auto stage = [&](int buf, int base) {
+            StageMeta m;
+            m.r0 = 0; m.nrow = 0; m.c0 = 0; m.ncol = 0; m.w = 0.0; m.pad = 0.0;
             if (base + warp < n_chunk) {
                 const int sid = ids[base + warp];
                 const SpotRec rec = spots[sid];
                 const int r_lo = max(rec.imin, row0), r_hi = min(rec.imax, row0 + kTile);
                 const int c_lo = max(rec.jmin, col0), c_hi = min(rec.jmax, col0 + kTile);
                 const int nrow = r_hi - r_lo, ncol = c_hi - c_lo;
-                // lane e < 17 holds row edge e, lane 17 + l holds column edge l (l < 15); the last
-                // two column edges ride in a second register of lanes 0 and 1
                 const uint16_t *e = edges + (size_t)sid * 2 * edge_cap;
-                int edge_a = 0, edge_b = 0;
-                if (lane <= nrow) edge_a = e[r_lo - rec.imin + lane];
-                else if (lane >= kEdge && lane - kEdge <= ncol) edge_a = e[edge_cap + c_lo - rec.jmin + lane - kEdge];
-                if (lane < 2 && 15 + lane <= ncol) edge_b = e[edge_cap + c_lo - rec.jmin + 15 + lane];
-                const int64_t *S = sat + (size_t)rec.slot * pitch * pitch;
-                const int ncl = ncol + 1;
-                const int n_corner = (nrow + 1) * ncl;
-                const float inv = 1.0f / (float)ncl;
-#pragma unroll
-                for (int t = 0; t < kCornersPerLane; ++t) {
-                    const int idx = lane + 32 * t;
-                    const int cid = min(idx, n_corner - 1);
-                    const int k = (int)(((float)cid + 0.5f) * inv);
-                    const int l = cid - k * ncl;
-                    const int a = __shfl_sync(0xffffffffu, edge_a, k);
-                    const int b_lo = __shfl_sync(0xffffffffu, edge_a, min(kEdge + l, 31));
-                    const int b_hi = __shfl_sync(0xffffffffu, edge_b, max(l - 15, 0));
-                    const int b = l < 15 ? b_lo : b_hi;
-                    v[t] = 0;
-                    if (idx < n_corner) v[t] = load_corner(S + (size_t)a * pitch + b);
+                const int my_row = (lane <= nrow) ? (int)e[r_lo - rec.imin + lane] : 0;
+                const int my_col = (lane <= ncol) ? (int)e[edge_cap + c_lo - rec.jmin + lane] : 0;
+                const int64_t *S = sat + (size_t)rec.slot * pitch * pitch + my_col;
+                long long *dst = &corners[buf][warp][lane];
+                for (int k = 0; k <= nrow; ++k) {
+                    const int a = __shfl_sync(0xffffffffu, my_row, k);
+                    if (lane <= ncol) cp_async_8(dst + k * kEdge, S + (size_t)a * pitch);
                 }
-                m_next.r0 = r_lo - row0; m_next.nrow = nrow; m_next.c0 = c_lo - col0; m_next.ncol = ncol;
-                m_next.w = rec.w;
-                ncl_next = ncl;
+                m.r0 = r_lo - row0; m.nrow = nrow; m.c0 = c_lo - col0; m.ncol = ncol;
+                m.w = rec.w;
             }
-        };
-        auto commit = [&]() {
-            // registers -> shared memory (waits for the gathers)
-            const int n_corner = (m_next.nrow + 1) * ncl_next;
-            const float inv = 1.0f / (float)ncl_next;
-            if (m_next.nrow > 0) {
-#pragma unroll
-                for (int t = 0; t < kCornersPerLane; ++t) {
-                    const int idx = lane + 32 * t;
-                    if (idx < n_corner) {
-                        const int k = (int)(((float)idx + 0.5f) * inv);
-                        const int l = idx - k * ncl_next;
-                        corners[warp][k * kEdge + l] = v[t];
-                    }
-                }
-            }
-            if (lane == 0) meta[warp] = m_next;
+            cp_async_commit();
+            if (lane == 0) meta[buf][warp] = m;
         };
 
-        issue(0);
-        commit();
-        __syncthreads();
-        for (int base = 0; base < n_chunk; base += kBatch) {
+        stage(0, 0);
+        int cur = 0;
+        for (int base = 0; base < n_chunk; base += kBatch, cur ^= 1) {
             const bool more = base + kBatch < n_chunk;
-            if (more) issue(base + kBatch);
+            if (more) {
+                stage(cur ^ 1, base + kBatch);   // next round's gathers fly during this round's math
+                cp_async_wait<1>();
+            } else {
+                cp_async_wait<0>();
+            }
+            __syncthreads();
             // ---- accumulate: thread (py, px) owns one pixel
 #pragma unroll
             for (int q = 0; q < kBatch; ++q) {
-                const StageMeta m = meta[q];
+                const StageMeta m = meta[cur][q];
                 const int rk = py - m.r0, rl = px - m.c0;
                 if ((unsigned)rk < (unsigned)m.nrow && (unsigned)rl < (unsigned)m.ncol) {
-                    const long long *c = &corners[q][rk * kEdge + rl];
+                    const long long *c = &corners[cur][q][rk * kEdge + rl];
                     const long long box = c[kEdge + 1] - c[kEdge] - c[1] + c[0];
                     if (box > 0) acc = __dadd_rn(acc, __dmul_rn((double)box, m.w));   // _epifm.py:280-282
                 }
             }
             __syncthreads();
-            if (more) {
-                commit();
-                __syncthreads();
-            }
         }
     }
 
@@ -442,6 +409,17 @@ extern "C" int scb_render_expected(const scb_geometry *geom, int64_t n_spots, co
                 workspace_bytes, w.bytes);
     cudaStream_t s = (cudaStream_t)stream;
     const int n_tiles = g.nti * g.ntj;
+    {
+        // The corner gathers use 8 bytes of every sector they touch; ask the L2 to fetch 32-byte
+        // sectors from HBM instead of 128-byte lines (measured 4 sectors per miss by default).
+        // Purely a performance hint, set once.
+        static bool hinted = false;
+        if (!hinted) {
+            cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
+            cudaGetLastError();
+            hinted = true;
+        }
+    }
     // tile_count and tile_cursor are adjacent 256-aligned blocks: clear both
     SCB_CUDA(cudaMemsetAsync(w.tile_count, 0, (size_t)((char *)w.tile_start - (char *)w.tile_count), s));
     if (n_spots > 0) {

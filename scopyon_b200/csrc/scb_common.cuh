@@ -53,26 +53,50 @@ struct Philox4 {
     uint32_t x, y, z, w;
 };
 
+// 32 x 32 -> (hi, lo): one IMAD.WIDE on the device (inline PTX keeps nvcc from splitting
+// the 64-bit product into extra carry adds).
+__host__ __device__ __forceinline__ void mulhilo32(uint32_t a, uint32_t b, uint32_t &hi, uint32_t &lo) {
+#ifdef __CUDA_ARCH__
+    asm("{\n\t.reg .u64 p;\n\tmul.wide.u32 p, %2, %3;\n\tmov.b64 {%1, %0}, p;\n\t}" : "=r"(hi), "=r"(lo) : "r"(a), "r"(b));
+#else
+    const uint64_t p = (uint64_t)a * b;
+    hi = (uint32_t)(p >> 32);
+    lo = (uint32_t)p;
+#endif
+}
+
 // Philox4x32-10 (Salmon et al., SC'11).  counter = (c0,c1,c2,c3), key = (k0,k1).
-__host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2,
-                                                          uint32_t c3, uint32_t k0, uint32_t k1) {
-    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
-    const uint32_t W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+struct PhiloxKeys {   // the ten round keys, hoisted out of per-element loops
+    uint32_t a[10], b[10];
+};
+__host__ __device__ __forceinline__ PhiloxKeys philox_round_keys(uint32_t k0, uint32_t k1) {
+    PhiloxKeys k;
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
-        uint64_t p0 = (uint64_t)M0 * c0;
-        uint64_t p1 = (uint64_t)M1 * c2;
-        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
-        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
-        c1 = (uint32_t)p1;
-        c3 = (uint32_t)p0;
-        c0 = n0;
-        c2 = n2;
-        k0 += W0;
-        k1 += W1;
+        k.a[r] = k0 + (uint32_t)r * 0x9E3779B9u;
+        k.b[r] = k1 + (uint32_t)r * 0xBB67AE85u;
+    }
+    return k;
+}
+__host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                          const PhiloxKeys &k) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0, lo0, hi1, lo1;
+        mulhilo32(M0, c0, hi0, lo0);
+        mulhilo32(M1, c2, hi1, lo1);
+        c0 = hi1 ^ c1 ^ k.a[r];
+        c2 = hi0 ^ c3 ^ k.b[r];
+        c1 = lo1;
+        c3 = lo0;
     }
     Philox4 out = {c0, c1, c2, c3};
     return out;
+}
+__host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2,
+                                                          uint32_t c3, uint32_t k0, uint32_t k1) {
+    return philox4x32_10(c0, c1, c2, c3, philox_round_keys(k0, k1));
 }
 
 __host__ __device__ __forceinline__ Philox4 philox_at(uint64_t seed, uint64_t entity, uint32_t step,

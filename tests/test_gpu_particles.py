@@ -26,6 +26,26 @@ def test_uniform_placement():
     assert abs(numpy.corrcoef(xyz[0], xyz[1])[0, 1]) < 0.02
 
 
+def test_device_philox_matches_known_answer_implementation():
+    """The device generator (inline-PTX Philox4x32-10) against the host one that passes the
+    Random123 known-answer vectors: placement is lower + u * (upper - lower) with
+    u = 53 bits of philox(seed; particle, 0, 'PLAC')."""
+    import ctypes
+    lib = _native.load()
+    seed, n = 0x0123456789ABCDEF, 1000
+    parts = DeviceParticles(n, 2)
+    parts.place_uniform(seed, [0.0, 0.0], [1.0, 1.0], first_particle=5)
+    got = parts.coords.cpu().numpy()
+    want = numpy.zeros((2, n))
+    key = (ctypes.c_uint32 * 2)(seed & 0xFFFFFFFF, seed >> 32)
+    out = (ctypes.c_uint32 * 4)()
+    for p in range(n):
+        lib.scb_philox4x32_10((ctypes.c_uint32 * 4)(p + 5, 0, 0, 0x504c4143), key, out)
+        want[0, p] = (((out[0] << 32) | out[1]) >> 11) * 2.0 ** -53
+        want[1, p] = (((out[2] << 32) | out[3]) >> 11) * 2.0 ** -53
+    assert numpy.array_equal(got[:2], want)
+
+
 def test_brownian_msd_and_normality():
     """x += N(0, sqrt(2 D dt)) per axis (sampling.py:116-118): MSD = 2 D dt per axis."""
     n, D, dt = 400000, numpy.array([1e-13, 4e-13, 0.0]), 0.033
