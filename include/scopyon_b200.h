@@ -59,6 +59,8 @@ typedef struct scb_geometry {
     int32_t n_radial;        /* radial samples: len(arange(0, radial_cutoff, 1 nm))   */
     int32_t n_depth_keys;    /* integer-nm depth keys 0..n_depth_keys-1; the frozen   */
                              /* beyond-cutoff table ("key -1") is key n_depth_keys    */
+    int32_t sat_modulus;     /* column interleave M of the SAT layout (see below), >= 1 */
+    int32_t reserved;
     double pixel_length;     /* detector.pixel_length / magnification  [m]            */
     double resolution;       /* table sample pitch, 1e-9 m                            */
     double depth_cutoff;     /* fluorophore.depth_cutoff [m]                          */
@@ -123,8 +125,15 @@ size_t scb_psf_sat_workspace_bytes(int n_radial, int n_keys);
  *   T[a][b]  = lerp(radial, min(sqrt((a-c)^2+(b-c)^2), c)),  c = n_radial-1, a,b in [0, 2c]
  *   Q[a][b]  = llrint(T[a][b] * scale_k),  scale_k a power of two chosen per table
  *   S[a][b]  = sum_{a'<a, b'<b} Q[a'][b']                     a,b in [0, 2c+1]
- * d_sat[n_keys][2c+2][2c+2] (int64), d_inv_scale[n_keys] = 1/scale_k. */
-int scb_psf_sat_build(const double *d_radial, int n_radial, int n_keys,
+ * Memory layout ("column polyphase"): the pixel edges of one spot are ~pixel_length/1nm
+ * samples apart, so a spot reads S at columns b0, b0+~M, b0+~2M, ...  With
+ * M = sat_modulus = round(pixel_length / 1 nm) the entry (a, b) is stored at
+ *   d_sat[key][a][ (b % M) * B + b / M ],   B = ceil((2c+2) / M),  row pitch = M * B,
+ * which puts those columns next to each other: one 128-byte line serves up to 16 corners
+ * instead of one (M = 1 is the plain row-major layout).
+ * d_sat[n_keys][2c+2][M*B] (int64), d_inv_scale[n_keys] = 1/scale_k. */
+int64_t scb_psf_sat_pitch(int n_radial, int sat_modulus);
+int scb_psf_sat_build(const double *d_radial, int n_radial, int n_keys, int sat_modulus,
                       int64_t *d_sat, double *d_inv_scale,
                       void *d_workspace, size_t workspace_bytes, void *stream);
 

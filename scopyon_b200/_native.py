@@ -29,6 +29,7 @@ class Geometry(ctypes.Structure):
     _fields_ = [
         ("n_w", ctypes.c_int32), ("n_h", ctypes.c_int32),
         ("n_radial", ctypes.c_int32), ("n_depth_keys", ctypes.c_int32),
+        ("sat_modulus", ctypes.c_int32), ("reserved", ctypes.c_int32),
         ("pixel_length", ctypes.c_double), ("resolution", ctypes.c_double),
         ("depth_cutoff", ctypes.c_double), ("focal", ctypes.c_double * 3),
     ]
@@ -62,8 +63,9 @@ SIGNATURES = {
     "scb_psf_radial_build": (ctypes.c_int, [
         ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.c_int, c_ptr, c_ptr, c_ptr]),
     "scb_psf_sat_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int]),
+    "scb_psf_sat_pitch": (ctypes.c_int64, [ctypes.c_int, ctypes.c_int]),
     "scb_psf_sat_build": (ctypes.c_int, [
-        c_ptr, ctypes.c_int, ctypes.c_int, c_ptr, c_ptr, c_ptr, ctypes.c_size_t, c_ptr]),
+        c_ptr, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_ptr, c_ptr, c_ptr, ctypes.c_size_t, c_ptr]),
     "scb_diffuse": (ctypes.c_int, [
         ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int, ctypes.c_int64, ctypes.c_int64,
         c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, ctypes.POINTER(ctypes.c_double),

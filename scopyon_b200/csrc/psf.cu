@@ -165,17 +165,30 @@ table_scale_kernel(const double *__restrict__ rowsum, int side, double *__restri
 // shuffles + one shared pass; int64 adds are associative so the result is exact.
 constexpr int kScanThreads = 256;
 
+struct SatLayout {
+    int modulus, blocks, pitch;   // entry (a, b) lives at a * pitch + (b % modulus) * blocks + b / modulus
+    __host__ __device__ int col(int b) const { return (b % modulus) * blocks + b / modulus; }
+};
+
+__host__ SatLayout make_layout(int n_radial, int modulus) {
+    SatLayout L;
+    const int cols = 2 * (n_radial - 1) + 2;
+    L.modulus = modulus < 1 ? 1 : modulus;
+    L.blocks = (cols + L.modulus - 1) / L.modulus;
+    L.pitch = L.modulus * L.blocks;
+    return L;
+}
+
 __global__ void __launch_bounds__(kScanThreads)
 sat_rows_kernel(const double *__restrict__ radial, int n_radial, const double *__restrict__ scale,
-                int64_t *__restrict__ sat) {
+                int64_t *__restrict__ sat, SatLayout L) {
     __shared__ int64_t warp_tot[kScanThreads / 32];
     const int c = n_radial - 1;
     const int side = 2 * c + 1;
-    const int pitch = side + 1;
     const int key = blockIdx.y, a = blockIdx.x;  // a in [0, side]: a == side writes the zero row 0
-    int64_t *S = sat + (size_t)key * pitch * pitch;
+    int64_t *S = sat + (size_t)key * (side + 1) * L.pitch;
     if (a == side) {
-        for (int b = threadIdx.x; b < pitch; b += blockDim.x) S[b] = 0;
+        for (int b = threadIdx.x; b < L.pitch; b += blockDim.x) S[b] = 0;
         return;
     }
     const double *prof = radial + (size_t)key * n_radial;
@@ -207,35 +220,43 @@ sat_rows_kernel(const double *__restrict__ radial, int n_radial, const double *_
     int64_t base = 0;
     for (int w = 0; w < warp; ++w) base += warp_tot[w];
     base += incl - run;
-    int64_t *row = S + (size_t)(a + 1) * pitch;
+    int64_t *row = S + (size_t)(a + 1) * L.pitch;
     if (threadIdx.x == 0) row[0] = 0;
+    // padding slots of the interleaved layout (never read) are cleared so the column pass
+    // works on defined values
+    for (int b = side + 1 + threadIdx.x; b < L.pitch; b += blockDim.x) row[L.col(b)] = 0;
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
         if (i < per) {
             int b = b0 + i;
-            if (b < side) row[b + 1] = base + local[i];
+            if (b < side) row[L.col(b + 1)] = base + local[i];
         }
     }
 }
 
 // Column pass: S[a][b] += S[a-1][b] down each column; threads cover columns (coalesced).
-__global__ void sat_cols_kernel(int pitch, int n_keys, int64_t *__restrict__ sat) {
-    int b = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void sat_cols_kernel(int rows, int pitch, int n_keys, int64_t *__restrict__ sat) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;   // storage column (layout independent)
     int key = blockIdx.y;
     if (b >= pitch || key >= n_keys) return;
-    int64_t *S = sat + (size_t)key * pitch * pitch + b;
+    int64_t *S = sat + (size_t)key * rows * pitch + b;
     int64_t run = 0;
     // software-pipelined: loads of later rows do not depend on the running sum
-    for (int a = 1; a < pitch; a += 4) {
+    for (int a = 1; a < rows; a += 4) {
         int64_t v0 = S[(size_t)a * pitch];
-        int64_t v1 = (a + 1 < pitch) ? S[(size_t)(a + 1) * pitch] : 0;
-        int64_t v2 = (a + 2 < pitch) ? S[(size_t)(a + 2) * pitch] : 0;
-        int64_t v3 = (a + 3 < pitch) ? S[(size_t)(a + 3) * pitch] : 0;
+        int64_t v1 = (a + 1 < rows) ? S[(size_t)(a + 1) * pitch] : 0;
+        int64_t v2 = (a + 2 < rows) ? S[(size_t)(a + 2) * pitch] : 0;
+        int64_t v3 = (a + 3 < rows) ? S[(size_t)(a + 3) * pitch] : 0;
         run += v0; S[(size_t)a * pitch] = run;
-        if (a + 1 < pitch) { run += v1; S[(size_t)(a + 1) * pitch] = run; }
-        if (a + 2 < pitch) { run += v2; S[(size_t)(a + 2) * pitch] = run; }
-        if (a + 3 < pitch) { run += v3; S[(size_t)(a + 3) * pitch] = run; }
+        if (a + 1 < rows) { run += v1; S[(size_t)(a + 1) * pitch] = run; }
+        if (a + 2 < rows) { run += v2; S[(size_t)(a + 2) * pitch] = run; }
+        if (a + 3 < rows) { run += v3; S[(size_t)(a + 3) * pitch] = run; }
     }
+}
+
+extern "C" int64_t scb_psf_sat_pitch(int n_radial, int sat_modulus) {
+    if (n_radial < 2) return 0;
+    return make_layout(n_radial, sat_modulus).pitch;
 }
 
 extern "C" size_t scb_psf_sat_workspace_bytes(int n_radial, int n_keys) {
@@ -244,9 +265,9 @@ extern "C" size_t scb_psf_sat_workspace_bytes(int n_radial, int n_keys) {
     return ((size_t)n_keys * side + (size_t)n_keys) * sizeof(double);
 }
 
-extern "C" int scb_psf_sat_build(const double *d_radial, int n_radial, int n_keys, int64_t *d_sat,
-                                 double *d_inv_scale, void *d_workspace, size_t workspace_bytes,
-                                 void *stream) {
+extern "C" int scb_psf_sat_build(const double *d_radial, int n_radial, int n_keys, int sat_modulus,
+                                 int64_t *d_sat, double *d_inv_scale, void *d_workspace,
+                                 size_t workspace_bytes, void *stream) {
     SCB_REQUIRE(d_radial && d_sat && d_inv_scale && d_workspace, SCB_E_NULL,
                 "scb_psf_sat_build: NULL pointer");
     SCB_REQUIRE(n_radial >= 2 && n_radial <= 2048 && n_keys >= 1, SCB_E_INVALID,
@@ -256,14 +277,15 @@ extern "C" int scb_psf_sat_build(const double *d_radial, int n_radial, int n_key
                 scb_psf_sat_workspace_bytes(n_radial, n_keys));
     SCB_REQUIRE(n_keys <= 65535, SCB_E_INVALID, "scb_psf_sat_build: n_keys=%d > 65535", n_keys);
     cudaStream_t s = (cudaStream_t)stream;
+    SCB_REQUIRE(sat_modulus >= 1 && sat_modulus <= 4096, SCB_E_INVALID, "scb_psf_sat_build: sat_modulus=%d", sat_modulus);
     const int side = 2 * (n_radial - 1) + 1;
-    const int pitch = side + 1;
+    const SatLayout L = make_layout(n_radial, sat_modulus);
     double *rowsum = (double *)d_workspace;
     double *scale = rowsum + (size_t)n_keys * side;
     table_rowsum_kernel<<<dim3(side, n_keys), 256, 0, s>>>(d_radial, n_radial, rowsum);
     table_scale_kernel<<<n_keys, 256, 0, s>>>(rowsum, side, scale, d_inv_scale);
-    sat_rows_kernel<<<dim3(side + 1, n_keys), kScanThreads, 0, s>>>(d_radial, n_radial, scale, d_sat);
-    sat_cols_kernel<<<dim3((pitch + 127) / 128, n_keys), 128, 0, s>>>(pitch, n_keys, d_sat);
+    sat_rows_kernel<<<dim3(side + 1, n_keys), kScanThreads, 0, s>>>(d_radial, n_radial, scale, d_sat, L);
+    sat_cols_kernel<<<dim3((L.pitch + 127) / 128, n_keys), 128, 0, s>>>(side + 1, L.pitch, n_keys, d_sat);
     SCB_CUDA_LAUNCH_CHECK("scb_psf_sat_build");
     return 0;
 }

@@ -34,6 +34,7 @@ struct Geo {
     int n_w, n_h, nti, ntj;
     int side;           // table samples per axis (2*(n_radial-1)+1)
     int n_depth_keys;
+    int modulus, blocks, pitch;   // SAT column interleave: (a, b) at a*pitch + (b % modulus)*blocks + b/modulus
     double pl, res, sw, half_w, half_h, depth_cutoff;
     double f0, f1, f2;
 };
@@ -106,8 +107,10 @@ spot_prepare_kernel(Geo g, int64_t n, const double *__restrict__ depth, const do
                 uint16_t *e = edges + (size_t)s * 2 * edge_cap;
                 for (int i = rec.imin; i <= rec.imax; ++i)
                     e[i - rec.imin] = (uint16_t)edge_index(i, rec.imin, rec.imax, rec.ox, g);
-                for (int j = rec.jmin; j <= rec.jmax; ++j)
-                    e[edge_cap + j - rec.jmin] = (uint16_t)edge_index(j, rec.jmin, rec.jmax, rec.oy, g);
+                for (int j = rec.jmin; j <= rec.jmax; ++j) {   // columns: stored as SAT storage offsets
+                    const int b = edge_index(j, rec.jmin, rec.jmax, rec.oy, g);
+                    e[edge_cap + j - rec.jmin] = (uint16_t)((b % g.modulus) * g.blocks + b / g.modulus);
+                }
             }
         }
     }
@@ -193,7 +196,7 @@ render_tiles_kernel(Geo g, const SpotRec *__restrict__ spots, const uint16_t *__
     const int py = threadIdx.x / kTile, px = threadIdx.x % kTile;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int seg_begin = tile_start[tile], seg_end = tile_start[tile + 1];
-    const size_t pitch = (size_t)g.side + 1;
+    const size_t pitch = (size_t)g.pitch, table = (size_t)(g.side + 1) * g.pitch;
 
     double acc = 0.0;
 
@@ -226,7 +229,7 @@ render_tiles_kernel(Geo g, const SpotRec *__restrict__ spots, const uint16_t *__
                 const uint16_t *e = edges + (size_t)sid * 2 * edge_cap;
                 const int my_row = (lane <= nrow) ? (int)e[r_lo - rec.imin + lane] : 0;
                 const int my_col = (lane <= ncol) ? (int)e[edge_cap + c_lo - rec.jmin + lane] : 0;
-                const int64_t *S = sat + (size_t)rec.slot * pitch * pitch + my_col;
+                const int64_t *S = sat + (size_t)rec.slot * table + my_col;
                 long long *dst = &corners[buf][warp][lane];
                 for (int k = 0; k <= nrow; ++k) {
                     const int a = __shfl_sync(0xffffffffu, my_row, k);
@@ -296,6 +299,9 @@ Geo make_geo(const scb_geometry *geom) {
     g.half_w = ((double)geom->n_w * geom->pixel_length) * 0.5;  // _epifm.py:230,233
     g.half_h = ((double)geom->n_h * geom->pixel_length) * 0.5;
     g.depth_cutoff = geom->depth_cutoff;
+    g.modulus = geom->sat_modulus < 1 ? 1 : geom->sat_modulus;
+    g.blocks = (g.side + 1 + g.modulus - 1) / g.modulus;
+    g.pitch = g.modulus * g.blocks;
     g.f0 = geom->focal[0]; g.f1 = geom->focal[1]; g.f2 = geom->focal[2];
     return g;
 }
@@ -341,6 +347,7 @@ int check_geometry(const scb_geometry *geom) {
     SCB_REQUIRE(geom->pixel_length > 0 && geom->resolution > 0, SCB_E_INVALID,
                 "pixel_length=%g resolution=%g", geom->pixel_length, geom->resolution);
     SCB_REQUIRE(geom->n_depth_keys >= 1, SCB_E_INVALID, "n_depth_keys=%d", geom->n_depth_keys);
+    SCB_REQUIRE(geom->sat_modulus >= 1 && geom->sat_modulus <= 4096, SCB_E_INVALID, "sat_modulus=%d", geom->sat_modulus);
     return 0;
 }
 

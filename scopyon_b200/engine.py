@@ -89,7 +89,7 @@ class SatStore:
     def shared(cls, engine):
         cfg = engine.configs
         key = (str(engine.device), engine.psf_type, float(cfg.psf_wavelength), cfg.psf_radial_width,
-               engine.geom.n_radial, engine.geom.n_depth_keys, float(cfg.depth_cutoff))
+               engine.geom.n_radial, engine.geom.n_depth_keys, float(cfg.depth_cutoff), engine.geom.sat_modulus)
         store = cls._shared.get(key)
         if store is None:
             store = cls._shared[key] = cls(engine)
@@ -109,7 +109,9 @@ class SatStore:
         self.depth_cutoff = float(cfg.depth_cutoff)
         self.n_radial = int(engine.geom.n_radial)
         self.n_depth_keys = int(engine.geom.n_depth_keys)
-        self.pitch = 2 * (self.n_radial - 1) + 2
+        self.modulus = int(engine.geom.sat_modulus)
+        self.rows = 2 * (self.n_radial - 1) + 2
+        self.pitch = int(self.lib.scb_psf_sat_pitch(self.n_radial, self.modulus))
         self.sat = None
         self.inv_scale = None
         self.n_tables = 0
@@ -120,6 +122,13 @@ class SatStore:
     def table_depth(self, key):
         """Depth a table is evaluated at (``_epifm.py:80-84``)."""
         return float(key) * RESOLUTION if key < self.n_depth_keys else self.depth_cutoff
+
+    def plain(self, slot):
+        """Table ``slot`` on the host in plain ``S[a][b]`` order (undoes the column interleave)."""
+        stored = self.sat[slot].cpu().numpy()
+        b = numpy.arange(self.rows)
+        blocks = self.pitch // self.modulus
+        return stored[:, (b % self.modulus) * blocks + b // self.modulus]
 
     def all_resident(self):
         return self.n_tables > 0 and bool((self.slot_host >= 0).all())
@@ -150,7 +159,7 @@ class SatStore:
         capacity = 0 if self.sat is None else self.sat.shape[0]
         if need > capacity:
             new_cap = max(min(max(need, 2 * capacity, 1), self.n_depth_keys + 1), need)
-            sat = torch.empty((new_cap, self.pitch, self.pitch), dtype=torch.int64, device=self.device)
+            sat = torch.empty((new_cap, self.rows, self.pitch), dtype=torch.int64, device=self.device)
             inv = torch.zeros(new_cap, dtype=torch.float64, device=self.device)
             if self.n_tables:
                 sat[:self.n_tables].copy_(self.sat[:self.n_tables])
@@ -166,7 +175,7 @@ class SatStore:
         work = torch.empty(work_bytes, dtype=torch.uint8, device=self.device)
         first = self.n_tables
         _native.check(self.lib.scb_psf_sat_build(
-            _native.ptr(radial), self.n_radial, n_new, ctypes.c_void_p(self.sat[first].data_ptr()),
+            _native.ptr(radial), self.n_radial, n_new, self.modulus, ctypes.c_void_p(self.sat[first].data_ptr()),
             ctypes.c_void_p(self.inv_scale[first:].data_ptr()), _native.ptr(work), work_bytes, stream),
             "scb_psf_sat_build")
         self.n_tables = need
@@ -193,7 +202,6 @@ class DeviceEngine:
         if self.psf_type == _native.PSF_GAUSSIAN and configs.psf_radial_width is None:
             raise ValueError('fluorophore.radial_width must be given for Gaussian type fluorophore.')
         self.n_w, self.n_h = int(self.geom.n_w), int(self.geom.n_h)
-        self.pitch = 2 * (self.geom.n_radial - 1) + 2
 
         # PSF summed-area tables: shared by every engine of this process with the same PSF
         # (the reference rebuilds its table cache on each form_image call, base.py:56-59)

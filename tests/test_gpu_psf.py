@@ -37,7 +37,8 @@ default:
 def test_sat_bit_exact_against_c_oracle():
     _, _, params, engine = gpu_engine()
     sats, inv, _ = oracle_tables(params, engine, [0, 800, engine.geom.n_depth_keys])
-    got = engine.sat[:3].cpu().numpy()
+    got = numpy.stack([engine.tables.plain(k) for k in range(3)])
+    assert engine.geom.sat_modulus == 66 and engine.tables.pitch == 66 * 31      # 16 um / 241 = 66.39 nm
     assert numpy.array_equal(engine.inv_scale[:3].cpu().numpy(), inv)
     assert numpy.array_equal(got, sats)                                # int64, bit for bit
     # and the table integral equals the reference's (known answer 0.9788254597277128)
@@ -48,7 +49,7 @@ def test_sat_bit_exact_against_c_oracle():
 def test_sat_from_device_profile_close_to_reference_table():
     _, _, params, engine = gpu_engine()
     engine.ensure_tables([100])
-    S = engine.sat[0].cpu().numpy().astype(numpy.float64) * float(engine.inv_scale[0])
+    S = engine.tables.plain(0).astype(numpy.float64) * float(engine.inv_scale[0])
     # key 100 is the table at 100 * 1 nm; note int(100e-9 / 1e-9) == 99 in fp64 (_epifm.py:80)
     key, table = orc.PsfTables(params).get(engine.table_depth(100))
     assert key == 100

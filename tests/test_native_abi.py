@@ -26,7 +26,7 @@ def test_library_builds_and_exports_header_symbols():
 
 def test_struct_layouts_match_header():
     # sizes implied by the header's field lists (natural alignment)
-    assert ctypes.sizeof(_native.Geometry) == 4 * 4 + 3 * 8 + 3 * 8
+    assert ctypes.sizeof(_native.Geometry) == 6 * 4 + 3 * 8 + 3 * 8
     assert ctypes.sizeof(_native.Photophysics) == 7 * 8
     assert ctypes.sizeof(_native.Detector) == 4 * 4 + 7 * 8
 
@@ -34,7 +34,7 @@ def test_struct_layouts_match_header():
 def test_argument_validation_without_gpu():
     lib = _native.load()
     geom = _native.Geometry(n_w=0, n_h=16, n_radial=1000, n_depth_keys=1002, pixel_length=1e-7, resolution=1e-9,
-                            depth_cutoff=1e-6)
+                            depth_cutoff=1e-6, sat_modulus=65)
     assert lib.scb_render_workspace_bytes(ctypes.byref(geom), 10) == 0
     assert b"image_size" in lib.scb_last_error()
     geom.n_w = 512
