@@ -221,6 +221,7 @@ class DeviceEngine:
             self._call("scb_adc_offsets", configs.fpn_seed, n, float(configs.ADConverter_offset0),
                        float(configs.ADConverter_fpn_count), _native.ptr(self.offset), self.elem_type,
                        self._stream())
+        self.max_pinned_planes = 16
         self._workspace = None
         self._det_work = torch.empty(self.lib.scb_detector_workspace_bytes(self.n_w, self.n_h), dtype=torch.uint8,
                                      device=self.device)
@@ -238,6 +239,33 @@ class DeviceEngine:
         if dtype is not None:
             host = host.to(dtype)
         return host.pin_memory().to(self.device, non_blocking=True)
+
+    def _h2d_stage(self, n):
+        """Pinned (4, capacity) float64 staging area for particle uploads.  Reuse is safe
+        because every frame ends with a stream synchronisation before the host touches it
+        again; within a frame snapshots use disjoint column ranges."""
+        stage = getattr(self, "_stage_h2d", None)
+        if stage is None or stage.shape[1] < n:
+            capacity = max(n, 2 * (0 if stage is None else stage.shape[1]), 1024)
+            new = torch.empty((4, capacity), dtype=torch.float64).pin_memory()
+            if stage is not None:
+                new[:, : stage.shape[1]].copy_(stage)
+            self._stage_h2d = stage = new
+        return stage
+
+    def _host_plane(self):
+        """A float64 (Nw, Nh) host array for one returned plane.  While few planes are alive
+        (streaming use) it is pinned memory the device writes directly, so no host copy
+        is needed; when the caller retains many frames it falls back to pageable memory."""
+        import weakref
+        live = getattr(self, "_live_planes", None)
+        if live is None:
+            live = self._live_planes = weakref.WeakSet()
+        if len(live) < self.max_pinned_planes:
+            t = torch.empty((self.n_w, self.n_h), dtype=torch.float64, pin_memory=True)
+            live.add(t)
+            return t, True
+        return torch.empty((self.n_w, self.n_h), dtype=torch.float64), False
 
     def _render_workspace(self, n_spots):
         need = self.lib.scb_render_workspace_bytes(ctypes.byref(self.geom), n_spots)
@@ -314,9 +342,12 @@ class DeviceEngine:
                 order, rounds, slots_dev, ids_dev = self._molecule_slots(table_ids, ids)
                 if order is not None:
                     particles = particles[order]
-            seg = soa[:, offset: offset + n]
-            cols = numpy.ascontiguousarray(particles[:, [0, 1, 2, 4]].T)
-            seg.copy_(torch.from_numpy(cols).pin_memory(), non_blocking=True)
+            # columns (depth, x, y, p_state) -> SoA rows through a persistent pinned staging area
+            stage = self._h2d_stage(offset + n)
+            stage_np = stage.numpy()
+            for row, col in enumerate((0, 1, 2, 4)):
+                stage_np[row, offset: offset + n] = particles[:, col]
+            soa[:, offset: offset + n].copy_(stage[:, offset: offset + n], non_blocking=True)
             if not all_resident:
                 keys.append(depth_keys_of(particles[:, 0] - focal[0], cfg.depth_cutoff, self.geom.n_depth_keys))
             for lo, hi in rounds:
@@ -412,22 +443,29 @@ class DeviceEngine:
     def form_frame(self, snapshots, frame_index, noise_seed, states, exposure_time, want_true_data,
                    want_expectation=True):
         """One frame on the host: ``(adc (Nw, Nh) float64, expectation (Nw, Nh) float64 or None,
-        true_data)``.  The planes are widened to float64 on the device and come back through a
-        pinned staging buffer, so the host only does one memcpy per plane."""
+        true_data)``.  Planes are widened to float64 on the device and written straight into
+        pinned host arrays (one DMA per plane, no host-side conversion or copy)."""
         photons, true_data = self.render_expected(
             snapshots, states=states, want_true_data=want_true_data, exposure_time=exposure_time)
-        planes = 2 if want_expectation else 1
-        pair = torch.empty((2, self.n_w, self.n_h), dtype=self.dtype, device=self.device)
-        self.detect(photons, frame_index, noise_seed, adc=pair[0], expectation=pair[1] if want_expectation else None)
-        if getattr(self, "_staging", None) is None:
-            self._staging = torch.empty((2, self.n_w, self.n_h), dtype=torch.float64).pin_memory()
-        self._staging[:planes].copy_(pair[:planes], non_blocking=True)   # widening copy, device -> pinned host
+        if getattr(self, "_planes32", None) is None:
+            self._planes32 = torch.empty((2, self.n_w, self.n_h), dtype=self.dtype, device=self.device)
+            self._planes64 = torch.empty((2, self.n_w, self.n_h), dtype=torch.float64, device=self.device)
+        p32, p64 = self._planes32, self._planes64
+        self.detect(photons, frame_index, noise_seed, adc=p32[0], expectation=p32[1] if want_expectation else None)
+        outs = []
+        for k in range(2 if want_expectation else 1):
+            src = p32[k]
+            if src.dtype != torch.float64:
+                p64[k].copy_(src)
+                src = p64[k]
+            host, _ = self._host_plane()
+            host.copy_(src, non_blocking=True)
+            outs.append(host)
         torch.cuda.current_stream(self.device).synchronize()
         n_err = int(self.errors.item())
         if n_err:
             self.errors.zero_()
             raise _native.NativeError("{} spots referenced a PSF table that was not built".format(n_err))
-        host = self._staging.numpy()
-        adc = numpy.array(host[0])
-        expectation = numpy.array(host[1]) if want_expectation else None
+        adc = outs[0].numpy()
+        expectation = outs[1].numpy() if want_expectation else None
         return adc, expectation, true_data
