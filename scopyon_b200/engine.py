@@ -183,7 +183,28 @@ class SatStore:
         return first
 
 
+class _Trace:
+    """Optional host-side stage timer (``engine.trace = {}`` enables it; bench.py reports it)."""
+
+    def __init__(self, engine, name, sync=False):
+        self.engine, self.name, self.sync = engine, name, sync
+
+    def __enter__(self):
+        import time
+        self.t0 = time.perf_counter() if self.engine.trace is not None else None
+
+    def __exit__(self, *exc):
+        if self.t0 is not None:
+            import time
+            if self.sync:
+                torch.cuda.current_stream(self.engine.device).synchronize()
+            acc = self.engine.trace
+            acc[self.name] = acc.get(self.name, 0.0) + (time.perf_counter() - self.t0) * 1e3
+
+
 class DeviceEngine:
+
+    trace = None
 
     def __init__(self, configs, device=None, precision=None):
         require_cuda()
@@ -316,6 +337,14 @@ class DeviceEngine:
             out.zero_()
             return out, ({} if want_true_data else None)
 
+        with _Trace(self, "host_prepare"):
+            return self._render_expected(snapshots, states, want_true_data, out, exposure_time, sizes, total)
+
+    def _render_expected(self, snapshots, states, want_true_data, out, exposure_time, sizes, total):
+        cfg = self.configs
+        stream = self._stream()
+        focal = cfg.detector_focal_point
+        true_dev, true_ids = None, None
         soa = torch.empty((4, total), dtype=torch.float64, device=self.device)     # depth, x, y, p_state
         weight = torch.empty(total, dtype=torch.float64, device=self.device)
         all_ids = numpy.concatenate([numpy.asarray(p[:, 3], dtype=numpy.int64) for _, p in snapshots])
@@ -453,15 +482,18 @@ class DeviceEngine:
         p32, p64 = self._planes32, self._planes64
         self.detect(photons, frame_index, noise_seed, adc=p32[0], expectation=p32[1] if want_expectation else None)
         outs = []
-        for k in range(2 if want_expectation else 1):
-            src = p32[k]
-            if src.dtype != torch.float64:
-                p64[k].copy_(src)
-                src = p64[k]
-            host, _ = self._host_plane()
-            host.copy_(src, non_blocking=True)
-            outs.append(host)
-        torch.cuda.current_stream(self.device).synchronize()
+        with _Trace(self, "host_alloc_planes"):
+            hosts = [self._host_plane()[0] for _ in range(2 if want_expectation else 1)]
+        with _Trace(self, "enqueue_d2h"):
+            for k, host in enumerate(hosts):
+                src = p32[k]
+                if src.dtype != torch.float64:
+                    p64[k].copy_(src)
+                    src = p64[k]
+                host.copy_(src, non_blocking=True)
+                outs.append(host)
+        with _Trace(self, "wait_device"):
+            torch.cuda.current_stream(self.device).synchronize()
         n_err = int(self.errors.item())
         if n_err:
             self.errors.zero_()
