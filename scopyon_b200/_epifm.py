@@ -334,20 +334,48 @@ class _EPIFMSimulator:
             self, input_data, num_frames, start_time=0.0, exposure_time=None,
             rng=None, processes=None, full_output=True):
         """Yield ``(camera, infodict)`` per frame (``_epifm.py:1017-1049``).  The photon
-        budgets -- the only state carried from frame to frame -- stay on the device."""
+        budgets -- the only state carried from frame to frame -- stay on the device, and
+        frame f+1 is enqueued before frame f is awaited (one-frame lookahead), so the host
+        preparation of the next frame overlaps the device work and the download of this one."""
         if rng is None:
             _log.info('A random number generator was initialized.')
             rng = numpy.random.RandomState()
+        engine = self.engine
         states = None
         if self.configs.effects.photobleaching_switch:
-            states = self.engine.new_budget_state(input_data, draw_seed(rng))
+            states = engine.new_budget_state(input_data, draw_seed(rng))
         exposure_time = exposure_time or self.configs.detector_exposure_time
         noise_seed = draw_seed(rng)
+        times = numpy.array([t for t, _ in input_data])
+
+        def begin(frame_index):
+            windows, t, exposure = frame_windows(times, frame_index, start_time, exposure_time, self.configs)
+            _log.info('time: {} sec ({})'.format(t, frame_index))
+            snapshots = [(unit_time, input_data[k][1]) for k, unit_time in windows]
+            return engine.begin_frame(
+                snapshots, frame_index=frame_index, noise_seed=noise_seed, states=states, exposure_time=exposure,
+                want_true_data=full_output, want_expectation=full_output, snapshot_states=full_output)
+
+        def finish(pending):
+            adc, expectation, true_data, budgets = engine.finish_frame(pending)
+            if not full_output:
+                return adc, dict(true_data={})
+            camera = numpy.empty(adc.shape + (2,), dtype=numpy.float64)   # _epifm.py:1177
+            camera[:, :, 0] = expectation
+            camera[:, :, 1] = adc
+            infodict = dict(true_data=true_data if true_data is not None else {})
+            if budgets is not None:
+                infodict['fluorescence_states'] = budgets
+            return camera, infodict
+
+        pending = None
         for frame_index in range(num_frames):
-            yield self.output_frame(
-                input_data, frame_index=frame_index, start_time=start_time, exposure_time=exposure_time,
-                fluorescence_states=states, rng=rng, processes=processes,
-                _noise_seed=noise_seed, _full_output=full_output, _planes=not full_output)
+            following = begin(frame_index)
+            if pending is not None:
+                yield finish(pending)
+            pending = following
+        if pending is not None:
+            yield finish(pending)
 
     def output_frame(
             self, input_data, frame_index=0, start_time=0.0, exposure_time=None,

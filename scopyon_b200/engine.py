@@ -205,6 +205,7 @@ class _Trace:
 class DeviceEngine:
 
     trace = None
+    _defer_true_data = False
 
     def __init__(self, configs, device=None, precision=None):
         require_cuda()
@@ -243,6 +244,7 @@ class DeviceEngine:
                        float(configs.ADConverter_fpn_count), _native.ptr(self.offset), self.elem_type,
                        self._stream())
         self.max_pinned_planes = 16
+        self._soa_cols = torch.tensor([0, 1, 2, 4], device=self.device)
         self._workspace = None
         self._det_work = torch.empty(self.lib.scb_detector_workspace_bytes(self.n_w, self.n_h), dtype=torch.uint8,
                                      device=self.device)
@@ -262,16 +264,16 @@ class DeviceEngine:
         return host.pin_memory().to(self.device, non_blocking=True)
 
     def _h2d_stage(self, n):
-        """Pinned (4, capacity) float64 staging area for particle uploads.  Reuse is safe
-        because every frame ends with a stream synchronisation before the host touches it
-        again; within a frame snapshots use disjoint column ranges."""
-        stage = getattr(self, "_stage_h2d", None)
-        if stage is None or stage.shape[1] < n:
-            capacity = max(n, 2 * (0 if stage is None else stage.shape[1]), 1024)
-            new = torch.empty((4, capacity), dtype=torch.float64).pin_memory()
-            if stage is not None:
-                new[:, : stage.shape[1]].copy_(stage)
-            self._stage_h2d = stage = new
+        """Pinned (capacity, 5) float64 staging area for particle uploads.  Two areas alternate
+        per frame: with the one-frame lookahead of ``generate_frames`` the upload of frame f may
+        still be queued while the host already fills the area for frame f+1."""
+        stages = getattr(self, "_stage_h2d", None)
+        if stages is None:
+            stages = self._stage_h2d = [None, None]
+        stage = stages[self._stage_turn]
+        if stage is None or stage.shape[0] < n:
+            capacity = max(n, 2 * (0 if stage is None else stage.shape[0]), 1024)
+            stage = stages[self._stage_turn] = torch.empty((capacity, 5), dtype=torch.float64).pin_memory()
         return stage
 
     def _host_plane(self):
@@ -346,7 +348,9 @@ class DeviceEngine:
         focal = cfg.detector_focal_point
         true_dev, true_ids = None, None
         soa = torch.empty((4, total), dtype=torch.float64, device=self.device)     # depth, x, y, p_state
+        rows_dev = torch.empty((total, 5), dtype=torch.float64, device=self.device)
         weight = torch.empty(total, dtype=torch.float64, device=self.device)
+        self._stage_turn = getattr(self, "_stage_turn", 0) ^ 1     # this frame's staging area (see _h2d_stage)
         all_ids = numpy.concatenate([numpy.asarray(p[:, 3], dtype=numpy.int64) for _, p in snapshots])
         if states is not None:
             table_ids = states.ids
@@ -371,14 +375,14 @@ class DeviceEngine:
                 order, rounds, slots_dev, ids_dev = self._molecule_slots(table_ids, ids)
                 if order is not None:
                     particles = particles[order]
-            # columns (depth, x, y, p_state) -> SoA rows through a persistent pinned staging area
-            stage = self._h2d_stage(offset + n)
-            stage_np = stage.numpy()
-            for row, col in enumerate((0, 1, 2, 4)):
-                stage_np[row, offset: offset + n] = particles[:, col]
-            soa[:, offset: offset + n].copy_(stage[:, offset: offset + n], non_blocking=True)
+            # rows go up as they are (one memcpy into pinned memory, one DMA); the transpose to
+            # SoA (depth, x, y, p_state) happens on the device
+            stage = self._h2d_stage(total)
+            numpy.copyto(stage.numpy()[offset: offset + n], particles)
+            rows_dev[offset: offset + n].copy_(stage[offset: offset + n], non_blocking=True)
             if not all_resident:
                 keys.append(depth_keys_of(particles[:, 0] - focal[0], cfg.depth_cutoff, self.geom.n_depth_keys))
+            soa[:, offset: offset + n].copy_(rows_dev[offset: offset + n, self._soa_cols].t())
             for lo, hi in rounds:
                 sl = slice(offset + lo, offset + hi)
                 self._call(
@@ -407,6 +411,8 @@ class DeviceEngine:
             _native.ptr(out), _native.F32 if out.dtype == torch.float32 else _native.F64, 0,
             _native.ptr(work), work.numel(), _native.ptr(self.errors), stream)
 
+        if self._defer_true_data:
+            return out, (true_dev, true_ids) if want_true_data else None
         true_data = None
         if want_true_data:
             true_data = self._finish_true_data(true_dev.cpu().numpy(), true_ids, exposure_time)
@@ -469,19 +475,23 @@ class DeviceEngine:
             self._stream())
         return adc
 
-    def form_frame(self, snapshots, frame_index, noise_seed, states, exposure_time, want_true_data,
-                   want_expectation=True):
-        """One frame on the host: ``(adc (Nw, Nh) float64, expectation (Nw, Nh) float64 or None,
-        true_data)``.  Planes are widened to float64 on the device and written straight into
-        pinned host arrays (one DMA per plane, no host-side conversion or copy)."""
-        photons, true_data = self.render_expected(
-            snapshots, states=states, want_true_data=want_true_data, exposure_time=exposure_time)
+    def begin_frame(self, snapshots, frame_index, noise_seed, states, exposure_time, want_true_data,
+                    want_expectation=True, snapshot_states=False):
+        """Enqueue one frame (upload, kernels, download into pinned host planes) and return a
+        handle without waiting for the device; ``finish_frame`` waits and hands out the arrays.
+        Planes are widened to float64 on the device and written straight into pinned host
+        arrays (one DMA per plane, no host-side conversion or copy)."""
+        self._defer_true_data = True
+        try:
+            photons, true_pending = self.render_expected(
+                snapshots, states=states, want_true_data=want_true_data, exposure_time=exposure_time)
+        finally:
+            self._defer_true_data = False
         if getattr(self, "_planes32", None) is None:
             self._planes32 = torch.empty((2, self.n_w, self.n_h), dtype=self.dtype, device=self.device)
             self._planes64 = torch.empty((2, self.n_w, self.n_h), dtype=torch.float64, device=self.device)
         p32, p64 = self._planes32, self._planes64
         self.detect(photons, frame_index, noise_seed, adc=p32[0], expectation=p32[1] if want_expectation else None)
-        outs = []
         with _Trace(self, "host_alloc_planes"):
             hosts = [self._host_plane()[0] for _ in range(2 if want_expectation else 1)]
         with _Trace(self, "enqueue_d2h"):
@@ -491,13 +501,46 @@ class DeviceEngine:
                     p64[k].copy_(src)
                     src = p64[k]
                 host.copy_(src, non_blocking=True)
-                outs.append(host)
+        true_host = None
+        if isinstance(true_pending, tuple):
+            true_host = (torch.empty(true_pending[0].shape, dtype=torch.float64, pin_memory=True), true_pending[1])
+            true_host[0].copy_(true_pending[0], non_blocking=True)
+        elif true_pending is not None:
+            true_host = true_pending                       # the empty-frame dict
+        budget_host = None
+        if snapshot_states and states is not None:
+            budget_host = torch.empty(states.budget.shape, dtype=torch.float64, pin_memory=True)
+            budget_host.copy_(states.budget, non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(torch.cuda.current_stream(self.device))
+        return dict(hosts=hosts, true=true_host, budget=budget_host, states=states, done=done,
+                    exposure_time=exposure_time, want_expectation=want_expectation)
+
+    def finish_frame(self, pending):
+        """Wait for a frame started by ``begin_frame``: ``(adc, expectation or None, true_data,
+        budgets dict or None)``."""
         with _Trace(self, "wait_device"):
-            torch.cuda.current_stream(self.device).synchronize()
+            pending["done"].synchronize()
         n_err = int(self.errors.item())
         if n_err:
             self.errors.zero_()
             raise _native.NativeError("{} spots referenced a PSF table that was not built".format(n_err))
-        adc = outs[0].numpy()
-        expectation = outs[1].numpy() if want_expectation else None
+        hosts = pending["hosts"]
+        adc = hosts[0].numpy()
+        expectation = hosts[1].numpy() if pending["want_expectation"] else None
+        true_data = pending["true"]
+        if isinstance(true_data, tuple):
+            true_data = self._finish_true_data(true_data[0].numpy().copy(), true_data[1], pending["exposure_time"])
+        budgets = None
+        if pending["budget"] is not None:
+            host = pending["budget"].numpy()
+            keep = ~numpy.isnan(host)
+            budgets = {int(i): float(b) for i, b in zip(pending["states"].ids[keep], host[keep])}
+        return adc, expectation, true_data, budgets
+
+    def form_frame(self, snapshots, frame_index, noise_seed, states, exposure_time, want_true_data,
+                   want_expectation=True):
+        """One frame on the host: ``(adc (Nw, Nh) float64, expectation or None, true_data)``."""
+        adc, expectation, true_data, _ = self.finish_frame(self.begin_frame(
+            snapshots, frame_index, noise_seed, states, exposure_time, want_true_data, want_expectation))
         return adc, expectation, true_data
