@@ -511,9 +511,11 @@ class DeviceEngine:
         if snapshot_states and states is not None:
             budget_host = torch.empty(states.budget.shape, dtype=torch.float64, pin_memory=True)
             budget_host.copy_(states.budget, non_blocking=True)
+        errors_host = torch.empty(1, dtype=torch.int32, pin_memory=True)
+        errors_host.copy_(self.errors, non_blocking=True)
         done = torch.cuda.Event()
         done.record(torch.cuda.current_stream(self.device))
-        return dict(hosts=hosts, true=true_host, budget=budget_host, states=states, done=done,
+        return dict(hosts=hosts, true=true_host, budget=budget_host, states=states, done=done, errors=errors_host,
                     exposure_time=exposure_time, want_expectation=want_expectation)
 
     def finish_frame(self, pending):
@@ -521,7 +523,7 @@ class DeviceEngine:
         budgets dict or None)``."""
         with _Trace(self, "wait_device"):
             pending["done"].synchronize()
-        n_err = int(self.errors.item())
+        n_err = int(pending["errors"][0])      # read from pinned memory: no further device sync
         if n_err:
             self.errors.zero_()
             raise _native.NativeError("{} spots referenced a PSF table that was not built".format(n_err))
