@@ -222,6 +222,23 @@ int scb_render_expected(const scb_geometry *geom, int64_t n_spots,
                         void *d_workspace, size_t workspace_bytes,
                         int32_t *d_errors, void *stream);
 
+/* Tensor-core variant of scb_render_expected for the separable Gaussian PSF
+ * (fluorophore.type == 'Gaussian', _epifm.py:133-134): a 128 x 128 screen tile is the
+ * contraction D[i][j] = sum_s (w_s Ex_s(i)) Ey_s(j) over the spots binned to it, issued as
+ * tcgen05.mma.kind::tf32 (3 x tf32 split operands, fp32 accumulator in TMEM).  Ex/Ey are
+ * differences of d_prefix[0 .. 2c+1], the prefix sums of the 1-D Gaussian on the 1-nm grid
+ * (times 1 nm), staged into shared memory by a TMA bulk copy.  Agrees with the reference
+ * table to <= 1e-5 of the image maximum (the reference interpolates the radial profile
+ * linearly, which is not exactly separable); the SAT path stays exact.  Requires
+ * pixel_length >= ~33 nm (footprint <= 64 pixels), else returns SCB_E_UNSUPPORTED. */
+size_t scb_gaussian_tc_workspace_bytes(const scb_geometry *geom, int64_t n_spots);
+int scb_render_gaussian_tc(const scb_geometry *geom, int64_t n_spots,
+                           const double *d_x, const double *d_y, const double *d_weight,
+                           const double *d_prefix,
+                           void *d_out, int out_type, int accumulate,
+                           void *d_workspace, size_t workspace_bytes,
+                           int32_t *d_errors, void *stream);
+
 /* Measurement hook (bench.py): between scb_profile_begin and scb_profile_end every
  * scb_render_expected brackets its tile-render kernel with CUDA events on the stream it
  * was given; scb_profile_end synchronises those events and returns the summed device time

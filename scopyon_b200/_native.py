@@ -87,6 +87,10 @@ SIGNATURES = {
     "scb_render_expected": (ctypes.c_int, [
         ctypes.POINTER(Geometry), ctypes.c_int64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
         c_ptr, ctypes.c_int, ctypes.c_int, c_ptr, ctypes.c_size_t, c_ptr, c_ptr]),
+    "scb_gaussian_tc_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(Geometry), ctypes.c_int64]),
+    "scb_render_gaussian_tc": (ctypes.c_int, [
+        ctypes.POINTER(Geometry), ctypes.c_int64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, ctypes.c_int, ctypes.c_int,
+        c_ptr, ctypes.c_size_t, c_ptr, c_ptr]),
     "scb_profile_begin": (ctypes.c_int, [ctypes.c_int]),
     "scb_profile_end": (ctypes.c_int, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64)]),
     "scb_adc_offsets": (ctypes.c_int, [

@@ -207,7 +207,7 @@ class DeviceEngine:
     trace = None
     _defer_true_data = False
 
-    def __init__(self, configs, device=None, precision=None):
+    def __init__(self, configs, device=None, precision=None, gaussian_tc=None):
         require_cuda()
         self.lib = _native.load()
         self.configs = configs
@@ -224,6 +224,20 @@ class DeviceEngine:
         if self.psf_type == _native.PSF_GAUSSIAN and configs.psf_radial_width is None:
             raise ValueError('fluorophore.radial_width must be given for Gaussian type fluorophore.')
         self.n_w, self.n_h = int(self.geom.n_w), int(self.geom.n_h)
+        # opt-in tensor-core renderer for the separable Gaussian PSF (1e-5 of the image maximum
+        # instead of exact; see csrc/gaussian_tc.cu)
+        if gaussian_tc is None:
+            import os
+            gaussian_tc = os.environ.get("SCOPYON_B200_GAUSSIAN_TC", "0") == "1"
+        self.gaussian_tc = bool(gaussian_tc) and self.psf_type == _native.PSF_GAUSSIAN
+        self.gaussian_prefix = None
+        if self.gaussian_tc:
+            c = self.geom.n_radial - 1
+            a = (numpy.arange(2 * c + 1) - c) * RESOLUTION
+            sigma = float(configs.psf_radial_width)
+            g1 = numpy.exp(-0.5 * (a / sigma) ** 2) / (numpy.sqrt(2 * numpy.pi) * sigma) * RESOLUTION
+            prefix = numpy.concatenate([[0.0], numpy.cumsum(g1)])
+            self.gaussian_prefix = torch.from_numpy(prefix).to(self.device)
 
         # PSF summed-area tables: shared by every engine of this process with the same PSF
         # (the reference rebuilds its table cache on each form_image call, base.py:56-59)
@@ -351,7 +365,7 @@ class DeviceEngine:
         rows_dev = torch.empty((total, 5), dtype=torch.float64, device=self.device)
         weight = torch.empty(total, dtype=torch.float64, device=self.device)
         self._stage_turn = getattr(self, "_stage_turn", 0) ^ 1     # this frame's staging area (see _h2d_stage)
-        all_ids = numpy.concatenate([numpy.asarray(p[:, 3], dtype=numpy.int64) for _, p in snapshots])
+        all_ids = self._ids_of(snapshots)
         if states is not None:
             table_ids = states.ids
         elif want_true_data:
@@ -396,20 +410,26 @@ class DeviceEngine:
                     _native.ptr(weight[sl]), None if true_dev is None else _native.ptr(true_dev), stream)
             offset += n
 
-        if keys:
+        if self.gaussian_tc:
+            need = self.lib.scb_gaussian_tc_workspace_bytes(ctypes.byref(self.geom), total)
+            if self._workspace is None or self._workspace.numel() < need:
+                self._workspace = torch.empty(int(need * 1.25) + 256, dtype=torch.uint8, device=self.device)
+            self._call(
+                "scb_render_gaussian_tc", ctypes.byref(self.geom), total, _native.ptr(soa[1]), _native.ptr(soa[2]),
+                _native.ptr(weight), _native.ptr(self.gaussian_prefix), _native.ptr(out),
+                _native.F32 if out.dtype == torch.float32 else _native.F64, 0, _native.ptr(self._workspace),
+                self._workspace.numel(), _native.ptr(self.errors), stream)
+            keys = None
+        elif keys:
             needed = numpy.unique(numpy.concatenate(keys))
             # a 3-D scene that touches many depth keys will touch all of them soon: build the lot
             if self.psf_type != _native.PSF_GAUSSIAN and (self.slot_host[needed] < 0).sum() > 128:
                 self.ensure_all_tables()
             else:
                 self.ensure_tables(needed)
-        work = self._render_workspace(total)
-        self._call(
-            "scb_render_expected", ctypes.byref(self.geom), total,
-            _native.ptr(soa[0]), _native.ptr(soa[1]), _native.ptr(soa[2]), _native.ptr(weight),
-            _native.ptr(self.sat), _native.ptr(self.inv_scale), _native.ptr(self.slot_of_key),
-            _native.ptr(out), _native.F32 if out.dtype == torch.float32 else _native.F64, 0,
-            _native.ptr(work), work.numel(), _native.ptr(self.errors), stream)
+        if not self.gaussian_tc:
+            self._render_sat(soa, weight, total, out, stream)
+
 
         if self._defer_true_data:
             return out, (true_dev, true_ids) if want_true_data else None
@@ -418,14 +438,35 @@ class DeviceEngine:
             true_data = self._finish_true_data(true_dev.cpu().numpy(), true_ids, exposure_time)
         return out, true_data
 
+    def _ids_of(self, snapshots):
+        """int64 molecule ids of all snapshot rows; reuses the previous frame's conversion when
+        the (float) id columns are unchanged."""
+        cols = [numpy.asarray(p)[:, 3] for _, p in snapshots]
+        cache = getattr(self, "_ids_cache", None)
+        if cache is not None and len(cache[0]) == len(cols) and all(
+                a.shape == b.shape and numpy.array_equal(a, b) for a, b in zip(cache[0], cols)):
+            return cache[1]
+        ids = numpy.concatenate([c.astype(numpy.int64) for c in cols]) if cols else numpy.zeros(0, numpy.int64)
+        self._ids_cache = ([c.copy() for c in cols], ids)
+        return ids
+
+    def _render_sat(self, soa, weight, total, out, stream):
+        work = self._render_workspace(total)
+        self._call(
+            "scb_render_expected", ctypes.byref(self.geom), total,
+            _native.ptr(soa[0]), _native.ptr(soa[1]), _native.ptr(soa[2]), _native.ptr(weight),
+            _native.ptr(self.sat), _native.ptr(self.inv_scale), _native.ptr(self.slot_of_key),
+            _native.ptr(out), _native.F32 if out.dtype == torch.float32 else _native.F64, 0,
+            _native.ptr(work), work.numel(), _native.ptr(self.errors), stream)
+
     def _molecule_slots(self, table_ids, ids):
         """Device copies of (budget/true_data slot, molecule id) per particle row, cached while
         consecutive snapshots carry the same id column (the usual case).  When an id repeats
         inside one snapshot the reference updates its budget row by row, so the rows are
         reordered into rounds (occurrence k launched after occurrence k-1)."""
         cache = getattr(self, "_slot_cache", None)
-        if cache is not None and cache[0] is table_ids and cache[1].shape == ids.shape \
-                and numpy.array_equal(cache[1], ids):
+        if cache is not None and cache[0] is table_ids and (cache[1] is ids or (
+                cache[1].shape == ids.shape and numpy.array_equal(cache[1], ids))):
             return cache[2]
         n = len(ids)
         order, rounds = None, [(0, n)]
@@ -441,7 +482,7 @@ class DeviceEngine:
         ordered = ids if order is None else ids[order]
         slots = numpy.searchsorted(table_ids, ordered).astype(numpy.int32)
         result = (order, rounds, self._to_device(slots), self._to_device(ordered))
-        self._slot_cache = (table_ids, ids.copy(), result)
+        self._slot_cache = (table_ids, ids, result)
         return result
 
     def _finish_true_data(self, acc, ids, exposure_time):
@@ -488,19 +529,34 @@ class DeviceEngine:
         finally:
             self._defer_true_data = False
         if getattr(self, "_planes32", None) is None:
-            self._planes32 = torch.empty((2, self.n_w, self.n_h), dtype=self.dtype, device=self.device)
-            self._planes64 = torch.empty((2, self.n_w, self.n_h), dtype=torch.float64, device=self.device)
-        p32, p64 = self._planes32, self._planes64
+            # two plane sets alternate per frame: the download of frame f (copy stream) overlaps the
+            # kernels of frame f+1; generate_frames awaits frame f before it starts frame f+2
+            self._planes32 = torch.empty((2, 2, self.n_w, self.n_h), dtype=self.dtype, device=self.device)
+            self._planes64 = torch.empty((2, 2, self.n_w, self.n_h), dtype=torch.float64, device=self.device)
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._plane_turn = 0
+        self._plane_turn ^= 1
+        p32, p64 = self._planes32[self._plane_turn], self._planes64[self._plane_turn]
         self.detect(photons, frame_index, noise_seed, adc=p32[0], expectation=p32[1] if want_expectation else None)
         with _Trace(self, "host_alloc_planes"):
             hosts = [self._host_plane()[0] for _ in range(2 if want_expectation else 1)]
+        main = torch.cuda.current_stream(self.device)
         with _Trace(self, "enqueue_d2h"):
-            for k, host in enumerate(hosts):
+            srcs = []
+            for k in range(len(hosts)):
                 src = p32[k]
                 if src.dtype != torch.float64:
                     p64[k].copy_(src)
                     src = p64[k]
-                host.copy_(src, non_blocking=True)
+                srcs.append(src)
+            ready = torch.cuda.Event()
+            ready.record(main)
+            self._copy_stream.wait_event(ready)
+            with torch.cuda.stream(self._copy_stream):
+                for host, src in zip(hosts, srcs):
+                    host.copy_(src, non_blocking=True)
+                planes_done = torch.cuda.Event()
+                planes_done.record(self._copy_stream)
         true_host = None
         if isinstance(true_pending, tuple):
             true_host = (torch.empty(true_pending[0].shape, dtype=torch.float64, pin_memory=True), true_pending[1])
@@ -516,6 +572,7 @@ class DeviceEngine:
         done = torch.cuda.Event()
         done.record(torch.cuda.current_stream(self.device))
         return dict(hosts=hosts, true=true_host, budget=budget_host, states=states, done=done, errors=errors_host,
+                    planes_done=planes_done,
                     exposure_time=exposure_time, want_expectation=want_expectation)
 
     def finish_frame(self, pending):
@@ -523,6 +580,7 @@ class DeviceEngine:
         budgets dict or None)``."""
         with _Trace(self, "wait_device"):
             pending["done"].synchronize()
+            pending["planes_done"].synchronize()
         n_err = int(pending["errors"][0])      # read from pinned memory: no further device sync
         if n_err:
             self.errors.zero_()

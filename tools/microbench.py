@@ -123,6 +123,61 @@ def bench_render():
                           "table_build_s": build_s, "errors": int(eng.errors.item())}))
 
 
+def bench_gaussian():
+    """BASELINE config 5: separable-Gaussian stress, 1e6 spots, 4096 x 4096."""
+    from scopyon_b200.engine import SatStore
+    sys.path.insert(0, ROOT)
+    from bench import count_spot_pixel_evals
+    size, n = 4096, 1000000
+    yaml = """
+default:
+    fluorophore: {type: Gaussian, radial_width: {value: 100.0e-9, units: m}, wave_length: {value: 600.0e-9, units: m}}
+    magnification: 100
+    detector: {type: CMOS, image_size: [%d, %d], pixel_length: {value: 6.5e-6, units: m}, QE: 0.73}
+""" % (size, size)
+    rng = numpy.random.RandomState(1)
+    results = {}
+    for tc in (False, True):
+        import warnings
+        config = scopyon_b200.DefaultConfiguration()
+        config.update(yaml)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            configs = _epifm.EPIFMConfigs(config.default, rng=numpy.random.RandomState(0))
+        eng = DeviceEngine(configs, precision="f32", gaussian_tc=tc)
+        pl = configs.pixel_length
+        data = numpy.zeros((n, 5))
+        data[:, 1:3] = numpy.random.RandomState(1).uniform(-size * pl / 2, size * pl / 2, (n, 2))
+        data[:, 3] = numpy.arange(n)
+        data[:, 4] = 1
+        snap = [(0.033, data)]
+        out = torch.empty((size, size), dtype=torch.float32, device="cuda")
+        eng.render_expected(snap, out=out)                      # builds tables, uploads
+        torch.cuda.synchronize()
+        # time the device part only: re-issue the render on resident spots
+        soa = torch.from_numpy(numpy.ascontiguousarray(data[:, [0, 1, 2, 4]].T)).cuda()
+        w = torch.full((n,), 30.0, dtype=torch.float64, device="cuda")
+        if tc:
+            need = eng.lib.scb_gaussian_tc_workspace_bytes(ctypes.byref(eng.geom), n)
+            work = torch.empty(need + 256, dtype=torch.uint8, device="cuda")
+
+            def go():
+                eng._call("scb_render_gaussian_tc", ctypes.byref(eng.geom), n, _native.ptr(soa[1]), _native.ptr(soa[2]),
+                          _native.ptr(w), _native.ptr(eng.gaussian_prefix), _native.ptr(out), _native.F32, 0,
+                          _native.ptr(work), work.numel(), _native.ptr(eng.errors), eng._stream())
+        else:
+            def go():
+                eng._render_sat(soa, w, n, out, eng._stream())
+        ms, best = timed(go, iters=5, warm=2)
+        results[tc] = out.double().cpu().numpy()
+        evals = count_spot_pixel_evals(data, size, pl)
+        print(json.dumps({"kernel": "scb_render_gaussian_tc" if tc else "scb_render_expected (SAT, Gaussian table)",
+                          "config": "C5: 1e6 Gaussian spots, 4096^2", "ms": ms, "ms_best": best, "evals": evals,
+                          "evals/s": evals / (ms * 1e-3), "frames/s (render only)": 1e3 / ms}))
+    diff = abs(results[True] - results[False]).max() / results[False].max()
+    print(json.dumps({"check": "tensor-core vs exact SAT image, max|diff|/max", "value": diff}))
+
+
 if __name__ == "__main__":
     what = sys.argv[1:] or ["detector", "diffuse", "render"]
     print(json.dumps({"gpu": torch.cuda.get_device_name(0), "hbm_peak_gbs": PEAK}))
@@ -132,3 +187,5 @@ if __name__ == "__main__":
         bench_diffuse()
     if "render" in what:
         bench_render()
+    if "gaussian" in what:
+        bench_gaussian()
