@@ -26,8 +26,14 @@ constexpr int kThreadsTC = 256;
 constexpr int kMaxFoot = 64;            // footprint rows / columns per spot the panels can hold
 constexpr int kSortCapTC = 4096;        // spots per tile ordered in shared memory per segment
 constexpr int kPanelBytes = KC * TM * 4;            // one operand panel (8 KB)
-constexpr uint32_t kLBO = 8 * TM * 4;               // bytes between K groups of 8 spots (4096)
-constexpr uint32_t kSBO = 128;                      // bytes between groups of 4 rows
+// K-major operand panels without swizzle (the canonical layout of cute::UMMA::Layout_K_INTER):
+// a core matrix is 8 rows (pixels) x 16 bytes (4 spots) = 128 contiguous bytes; the second
+// half of a K = 8 step lies kLBO further, the next 8 rows kSBO further, the next 8 spots
+// kKGroup further.  (MN-major tf32 operands return zeros on this part -- see
+// tools/probes/umma_probe.cu, which also verified this layout element by element.)
+constexpr uint32_t kLBO = 128;
+constexpr uint32_t kSBO = 256;
+constexpr uint32_t kKGroup = (TM / 8) * kSBO;       // 4096 bytes per 8 spots
 
 struct TcSmem {
     double G[2048];                                  // prefix sums of g on the 1-nm grid (TMA staged)
@@ -67,17 +73,17 @@ __device__ __forceinline__ void tma_bulk_load(void *dst, const void *src, uint32
                  : "memory");
 }
 
-// UMMA shared-memory matrix descriptor, MN-major, no swizzle (cute::UMMA::SmemDescriptor):
-// start address >> 4 in bits [0,14), leading byte offset >> 4 in [16,30) (between K groups of 8),
-// stride byte offset >> 4 in [32,46) (between groups of 4 MN elements), version 1 in [46,48).
+// UMMA shared-memory matrix descriptor, K-major, no swizzle (cute::UMMA::SmemDescriptor):
+// start address >> 4 in bits [0,14), leading byte offset >> 4 in [16,30), stride byte offset >> 4
+// in [32,46), descriptor version 1 in [46,48).
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
     return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(kLBO >> 4) << 16) | ((uint64_t)(kSBO >> 4) << 32) |
            ((uint64_t)1 << 46);
 }
 // Instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 (bit 4), A = B = TF32 (2 << 7,
-// 2 << 10), A and B MN-major (bits 15, 16), N >> 3 in [17,23), M >> 4 in [24,29).
-constexpr uint32_t kInstrDesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
-                                ((uint32_t)(TM >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+// 2 << 10), both K-major (bits 15, 16 clear), N >> 3 in [17,23), M >> 4 in [24,29).
+constexpr uint32_t kInstrDesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TM >> 3) << 17) |
+                                ((uint32_t)(TM >> 4) << 24);
 
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t a, uint64_t b, uint32_t accumulate) {
     asm volatile(
@@ -96,13 +102,14 @@ __device__ __forceinline__ void umma_commit(void *bar) {
 __device__ __forceinline__ void tmem_ld32(uint32_t addr, uint32_t (&v)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
           "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
           "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
           "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(addr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        : "r"(addr)
+        : "memory");
 }
 
 __device__ __forceinline__ float to_tf32(float v) {
@@ -215,19 +222,18 @@ gaussian_tc_kernel(Geo g, const SpotRec *__restrict__ spots, const uint16_t *__r
             }
             __syncthreads();
 
-            // ---- step B: operand panels, MN-major core matrices of 8 spots x 4 rows (128 B each):
-            // byte offset of (spot s, row i) = (s/8)*4096 + (i/4)*128 + (s%8)*16 + (i%4)*4, so a warp
-            // task (K group, row group) writes 128 contiguous bytes
+            // ---- step B: operand panels.  A warp task fills one 128-byte core matrix: 8 tile rows x
+            // 4 spots, lane = (row % 8) * 4 + (spot % 4), hence conflict-free contiguous stores.
             for (int task = warp; task < 128; task += kThreadsTC / 32) {
                 const bool is_b = task >= 64;
-                const int kg = (task >> 5) & 1, m1 = task & 31;
-                const int s = kg * 8 + (lane >> 2), i = m1 * 4 + (lane & 3);
+                const int kg = (task >> 5) & 1, half = (task >> 4) & 1, rg = task & 15;
+                const int s = kg * 8 + half * 4 + (lane & 3), i = rg * 8 + (lane >> 2);
                 const int k = i - (is_b ? sm.c0[s] : sm.r0[s]);
                 const bool inside = (unsigned)k < (unsigned)(is_b ? sm.nc[s] : sm.nr[s]);
                 const int kk = inside ? k : 0;
                 const float hi = is_b ? sm.ey_hi[s][kk] : sm.ex_hi[s][kk];
                 const float lo = is_b ? sm.ey_lo[s][kk] : sm.ex_lo[s][kk];
-                const int off = kg * (int)kLBO + m1 * (int)kSBO + lane * 4;
+                const int off = kg * (int)kKGroup + rg * (int)kSBO + half * (int)kLBO + lane * 4;
                 *reinterpret_cast<float *>(&sm.panels[buf][is_b ? 2 : 0][off]) = inside ? hi : 0.0f;
                 *reinterpret_cast<float *>(&sm.panels[buf][is_b ? 3 : 1][off]) = inside ? lo : 0.0f;
             }
@@ -242,7 +248,7 @@ gaussian_tc_kernel(Geo g, const SpotRec *__restrict__ spots, const uint16_t *__r
                 const uint32_t b_hi = smem_u32(sm.panels[buf][2]), b_lo = smem_u32(sm.panels[buf][3]);
 #pragma unroll
                 for (int kg = 0; kg < KC / 8; ++kg) {
-                    const uint32_t o = (uint32_t)kg * kLBO;
+                    const uint32_t o = (uint32_t)kg * kKGroup;
                     umma_tf32(tmem, umma_desc(a_hi + o), umma_desc(b_hi + o), (chunk_index | kg) != 0);
                     umma_tf32(tmem, umma_desc(a_hi + o), umma_desc(b_lo + o), 1u);
                     umma_tf32(tmem, umma_desc(a_lo + o), umma_desc(b_hi + o), 1u);
