@@ -22,9 +22,10 @@ namespace {
 
 constexpr int TM = 128;                 // tile edge = UMMA M = UMMA N
 constexpr int KC = 16;                  // spots per chunk = two K = 8 steps
-constexpr int kThreadsTC = 256;
+constexpr int kThreadsTC = 512;           // 16 warps: one per chunk spot in step A
 constexpr int kMaxFoot = 64;            // footprint rows / columns per spot the panels can hold
-constexpr int kSortCapTC = 4096;        // spots per tile ordered in shared memory per segment
+constexpr int kSortCapTC = 2048;        // spots per tile ordered in shared memory per segment
+constexpr int kFootPitch = kMaxFoot + 8; // row pitch of the partial-sum arrays: 72 floats -> spots 0..3 hit disjoint banks
 constexpr int kPanelBytes = KC * TM * 4;            // one operand panel (8 KB)
 // K-major operand panels without swizzle (the canonical layout of cute::UMMA::Layout_K_INTER):
 // a core matrix is 8 rows (pixels) x 16 bytes (4 spots) = 128 contiguous bytes; the second
@@ -37,8 +38,8 @@ constexpr uint32_t kKGroup = (TM / 8) * kSBO;       // 4096 bytes per 8 spots
 
 struct TcSmem {
     double G[2048];                                  // prefix sums of g on the 1-nm grid (TMA staged)
-    float ex_hi[KC][kMaxFoot], ex_lo[KC][kMaxFoot];  // w_s * Ex_s split into tf32 hi + lo
-    float ey_hi[KC][kMaxFoot], ey_lo[KC][kMaxFoot];
+    float ex_hi[KC][kFootPitch], ex_lo[KC][kFootPitch];  // w_s * Ex_s split into tf32 hi + lo
+    float ey_hi[KC][kFootPitch], ey_lo[KC][kFootPitch];
     int r0[KC], nr[KC], c0[KC], nc[KC];              // footprint rectangle of each chunk spot inside the tile
     int ids[kSortCapTC];
     alignas(128) unsigned char panels[2][4][kPanelBytes];   // [buffer][A_hi, A_lo, B_hi, B_lo]
@@ -192,9 +193,9 @@ gaussian_tc_kernel(Geo g, const SpotRec *__restrict__ spots, const uint16_t *__r
             // the MMAs that last read this buffer (chunk_index - 2) must have completed
             if (chunk_index >= 2) mbar_wait(&sm.mbar_mma[buf], ((chunk_index >> 1) - 1) & 1);
 
-            // ---- step A: 1-D partial sums of every chunk spot (warp w: spots 2w, 2w+1)
-            for (int q = 0; q < 2; ++q) {
-                const int s = 2 * warp + q;
+            // ---- step A: 1-D partial sums of every chunk spot (warp w: spot w)
+            {
+                const int s = warp;
                 int r0 = 0, nr = 0, c0 = 0, nc = 0;
                 if (base + s < n_seg) {
                     const int sid = sm.ids[base + s];
@@ -222,20 +223,28 @@ gaussian_tc_kernel(Geo g, const SpotRec *__restrict__ spots, const uint16_t *__r
             }
             __syncthreads();
 
-            // ---- step B: operand panels.  A warp task fills one 128-byte core matrix: 8 tile rows x
-            // 4 spots, lane = (row % 8) * 4 + (spot % 4), hence conflict-free contiguous stores.
-            for (int task = warp; task < 128; task += kThreadsTC / 32) {
-                const bool is_b = task >= 64;
-                const int kg = (task >> 5) & 1, half = (task >> 4) & 1, rg = task & 15;
-                const int s = kg * 8 + half * 4 + (lane & 3), i = rg * 8 + (lane >> 2);
-                const int k = i - (is_b ? sm.c0[s] : sm.r0[s]);
-                const bool inside = (unsigned)k < (unsigned)(is_b ? sm.nc[s] : sm.nr[s]);
-                const int kk = inside ? k : 0;
-                const float hi = is_b ? sm.ey_hi[s][kk] : sm.ex_hi[s][kk];
-                const float lo = is_b ? sm.ey_lo[s][kk] : sm.ex_lo[s][kk];
-                const int off = kg * (int)kKGroup + rg * (int)kSBO + half * (int)kLBO + lane * 4;
-                *reinterpret_cast<float *>(&sm.panels[buf][is_b ? 2 : 0][off]) = inside ? hi : 0.0f;
-                *reinterpret_cast<float *>(&sm.panels[buf][is_b ? 3 : 1][off]) = inside ? lo : 0.0f;
+            // ---- step B: operand panels.  A lane owns one tile row of one 4-spot group and writes
+            // that row of the core matrix (4 spots x 4 B) with one 16-byte store; a warp task covers
+            // 32 consecutive rows (four core matrices, 512 contiguous bytes apart by kSBO).
+            for (int task = warp; task < 32; task += kThreadsTC / 32) {
+                const bool is_b = task >= 16;
+                const int kg = (task >> 3) & 1, half = (task >> 2) & 1, rq = task & 3;
+                const int i = rq * 32 + lane, s0 = kg * 8 + half * 4;
+                float hi[4], lo[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int s = s0 + q;
+                    const int k = i - (is_b ? sm.c0[s] : sm.r0[s]);
+                    const bool inside = (unsigned)k < (unsigned)(is_b ? sm.nc[s] : sm.nr[s]);
+                    const int kk = inside ? k : 0;
+                    const float h = is_b ? sm.ey_hi[s][kk] : sm.ex_hi[s][kk];
+                    const float l = is_b ? sm.ey_lo[s][kk] : sm.ex_lo[s][kk];
+                    hi[q] = inside ? h : 0.0f;
+                    lo[q] = inside ? l : 0.0f;
+                }
+                const int off = kg * (int)kKGroup + (i >> 3) * (int)kSBO + half * (int)kLBO + (i & 7) * 16;
+                *reinterpret_cast<float4 *>(&sm.panels[buf][is_b ? 2 : 0][off]) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<float4 *>(&sm.panels[buf][is_b ? 3 : 1][off]) = make_float4(lo[0], lo[1], lo[2], lo[3]);
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor core
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

