@@ -105,15 +105,47 @@ spot_prepare_kernel(Geo g, int64_t n, const double *__restrict__ depth, const do
     spots[s] = rec;
 }
 
-// Exclusive scan of the tile census (one CTA; n_tiles is at most a few 10^5).
+// Exclusive scan of the tile census (one CTA; n_tiles is at most a few 10^5).  Each thread
+// owns `per` consecutive counters; they are fetched up front (independent loads, 16-byte
+// when possible) so the pass costs one memory round trip instead of `per`.
+constexpr int kScanPerMax = 32;
+
 __global__ void __launch_bounds__(1024)
 tile_scan_kernel(int n_tiles, const int *__restrict__ tile_count, int *__restrict__ tile_start) {
     __shared__ int warp_tot[32];
     const int per = (n_tiles + 1023) / 1024;
     const int b0 = threadIdx.x * per;
     int run = 0;
-    for (int i = 0; i < per; ++i)
-        if (b0 + i < n_tiles) run += tile_count[b0 + i];
+    int local[kScanPerMax];
+    const bool cached = per <= kScanPerMax;
+    if (cached) {
+        if ((per & 3) == 0) {
+            const int4 *src = reinterpret_cast<const int4 *>(tile_count + b0);
+#pragma unroll
+            for (int i = 0; i < kScanPerMax / 4; ++i) {
+                if (4 * i < per) {
+                    int4 v = make_int4(0, 0, 0, 0);
+                    if (b0 + 4 * i + 3 < n_tiles) v = src[i];
+                    else {
+                        if (b0 + 4 * i + 0 < n_tiles) v.x = tile_count[b0 + 4 * i + 0];
+                        if (b0 + 4 * i + 1 < n_tiles) v.y = tile_count[b0 + 4 * i + 1];
+                        if (b0 + 4 * i + 2 < n_tiles) v.z = tile_count[b0 + 4 * i + 2];
+                    }
+                    local[4 * i + 0] = v.x; local[4 * i + 1] = v.y; local[4 * i + 2] = v.z; local[4 * i + 3] = v.w;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < kScanPerMax; ++i)
+                if (i < per) local[i] = (b0 + i < n_tiles) ? tile_count[b0 + i] : 0;
+        }
+#pragma unroll
+        for (int i = 0; i < kScanPerMax; ++i)
+            if (i < per) run += local[i];
+    } else {
+        for (int i = 0; i < per; ++i)
+            if (b0 + i < n_tiles) run += tile_count[b0 + i];
+    }
     int incl = run;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -125,10 +157,20 @@ tile_scan_kernel(int n_tiles, const int *__restrict__ tile_count, int *__restric
     __syncthreads();
     int base = incl - run;
     for (int w = 0; w < warp; ++w) base += warp_tot[w];
-    for (int i = 0; i < per; ++i) {
-        if (b0 + i < n_tiles) {
-            tile_start[b0 + i] = base;
-            base += tile_count[b0 + i];
+    if (cached) {
+#pragma unroll
+        for (int i = 0; i < kScanPerMax; ++i) {
+            if (i < per && b0 + i < n_tiles) {
+                tile_start[b0 + i] = base;
+                base += local[i];
+            }
+        }
+    } else {
+        for (int i = 0; i < per; ++i) {
+            if (b0 + i < n_tiles) {
+                tile_start[b0 + i] = base;
+                base += tile_count[b0 + i];
+            }
         }
     }
     if (threadIdx.x == 1023) tile_start[n_tiles] = base;

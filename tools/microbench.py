@@ -175,7 +175,9 @@ default:
                           "config": "C5: 1e6 Gaussian spots, 4096^2", "ms": ms, "ms_best": best, "evals": evals,
                           "evals/s": evals / (ms * 1e-3), "frames/s (render only)": 1e3 / ms}))
     diff = abs(results[True] - results[False]).max() / results[False].max()
-    print(json.dumps({"check": "tensor-core vs exact SAT image, max|diff|/max", "value": diff}))
+    print(json.dumps({"check": "tensor-core vs exact SAT image, max|diff|/max", "value": diff,
+                      "sum_sat": float(results[False].sum()), "sum_tc": float(results[True].sum()),
+                      "identical": bool((results[True] == results[False]).all())}))
 
 
 if __name__ == "__main__":
