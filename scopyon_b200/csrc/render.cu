@@ -112,11 +112,15 @@ render_tiles_kernel(Geo g, const SpotRec *__restrict__ spots, const uint16_t *__
 #pragma unroll
             for (int q = 0; q < kBatch; ++q) {
                 const StageMeta m = meta[cur][q];
+                // a warp covers tile rows 2*warp and 2*warp+1: skip spots that miss both (warp uniform)
+                if (m.r0 > 2 * warp + 1 || m.r0 + m.nrow <= 2 * warp) continue;
                 const int rk = py - m.r0, rl = px - m.c0;
                 if ((unsigned)rk < (unsigned)m.nrow && (unsigned)rl < (unsigned)m.ncol) {
                     const long long *c = &corners[cur][q][rk * kEdge + rl];
                     const long long box = c[kEdge + 1] - c[kEdge] - c[1] + c[0];
-                    if (box > 0) acc = __dadd_rn(acc, __dmul_rn((double)box, m.w));   // _epifm.py:280-282
+                    // box >= 0 (the table is non-negative, edges are monotone), and adding a zero
+                    // leaves acc unchanged, so the reference's `if photons > 0` needs no branch
+                    acc = __dadd_rn(acc, __dmul_rn((double)box, m.w));   // _epifm.py:280-282
                 }
             }
             __syncthreads();
