@@ -7,7 +7,9 @@ Workload (config.workload = "C4"): EPI 3-D movie, 1e5 molecules diffusing in
 one snapshot per 33 ms frame.
 
 One "step" = one block of --frames-per-step frames: emission/bleaching -> tile binning
--> PSF render -> detector/ADC -> Brownian step, everything resident in HBM.  With N GPUs
+-> PSF render -> detector/ADC -> Brownian step, everything resident in HBM (9 kernels per
+frame: emit_bleach, spot_prepare, spot_edges, tile_scan, tile_fill, render_tiles,
+detector_fast, detector_slow, diffuse).  With N GPUs
 the movie is partitioned by frame blocks (weak scaling: every rank renders the same
 number of frames per step; a rank first replays the trajectory prefix of the frames
 before its block, reported as replay_ms, outside the timed steps).
@@ -317,16 +319,21 @@ def run_ours(args):
             peaks = json.load(open(peaks_path))
         peak = float(peaks.get("hbm_gbs", 6650.0))
         per_launch_ms = render_ms.value / max(1, render_launches.value)
+        # DRAM bytes per launch of the same kernel from the committed `ncu --set full` capture
+        traffic = None
+        traffic_path = os.path.join(ROOT, "profiles", "traffic_r1.json")
+        if os.path.exists(traffic_path) and args.molecules == 100000 and args.size == 2048:
+            traffic = json.load(open(traffic_path)).get("render_tiles_kernel<float>", {}).get("dram_bytes_per_launch")
         achieved = evals * 8.5 / (per_launch_ms * 1e-3) / 1e9
         line = {
             "metric": "frames/sec (2048^2 sCMOS, 1e5 spots)", "value": value, "unit": "frames/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": elapsed_ms / K,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 accumulate / f32 frames",
             "data": "synthetic", "config": workload_config(args),
-            "clocks": clocks, "e2e": e2e, "gpu_launches": 7 * F * K,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": 9 * F * K,
             "roofline": {
                 "kernel": "render_tiles_kernel<float>", "bound": "hbm", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                 "algorithmic_bytes_per_launch": evals * 8.5, "spot_pixel_evals_per_launch": evals,
                 "spot_pixel_evals_per_s": evals / (per_launch_ms * 1e-3), "ms_per_launch": per_launch_ms,

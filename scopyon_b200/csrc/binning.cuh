@@ -47,8 +47,7 @@ __global__ void __launch_bounds__(256)
 spot_prepare_kernel(Geo g, int64_t n, const double *__restrict__ depth, const double *__restrict__ x,
                     const double *__restrict__ y, const double *__restrict__ weight,
                     const double *__restrict__ inv_scale, const int32_t *__restrict__ slot_of_key,
-                    SpotRec *__restrict__ spots, uint16_t *__restrict__ edges, int edge_cap,
-                    int *__restrict__ tile_count, int32_t *__restrict__ errors) {
+                    SpotRec *__restrict__ spots, int *__restrict__ tile_count, int32_t *__restrict__ errors) {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
     SpotRec rec;
@@ -90,19 +89,29 @@ spot_prepare_kernel(Geo g, int64_t n, const double *__restrict__ depth, const do
                 const int u0 = rec.jmin / g.tile, u1 = (rec.jmax - 1) / g.tile;
                 for (int ti = t0; ti <= t1; ++ti)
                     for (int tj = u0; tj <= u1; ++tj) atomicAdd(&tile_count[ti * g.ntj + tj], 1);
-                // table sample index of every pixel edge the footprint touches (_epifm.py:236-253):
-                // rows first, then columns; the render kernel only looks them up
-                uint16_t *e = edges + (size_t)s * 2 * edge_cap;
-                for (int i = rec.imin; i <= rec.imax; ++i)
-                    e[i - rec.imin] = (uint16_t)edge_index(i, rec.imin, rec.imax, rec.ox, g);
-                for (int j = rec.jmin; j <= rec.jmax; ++j) {   // columns: stored as SAT storage offsets
-                    const int b = edge_index(j, rec.jmin, rec.jmax, rec.oy, g);
-                    e[edge_cap + j - rec.jmin] = (uint16_t)((b % g.modulus) * g.blocks + b / g.modulus);
-                }
             }
         }
     }
     spots[s] = rec;
+}
+
+// Table sample index of every pixel edge a footprint touches (_epifm.py:236-253): one thread
+// per (spot, axis, edge).  Rows are stored as sample indices, columns as SAT storage offsets
+// (column interleave); the render kernels only look them up.
+__global__ void __launch_bounds__(256)
+spot_edges_kernel(Geo g, int64_t n, const SpotRec *__restrict__ spots, uint16_t *__restrict__ edges, int edge_cap) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int per_spot = 2 * edge_cap;
+    const int64_t s = idx / per_spot;
+    if (s >= n) return;
+    const int e = (int)(idx - s * per_spot);
+    const int axis = e >= edge_cap, k = e - axis * edge_cap;
+    const SpotRec rec = spots[s];
+    if (rec.slot < 0) return;
+    const int first = axis ? rec.jmin : rec.imin, last = axis ? rec.jmax : rec.imax;
+    if (k > last - first) return;
+    const int b = edge_index(first + k, first, last, axis ? rec.oy : rec.ox, g);
+    edges[s * per_spot + e] = (uint16_t)(axis ? (b % g.modulus) * g.blocks + b / g.modulus : b);
 }
 
 // Exclusive scan of the tile census (one CTA; n_tiles is at most a few 10^5).  Each thread

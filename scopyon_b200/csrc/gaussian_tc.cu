@@ -333,8 +333,9 @@ extern "C" int scb_render_gaussian_tc(const scb_geometry *geom, int64_t n_spots,
     if (n_spots > 0) {
         // depth plays no role for the Gaussian (depth-independent PSF): x doubles as a dummy depth
         spot_prepare_kernel<<<scb_grid_for(n_spots, 256), 256, 0, s>>>(
-            g, n_spots, nullptr, d_x, d_y, d_weight, nullptr, nullptr, w.spots, w.edges, w.edge_cap, w.tile_count,
-            d_errors);
+            g, n_spots, nullptr, d_x, d_y, d_weight, nullptr, nullptr, w.spots, w.tile_count, d_errors);
+        spot_edges_kernel<<<scb_grid_for(n_spots * 2 * w.edge_cap, 256), 256, 0, s>>>(g, n_spots, w.spots, w.edges,
+                                                                                     w.edge_cap);
     }
     tile_scan_kernel<<<1, 1024, 0, s>>>(n_tiles, w.tile_count, w.tile_start);
     if (n_spots > 0) {

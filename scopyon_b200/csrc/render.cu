@@ -215,8 +215,9 @@ extern "C" int scb_render_expected(const scb_geometry *geom, int64_t n_spots, co
     SCB_CUDA(cudaMemsetAsync(w.tile_count, 0, (size_t)((char *)w.tile_start - (char *)w.tile_count), s));
     if (n_spots > 0) {
         spot_prepare_kernel<<<scb_grid_for(n_spots, 256), 256, 0, s>>>(
-            g, n_spots, d_depth, d_x, d_y, d_weight, d_inv_scale, d_slot_of_key, w.spots, w.edges, w.edge_cap,
-            w.tile_count, d_errors);
+            g, n_spots, d_depth, d_x, d_y, d_weight, d_inv_scale, d_slot_of_key, w.spots, w.tile_count, d_errors);
+        spot_edges_kernel<<<scb_grid_for(n_spots * 2 * w.edge_cap, 256), 256, 0, s>>>(g, n_spots, w.spots, w.edges,
+                                                                                     w.edge_cap);
     }
     tile_scan_kernel<<<1, 1024, 0, s>>>(n_tiles, w.tile_count, w.tile_start);
     if (n_spots > 0) {
