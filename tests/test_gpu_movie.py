@@ -1,0 +1,108 @@
+"""Device-resident movies (scopyon_b200.movie.DeviceMovie): frame-block sharding must
+reproduce the sequential movie exactly, and frames must agree with the oracle."""
+import numpy
+import pytest
+import torch
+
+import epifm_oracle as orc
+import scopyon_b200
+from conftest import make_configs
+from scopyon_b200.movie import DeviceMovie, frame_block
+
+pytestmark = pytest.mark.gpu
+
+YAML = """
+default:
+    magnification: 100
+    light_source: {angle: {value: %s, units: radian}}
+    detector: {type: CMOS, image_size: [96, 80], pixel_length: {value: 6.5e-6, units: m}, QE: 0.73, exposure_time: 0.033}
+    analog_to_digital_converter: {bit: 16, offset: 100, fullwell: 30000, type: column, count: 2.0}
+    effects: {photo_bleaching: {switch: %s, half_life: {value: 0.08, units: s}}}
+"""
+
+
+def make_movie(angle, bleaching, n=400, seed=11, precision="f32"):
+    config = scopyon_b200.DefaultConfiguration()
+    config.update(YAML % (angle, bleaching))
+    pl = 6.5e-8
+    lower, upper = [-48 * pl, -40 * pl, 0.0], [48 * pl, 40 * pl, 1.3e-6]
+    return config, DeviceMovie(config, n, lower, upper, 2e-13, seed, precision=precision)
+
+
+@pytest.mark.parametrize("angle", ["0.0", "1.2566370614359172"])      # epi, TIRF (depth-dependent emission)
+def test_frame_blocks_reproduce_the_sequential_movie(angle):
+    _, whole = make_movie(angle, "true")
+    frames = torch.empty((7, 96, 80), dtype=torch.float32, device=whole.engine.device)
+    positions = []
+    for k in range(7):
+        positions.append(whole.positions())
+        whole.render_next(frames[k])
+    frames = frames.cpu().numpy()
+    budgets = whole.budget.cpu().numpy()
+    assert (budgets == 0).sum() > 20 and (budgets > 0).sum() > 20     # bleaching is at work
+
+    world = 3
+    for rank in range(world):
+        first, last = frame_block(7, rank, world)
+        _, part = make_movie(angle, "true")
+        part.reset(first_frame=first)                                   # replay, no rendering
+        assert numpy.array_equal(part.positions(), positions[first])
+        block = torch.empty((last - first, 96, 80), dtype=torch.float32, device=part.engine.device)
+        part.render_block(block)
+        assert numpy.array_equal(block.cpu().numpy(), frames[first:last])   # bit for bit
+    other = make_movie(angle, "true", seed=12)[1]
+    one = torch.empty((1, 96, 80), dtype=torch.float32, device=other.engine.device)
+    other.render_block(one)
+    assert not numpy.array_equal(one.cpu().numpy()[0], frames[0])
+
+
+def test_movie_frame_matches_oracle_expectation():
+    config, movie = make_movie("0.0", "false", precision="f64")
+    _, _, params = make_configs(YAML % ("0.0", "false"))
+    for _ in range(2):
+        data = movie.positions()
+        adc = torch.empty((96, 80), dtype=torch.float64, device=movie.engine.device)
+        expectation = torch.empty_like(adc)
+        movie.render_next(adc, expectation_out=expectation)
+        photons, _ = orc.expected_frame([(0.0, data)], params, exposure_time=0.033)
+        want = orc.detector_expectation(photons, params)
+        got = expectation.cpu().numpy()
+        assert abs(got - want).max() / want.max() < 1e-9
+    # Brownian step between the two frames: displacement variance 2 D dt per axis
+    step = movie.positions()[:, :3] - data[:, :3]
+    assert abs(step.std(axis=0) / numpy.sqrt(2 * 2e-13 * 0.033) - 1).max() < 0.15
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_gather_frames_nccl_two_gpus(tmp_path):
+    import os
+    import socket
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_nccl_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    a = numpy.load(os.path.join(str(tmp_path), "stack0.npy"))
+    b = numpy.load(os.path.join(str(tmp_path), "stack1.npy"))
+    assert a.shape == (5, 96, 80) and numpy.array_equal(a, b)
+    _, whole = make_movie("0.0", "true")
+    frames = torch.empty((5, 96, 80), dtype=torch.float32, device=whole.engine.device)
+    whole.render_block(frames)
+    assert numpy.array_equal(frames.cpu().numpy(), a)
+
+
+def _nccl_worker(rank, world, port, out_dir):
+    import os
+    import torch.distributed as dist
+    from scopyon_b200.movie import gather_frames
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    first, last = frame_block(5, rank, world)
+    _, movie = make_movie("0.0", "true")
+    movie.reset(first_frame=first)
+    block = torch.empty((last - first, 96, 80), dtype=torch.float32, device=movie.engine.device)
+    movie.render_block(block)
+    stack = gather_frames(block, 5)
+    numpy.save(os.path.join(out_dir, "stack{}.npy".format(rank)), stack.cpu().numpy())
+    dist.destroy_process_group()
