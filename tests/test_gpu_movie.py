@@ -14,6 +14,7 @@ pytestmark = pytest.mark.gpu
 YAML = """
 default:
     magnification: 100
+    fluorophore: {depth_cutoff: {value: 200.0e-9, units: m}}     # 203 depth tables instead of 1003: quick to build
     light_source: {angle: {value: %s, units: radian}}
     detector: {type: CMOS, image_size: [96, 80], pixel_length: {value: 6.5e-6, units: m}, QE: 0.73, exposure_time: 0.033}
     analog_to_digital_converter: {bit: 16, offset: 100, fullwell: 30000, type: column, count: 2.0}
