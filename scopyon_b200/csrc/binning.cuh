@@ -4,6 +4,7 @@
 // census, an exclusive scan and a scatter of spot indices (counting sort by tile).
 #pragma once
 #include "scb_common.cuh"
+#include <cooperative_groups.h>
 
 namespace {
 
@@ -19,11 +20,15 @@ struct __align__(16) SpotRec {
 
 struct Geo {
     int n_w, n_h, nti, ntj;
-    int tile;           // screen-tile edge in pixels (16: SAT render, 128: Gaussian tensor-core render)
+    int tile_h, tile_w; // screen tile in pixels (8 x 128: SAT render strips, 128 x 128: Gaussian tensor-core render)
+    int chunk;          // >0: a (spot, tile) pair is listed once per `chunk` columns of the overlap
+    int stripes;        // copies of the per-tile counters (power of two): spreads the census atomics
+    uint32_t modulus_magic;   // ceil(2^32 / modulus): b / modulus == umulhi(b, magic) for b < 2^16
+    int special_edges;  // 1: column edges carry kEdgeZero / last-column codes (SAT render); 0: plain
     int side;           // table samples per axis (2*(n_radial-1)+1)
     int n_depth_keys;
     int modulus, blocks, pitch;   // SAT column interleave: (a, b) at a*pitch + (b % modulus)*blocks + b/modulus
-    double pl, res, sw, half_w, half_h, depth_cutoff;
+    double pl, res, inv_res, sw, half_w, half_h, depth_cutoff;
     double f0, f1, f2;
 };
 
@@ -34,155 +39,205 @@ __device__ __forceinline__ int clamp_to_int(double v, int lo, int hi) {
 }
 
 // ceil((i*pl - o)/res) with the reference's first/last clamps (_epifm.py:236-253).
+// The IEEE quotient is only needed when it lies within rounding distance of an integer:
+// t * (1/res) is within 2 ulp of t / res, so if no integer lies within 4 ulp of it both have
+// the same ceiling; otherwise the correctly rounded division decides.
 __device__ __forceinline__ int edge_index(int i, int i_first, int i_last, double o, const Geo &g) {
-    double v = __ddiv_rn(__dsub_rn(__dmul_rn((double)i, g.pl), o), g.res);
-    int e = clamp_to_int(ceil(v), -1, g.side + 1);
+    const double t = __dsub_rn(__dmul_rn((double)i, g.pl), o);
+    const double q = __dmul_rn(t, g.inv_res);
+    double c = ceil(q);
+    const double slack = __dmul_rn(fabs(q), 8.9e-16);      // 4 * 2^-52
+    if (!(c - q > slack && q - (c - 1.0) > slack)) c = ceil(__ddiv_rn(t, g.res));   // also NaN / inf
+    int e = clamp_to_int(c, -1, g.side + 1);
     if (i == i_first) e = max(e, 0);
     if (i == i_last) e = min(e, g.side);
     return min(max(e, 0), g.side);  // no-op for interior edges of a valid footprint
 }
+
+// List entries of one (spot, tile column) overlap: one, or one per `chunk` columns.
+__device__ __forceinline__ int overlap_entries(const Geo &g, int jmin, int jmax, int tj) {
+    if (g.chunk <= 0) return 1;
+    const int c_lo = max(jmin, tj * g.tile_w), c_hi = min(jmax, (tj + 1) * g.tile_w);
+    return (c_hi - c_lo + g.chunk - 1) / g.chunk;
+}
+
+__device__ __forceinline__ int stripe_of(const Geo &g, int64_t spot) { return (int)(spot >> 5) & (g.stripes - 1); }
 
 // One thread per spot: footprint, depth key, tile census.
 __global__ void __launch_bounds__(256)
 spot_prepare_kernel(Geo g, int64_t n, const double *__restrict__ depth, const double *__restrict__ x,
                     const double *__restrict__ y, const double *__restrict__ weight,
                     const double *__restrict__ inv_scale, const int32_t *__restrict__ slot_of_key,
-                    SpotRec *__restrict__ spots, int *__restrict__ tile_count, int32_t *__restrict__ errors) {
-    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n) return;
+                    SpotRec *__restrict__ spots, int *__restrict__ tile_count,
+                    unsigned long long *__restrict__ wmax_bits, int32_t *__restrict__ errors) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     SpotRec rec;
     rec.slot = -1;
     rec.imin = rec.imax = rec.jmin = rec.jmax = 0;
     rec.ox = rec.oy = rec.w = 0.0;
     rec.pad = 0;
-    const double w = weight[s];
-    const double xi = __dsub_rn(x[s], g.f1);
-    const double yi = __dsub_rn(y[s], g.f2);
-    const double dz = depth ? fabs(__dsub_rn(depth[s], g.f0)) : 0.0;
-    if (w > 0.0 && isfinite(xi) && isfinite(yi) && isfinite(dz)) {   // _epifm.py:217-218
-        // depth key, _epifm.py:76-84
-        int key;
-        if (dz < __dadd_rn(g.depth_cutoff, g.res)) {
-            key = clamp_to_int(__ddiv_rn(dz, g.res), 0, g.n_depth_keys - 1);
-        } else {
-            key = g.n_depth_keys;  // frozen at the cutoff ("key -1")
-        }
-        int slot = slot_of_key ? slot_of_key[key] : 0;
-        if (slot < 0) {
-            atomicAdd(errors, 1);
-        } else {
-            // _epifm.py:233-235 and 255-257
-            const double cx = __dadd_rn(g.half_w, xi), cy = __dadd_rn(g.half_h, yi);
-            const double hs = __dmul_rn(g.sw, 0.5);
-            rec.ox = __dsub_rn(cx, hs);
-            rec.oy = __dsub_rn(cy, hs);
-            int imin = clamp_to_int(floor(__ddiv_rn(rec.ox, g.pl)), -1, g.n_w + 1);
-            int imax = clamp_to_int(ceil(__ddiv_rn(__dadd_rn(cx, hs), g.pl)), -1, g.n_w + 1);
-            int jmin = clamp_to_int(floor(__ddiv_rn(rec.oy, g.pl)), -1, g.n_h + 1);
-            int jmax = clamp_to_int(ceil(__ddiv_rn(__dadd_rn(cy, hs), g.pl)), -1, g.n_h + 1);
-            rec.imin = max(0, imin); rec.imax = min(g.n_w, imax);
-            rec.jmin = max(0, jmin); rec.jmax = min(g.n_h, jmax);
-            if (rec.imax > rec.imin && rec.jmax > rec.jmin) {
-                rec.slot = slot;
-                rec.w = inv_scale ? w * (g.res * g.res) * inv_scale[slot] : w;
-                const int t0 = rec.imin / g.tile, t1 = (rec.imax - 1) / g.tile;
-                const int u0 = rec.jmin / g.tile, u1 = (rec.jmax - 1) / g.tile;
-                for (int ti = t0; ti <= t1; ++ti)
-                    for (int tj = u0; tj <= u1; ++tj) atomicAdd(&tile_count[ti * g.ntj + tj], 1);
+    double w_seen = 0.0;
+    if (s < n) {
+        const double w = weight[s];
+        const double xi = __dsub_rn(x[s], g.f1);
+        const double yi = __dsub_rn(y[s], g.f2);
+        const double dz = depth ? fabs(__dsub_rn(depth[s], g.f0)) : 0.0;
+        if (w > 0.0 && isfinite(xi) && isfinite(yi) && isfinite(dz)) {   // _epifm.py:217-218
+            // depth key, _epifm.py:76-84
+            int key;
+            if (dz < __dadd_rn(g.depth_cutoff, g.res)) {
+                key = clamp_to_int(__ddiv_rn(dz, g.res), 0, g.n_depth_keys - 1);
+            } else {
+                key = g.n_depth_keys;  // frozen at the cutoff ("key -1")
+            }
+            int slot = slot_of_key ? slot_of_key[key] : 0;
+            if (slot < 0) {
+                atomicAdd(errors, 1);
+            } else {
+                // _epifm.py:233-235 and 255-257
+                const double cx = __dadd_rn(g.half_w, xi), cy = __dadd_rn(g.half_h, yi);
+                const double hs = __dmul_rn(g.sw, 0.5);
+                rec.ox = __dsub_rn(cx, hs);
+                rec.oy = __dsub_rn(cy, hs);
+                int imin = clamp_to_int(floor(__ddiv_rn(rec.ox, g.pl)), -1, g.n_w + 1);
+                int imax = clamp_to_int(ceil(__ddiv_rn(__dadd_rn(cx, hs), g.pl)), -1, g.n_w + 1);
+                int jmin = clamp_to_int(floor(__ddiv_rn(rec.oy, g.pl)), -1, g.n_h + 1);
+                int jmax = clamp_to_int(ceil(__ddiv_rn(__dadd_rn(cy, hs), g.pl)), -1, g.n_h + 1);
+                rec.imin = max(0, imin); rec.imax = min(g.n_w, imax);
+                rec.jmin = max(0, jmin); rec.jmax = min(g.n_h, jmax);
+                if (rec.imax > rec.imin && rec.jmax > rec.jmin) {
+                    rec.slot = slot;
+                    rec.w = inv_scale ? w * (g.res * g.res) * inv_scale[slot] : w;
+                    w_seen = w;
+                    // census: the counters exist in `stripes` copies (one per group of 32 spots,
+                    // round robin) so that the atomics of a frame spread over more L2 sectors
+                    int *count = tile_count + (size_t)stripe_of(g, s) * g.nti * g.ntj;
+                    const int t0 = rec.imin / g.tile_h, t1 = (rec.imax - 1) / g.tile_h;
+                    const int u0 = rec.jmin / g.tile_w, u1 = (rec.jmax - 1) / g.tile_w;
+                    for (int tj = u0; tj <= u1; ++tj) {
+                        const int entries = overlap_entries(g, rec.jmin, rec.jmax, tj);
+                        for (int ti = t0; ti <= t1; ++ti) atomicAdd(&count[ti * g.ntj + tj], entries);
+                    }
+                }
             }
         }
+        spots[s] = rec;
     }
-    spots[s] = rec;
+    if (wmax_bits) {
+        // largest weight: positive doubles order like their bit patterns, so an integer max
+        // is exact and order free; one atomic per warp
+        unsigned long long bits = (unsigned long long)__double_as_longlong(w_seen);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, bits, d);
+            bits = other > bits ? other : bits;
+        }
+        if ((threadIdx.x & 31) == 0 && bits != 0) atomicMax(wmax_bits, bits);
+    }
 }
 
 // Table sample index of every pixel edge a footprint touches (_epifm.py:236-253): one thread
-// per (spot, axis, edge).  Rows are stored as sample indices, columns as SAT storage offsets
-// (column interleave); the render kernels only look them up.
+// per (spot, axis, edge); blockDim = (2 * edge_cap, spots per block).  Rows are stored as
+// sample indices, columns as SAT storage offsets (column interleave) with two special cases
+// the render kernels rely on: sample 0 (the clamped opening edge; S[.][0] == 0) carries
+// kEdgeZero and is never fetched, and the last sample (the clamped closing edge) points at the
+// copy of the last column kept in the phase block of the footprint's interior edges.
+constexpr uint16_t kEdgeZero = 0x8000;
+
 __global__ void __launch_bounds__(256)
 spot_edges_kernel(Geo g, int64_t n, const SpotRec *__restrict__ spots, uint16_t *__restrict__ edges, int edge_cap) {
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int per_spot = 2 * edge_cap;
-    const int64_t s = idx / per_spot;
+    const int64_t s = (int64_t)blockIdx.x * blockDim.y + threadIdx.y;
     if (s >= n) return;
-    const int e = (int)(idx - s * per_spot);
-    const int axis = e >= edge_cap, k = e - axis * edge_cap;
     const SpotRec rec = spots[s];
     if (rec.slot < 0) return;
-    const int first = axis ? rec.jmin : rec.imin, last = axis ? rec.jmax : rec.imax;
-    if (k > last - first) return;
-    const int b = edge_index(first + k, first, last, axis ? rec.oy : rec.ox, g);
-    edges[s * per_spot + e] = (uint16_t)(axis ? (b % g.modulus) * g.blocks + b / g.modulus : b);
+    for (int e = threadIdx.x; e < 2 * edge_cap; e += blockDim.x) {
+        const int axis = e >= edge_cap, k = e - axis * edge_cap;
+        const int first = axis ? rec.jmin : rec.imin, last = axis ? rec.jmax : rec.imax;
+        if (k > last - first) continue;
+        const double o = axis ? rec.oy : rec.ox;
+        const int b = edge_index(first + k, first, last, o, g);
+        uint32_t code = (uint32_t)b;
+        if (axis && g.special_edges) {
+            if (b == 0) {
+                code = kEdgeZero;
+            } else {
+                int phase_of = b;
+                if (b == g.side && k > 0) {           // closing edge: use the interior edges' phase block
+                    const int before = edge_index(first + k - 1, first, last, o, g);
+                    if (before > 0) phase_of = before;
+                }
+                const uint32_t q = g.modulus > 1 ? __umulhi((uint32_t)phase_of, g.modulus_magic)
+                                                 : (uint32_t)phase_of;           // phase_of / modulus
+                const uint32_t phase = (uint32_t)phase_of - q * (uint32_t)g.modulus;
+                code = phase * (uint32_t)g.blocks + (b == g.side ? (uint32_t)g.blocks - 1u : q);
+            }
+        }
+        edges[s * (2 * edge_cap) + e] = (uint16_t)code;
+    }
 }
 
-// Exclusive scan of the tile census (one CTA; n_tiles is at most a few 10^5).  Each thread
-// owns `per` consecutive counters; they are fetched up front (independent loads, 16-byte
-// when possible) so the pass costs one memory round trip instead of `per`.
-constexpr int kScanPerMax = 32;
+// launch shape of spot_edges_kernel
+inline void edges_launch_shape(int edge_cap, int64_t n, dim3 &grid, dim3 &block) {
+    const int x = 2 * edge_cap < 256 ? 2 * edge_cap : 256;
+    const int y = 256 / x;
+    block = dim3(x, y, 1);
+    grid = dim3((unsigned)((n + y - 1) / y), 1, 1);
+}
 
-__global__ void __launch_bounds__(1024)
-tile_scan_kernel(int n_tiles, const int *__restrict__ tile_count, int *__restrict__ tile_start) {
+// Exclusive scan of the tile census by one thread-block CLUSTER of 8 CTAs.  Logical entry
+// j = tile * stripes + stripe is stored at stripe * n_tiles + tile; start[j] gets the scan,
+// start[n] the total, so a tile's list is [start[tile * stripes], start[(tile + 1) * stripes]).
+// CTA c scans its contiguous share in rounds of 1024 entries (coalesced, one entry per thread),
+// publishes its total in shared memory, and after a cluster barrier reads the totals of the
+// CTAs before it through distributed shared memory -- one launch, no global round trip.
+constexpr int kScanCtas = 8;
+
+__global__ void __cluster_dims__(kScanCtas, 1, 1) __launch_bounds__(1024)
+tile_scan_kernel(int n_tiles, int stripes, const int *__restrict__ tile_count, int *__restrict__ tile_start) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
     __shared__ int warp_tot[32];
-    const int per = (n_tiles + 1023) / 1024;
-    const int b0 = threadIdx.x * per;
-    int run = 0;
-    int local[kScanPerMax];
-    const bool cached = per <= kScanPerMax;
-    if (cached) {
-        if ((per & 3) == 0) {
-            const int4 *src = reinterpret_cast<const int4 *>(tile_count + b0);
-#pragma unroll
-            for (int i = 0; i < kScanPerMax / 4; ++i) {
-                if (4 * i < per) {
-                    int4 v = make_int4(0, 0, 0, 0);
-                    if (b0 + 4 * i + 3 < n_tiles) v = src[i];
-                    else {
-                        if (b0 + 4 * i + 0 < n_tiles) v.x = tile_count[b0 + 4 * i + 0];
-                        if (b0 + 4 * i + 1 < n_tiles) v.y = tile_count[b0 + 4 * i + 1];
-                        if (b0 + 4 * i + 2 < n_tiles) v.z = tile_count[b0 + 4 * i + 2];
-                    }
-                    local[4 * i + 0] = v.x; local[4 * i + 1] = v.y; local[4 * i + 2] = v.z; local[4 * i + 3] = v.w;
-                }
-            }
-        } else {
-#pragma unroll
-            for (int i = 0; i < kScanPerMax; ++i)
-                if (i < per) local[i] = (b0 + i < n_tiles) ? tile_count[b0 + i] : 0;
-        }
-#pragma unroll
-        for (int i = 0; i < kScanPerMax; ++i)
-            if (i < per) run += local[i];
-    } else {
-        for (int i = 0; i < per; ++i)
-            if (b0 + i < n_tiles) run += tile_count[b0 + i];
-    }
-    int incl = run;
+    __shared__ int cta_total;
+    const int n = n_tiles * stripes;
+    const int shift = 31 - __clz(stripes), mask = stripes - 1;
+    const int rounds = (n + kScanCtas * 1024 - 1) / (kScanCtas * 1024);
+    const int share = rounds * 1024;
+    const int first = (int)cluster.block_rank() * share;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int carry = 0;
+    for (int r = 0; r < rounds; ++r) {
+        const int j = first + r * 1024 + threadIdx.x;
+        const int v = j < n ? tile_count[(size_t)(j & mask) * n_tiles + (j >> shift)] : 0;
+        int incl = v;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        int up = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += up;
-    }
-    if (lane == 31) warp_tot[warp] = incl;
-    __syncthreads();
-    int base = incl - run;
-    for (int w = 0; w < warp; ++w) base += warp_tot[w];
-    if (cached) {
+        for (int d = 1; d < 32; d <<= 1) {
+            const int up = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += up;
+        }
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        int before = 0, all = 0;
 #pragma unroll
-        for (int i = 0; i < kScanPerMax; ++i) {
-            if (i < per && b0 + i < n_tiles) {
-                tile_start[b0 + i] = base;
-                base += local[i];
-            }
+        for (int w = 0; w < 32; ++w) {
+            const int t = warp_tot[w];
+            if (w < warp) before += t;
+            all += t;
         }
-    } else {
-        for (int i = 0; i < per; ++i) {
-            if (b0 + i < n_tiles) {
-                tile_start[b0 + i] = base;
-                base += tile_count[b0 + i];
-            }
-        }
+        if (j < n) tile_start[j] = carry + before + incl - v;
+        carry += all;
+        __syncthreads();
     }
-    if (threadIdx.x == 1023) tile_start[n_tiles] = base;
+    if (threadIdx.x == 0) cta_total = carry;
+    cluster.sync();
+    int offset = 0;
+    for (unsigned c = 0; c < cluster.block_rank(); ++c) offset += *cluster.map_shared_rank(&cta_total, c);
+    if (offset)
+        for (int r = 0; r < rounds; ++r) {
+            const int j = first + r * 1024 + threadIdx.x;
+            if (j < n) tile_start[j] += offset;
+        }
+    if (cluster.block_rank() == kScanCtas - 1 && threadIdx.x == 0) tile_start[n] = offset + carry;
+    cluster.sync();      // keep cta_total alive until every CTA has read it
 }
 
 // Scatter spot indices into their tiles' segments (arrival order; the render kernel
@@ -196,12 +251,14 @@ tile_fill_kernel(Geo g, int64_t n, const SpotRec *__restrict__ spots,
     const int slot = spots[s].slot;
     if (slot < 0) return;
     const int imin = spots[s].imin, imax = spots[s].imax, jmin = spots[s].jmin, jmax = spots[s].jmax;
-    const int t0 = imin / g.tile, t1 = (imax - 1) / g.tile;
-    const int u0 = jmin / g.tile, u1 = (jmax - 1) / g.tile;
+    const int t0 = imin / g.tile_h, t1 = (imax - 1) / g.tile_h;
+    const int u0 = jmin / g.tile_w, u1 = (jmax - 1) / g.tile_w;
+    const int stripe = stripe_of(g, s);
+    int *cursor = tile_cursor + (size_t)stripe * g.nti * g.ntj;
     for (int ti = t0; ti <= t1; ++ti)
         for (int tj = u0; tj <= u1; ++tj) {
             const int tile = ti * g.ntj + tj;
-            pair_spot[tile_start[tile] + atomicAdd(&tile_cursor[tile], 1)] = (int)s;
+            pair_spot[tile_start[tile * g.stripes + stripe] + atomicAdd(&cursor[tile], 1)] = (int)s;
         }
 }
 
@@ -209,43 +266,54 @@ struct Workspace {
     SpotRec *spots;
     uint16_t *edges;
     int edge_cap;            // edge slots per axis per spot
-    int *tile_count, *tile_cursor, *tile_start, *pair_spot;
+    int *tile_count, *tile_cursor, *tile_start;
+    unsigned long long *wmax_bits;   // bit pattern of the largest spot weight (cleared with the census)
+    int *next_tile;                  // dynamic tile queue of the persistent render kernel (cleared likewise)
+    int *pair_spot;                  // list entries: spot indices (entry_bytes = 4) or render units
     size_t bytes;
     int64_t pair_capacity;
 };
 
 inline size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
 
-Geo make_geo(const scb_geometry *geom, int tile) {
+Geo make_geo(const scb_geometry *geom, int tile_h, int tile_w, int chunk = 0) {
     Geo g;
-    g.tile = tile;
+    g.special_edges = 0;
+    g.tile_h = tile_h; g.tile_w = tile_w; g.chunk = chunk;
     g.n_w = geom->n_w; g.n_h = geom->n_h;
-    g.nti = (geom->n_w + tile - 1) / tile;
-    g.ntj = (geom->n_h + tile - 1) / tile;
+    g.nti = (geom->n_w + tile_h - 1) / tile_h;
+    g.ntj = (geom->n_h + tile_w - 1) / tile_w;
     g.side = 2 * (geom->n_radial - 1) + 1;
     g.n_depth_keys = geom->n_depth_keys;
     g.pl = geom->pixel_length; g.res = geom->resolution;
+    g.inv_res = 1.0 / geom->resolution;
     g.sw = geom->resolution * (double)(g.side - 1);            // _epifm.py:228
     g.half_w = ((double)geom->n_w * geom->pixel_length) * 0.5;  // _epifm.py:230,233
     g.half_h = ((double)geom->n_h * geom->pixel_length) * 0.5;
     g.depth_cutoff = geom->depth_cutoff;
     g.modulus = geom->sat_modulus < 1 ? 1 : geom->sat_modulus;
-    g.blocks = (g.side + 1 + g.modulus - 1) / g.modulus;
+    g.blocks = scb_sat_blocks(g.side + 1, g.modulus);
     g.pitch = g.modulus * g.blocks;
+    g.modulus_magic = (uint32_t)((((uint64_t)1 << 32) + g.modulus - 1) / g.modulus);
+    // counter copies: as many as keep the scan's register-resident path (<= 32768 entries), at most 8
+    g.stripes = 1;
+    while (g.stripes < 8 && (int64_t)g.nti * g.ntj * g.stripes * 2 <= 32768) g.stripes *= 2;
     g.f0 = geom->focal[0]; g.f1 = geom->focal[1]; g.f2 = geom->focal[2];
     return g;
 }
 
-// most tiles one spot can touch: footprint rows <= ceil(sw/pl)+1
+// most list entries one spot can produce: footprint rows/columns <= ceil(sw/pl)+1
 int64_t max_tiles_per_spot(const Geo &g) {
-    double rows = ceil(g.sw / g.pl) + 2.0;
-    int64_t per_axis = (int64_t)((rows + g.tile - 2) / g.tile) + 1;
-    int64_t a = per_axis < g.nti ? per_axis : g.nti;
-    int64_t b = per_axis < g.ntj ? per_axis : g.ntj;
+    const double rows = ceil(g.sw / g.pl) + 2.0;
+    int64_t a = (int64_t)((rows + g.tile_h - 2) / g.tile_h) + 1;
+    int64_t b = (int64_t)((rows + g.tile_w - 2) / g.tile_w) + 1;
+    if (a > g.nti) a = g.nti;
+    if (b > g.ntj) b = g.ntj;
+    if (g.chunk > 0) b += (int64_t)(rows / g.chunk) + 1;   // sum over touched tiles of ceil(overlap / chunk)
     return a * b;
 }
 
-Workspace carve(const Geo &g, int64_t n, void *base) {
+Workspace carve(const Geo &g, int64_t n, void *base, size_t entry_bytes = sizeof(int)) {
     Workspace w;
     const size_t n_tiles = (size_t)g.nti * g.ntj;
     w.pair_capacity = (n > 0 ? n : 1) * max_tiles_per_spot(g);
@@ -261,10 +329,12 @@ Workspace carve(const Geo &g, int64_t n, void *base) {
         w.edge_cap = (int)((cap + 7) & ~(int64_t)7);
     }
     w.edges = (uint16_t *)(p + off); off += align_up((size_t)(n > 0 ? n : 1) * 2 * w.edge_cap * sizeof(uint16_t));
-    w.tile_count = (int *)(p + off); off += align_up(n_tiles * sizeof(int));
-    w.tile_cursor = (int *)(p + off); off += align_up(n_tiles * sizeof(int));
-    w.tile_start = (int *)(p + off); off += align_up((n_tiles + 1) * sizeof(int));
-    w.pair_spot = (int *)(p + off); off += align_up((size_t)w.pair_capacity * sizeof(int));
+    w.tile_count = (int *)(p + off); off += align_up(n_tiles * g.stripes * sizeof(int));
+    w.tile_cursor = (int *)(p + off); off += align_up(n_tiles * g.stripes * sizeof(int));
+    w.wmax_bits = (unsigned long long *)(p + off);
+    w.next_tile = (int *)(p + off + 8); off += 256;
+    w.tile_start = (int *)(p + off); off += align_up((n_tiles * g.stripes + 1) * sizeof(int));
+    w.pair_spot = (int *)(p + off); off += align_up((size_t)w.pair_capacity * entry_bytes);
     w.bytes = off;
     return w;
 }

@@ -131,7 +131,7 @@ gaussian_tc_kernel(Geo g, const SpotRec *__restrict__ spots, const uint16_t *__r
     const int ti = tile / g.ntj, tj = tile - ti * g.ntj;
     const int row0 = ti * TM, col0 = tj * TM;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int seg_begin = tile_start[tile], seg_end = tile_start[tile + 1];
+    const int seg_begin = tile_start[tile * g.stripes], seg_end = tile_start[(tile + 1) * g.stripes];
     const int n_spots = seg_end - seg_begin;
 
     if (n_spots == 0) {   // nothing lands on this tile
@@ -302,7 +302,7 @@ gaussian_tc_kernel(Geo g, const SpotRec *__restrict__ spots, const uint16_t *__r
 
 extern "C" size_t scb_gaussian_tc_workspace_bytes(const scb_geometry *geom, int64_t n_spots) {
     if (check_geometry(geom) != 0 || n_spots < 0) return 0;
-    Geo g = make_geo(geom, TM);
+    Geo g = make_geo(geom, TM, TM);
     return carve(g, n_spots, nullptr).bytes;
 }
 
@@ -316,7 +316,7 @@ extern "C" int scb_render_gaussian_tc(const scb_geometry *geom, int64_t n_spots,
     SCB_REQUIRE(d_out && d_workspace && d_errors && d_prefix, SCB_E_NULL, "scb_render_gaussian_tc: NULL pointer");
     SCB_REQUIRE(n_spots == 0 || (d_x && d_y && d_weight), SCB_E_NULL, "scb_render_gaussian_tc: NULL spot pointer");
     SCB_REQUIRE(out_type == SCB_F32 || out_type == SCB_F64, SCB_E_INVALID, "out_type=%d", out_type);
-    Geo g = make_geo(geom, TM);
+    Geo g = make_geo(geom, TM, TM);
     g.modulus = 1;                       // plain column indices: no SAT in this path
     g.blocks = g.side + 1;
     g.pitch = g.side + 1;
@@ -333,11 +333,12 @@ extern "C" int scb_render_gaussian_tc(const scb_geometry *geom, int64_t n_spots,
     if (n_spots > 0) {
         // depth plays no role for the Gaussian (depth-independent PSF): x doubles as a dummy depth
         spot_prepare_kernel<<<scb_grid_for(n_spots, 256), 256, 0, s>>>(
-            g, n_spots, nullptr, d_x, d_y, d_weight, nullptr, nullptr, w.spots, w.tile_count, d_errors);
-        spot_edges_kernel<<<scb_grid_for(n_spots * 2 * w.edge_cap, 256), 256, 0, s>>>(g, n_spots, w.spots, w.edges,
-                                                                                     w.edge_cap);
+            g, n_spots, nullptr, d_x, d_y, d_weight, nullptr, nullptr, w.spots, w.tile_count, nullptr, d_errors);
+        dim3 egrid, eblock;
+        edges_launch_shape(w.edge_cap, n_spots, egrid, eblock);
+        spot_edges_kernel<<<egrid, eblock, 0, s>>>(g, n_spots, w.spots, w.edges, w.edge_cap);
     }
-    tile_scan_kernel<<<1, 1024, 0, s>>>(n_tiles, w.tile_count, w.tile_start);
+    tile_scan_kernel<<<kScanCtas, 1024, 0, s>>>(n_tiles, g.stripes, w.tile_count, w.tile_start);
     if (n_spots > 0) {
         tile_fill_kernel<<<scb_grid_for(n_spots, 256), 256, 0, s>>>(g, n_spots, w.spots, w.tile_start, w.tile_cursor,
                                                                    w.pair_spot);

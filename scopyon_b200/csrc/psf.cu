@@ -174,7 +174,7 @@ __host__ SatLayout make_layout(int n_radial, int modulus) {
     SatLayout L;
     const int cols = 2 * (n_radial - 1) + 2;
     L.modulus = modulus < 1 ? 1 : modulus;
-    L.blocks = (cols + L.modulus - 1) / L.modulus;
+    L.blocks = scb_sat_blocks(cols, L.modulus);
     L.pitch = L.modulus * L.blocks;
     return L;
 }
@@ -217,14 +217,20 @@ sat_rows_kernel(const double *__restrict__ radial, int n_radial, const double *_
     }
     if (lane == 31) warp_tot[warp] = incl;
     __syncthreads();
-    int64_t base = 0;
-    for (int w = 0; w < warp; ++w) base += warp_tot[w];
+    int64_t base = 0, total = 0;
+    for (int w = 0; w < kScanThreads / 32; ++w) {
+        if (w < warp) base += warp_tot[w];
+        total += warp_tot[w];
+    }
     base += incl - run;
     int64_t *row = S + (size_t)(a + 1) * L.pitch;
     if (threadIdx.x == 0) row[0] = 0;
-    // padding slots of the interleaved layout (never read) are cleared so the column pass
-    // works on defined values
+    // spare slots of the interleaved layout are cleared so the column pass works on defined
+    // values; the last slot of every phase block then receives a copy of the row total, i.e.
+    // (after the column pass) of the last column S[a][side]
     for (int b = side + 1 + threadIdx.x; b < L.pitch; b += blockDim.x) row[L.col(b)] = 0;
+    __syncthreads();
+    for (int ph = threadIdx.x; ph < L.modulus; ph += blockDim.x) row[ph * L.blocks + L.blocks - 1] = total;
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
         if (i < per) {

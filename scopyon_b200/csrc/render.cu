@@ -1,5 +1,5 @@
-// Expected-image rendering: spot -> screen-tile binning (counting sort) and
-// tile-per-CTA accumulation from summed-area-table corners.
+// Expected-image rendering: spot -> screen-strip binning (counting sort) and warp-per-strip
+// accumulation from summed-area-table corners.
 //
 // Reference: _EPIFMSimulator.get_molecule_plane + PointSpreadingFunction.overlay_signal_
 // (/root/reference/src/scopyon/_epifm.py:1262-1264, 224-282).  The reference walks, per
@@ -8,130 +8,223 @@
 //   * the pixel-edge -> table-index arithmetic is evaluated with the same IEEE fp64
 //     operations in the same order (explicit __d*_rn intrinsics: never contracted to FMA);
 //   * each slice sum is S[i1][j1] - S[i0][j1] - S[i1][j0] + S[i0][j0] on the int64 SAT
-//     built by scb_psf_sat_build -- exact, so results do not depend on tile shape;
-//   * one CTA owns one 16x16-pixel tile: a thread owns a pixel and accumulates in a
-//     register, in ascending spot order -> no atomics on the image, bitwise reproducible.
+//     built by scb_psf_sat_build -- exact, so results do not depend on how a footprint is cut;
+//   * one WARP owns one 8 x 128-pixel strip of the image and keeps its 1024 accumulators in
+//     shared memory.  The strip's work list holds one 32-byte unit per (spot, <=8 rows,
+//     <=32 columns) overlap; lane l owns column l of the unit, loads the SAT corners of its
+//     column straight from global memory into registers (two coalesced 8-byte loads per row
+//     edge, the loads of the next unit in flight while this one is summed), differences them
+//     down the rows and adds `box * weight` to its accumulator.  Every lane of a unit carries
+//     a footprint pixel (no idle pixels as in a thread-per-pixel tile), no staging buffer, no
+//     block-wide barrier and no atomics on the image;
+//   * accumulators are 64-bit fixed point (LSB 2^-K photons, K chosen per call from the
+//     largest spot weight so that the sum cannot overflow): integer addition is associative,
+//     so the image is bitwise reproducible whatever order the work list was filled in.
 #include "binning.cuh"
 
 namespace {
 
-constexpr int kTile = 16;             // pixels per tile edge
-constexpr int kEdge = kTile + 1;      // pixel edges per tile edge
-constexpr int kBatch = 8;             // spots staged per round = warps per CTA
-constexpr int kThreads = kTile * kTile;
-constexpr int kSortCap = 1024;        // spots per tile ordered in shared memory per chunk
+constexpr int kStripRows = 8;         // pixel rows per strip
+constexpr int kStripCols = 128;       // pixel columns per strip
+constexpr int kUnitCols = 32;         // columns per unit = lanes
+constexpr int kMaxWarps = 7;          // warps (= strips in flight) per CTA
+constexpr int kBatch = 32;            // units fetched per round (one per lane)
+constexpr int kEdges = kStripRows + 1;
 
-struct __align__(16) StageMeta {
-    int r0, nrow, c0, ncol;   // footprint rectangle inside the tile (pixels)
-    double w;
-    double pad;
+// One work-list entry: the overlap of a spot with (<= 8 rows) x (<= 32 columns) of a strip.
+struct __align__(16) Unit {
+    double ws;             // weight * res^2 / table scale * 2^K
+    const long long *S;    // summed-area table of the spot's depth key
+    uint32_t erow, ecol;   // first row / column edge of the overlap inside `edges`
+    uint32_t shape;        // rows | cols << 8 | first strip row << 16 | first strip column << 24
+    uint32_t pad;
 };
 
-// 8-byte asynchronous global -> shared copy (LDGSTS): the SAT corner gathers of a whole
-// round are in flight at once and need no registers.
-__device__ __forceinline__ void cp_async_8(void *smem, const void *gmem) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem));
+// Fixed-point exponent of the accumulators: every pixel is below 2 * n_spots * max weight
+// (a spot spreads at most ~1.00001 of its weight over its footprint), so with
+// LSB = 2^-K, K = 62 - ceil(log2(bound)), a pixel sum stays below 2^62.
+__device__ __forceinline__ int accumulator_shift(unsigned long long wmax_bits, int64_t n_spots) {
+    const double wmax = __longlong_as_double((long long)wmax_bits);
+    if (!(wmax > 0.0)) return 0;
+    int e;
+    frexp(2.0 * (double)n_spots * wmax, &e);
+    return max(-900, min(62 - e, 900));
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
-template <typename OutT>
-__global__ void __launch_bounds__(kThreads)
-render_tiles_kernel(Geo g, const SpotRec *__restrict__ spots, const uint16_t *__restrict__ edges,
-                    int edge_cap, const int *__restrict__ tile_start, const int *__restrict__ pair_spot,
-                    const int64_t *__restrict__ sat, OutT *__restrict__ out, int accumulate) {
-    __shared__ long long corners[2][kBatch][kEdge * kEdge];
-    __shared__ StageMeta meta[2][kBatch];
-    __shared__ int ids_raw[kSortCap], ids[kSortCap];
-
-    const int tile = blockIdx.x;
-    const int ti = tile / g.ntj, tj = tile - ti * g.ntj;
-    const int row0 = ti * kTile, col0 = tj * kTile;
-    const int py = threadIdx.x / kTile, px = threadIdx.x % kTile;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int seg_begin = tile_start[tile], seg_end = tile_start[tile + 1];
-    const size_t pitch = (size_t)g.pitch, table = (size_t)(g.side + 1) * g.pitch;
-
-    double acc = 0.0;
-
-    for (int chunk = seg_begin; chunk < seg_end; chunk += kSortCap) {
-        const int n_chunk = min(kSortCap, seg_end - chunk);
-        // ---- order the chunk by spot index (rank sort; indices are distinct)
-        __syncthreads();
-        for (int t = threadIdx.x; t < n_chunk; t += kThreads) ids_raw[t] = pair_spot[chunk + t];
-        __syncthreads();
-        for (int t = threadIdx.x; t < n_chunk; t += kThreads) {
-            const int mine = ids_raw[t];
-            int rank = 0;
-            for (int u = 0; u < n_chunk; ++u) rank += (ids_raw[u] < mine);
-            ids[rank] = mine;
-        }
-        __syncthreads();
-
-        // Warp b stages spot base+b of a round: lane l owns column edge l, the row edge of
-        // each footprint row is broadcast, and lane l copies corner (row k, col l) straight
-        // into shared memory with cp.async.
-        auto stage = [&](int buf, int base) {
-            StageMeta m;
-            m.r0 = 0; m.nrow = 0; m.c0 = 0; m.ncol = 0; m.w = 0.0; m.pad = 0.0;
-            if (base + warp < n_chunk) {
-                const int sid = ids[base + warp];
-                const SpotRec rec = spots[sid];
-                const int r_lo = max(rec.imin, row0), r_hi = min(rec.imax, row0 + kTile);
-                const int c_lo = max(rec.jmin, col0), c_hi = min(rec.jmax, col0 + kTile);
-                const int nrow = r_hi - r_lo, ncol = c_hi - c_lo;
-                const uint16_t *e = edges + (size_t)sid * 2 * edge_cap;
-                const int my_row = (lane <= nrow) ? (int)e[r_lo - rec.imin + lane] : 0;
-                const int my_col = (lane <= ncol) ? (int)e[edge_cap + c_lo - rec.jmin + lane] : 0;
-                const int64_t *S = sat + (size_t)rec.slot * table + my_col;
-                long long *dst = &corners[buf][warp][lane];
-                for (int k = 0; k <= nrow; ++k) {
-                    const int a = __shfl_sync(0xffffffffu, my_row, k);
-                    if (lane <= ncol) cp_async_8(dst + k * kEdge, S + (size_t)a * pitch);
-                }
-                m.r0 = r_lo - row0; m.nrow = nrow; m.c0 = c_lo - col0; m.ncol = ncol;
-                m.w = rec.w;
+// One thread per spot: write the spot's units into the strips' list segments.
+__global__ void __launch_bounds__(256)
+strip_fill_kernel(Geo g, int64_t n, const SpotRec *__restrict__ spots, int edge_cap,
+                  const int64_t *__restrict__ sat, const int *__restrict__ tile_start,
+                  int *__restrict__ tile_cursor, const unsigned long long *__restrict__ wmax_bits,
+                  Unit *__restrict__ units) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const SpotRec rec = spots[s];
+    if (rec.slot < 0) return;
+    Unit u;
+    u.ws = scalbn(rec.w, accumulator_shift(*wmax_bits, n));
+    u.S = (const long long *)sat + (size_t)rec.slot * ((size_t)(g.side + 1) * g.pitch);
+    u.pad = 0;
+    const uint32_t ebase = (uint32_t)s * 2u * (uint32_t)edge_cap;
+    const int stripe = stripe_of(g, s);
+    int *cursor = tile_cursor + (size_t)stripe * g.nti * g.ntj;
+    const int t0 = rec.imin / g.tile_h, t1 = (rec.imax - 1) / g.tile_h;
+    const int u0 = rec.jmin / g.tile_w, u1 = (rec.jmax - 1) / g.tile_w;
+    for (int tj = u0; tj <= u1; ++tj) {
+        const int c_lo = max(rec.jmin, tj * g.tile_w), c_hi = min(rec.jmax, (tj + 1) * g.tile_w);
+        const int entries = (c_hi - c_lo + g.chunk - 1) / g.chunk;
+        for (int ti = t0; ti <= t1; ++ti) {
+            const int r_lo = max(rec.imin, ti * g.tile_h), r_hi = min(rec.imax, (ti + 1) * g.tile_h);
+            const int tile = ti * g.ntj + tj;
+            Unit *dst = units + tile_start[tile * g.stripes + stripe] + atomicAdd(&cursor[tile], entries);
+            u.erow = ebase + (uint32_t)(r_lo - rec.imin);
+            for (int q = 0; q < entries; ++q) {
+                const int c = c_lo + q * g.chunk;
+                u.ecol = ebase + (uint32_t)(edge_cap + c - rec.jmin);
+                u.shape = (uint32_t)(r_hi - r_lo) | (uint32_t)min(g.chunk, c_hi - c) << 8 |
+                          (uint32_t)(r_lo - ti * g.tile_h) << 16 | (uint32_t)(c - tj * g.tile_w) << 24;
+                dst[q] = u;
             }
-            cp_async_commit();
-            if (lane == 0) meta[buf][warp] = m;
-        };
-
-        stage(0, 0);
-        int cur = 0;
-        for (int base = 0; base < n_chunk; base += kBatch, cur ^= 1) {
-            const bool more = base + kBatch < n_chunk;
-            if (more) {
-                stage(cur ^ 1, base + kBatch);   // next round's gathers fly during this round's math
-                cp_async_wait<1>();
-            } else {
-                cp_async_wait<0>();
-            }
-            __syncthreads();
-            // ---- accumulate: thread (py, px) owns one pixel
-#pragma unroll
-            for (int q = 0; q < kBatch; ++q) {
-                const StageMeta m = meta[cur][q];
-                // a warp covers tile rows 2*warp and 2*warp+1: skip spots that miss both (warp uniform)
-                if (m.r0 > 2 * warp + 1 || m.r0 + m.nrow <= 2 * warp) continue;
-                const int rk = py - m.r0, rl = px - m.c0;
-                if ((unsigned)rk < (unsigned)m.nrow && (unsigned)rl < (unsigned)m.ncol) {
-                    const long long *c = &corners[cur][q][rk * kEdge + rl];
-                    const long long box = c[kEdge + 1] - c[kEdge] - c[1] + c[0];
-                    // box >= 0 (the table is non-negative, edges are monotone), and adding a zero
-                    // leaves acc unchanged, so the reference's `if photons > 0` needs no branch
-                    acc = __dadd_rn(acc, __dmul_rn((double)box, m.w));   // _epifm.py:280-282
-                }
-            }
-            __syncthreads();
         }
     }
+}
 
-    const int i = row0 + py, j = col0 + px;
-    if (i < g.n_w && j < g.n_h) {
-        const size_t o = (size_t)i * g.n_h + j;
-        if (accumulate) out[o] = (OutT)((double)out[o] + acc);
-        else out[o] = (OutT)acc;
+struct LaneEdges {        // raw edge-table entries of one lane; consumed one pipeline stage later
+    uint32_t left, right;   // storage offsets (in table entries) of the lane's two column edges
+    uint32_t row;           // lane k <= rows: table row of row edge k
+};
+
+__device__ __forceinline__ LaneEdges unit_edges(const Unit *meta, int u, int lane,
+                                                const uint16_t *__restrict__ edges) {
+    const uint4 tail = *reinterpret_cast<const uint4 *>(&meta[u].erow);     // erow, ecol, shape, pad
+    const int rows = tail.z & 0xff, cols = (tail.z >> 8) & 0xff;
+    const uint32_t c = tail.y + (uint32_t)min(lane, cols - 1);   // idle lanes repeat the last column: no extra sectors
+    LaneEdges e;
+    e.left = __ldg(edges + c);
+    e.right = __ldg(edges + c + 1);
+    e.row = __ldg(edges + tail.x + (uint32_t)min(lane, rows));
+    return e;
+}
+
+// corner address = row * pitch_bytes + (table + column offset): one IMAD.WIDE
+__device__ __forceinline__ long long load_corner(const long long *column, uint32_t row, uint32_t pitch_bytes) {
+    const long long *p;
+    // volatile: keeps ptxas from splitting it into a shared product plus two 64-bit adds
+    asm volatile("mad.wide.u32 %0, %1, %2, %3;" : "=l"(p) : "r"(row), "r"(pitch_bytes), "l"(column));
+    return __ldg(p);
+}
+
+__device__ __forceinline__ void unit_gather(const Unit *meta, int u, const LaneEdges &e, uint32_t pitch_bytes,
+                                            long long (&L)[kEdges], long long (&R)[kEdges]) {
+    const long long *S = meta[u].S;
+    const int rows = meta[u].shape & 0xff;
+    // an edge at table sample 0 (kEdgeZero) reads S[0][0] == 0 for every row: its row stride is 0
+    const long long *left = S + (e.left & 0x7fffu), *right = S + (e.right & 0x7fffu);
+    const uint32_t left_pitch = (e.left & kEdgeZero) ? 0u : pitch_bytes;
+    const uint32_t right_pitch = (e.right & kEdgeZero) ? 0u : pitch_bytes;
+    uint32_t row[kEdges];
+#pragma unroll
+    for (int k = 0; k < kEdges; ++k) row[k] = __shfl_sync(0xffffffffu, e.row, k);
+#pragma unroll
+    for (int k = 0; k < kEdges; ++k) {
+        if (k <= rows) {                       // warp uniform
+            L[k] = load_corner(left, row[k], left_pitch);
+            R[k] = load_corner(right, row[k], right_pitch);
+        }
+    }
+}
+
+// Rows beyond the unit's last carry stale corner values: their products are computed and
+// dropped (only the accumulator update is predicated), which keeps the loop branch free.
+__device__ __forceinline__ void unit_accumulate(const Unit *meta, int u, int lane, long long *acc,
+                                                const long long (&L)[kEdges], const long long (&R)[kEdges]) {
+    const double ws = meta[u].ws;
+    const uint32_t shape = meta[u].shape;
+    const int rows = (lane < (int)((shape >> 8) & 0xff)) ? (int)(shape & 0xff) : 0;   // idle lanes: no rows
+    long long *a = acc + ((shape >> 16) & 0xff) * kStripCols + (shape >> 24) + lane;
+    long long above = R[0] - L[0];
+#pragma unroll
+    for (int k = 1; k < kEdges; ++k) {
+        const long long here = R[k] - L[k];
+        const long long box = here - above;   // >= 0: the table is non-negative, edges are monotone
+        above = here;
+        // _epifm.py:280-282 (`if photons > 0` needs no branch: adding zero changes nothing)
+        const long long q = __double2ll_rn(__dmul_rn((double)box, ws));
+        if (k <= rows) a[(k - 1) * kStripCols] += q;
+    }
+}
+
+template <typename OutT>
+__global__ void __launch_bounds__(kMaxWarps * 32, 2)
+render_strips_kernel(Geo g, const Unit *__restrict__ units, const uint16_t *__restrict__ edges,
+                     const int *__restrict__ tile_start, int *__restrict__ next_tile,
+                     const unsigned long long *__restrict__ wmax_bits, int64_t n_spots,
+                     OutT *__restrict__ out, int accumulate) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    long long *acc = reinterpret_cast<long long *>(smem_raw) + warp * (kStripRows * kStripCols);
+    Unit *meta = reinterpret_cast<Unit *>(smem_raw + (size_t)n_warps * kStripRows * kStripCols * 8) + warp * kBatch;
+
+    const int n_tiles = g.nti * g.ntj;
+    const uint32_t pitch = (uint32_t)g.pitch * 8u;
+    const double lsb = scalbn(1.0, -accumulator_shift(*wmax_bits, n_spots));
+
+    for (int i = lane; i < kStripRows * kStripCols; i += 32) acc[i] = 0;
+    long long LA[kEdges] = {}, RA[kEdges] = {}, LB[kEdges] = {}, RB[kEdges] = {};   // corner registers of two units
+
+    for (;;) {
+        int tile = 0;
+        if (lane == 0) tile = atomicAdd(next_tile, 1);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
+        if (tile >= n_tiles) break;
+        const int ti = tile / g.ntj, tj = tile - ti * g.ntj;
+        const int row0 = ti * kStripRows, col0 = tj * kStripCols;
+        const int seg_begin = tile_start[tile * g.stripes], seg_end = tile_start[(tile + 1) * g.stripes];
+
+        for (int base = seg_begin; base < seg_end; base += kBatch) {
+            const int nb = min(kBatch, seg_end - base);
+            __syncwarp();
+            if (lane < nb) {
+                const uint4 *src = reinterpret_cast<const uint4 *>(units + base + lane);
+                uint4 *dst = reinterpret_cast<uint4 *>(meta + lane);
+                dst[0] = __ldg(src);
+                dst[1] = __ldg(src + 1);
+            }
+            __syncwarp();
+
+            // software pipeline: edges two units ahead, corner loads one unit ahead
+            LaneEdges e0 = unit_edges(meta, 0, lane, edges), e1 = e0;
+            unit_gather(meta, 0, e0, pitch, LA, RA);
+            if (nb > 1) e1 = unit_edges(meta, 1, lane, edges);
+            for (int u = 0; u < nb; u += 2) {
+                if (u + 1 < nb) unit_gather(meta, u + 1, e1, pitch, LB, RB);
+                if (u + 2 < nb) e0 = unit_edges(meta, u + 2, lane, edges);
+                unit_accumulate(meta, u, lane, acc, LA, RA);
+                if (u + 1 < nb) {
+                    if (u + 2 < nb) unit_gather(meta, u + 2, e0, pitch, LA, RA);
+                    if (u + 3 < nb) e1 = unit_edges(meta, u + 3, lane, edges);
+                    unit_accumulate(meta, u + 1, lane, acc, LB, RB);
+                }
+            }
+        }
+
+        // ---- write the strip (coalesced rows) and clear the accumulators for the next one
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < kStripRows; ++r) {
+            const int i = row0 + r;
+#pragma unroll
+            for (int q = 0; q < kStripCols / 32; ++q) {
+                const int cc = q * 32 + lane, j = col0 + cc;
+                const double v = (double)acc[r * kStripCols + cc] * lsb;
+                acc[r * kStripCols + cc] = 0;
+                if (i < g.n_w && j < g.n_h) {
+                    const size_t o = (size_t)i * g.n_h + j;
+                    if (accumulate) out[o] = (OutT)((double)out[o] + v);
+                    else out[o] = (OutT)v;
+                }
+            }
+        }
     }
 }
 
@@ -175,10 +268,39 @@ extern "C" int scb_profile_end(double *total_ms, int64_t *launches) {
     return 0;
 }
 
+static Geo strip_geo(const scb_geometry *geom) {
+    Geo g = make_geo(geom, kStripRows, kStripCols, kUnitCols);
+    g.special_edges = 1;
+    return g;
+}
+
 extern "C" size_t scb_render_workspace_bytes(const scb_geometry *geom, int64_t n_spots) {
     if (check_geometry(geom) != 0 || n_spots < 0) return 0;
-    Geo g = make_geo(geom, kTile);
-    return carve(g, n_spots, nullptr).bytes;
+    Geo g = strip_geo(geom);
+    return carve(g, n_spots, nullptr, sizeof(Unit)).bytes;
+}
+
+template <typename OutT>
+static int launch_render(const Geo &g, const Workspace &w, int64_t n_spots, OutT *out, int accumulate,
+                         cudaStream_t s) {
+    const int n_tiles = g.nti * g.ntj;
+    // persistent grid: two CTAs per SM, each warp pulls strips from a queue; small images get
+    // narrower CTAs so that the strips still spread over all SMs
+    const int slots = 2 * SCB_SM_COUNT;
+    int warps = (n_tiles + slots - 1) / slots;
+    warps = warps < 1 ? 1 : (warps > kMaxWarps ? kMaxWarps : warps);
+    int ctas = (n_tiles + warps - 1) / warps;
+    if (ctas > slots) ctas = slots;
+    const size_t smem = (size_t)warps * (kStripRows * kStripCols * 8 + kBatch * sizeof(Unit));
+    static bool configured = false;     // per template instance
+    if (!configured) {
+        SCB_CUDA(cudaFuncSetAttribute(render_strips_kernel<OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(kMaxWarps * (kStripRows * kStripCols * 8 + kBatch * sizeof(Unit)))));
+        configured = true;
+    }
+    render_strips_kernel<OutT><<<ctas, warps * 32, smem, s>>>(g, (const Unit *)w.pair_spot, w.edges, w.tile_start,
+                                                            w.next_tile, w.wmax_bits, n_spots, out, accumulate);
+    return 0;
 }
 
 extern "C" int scb_render_expected(const scb_geometry *geom, int64_t n_spots, const double *d_depth,
@@ -189,15 +311,19 @@ extern "C" int scb_render_expected(const scb_geometry *geom, int64_t n_spots, co
                                    int32_t *d_errors, void *stream) {
     int rc = check_geometry(geom);
     if (rc) return rc;
-    SCB_REQUIRE(n_spots >= 0 && n_spots < (int64_t)1 << 31, SCB_E_INVALID, "n_spots=%lld", (long long)n_spots);
+    SCB_REQUIRE(n_spots >= 0 && n_spots < (int64_t)1 << 30, SCB_E_INVALID, "n_spots=%lld", (long long)n_spots);
     SCB_REQUIRE(d_out && d_workspace && d_errors, SCB_E_NULL, "scb_render_expected: NULL out/workspace/errors");
     SCB_REQUIRE(n_spots == 0 || (d_depth && d_x && d_y && d_weight && d_sat && d_inv_scale && d_slot_of_key),
                 SCB_E_NULL, "scb_render_expected: NULL spot/table pointer");
     SCB_REQUIRE(out_type == SCB_F32 || out_type == SCB_F64, SCB_E_INVALID, "out_type=%d", out_type);
-    Geo g = make_geo(geom, kTile);
-    Workspace w = carve(g, n_spots, d_workspace);
+    Geo g = strip_geo(geom);
+    Workspace w = carve(g, n_spots, d_workspace, sizeof(Unit));
     SCB_REQUIRE(workspace_bytes >= w.bytes, SCB_E_WORKSPACE, "scb_render_expected: workspace %zu < %zu",
                 workspace_bytes, w.bytes);
+    SCB_REQUIRE(g.pitch <= 32768, SCB_E_UNSUPPORTED, "scb_render_expected: SAT row pitch %d > 32768 entries", g.pitch);
+    SCB_REQUIRE((double)n_spots * 2.0 * w.edge_cap < 4294967296.0, SCB_E_UNSUPPORTED,
+                "scb_render_expected: %lld spots x %d pixel edges exceed the 32-bit edge index",
+                (long long)n_spots, 2 * w.edge_cap);
     cudaStream_t s = (cudaStream_t)stream;
     const int n_tiles = g.nti * g.ntj;
     {
@@ -211,27 +337,27 @@ extern "C" int scb_render_expected(const scb_geometry *geom, int64_t n_spots, co
             hinted = true;
         }
     }
-    // tile_count and tile_cursor are adjacent 256-aligned blocks: clear both
+    // census, cursors, weight maximum and the strip queue are adjacent 256-aligned blocks: clear them all
     SCB_CUDA(cudaMemsetAsync(w.tile_count, 0, (size_t)((char *)w.tile_start - (char *)w.tile_count), s));
     if (n_spots > 0) {
         spot_prepare_kernel<<<scb_grid_for(n_spots, 256), 256, 0, s>>>(
-            g, n_spots, d_depth, d_x, d_y, d_weight, d_inv_scale, d_slot_of_key, w.spots, w.tile_count, d_errors);
-        spot_edges_kernel<<<scb_grid_for(n_spots * 2 * w.edge_cap, 256), 256, 0, s>>>(g, n_spots, w.spots, w.edges,
-                                                                                     w.edge_cap);
+            g, n_spots, d_depth, d_x, d_y, d_weight, d_inv_scale, d_slot_of_key, w.spots, w.tile_count,
+            w.wmax_bits, d_errors);
+        dim3 egrid, eblock;
+        edges_launch_shape(w.edge_cap, n_spots, egrid, eblock);
+        spot_edges_kernel<<<egrid, eblock, 0, s>>>(g, n_spots, w.spots, w.edges, w.edge_cap);
     }
-    tile_scan_kernel<<<1, 1024, 0, s>>>(n_tiles, w.tile_count, w.tile_start);
+    tile_scan_kernel<<<kScanCtas, 1024, 0, s>>>(n_tiles, g.stripes, w.tile_count, w.tile_start);
     if (n_spots > 0) {
-        tile_fill_kernel<<<scb_grid_for(n_spots, 256), 256, 0, s>>>(g, n_spots, w.spots, w.tile_start,
-                                                                   w.tile_cursor, w.pair_spot);
+        strip_fill_kernel<<<scb_grid_for(n_spots, 256), 256, 0, s>>>(g, n_spots, w.spots, w.edge_cap, d_sat,
+                                                                    w.tile_start, w.tile_cursor, w.wmax_bits,
+                                                                    (Unit *)w.pair_spot);
     }
     const bool timed = g_profile.enabled && g_profile.used < g_profile.capacity;
     if (timed) cudaEventRecord(g_profile.start[g_profile.used], s);
-    if (out_type == SCB_F32)
-        render_tiles_kernel<float><<<n_tiles, kThreads, 0, s>>>(g, w.spots, w.edges, w.edge_cap, w.tile_start,
-                                                               w.pair_spot, d_sat, (float *)d_out, accumulate);
-    else
-        render_tiles_kernel<double><<<n_tiles, kThreads, 0, s>>>(g, w.spots, w.edges, w.edge_cap, w.tile_start,
-                                                                w.pair_spot, d_sat, (double *)d_out, accumulate);
+    if (out_type == SCB_F32) rc = launch_render<float>(g, w, n_spots, (float *)d_out, accumulate, s);
+    else rc = launch_render<double>(g, w, n_spots, (double *)d_out, accumulate, s);
+    if (rc) return rc;
     if (timed) cudaEventRecord(g_profile.stop[g_profile.used++], s);
     SCB_CUDA_LAUNCH_CHECK("scb_render_expected");
     return 0;

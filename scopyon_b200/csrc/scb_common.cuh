@@ -129,6 +129,17 @@ __device__ __forceinline__ void box_muller(uint32_t r0, uint32_t r1, float &n0, 
     n1 = radius * s;
 }
 
+// SAT column layout shared by the builder (psf.cu) and the renderers: with M = sat_modulus,
+// column b of a table row lives at (b % M) * blocks + b / M.  `blocks` leaves at least one
+// spare slot per phase block (the builder stores the row's last column there, so the
+// clamped closing edge of a footprint is read from the same cache lines as its interior
+// edges) and is rounded up to 16 entries so that a phase block starts on a 128-byte line.
+static inline int scb_sat_blocks(int cols, int modulus) {
+    const int used = (cols + modulus - 1) / modulus;
+    const int padded = (used + 1 + 15) & ~15;
+    return ((int64_t)padded * modulus <= 32768) ? padded : used + 1;
+}
+
 static inline unsigned int scb_grid_for(int64_t n, int block, int per_thread = 1) {
     int64_t work = (n + (int64_t)block * per_thread - 1) / ((int64_t)block * per_thread);
     if (work < 1) work = 1;

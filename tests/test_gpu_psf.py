@@ -38,12 +38,19 @@ def test_sat_bit_exact_against_c_oracle():
     _, _, params, engine = gpu_engine()
     sats, inv, _ = oracle_tables(params, engine, [0, 800, engine.geom.n_depth_keys])
     got = numpy.stack([engine.tables.plain(k) for k in range(3)])
-    assert engine.geom.sat_modulus == 66 and engine.tables.pitch == 66 * 31      # 16 um / 241 = 66.39 nm
+    # 16 um / 241 = 66.39 nm: 66 phase blocks of 31 used + 1 spare slots (the block is 256 bytes)
+    assert engine.geom.sat_modulus == 66 and engine.tables.pitch == 66 * 32
     assert numpy.array_equal(engine.inv_scale[:3].cpu().numpy(), inv)
     assert numpy.array_equal(got, sats)                                # int64, bit for bit
     # and the table integral equals the reference's (known answer 0.9788254597277128)
     total = got[0][-1, -1] * inv[0] * 1e-18
     assert abs(total - 0.9788254597277128) < 1e-12
+    # the spare slot of every phase block repeats the last column (what the closing edge of a
+    # footprint reads), the other spare slots are zero
+    stored = engine.tables.sat[0].cpu().numpy()
+    blocks = engine.tables.pitch // 66
+    for phase in (0, 1, 19, 65):
+        assert numpy.array_equal(stored[:, phase * blocks + blocks - 1], sats[0][:, -1])
 
 
 def test_sat_from_device_profile_close_to_reference_table():

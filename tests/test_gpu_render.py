@@ -37,8 +37,12 @@ def test_tirf_c1_expectation_matches_reference(known_answers):
     assert rel_err(got32.astype(numpy.float64), g["photons"]) < 2e-7
 
 
-def test_bit_exact_against_c_oracle_sat_form():
-    """Same tables in, same index arithmetic, same accumulation order -> identical bits."""
+FIXED = 1e-12   # fixed-point accumulators: LSB <= 2^-62 * 2 * n_spots * max weight per term
+
+
+def test_against_c_oracle_sat_form_and_order_independence():
+    """Same tables in, same index arithmetic -> the C oracle's image to the accumulator LSB,
+    and identical bits for any order of the spots (integer accumulation is associative)."""
     g = golden("border_depth_case.npz")
     config, configs, params, engine = gpu_engine("default: {detector: {image_size: [96, 80], exposure_time: 0.033}}")
     data = g["formatted"]
@@ -53,7 +57,10 @@ def test_bit_exact_against_c_oracle_sat_form():
     dev_w = device_weights(engine, data, 0.033)
     assert abs(dev_w - weight).max() / weight.max() < 1e-15
     want = c_oracle.render_sat(c_oracle.geometry(params), data[:, 0], data[:, 1], data[:, 2], dev_w, sats, inv, slot)
-    assert numpy.array_equal(got, want)                     # bit for bit
+    assert rel_err(got, want) < FIXED
+    assert ((got > 0) == (want > 0)).all()                   # identical pixel footprints
+    perm = numpy.random.RandomState(1).permutation(len(data))
+    assert numpy.array_equal(render(engine, data[perm]), got)   # bit for bit, any spot order
 
 
 def engine_keys(engine, configs, data):
@@ -84,8 +91,8 @@ default:
 
 
 def test_large_random_scene_bit_exact_and_properties():
-    """20 000 spots on 1024 x 1000 (ragged tiles), a 3 000-spot cluster inside one tile
-    (exercises the > 2048-per-tile chunking), off-screen and zero-weight spots."""
+    """20 000 spots on 1024 x 1000 (ragged strips), a 3 000-spot cluster inside a few strips
+    (a long work list for one warp), off-screen and zero-weight spots."""
     config, configs, params, engine = gpu_engine("""
 default:
     detector: {type: CMOS, image_size: [1024, 1000], pixel_length: {value: 6.5e-6, units: m}, exposure_time: 0.033}
@@ -106,16 +113,14 @@ default:
     dev_w = device_weights(engine, data, 0.033)
     assert (dev_w[data[:, 4] == 0] == 0).all()
     want = c_oracle.render_sat(c_oracle.geometry(params), data[:, 0], data[:, 1], data[:, 2], dev_w, sats, inv, slot)
-    tiles_big = 3000 > 2048   # the cluster tile is accumulated in two chunks, order inside a chunk fixed
-    assert rel_err(got, want) < 1e-13
-    outside_cluster = numpy.ones_like(got, dtype=bool)
-    ci, cj = int(512 + 100), int(500 - 200)
-    outside_cluster[ci - 60: ci + 60, cj - 60: cj + 60] = False
-    assert numpy.array_equal(got[outside_cluster], want[outside_cluster])
+    assert rel_err(got, want) < FIXED
+    assert ((got > 0) == (want > 0)).all()
+    perm = rng.permutation(n)
+    assert numpy.array_equal(render(engine, data[perm]), got)   # the cluster too: no order dependence
     # linearity: rendering two halves separately and adding equals rendering all
     a = render(engine, data[: n // 2])
     b = render(engine, data[n // 2:])
-    assert rel_err(a + b, got) < 1e-13
+    assert rel_err(a + b, got) < FIXED
     # mass: interior spots deposit weight * table integral
     interior = (abs(data[:, 1]) < 490 * pl) & (abs(data[:, 2]) < 480 * pl)
     only = render(engine, data[interior])
