@@ -59,7 +59,7 @@ typedef struct scb_geometry {
     int32_t n_radial;        /* radial samples: len(arange(0, radial_cutoff, 1 nm))   */
     int32_t n_depth_keys;    /* integer-nm depth keys 0..n_depth_keys-1; the frozen   */
                              /* beyond-cutoff table ("key -1") is key n_depth_keys    */
-    int32_t sat_modulus;     /* column interleave M of the SAT layout (see below), >= 1 */
+    int32_t sat_modulus;     /* phase count M of the SAT block layout (see below), >= 1 */
     int32_t reserved;
     double pixel_length;     /* detector.pixel_length / magnification  [m]            */
     double resolution;       /* table sample pitch, 1e-9 m                            */
@@ -125,16 +125,25 @@ size_t scb_psf_sat_workspace_bytes(int n_radial, int n_keys);
  *   T[a][b]  = lerp(radial, min(sqrt((a-c)^2+(b-c)^2), c)),  c = n_radial-1, a,b in [0, 2c]
  *   Q[a][b]  = llrint(T[a][b] * scale_k),  scale_k a power of two chosen per table
  *   S[a][b]  = sum_{a'<a, b'<b} Q[a'][b']                     a,b in [0, 2c+1]
- * Memory layout ("column polyphase"): the pixel edges of one spot are ~pixel_length/1nm
- * samples apart, so a spot reads S at columns b0, b0+~M, b0+~2M, ...  With
- * M = sat_modulus = round(pixel_length / 1 nm) the entry (a, b) is stored at
- *   d_sat[key][a][ (b % M) * B + b / M ],   B = ceil((2c+2) / M),  row pitch = M * B,
- * which puts those columns next to each other: one 128-byte line serves up to 16 corners
- * instead of one (M = 1 is the plain row-major layout).
- * d_sat[n_keys][2c+2][M*B] (int64), d_inv_scale[n_keys] = 1/scale_k. */
-int64_t scb_psf_sat_pitch(int n_radial, int sat_modulus);
+ * Memory layout ("phase blocks"): the pixel edges of one footprint are ~pixel_length/1nm
+ * samples apart on both axes.  With M = sat_modulus = round(pixel_length / 1 nm), entry (a, b)
+ * is stored in block (a % M, b % M) at slot (a / M, b / M):
+ *   d_sat[key][ (((a % M) * M + b % M) * B + a / M) * B + b / M ],
+ * B = scb_psf_sat_slots() >= ceil((2c+2) / M) + 1; slots past the last sample repeat the last
+ * row / column (value S[min(ir*M+pr, 2c+1)][min(ic*M+pc, 2c+1)]), so the clamped closing edge of a
+ * footprint is the next slot.  All corners of a footprint are then one dense rectangle of
+ * one B x B block: contiguous B*8-byte rows (two 128-byte lines for B = 32) that the render
+ * kernel moves with TMA bulk copies (M = 1 is the plain row-major layout).
+ * d_sat[n_keys][scb_psf_sat_table_entries()] (int64), d_inv_scale[n_keys] = 1/scale_k.
+ * d_box (optional, same shape, fp64): the "box table" -- entry (r, c) of block (pr, pc) is
+ * (double) of the box sum between slots (r-1, r) x (c-1, c) of that block (slot -1 = 0), i.e. the
+ * integrated PSF of one pixel for a footprint whose pixel edges have phases (pr, pc).  The
+ * render kernel reads it for footprints with evenly spaced edges (whole-nanometre pixel pitch);
+ * all other footprints are summed from d_sat.  Both give bit-identical pixel values. */
+int64_t scb_psf_sat_table_entries(int n_radial, int sat_modulus);
+int scb_psf_sat_slots(int n_radial, int sat_modulus);
 int scb_psf_sat_build(const double *d_radial, int n_radial, int n_keys, int sat_modulus,
-                      int64_t *d_sat, double *d_inv_scale,
+                      int64_t *d_sat, double *d_box, double *d_inv_scale,
                       void *d_workspace, size_t workspace_bytes, void *stream);
 
 /* ---- particles --------------------------------------------------------------- */
@@ -208,15 +217,17 @@ size_t scb_render_workspace_bytes(const scb_geometry *geom, int64_t n_spots);
  * PointSpreadingFunction.overlay_signal_ (_epifm.py:1262-1264, 224-282) with identical
  * pixel-edge index arithmetic (IEEE fp64, same operation order):
  *   out[i][j] (+)= sum_spots  weight * 1e-18 * box_sum(T_key; left_i..left_{i+1}, top_j..top_{j+1})
- * Spots are binned to 16x16-pixel screen tiles by a counting sort; one CTA renders one
- * tile, gathers summed-area-table corners into shared memory and accumulates in
- * registers (no atomics on the image).  d_slot_of_key[n_depth_keys+1] maps a depth key
- * to its table index in d_sat (-1: table absent -> the spot is counted in *d_errors).
- * out_type: SCB_F32 / SCB_F64; accumulate != 0 adds to the existing image. */
+ * Spots are binned to 8 x 128-pixel screen strips by a counting sort; one warp renders one
+ * strip with 64-bit fixed-point accumulators in shared memory (no atomics on the image, result
+ * independent of the order of the spots).  Footprints with evenly spaced pixel edges are read
+ * from d_box by TMA bulk copies (d_box may be NULL: every footprint then takes the SAT path);
+ * the others gather four corners per pixel from d_sat.  d_slot_of_key[n_depth_keys+1] maps a
+ * depth key to its table index in d_sat / d_box (-1: table absent -> the spot is counted in
+ * *d_errors).  out_type: SCB_F32 / SCB_F64; accumulate != 0 adds to the existing image. */
 int scb_render_expected(const scb_geometry *geom, int64_t n_spots,
                         const double *d_depth, const double *d_x, const double *d_y,
                         const double *d_weight,
-                        const int64_t *d_sat, const double *d_inv_scale,
+                        const int64_t *d_sat, const double *d_box, const double *d_inv_scale,
                         const int32_t *d_slot_of_key,
                         void *d_out, int out_type, int accumulate,
                         void *d_workspace, size_t workspace_bytes,

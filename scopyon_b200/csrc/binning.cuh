@@ -15,6 +15,10 @@ struct __align__(16) SpotRec {
     int imin, imax;     // pixel rows [imin, imax) touched on axis 0 (clipped to the image)
     int jmin, jmax;     // pixel cols [jmin, jmax) touched on axis 1
     int slot;           // SAT index, <0: skip
+    // "regular" footprints (written by spot_edges_kernel): the table samples of the pixel edges
+    // along an axis share one phase and occupy consecutive slots, edge e at slot0 + e (slot -1 =
+    // the zero sample before the table).  phase | (slot0 + 1) << 16, or -1 when irregular.
+    int row_run, col_run;
     int pad;
 };
 
@@ -27,7 +31,7 @@ struct Geo {
     int special_edges;  // 1: column edges carry kEdgeZero / last-column codes (SAT render); 0: plain
     int side;           // table samples per axis (2*(n_radial-1)+1)
     int n_depth_keys;
-    int modulus, blocks, pitch;   // SAT column interleave: (a, b) at a*pitch + (b % modulus)*blocks + b/modulus
+    int modulus, slots;           // SAT block layout (scb_common.cuh): phases per axis, slots per phase
     double pl, res, inv_res, sw, half_w, half_h, depth_cutoff;
     double f0, f1, f2;
 };
@@ -76,6 +80,7 @@ spot_prepare_kernel(Geo g, int64_t n, const double *__restrict__ depth, const do
     rec.imin = rec.imax = rec.jmin = rec.jmax = 0;
     rec.ox = rec.oy = rec.w = 0.0;
     rec.pad = 0;
+    rec.row_run = rec.col_run = -1;
     double w_seen = 0.0;
     if (s < n) {
         const double w = weight[s];
@@ -136,52 +141,76 @@ spot_prepare_kernel(Geo g, int64_t n, const double *__restrict__ depth, const do
     }
 }
 
-// Table sample index of every pixel edge a footprint touches (_epifm.py:236-253): one thread
-// per (spot, axis, edge); blockDim = (2 * edge_cap, spots per block).  Rows are stored as
-// sample indices, columns as SAT storage offsets (column interleave) with two special cases
-// the render kernels rely on: sample 0 (the clamped opening edge; S[.][0] == 0) carries
-// kEdgeZero and is never fetched, and the last sample (the clamped closing edge) points at the
-// copy of the last column kept in the phase block of the footprint's interior edges.
-constexpr uint16_t kEdgeZero = 0x8000;
+// Table sample of every pixel edge a footprint touches (_epifm.py:236-253): one thread per
+// (spot, axis) walks the axis' edges in order.  Output per edge: its offset inside a SAT table
+// in the block layout -- rows contribute (phase * M * B + slot) * B, columns
+// phase * B * B + slot, a corner is table + row + column -- or kEdgeZero for table sample 0
+// (S[0][.] == S[.][0] == 0: never fetched).  The clamped closing edge takes the slot after its
+// predecessor when that slot repeats the last sample.  While walking, the thread also decides
+// whether the axis is "regular" (SpotRec::row_run / col_run: one phase, consecutive slots),
+// which lets the render kernel fetch the footprint from the box table as dense rows.  With
+// special_edges == 0 the plain sample index is stored instead (Gaussian tensor-core path).
+constexpr uint32_t kEdgeZero = 0x80000000u;
 
-__global__ void __launch_bounds__(256)
-spot_edges_kernel(Geo g, int64_t n, const SpotRec *__restrict__ spots, uint16_t *__restrict__ edges, int edge_cap) {
-    const int64_t s = (int64_t)blockIdx.x * blockDim.y + threadIdx.y;
+__global__ void __launch_bounds__(128)
+spot_edges_kernel(Geo g, int64_t n, SpotRec *__restrict__ spots, uint32_t *__restrict__ edges, int edge_cap) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t s = t >> 1;
+    const int axis = (int)(t & 1);
     if (s >= n) return;
     const SpotRec rec = spots[s];
     if (rec.slot < 0) return;
-    for (int e = threadIdx.x; e < 2 * edge_cap; e += blockDim.x) {
-        const int axis = e >= edge_cap, k = e - axis * edge_cap;
-        const int first = axis ? rec.jmin : rec.imin, last = axis ? rec.jmax : rec.imax;
-        if (k > last - first) continue;
-        const double o = axis ? rec.oy : rec.ox;
-        const int b = edge_index(first + k, first, last, o, g);
-        uint32_t code = (uint32_t)b;
-        if (axis && g.special_edges) {
-            if (b == 0) {
-                code = kEdgeZero;
-            } else {
-                int phase_of = b;
-                if (b == g.side && k > 0) {           // closing edge: use the interior edges' phase block
-                    const int before = edge_index(first + k - 1, first, last, o, g);
-                    if (before > 0) phase_of = before;
-                }
-                const uint32_t q = g.modulus > 1 ? __umulhi((uint32_t)phase_of, g.modulus_magic)
-                                                 : (uint32_t)phase_of;           // phase_of / modulus
-                const uint32_t phase = (uint32_t)phase_of - q * (uint32_t)g.modulus;
-                code = phase * (uint32_t)g.blocks + (b == g.side ? (uint32_t)g.blocks - 1u : q);
+    const int first = axis ? rec.jmin : rec.imin, last = axis ? rec.jmax : rec.imax;
+    const double o = axis ? rec.oy : rec.ox;
+    uint32_t *out = edges + (s * 2 + axis) * edge_cap;
+    const uint32_t phase_stride = axis ? (uint32_t)(g.slots * g.slots) : (uint32_t)(g.modulus * g.slots) * (uint32_t)g.slots;
+    const uint32_t slot_stride = axis ? 1u : (uint32_t)g.slots;
+    bool regular = true;
+    int before = -1, before_phase = 0, before_slot = 0, run_phase = 0, run_slot0 = 0;
+    const int n_edges = last - first + 1;
+    for (int k0 = 0; k0 < n_edges; k0 += 4) {          // four edges per 16-byte store (edge_cap is a multiple of 8)
+        uint32_t code[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int k = k0 + j;
+            code[j] = 0;
+            if (k >= n_edges) continue;
+            const int b = edge_index(first + k, first, last, o, g);
+            int slot = g.modulus > 1 ? (int)__umulhi((uint32_t)b, g.modulus_magic) : b;     // b / modulus
+            int phase = b - slot * g.modulus;
+            // closing edge: the slot after an interior predecessor repeats the last sample when
+            // predecessor + M reaches it
+            if (b == g.side && before > 0 && before < g.side && before + g.modulus >= g.side &&
+                before_slot + 1 < g.slots) {
+                phase = before_phase;
+                slot = before_slot + 1;
             }
+            if (k == 0) {
+                run_phase = phase;
+                run_slot0 = b > 0 ? slot : -1;
+            } else if (before == 0) {
+                // opening edge at sample 0: virtual slot -1 before slot 0, or the real zero slot (0, 0) before (0, 1)
+                regular = regular && k == 1 && b > 0 && (slot == 0 || (slot == 1 && phase == 0));
+                run_phase = phase;
+                run_slot0 = slot - 1;
+            } else {
+                regular = regular && b > 0 && phase == before_phase && slot == before_slot + 1;
+            }
+            before = b; before_phase = phase; before_slot = slot;
+            code[j] = (uint32_t)b;
+            if (g.special_edges) code[j] = b > 0 ? (uint32_t)phase * phase_stride + (uint32_t)slot * slot_stride : kEdgeZero;
         }
-        edges[s * (2 * edge_cap) + e] = (uint16_t)code;
+        *reinterpret_cast<uint4 *>(out + k0) = make_uint4(code[0], code[1], code[2], code[3]);
     }
+    const int run = regular ? (run_phase | (run_slot0 + 1) << 16) : -1;
+    if (axis) spots[s].col_run = run; else spots[s].row_run = run;
 }
 
 // launch shape of spot_edges_kernel
 inline void edges_launch_shape(int edge_cap, int64_t n, dim3 &grid, dim3 &block) {
-    const int x = 2 * edge_cap < 256 ? 2 * edge_cap : 256;
-    const int y = 256 / x;
-    block = dim3(x, y, 1);
-    grid = dim3((unsigned)((n + y - 1) / y), 1, 1);
+    (void)edge_cap;
+    block = dim3(128, 1, 1);
+    grid = dim3((unsigned)((2 * n + 127) / 128), 1, 1);
 }
 
 // Exclusive scan of the tile census by one thread-block CLUSTER of 8 CTAs.  Logical entry
@@ -264,7 +293,7 @@ tile_fill_kernel(Geo g, int64_t n, const SpotRec *__restrict__ spots,
 
 struct Workspace {
     SpotRec *spots;
-    uint16_t *edges;
+    uint32_t *edges;
     int edge_cap;            // edge slots per axis per spot
     int *tile_count, *tile_cursor, *tile_start;
     unsigned long long *wmax_bits;   // bit pattern of the largest spot weight (cleared with the census)
@@ -292,8 +321,7 @@ Geo make_geo(const scb_geometry *geom, int tile_h, int tile_w, int chunk = 0) {
     g.half_h = ((double)geom->n_h * geom->pixel_length) * 0.5;
     g.depth_cutoff = geom->depth_cutoff;
     g.modulus = geom->sat_modulus < 1 ? 1 : geom->sat_modulus;
-    g.blocks = scb_sat_blocks(g.side + 1, g.modulus);
-    g.pitch = g.modulus * g.blocks;
+    g.slots = scb_sat_layout(geom->n_radial, g.modulus).slots;
     g.modulus_magic = (uint32_t)((((uint64_t)1 << 32) + g.modulus - 1) / g.modulus);
     // counter copies: as many as keep the scan's register-resident path (<= 32768 entries), at most 8
     g.stripes = 1;
@@ -328,7 +356,7 @@ Workspace carve(const Geo &g, int64_t n, void *base, size_t entry_bytes = sizeof
         if (cap > most) cap = most;
         w.edge_cap = (int)((cap + 7) & ~(int64_t)7);
     }
-    w.edges = (uint16_t *)(p + off); off += align_up((size_t)(n > 0 ? n : 1) * 2 * w.edge_cap * sizeof(uint16_t));
+    w.edges = (uint32_t *)(p + off); off += align_up((size_t)(n > 0 ? n : 1) * 2 * w.edge_cap * sizeof(uint32_t));
     w.tile_count = (int *)(p + off); off += align_up(n_tiles * g.stripes * sizeof(int));
     w.tile_cursor = (int *)(p + off); off += align_up(n_tiles * g.stripes * sizeof(int));
     w.wmax_bits = (unsigned long long *)(p + off);

@@ -121,7 +121,7 @@ __device__ __forceinline__ float to_tf32(float v) {
 
 template <typename OutT>
 __global__ void __launch_bounds__(kThreadsTC)
-gaussian_tc_kernel(Geo g, const SpotRec *__restrict__ spots, const uint16_t *__restrict__ edges, int edge_cap,
+gaussian_tc_kernel(Geo g, const SpotRec *__restrict__ spots, const uint32_t *__restrict__ edges, int edge_cap,
                    const int *__restrict__ tile_start, const int *__restrict__ pair_spot,
                    const double *__restrict__ prefix, int prefix_len, OutT *__restrict__ out, int accumulate) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -203,7 +203,7 @@ gaussian_tc_kernel(Geo g, const SpotRec *__restrict__ spots, const uint16_t *__r
                     const int r_lo = max(rec.imin, row0), r_hi = min(rec.imax, row0 + TM);
                     const int c_lo = max(rec.jmin, col0), c_hi = min(rec.jmax, col0 + TM);
                     r0 = r_lo - row0; nr = r_hi - r_lo; c0 = c_lo - col0; nc = c_hi - c_lo;
-                    const uint16_t *e = edges + (size_t)sid * 2 * edge_cap;
+                    const uint32_t *e = edges + (size_t)sid * 2 * edge_cap;
                     for (int k = lane; k < nr; k += 32) {
                         const int idx = r_lo - rec.imin + k;
                         const float a = (float)(rec.w * (sm.G[e[idx + 1]] - sm.G[e[idx]]));
@@ -317,9 +317,7 @@ extern "C" int scb_render_gaussian_tc(const scb_geometry *geom, int64_t n_spots,
     SCB_REQUIRE(n_spots == 0 || (d_x && d_y && d_weight), SCB_E_NULL, "scb_render_gaussian_tc: NULL spot pointer");
     SCB_REQUIRE(out_type == SCB_F32 || out_type == SCB_F64, SCB_E_INVALID, "out_type=%d", out_type);
     Geo g = make_geo(geom, TM, TM);
-    g.modulus = 1;                       // plain column indices: no SAT in this path
-    g.blocks = g.side + 1;
-    g.pitch = g.side + 1;
+    g.modulus = 1;                       // plain sample indices (special_edges == 0): no SAT in this path
     SCB_REQUIRE(g.side + 1 <= 2048, SCB_E_UNSUPPORTED, "scb_render_gaussian_tc: table side %d > 2047", g.side);
     SCB_REQUIRE(ceil(g.sw / g.pl) + 2 <= kMaxFoot, SCB_E_UNSUPPORTED,
                 "scb_render_gaussian_tc: footprint of %g pixels exceeds %d (pixel_length too small)",

@@ -160,35 +160,23 @@ table_scale_kernel(const double *__restrict__ rowsum, int side, double *__restri
     }
 }
 
-// Row pass: quantise one table row and write its inclusive prefix sum into S[a+1][1..].
-// Row 0 and column 0 of S are zero.  Block-wide scan: per-thread serial chunk + warp
-// shuffles + one shared pass; int64 adds are associative so the result is exact.
+// Row pass: quantise one table row and write its inclusive prefix sum into the plain
+// scratch table P[a+1][1..] ((side+1)^2, row major).  Row 0 and column 0 of S are zero.
+// Block-wide scan: per-thread serial chunk + warp shuffles + one shared pass; int64 adds are
+// associative so the result is exact.
 constexpr int kScanThreads = 256;
-
-struct SatLayout {
-    int modulus, blocks, pitch;   // entry (a, b) lives at a * pitch + (b % modulus) * blocks + b / modulus
-    __host__ __device__ int col(int b) const { return (b % modulus) * blocks + b / modulus; }
-};
-
-__host__ SatLayout make_layout(int n_radial, int modulus) {
-    SatLayout L;
-    const int cols = 2 * (n_radial - 1) + 2;
-    L.modulus = modulus < 1 ? 1 : modulus;
-    L.blocks = scb_sat_blocks(cols, L.modulus);
-    L.pitch = L.modulus * L.blocks;
-    return L;
-}
+constexpr int kBuildBatch = 16;      // tables integrated per pass (scratch: 32 MB each)
 
 __global__ void __launch_bounds__(kScanThreads)
 sat_rows_kernel(const double *__restrict__ radial, int n_radial, const double *__restrict__ scale,
-                int64_t *__restrict__ sat, SatLayout L) {
+                int64_t *__restrict__ plain) {
     __shared__ int64_t warp_tot[kScanThreads / 32];
     const int c = n_radial - 1;
-    const int side = 2 * c + 1;
+    const int side = 2 * c + 1, cols = side + 1;
     const int key = blockIdx.y, a = blockIdx.x;  // a in [0, side]: a == side writes the zero row 0
-    int64_t *S = sat + (size_t)key * (side + 1) * L.pitch;
+    int64_t *S = plain + (size_t)key * cols * cols;
     if (a == side) {
-        for (int b = threadIdx.x; b < L.pitch; b += blockDim.x) S[b] = 0;
+        for (int b = threadIdx.x; b < cols; b += blockDim.x) S[b] = 0;
         return;
     }
     const double *prof = radial + (size_t)key * n_radial;
@@ -217,62 +205,89 @@ sat_rows_kernel(const double *__restrict__ radial, int n_radial, const double *_
     }
     if (lane == 31) warp_tot[warp] = incl;
     __syncthreads();
-    int64_t base = 0, total = 0;
-    for (int w = 0; w < kScanThreads / 32; ++w) {
-        if (w < warp) base += warp_tot[w];
-        total += warp_tot[w];
-    }
+    int64_t base = 0;
+    for (int w = 0; w < warp; ++w) base += warp_tot[w];
     base += incl - run;
-    int64_t *row = S + (size_t)(a + 1) * L.pitch;
+    int64_t *row = S + (size_t)(a + 1) * cols;
     if (threadIdx.x == 0) row[0] = 0;
-    // spare slots of the interleaved layout are cleared so the column pass works on defined
-    // values; the last slot of every phase block then receives a copy of the row total, i.e.
-    // (after the column pass) of the last column S[a][side]
-    for (int b = side + 1 + threadIdx.x; b < L.pitch; b += blockDim.x) row[L.col(b)] = 0;
-    __syncthreads();
-    for (int ph = threadIdx.x; ph < L.modulus; ph += blockDim.x) row[ph * L.blocks + L.blocks - 1] = total;
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
         if (i < per) {
             int b = b0 + i;
-            if (b < side) row[L.col(b + 1)] = base + local[i];
+            if (b < side) row[b + 1] = base + local[i];
         }
     }
 }
 
-// Column pass: S[a][b] += S[a-1][b] down each column; threads cover columns (coalesced).
-__global__ void sat_cols_kernel(int rows, int pitch, int n_keys, int64_t *__restrict__ sat) {
-    int b = blockIdx.x * blockDim.x + threadIdx.x;   // storage column (layout independent)
+// Column pass: P[a][b] += P[a-1][b] down each column; threads cover columns (coalesced).
+__global__ void sat_cols_kernel(int cols, int n_keys, int64_t *__restrict__ plain) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
     int key = blockIdx.y;
-    if (b >= pitch || key >= n_keys) return;
-    int64_t *S = sat + (size_t)key * rows * pitch + b;
+    if (b >= cols || key >= n_keys) return;
+    int64_t *S = plain + (size_t)key * cols * cols + b;
     int64_t run = 0;
     // software-pipelined: loads of later rows do not depend on the running sum
-    for (int a = 1; a < rows; a += 4) {
-        int64_t v0 = S[(size_t)a * pitch];
-        int64_t v1 = (a + 1 < rows) ? S[(size_t)(a + 1) * pitch] : 0;
-        int64_t v2 = (a + 2 < rows) ? S[(size_t)(a + 2) * pitch] : 0;
-        int64_t v3 = (a + 3 < rows) ? S[(size_t)(a + 3) * pitch] : 0;
-        run += v0; S[(size_t)a * pitch] = run;
-        if (a + 1 < rows) { run += v1; S[(size_t)(a + 1) * pitch] = run; }
-        if (a + 2 < rows) { run += v2; S[(size_t)(a + 2) * pitch] = run; }
-        if (a + 3 < rows) { run += v3; S[(size_t)(a + 3) * pitch] = run; }
+    for (int a = 1; a < cols; a += 4) {
+        int64_t v0 = S[(size_t)a * cols];
+        int64_t v1 = (a + 1 < cols) ? S[(size_t)(a + 1) * cols] : 0;
+        int64_t v2 = (a + 2 < cols) ? S[(size_t)(a + 2) * cols] : 0;
+        int64_t v3 = (a + 3 < cols) ? S[(size_t)(a + 3) * cols] : 0;
+        run += v0; S[(size_t)a * cols] = run;
+        if (a + 1 < cols) { run += v1; S[(size_t)(a + 1) * cols] = run; }
+        if (a + 2 < cols) { run += v2; S[(size_t)(a + 2) * cols] = run; }
+        if (a + 3 < cols) { run += v3; S[(size_t)(a + 3) * cols] = run; }
     }
 }
 
-extern "C" int64_t scb_psf_sat_pitch(int n_radial, int sat_modulus) {
+// Re-tile the plain table into the block layout (see SatLayout): one CTA per (phase block, key);
+// writes are contiguous, reads gather every M-th sample (the scratch table is L2 resident).
+//
+// The optional second output is the "box table": entry (r, c) of block (pr, pc) is the box sum
+// between slots (r-1, r) x (c-1, c) of that block (slot -1 = the zero sample before the table),
+// converted to fp64 -- i.e. exactly the value (double)box that a pixel of a footprint with
+// edge phases (pr, pc) multiplies by its weight.  A footprint whose edges are evenly spaced
+// reads one dense rectangle of one box block and never touches the SAT itself.
+__global__ void __launch_bounds__(256)
+sat_blocks_kernel(const int64_t *__restrict__ plain, int64_t *__restrict__ sat, double *__restrict__ box,
+                  SatLayout L) {
+    const int cols = L.side + 1;
+    const int block = blockIdx.x, key = blockIdx.y;
+    const int pr = block / L.modulus, pc = block - pr * L.modulus;
+    const int64_t *P = plain + (size_t)key * cols * cols;
+    const size_t at = (size_t)key * L.table_entries() + (size_t)block * L.block_entries();
+    const int n = L.slots * L.slots;
+    auto value = [&](int ir, int ic) -> int64_t {       // S at slot (ir, ic); slot -1 is zero
+        if (ir < 0 || ic < 0) return 0;
+        const int a = min(ir * L.modulus + pr, L.side), b = min(ic * L.modulus + pc, L.side);
+        return P[(size_t)a * cols + b];
+    };
+    for (int e = threadIdx.x; e < n; e += blockDim.x) {
+        const int ir = e / L.slots, ic = e - ir * L.slots;
+        const int64_t here = value(ir, ic);
+        sat[at + e] = here;
+        if (box) box[at + e] = (double)((here - value(ir - 1, ic)) - (value(ir, ic - 1) - value(ir - 1, ic - 1)));
+    }
+}
+
+extern "C" int64_t scb_psf_sat_table_entries(int n_radial, int sat_modulus) {
     if (n_radial < 2) return 0;
-    return make_layout(n_radial, sat_modulus).pitch;
+    return scb_sat_layout(n_radial, sat_modulus).table_entries();
+}
+
+extern "C" int scb_psf_sat_slots(int n_radial, int sat_modulus) {
+    if (n_radial < 2) return 0;
+    return scb_sat_layout(n_radial, sat_modulus).slots;
 }
 
 extern "C" size_t scb_psf_sat_workspace_bytes(int n_radial, int n_keys) {
     if (n_radial < 2 || n_keys < 1) return 0;
-    size_t side = 2 * (size_t)(n_radial - 1) + 1;
-    return ((size_t)n_keys * side + (size_t)n_keys) * sizeof(double);
+    const size_t side = 2 * (size_t)(n_radial - 1) + 1;
+    const size_t batch = n_keys < kBuildBatch ? n_keys : kBuildBatch;
+    return ((size_t)n_keys * side + (size_t)n_keys) * sizeof(double) + 256 + batch * (side + 1) * (side + 1) * sizeof(int64_t);
 }
 
 extern "C" int scb_psf_sat_build(const double *d_radial, int n_radial, int n_keys, int sat_modulus,
-                                 int64_t *d_sat, double *d_inv_scale, void *d_workspace,
+                                 int64_t *d_sat, double *d_box, double *d_inv_scale, void *d_workspace,
                                  size_t workspace_bytes, void *stream) {
     SCB_REQUIRE(d_radial && d_sat && d_inv_scale && d_workspace, SCB_E_NULL,
                 "scb_psf_sat_build: NULL pointer");
@@ -284,14 +299,25 @@ extern "C" int scb_psf_sat_build(const double *d_radial, int n_radial, int n_key
     SCB_REQUIRE(n_keys <= 65535, SCB_E_INVALID, "scb_psf_sat_build: n_keys=%d > 65535", n_keys);
     cudaStream_t s = (cudaStream_t)stream;
     SCB_REQUIRE(sat_modulus >= 1 && sat_modulus <= 4096, SCB_E_INVALID, "scb_psf_sat_build: sat_modulus=%d", sat_modulus);
-    const int side = 2 * (n_radial - 1) + 1;
-    const SatLayout L = make_layout(n_radial, sat_modulus);
+    const int side = 2 * (n_radial - 1) + 1, cols = side + 1;
+    const SatLayout L = scb_sat_layout(n_radial, sat_modulus);
+    SCB_REQUIRE(L.table_entries() < ((long long)1 << 31), SCB_E_UNSUPPORTED,
+                "scb_psf_sat_build: table of %lld entries (modulus %d, %d slots) is too large", L.table_entries(),
+                L.modulus, L.slots);
     double *rowsum = (double *)d_workspace;
     double *scale = rowsum + (size_t)n_keys * side;
+    int64_t *plain = (int64_t *)(((uintptr_t)(scale + n_keys) + 255) & ~(uintptr_t)255);
     table_rowsum_kernel<<<dim3(side, n_keys), 256, 0, s>>>(d_radial, n_radial, rowsum);
     table_scale_kernel<<<n_keys, 256, 0, s>>>(rowsum, side, scale, d_inv_scale);
-    sat_rows_kernel<<<dim3(side + 1, n_keys), kScanThreads, 0, s>>>(d_radial, n_radial, scale, d_sat, L);
-    sat_cols_kernel<<<dim3((L.pitch + 127) / 128, n_keys), 128, 0, s>>>(side + 1, L.pitch, n_keys, d_sat);
+    for (int first = 0; first < n_keys; first += kBuildBatch) {
+        const int nb = n_keys - first < kBuildBatch ? n_keys - first : kBuildBatch;
+        sat_rows_kernel<<<dim3(side + 1, nb), kScanThreads, 0, s>>>(d_radial + (size_t)first * n_radial, n_radial,
+                                                                   scale + first, plain);
+        sat_cols_kernel<<<dim3((cols + 127) / 128, nb), 128, 0, s>>>(cols, nb, plain);
+        sat_blocks_kernel<<<dim3(L.modulus * L.modulus, nb), 256, 0, s>>>(
+            plain, d_sat + (size_t)first * L.table_entries(),
+            d_box ? d_box + (size_t)first * L.table_entries() : nullptr, L);
+    }
     SCB_CUDA_LAUNCH_CHECK("scb_psf_sat_build");
     return 0;
 }

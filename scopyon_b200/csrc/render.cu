@@ -1,5 +1,5 @@
 // Expected-image rendering: spot -> screen-strip binning (counting sort) and warp-per-strip
-// accumulation from summed-area-table corners.
+// accumulation from summed-area-table corners staged by TMA.
 //
 // Reference: _EPIFMSimulator.get_molecule_plane + PointSpreadingFunction.overlay_signal_
 // (/root/reference/src/scopyon/_epifm.py:1262-1264, 224-282).  The reference walks, per
@@ -11,12 +11,17 @@
 //     built by scb_psf_sat_build -- exact, so results do not depend on how a footprint is cut;
 //   * one WARP owns one 8 x 128-pixel strip of the image and keeps its 1024 accumulators in
 //     shared memory.  The strip's work list holds one 32-byte unit per (spot, <=8 rows,
-//     <=32 columns) overlap; lane l owns column l of the unit, loads the SAT corners of its
-//     column straight from global memory into registers (two coalesced 8-byte loads per row
-//     edge, the loads of the next unit in flight while this one is summed), differences them
-//     down the rows and adds `box * weight` to its accumulator.  Every lane of a unit carries
-//     a footprint pixel (no idle pixels as in a thread-per-pixel tile), no staging buffer, no
-//     block-wide barrier and no atomics on the image;
+//     <=32 columns) overlap.  For a footprint whose pixel edges are evenly spaced (whole
+//     number of table samples per pixel) the box sums of all its pixels are one dense
+//     rectangle of one block of the "box table" (psf.cu), so a unit's (<= 8) x 32 values arrive
+//     by TMA: one bulk copy of up to 2 KB into a three-stage shared-memory ring, completion
+//     on an mbarrier, two units ahead of the arithmetic.  Lane l owns column l of the unit and
+//     adds `box * weight` to its accumulators: one shared-memory load, one multiply and one
+//     conversion per pixel.  Every lane of a unit carries a footprint pixel, there is no
+//     block-wide barrier and no atomic on the image.  Footprints whose edges are not evenly
+//     spaced (pixel pitch not a whole number of samples, or a rounding step in the edge
+//     arithmetic) gather the four SAT corners per pixel through per-edge offsets -- same
+//     integer box sums, bit-identical result;
 //   * accumulators are 64-bit fixed point (LSB 2^-K photons, K chosen per call from the
 //     largest spot weight so that the sum cannot overflow): integer addition is associative,
 //     so the image is bitwise reproducible whatever order the work list was filled in.
@@ -28,16 +33,20 @@ constexpr int kStripRows = 8;         // pixel rows per strip
 constexpr int kStripCols = 128;       // pixel columns per strip
 constexpr int kUnitCols = 32;         // columns per unit = lanes
 constexpr int kMaxWarps = 7;          // warps (= strips in flight) per CTA
-constexpr int kBatch = 32;            // units fetched per round (one per lane)
+constexpr int kBatch = 16;            // units fetched per round (one per lane of a half warp)
 constexpr int kEdges = kStripRows + 1;
+constexpr int kStages = 3;            // TMA ring depth
+constexpr int kFastSlots = 32;        // widest box-table block row the ring holds
+constexpr int kStageEntries = kStripRows * kFastSlots;
+constexpr uint32_t kUnitFast = 0x80000000u;
 
 // One work-list entry: the overlap of a spot with (<= 8 rows) x (<= 32 columns) of a strip.
 struct __align__(16) Unit {
     double ws;             // weight * res^2 / table scale * 2^K
-    const long long *S;    // summed-area table of the spot's depth key
-    uint32_t erow, ecol;   // first row / column edge of the overlap inside `edges`
+    const void *src;       // fast: first box-table row of the unit (`rows` rows of `slots` doubles);  gather: the spot's SAT
+    uint32_t erow, ecol;   // gather: first row / column edge of the overlap inside `edges`
     uint32_t shape;        // rows | cols << 8 | first strip row << 16 | first strip column << 24
-    uint32_t pad;
+    uint32_t extra;        // fast: kUnitFast | box-table column of lane 0
 };
 
 // Fixed-point exponent of the accumulators: every pixel is below 2 * n_spots * max weight
@@ -54,7 +63,8 @@ __device__ __forceinline__ int accumulator_shift(unsigned long long wmax_bits, i
 // One thread per spot: write the spot's units into the strips' list segments.
 __global__ void __launch_bounds__(256)
 strip_fill_kernel(Geo g, int64_t n, const SpotRec *__restrict__ spots, int edge_cap,
-                  const int64_t *__restrict__ sat, const int *__restrict__ tile_start,
+                  const int64_t *__restrict__ sat, const double *__restrict__ box_table,
+                  const int *__restrict__ tile_start,
                   int *__restrict__ tile_cursor, const unsigned long long *__restrict__ wmax_bits,
                   Unit *__restrict__ units) {
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -63,8 +73,13 @@ strip_fill_kernel(Geo g, int64_t n, const SpotRec *__restrict__ spots, int edge_
     if (rec.slot < 0) return;
     Unit u;
     u.ws = scalbn(rec.w, accumulator_shift(*wmax_bits, n));
-    u.S = (const long long *)sat + (size_t)rec.slot * ((size_t)(g.side + 1) * g.pitch);
-    u.pad = 0;
+    const size_t table_at = (size_t)rec.slot * ((size_t)g.modulus * g.modulus * g.slots * g.slots);
+    const bool fast = box_table && rec.row_run >= 0 && rec.col_run >= 0 && g.slots <= kFastSlots;
+    // edge e of a regular axis sits at slot slot0 + e (>= -1); the pixel between edges e and e + 1
+    // is box-table row / column slot0 + e + 1
+    const int row_slot0 = (rec.row_run >> 16) - 1, col_slot0 = (rec.col_run >> 16) - 1;
+    const double *block = box_table + table_at +
+                          ((size_t)(rec.row_run & 0xffff) * g.modulus + (rec.col_run & 0xffff)) * (size_t)(g.slots * g.slots);
     const uint32_t ebase = (uint32_t)s * 2u * (uint32_t)edge_cap;
     const int stripe = stripe_of(g, s);
     int *cursor = tile_cursor + (size_t)stripe * g.nti * g.ntj;
@@ -77,100 +92,150 @@ strip_fill_kernel(Geo g, int64_t n, const SpotRec *__restrict__ spots, int edge_
             const int r_lo = max(rec.imin, ti * g.tile_h), r_hi = min(rec.imax, (ti + 1) * g.tile_h);
             const int tile = ti * g.ntj + tj;
             Unit *dst = units + tile_start[tile * g.stripes + stripe] + atomicAdd(&cursor[tile], entries);
+            const int rows = r_hi - r_lo;
             u.erow = ebase + (uint32_t)(r_lo - rec.imin);
+            const int first_box_row = row_slot0 + (r_lo - rec.imin) + 1;
             for (int q = 0; q < entries; ++q) {
                 const int c = c_lo + q * g.chunk;
                 u.ecol = ebase + (uint32_t)(edge_cap + c - rec.jmin);
-                u.shape = (uint32_t)(r_hi - r_lo) | (uint32_t)min(g.chunk, c_hi - c) << 8 |
+                u.shape = (uint32_t)rows | (uint32_t)min(g.chunk, c_hi - c) << 8 |
                           (uint32_t)(r_lo - ti * g.tile_h) << 16 | (uint32_t)(c - tj * g.tile_w) << 24;
+                if (fast) {
+                    u.src = block + (size_t)first_box_row * g.slots;
+                    u.extra = kUnitFast | (uint32_t)(col_slot0 + (c - rec.jmin) + 1);
+                } else {
+                    u.src = sat + table_at;
+                    u.extra = 0;
+                }
                 dst[q] = u;
             }
         }
     }
 }
 
-struct LaneEdges {        // raw edge-table entries of one lane; consumed one pipeline stage later
-    uint32_t left, right;   // storage offsets (in table entries) of the lane's two column edges
-    uint32_t row;           // lane k <= rows: table row of row edge k
-};
+// ---- mbarrier / TMA helpers ------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ LaneEdges unit_edges(const Unit *meta, int u, int lane,
-                                                const uint16_t *__restrict__ edges) {
-    const uint4 tail = *reinterpret_cast<const uint4 *>(&meta[u].erow);     // erow, ecol, shape, pad
-    const int rows = tail.z & 0xff, cols = (tail.z >> 8) & 0xff;
-    const uint32_t c = tail.y + (uint32_t)min(lane, cols - 1);   // idle lanes repeat the last column: no extra sectors
-    LaneEdges e;
-    e.left = __ldg(edges + c);
-    e.right = __ldg(edges + c + 1);
-    e.row = __ldg(edges + tail.x + (uint32_t)min(lane, rows));
-    return e;
+__device__ __forceinline__ void mbar_init(void *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(void *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_row(void *dst, const void *src, uint32_t bytes, void *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_addr(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
 }
 
-// corner address = row * pitch_bytes + (table + column offset): one IMAD.WIDE
-__device__ __forceinline__ long long load_corner(const long long *column, uint32_t row, uint32_t pitch_bytes) {
-    const long long *p;
-    // volatile: keeps ptxas from splitting it into a shared product plus two 64-bit adds
-    asm volatile("mad.wide.u32 %0, %1, %2, %3;" : "=l"(p) : "r"(row), "r"(pitch_bytes), "l"(column));
-    return __ldg(p);
-}
-
-__device__ __forceinline__ void unit_gather(const Unit *meta, int u, const LaneEdges &e, uint32_t pitch_bytes,
-                                            long long (&L)[kEdges], long long (&R)[kEdges]) {
-    const long long *S = meta[u].S;
-    const int rows = meta[u].shape & 0xff;
-    // an edge at table sample 0 (kEdgeZero) reads S[0][0] == 0 for every row: its row stride is 0
-    const long long *left = S + (e.left & 0x7fffu), *right = S + (e.right & 0x7fffu);
-    const uint32_t left_pitch = (e.left & kEdgeZero) ? 0u : pitch_bytes;
-    const uint32_t right_pitch = (e.right & kEdgeZero) ? 0u : pitch_bytes;
-    uint32_t row[kEdges];
-#pragma unroll
-    for (int k = 0; k < kEdges; ++k) row[k] = __shfl_sync(0xffffffffu, e.row, k);
-#pragma unroll
-    for (int k = 0; k < kEdges; ++k) {
-        if (k <= rows) {                       // warp uniform
-            L[k] = load_corner(left, row[k], left_pitch);
-            R[k] = load_corner(right, row[k], right_pitch);
-        }
+// Fast unit, producer side: one bulk copy of the unit's box-table rows (contiguous in the block).
+__device__ __forceinline__ void unit_stage(const Unit *meta, int u, int lane, double *stage, void *bar,
+                                           uint32_t row_bytes) {
+    if (lane == 0) {
+        const uint32_t bytes = (meta[u].shape & 0xffu) * row_bytes;
+        mbar_expect_tx(bar, bytes);
+        tma_row(stage, meta[u].src, bytes, bar);
     }
 }
 
-// Rows beyond the unit's last carry stale corner values: their products are computed and
-// dropped (only the accumulator update is predicated), which keeps the loop branch free.
-__device__ __forceinline__ void unit_accumulate(const Unit *meta, int u, int lane, long long *acc,
-                                                const long long (&L)[kEdges], const long long (&R)[kEdges]) {
+// Accumulator update shared by both paths.  Rows beyond the unit's last carry stale values:
+// their products are computed and dropped (only the update is predicated), which keeps the
+// loop branch free.  _epifm.py:280-282 (`if photons > 0` needs no branch: adding zero changes nothing)
+__device__ __forceinline__ void unit_add(long long *a, int rows, double ws, const double (&box)[kStripRows]) {
+#pragma unroll
+    for (int k = 0; k < kStripRows; ++k) {
+        const long long q = __double2ll_rn(__dmul_rn(box[k], ws));
+        if (k < rows) a[k * kStripCols] += q;
+    }
+}
+
+// Fast unit, consumer side: lane l reads its column of the staged box rows.
+__device__ __forceinline__ void unit_accumulate_fast(const Unit *meta, int u, int lane, long long *acc,
+                                                     const double *stage, int slots) {
     const double ws = meta[u].ws;
     const uint32_t shape = meta[u].shape;
     const int rows = (lane < (int)((shape >> 8) & 0xff)) ? (int)(shape & 0xff) : 0;   // idle lanes: no rows
     long long *a = acc + ((shape >> 16) & 0xff) * kStripCols + (shape >> 24) + lane;
-    long long above = R[0] - L[0];
+    const double *st = stage + min((int)(meta[u].extra & 0xffu) + lane, slots - 1);   // idle lanes stay inside the row
+    double box[kStripRows];
 #pragma unroll
-    for (int k = 1; k < kEdges; ++k) {
-        const long long here = R[k] - L[k];
-        const long long box = here - above;   // >= 0: the table is non-negative, edges are monotone
-        above = here;
-        // _epifm.py:280-282 (`if photons > 0` needs no branch: adding zero changes nothing)
-        const long long q = __double2ll_rn(__dmul_rn((double)box, ws));
-        if (k <= rows) a[(k - 1) * kStripCols] += q;
+    for (int k = 0; k < kStripRows; ++k) box[k] = st[k * slots];
+    unit_add(a, rows, ws, box);
+}
+
+// Gather unit: per-edge table offsets from `edges`, corners straight from global memory.
+__device__ __forceinline__ void unit_accumulate_gather(const Unit *meta, int u, int lane, long long *acc,
+                                                       const uint32_t *__restrict__ edges) {
+    const double ws = meta[u].ws;
+    const uint32_t shape = meta[u].shape;
+    const int n_rows = shape & 0xff, n_cols = (shape >> 8) & 0xff;
+    const int rows = lane < n_cols ? n_rows : 0;
+    long long *a = acc + ((shape >> 16) & 0xff) * kStripCols + (shape >> 24) + lane;
+    const long long *table = static_cast<const long long *>(meta[u].src);
+    const uint32_t c = meta[u].ecol + (uint32_t)min(lane, n_cols - 1);   // idle lanes repeat the last column
+    const uint32_t left = __ldg(edges + c), right = __ldg(edges + c + 1);
+    const uint32_t my_row = __ldg(edges + meta[u].erow + (uint32_t)min(lane, n_rows));
+    long long L[kEdges], R[kEdges];
+#pragma unroll
+    for (int k = 0; k < kEdges; ++k) {
+        const uint32_t row = __shfl_sync(0xffffffffu, my_row, k);
+        L[k] = 0; R[k] = 0;
+        if (k <= n_rows) {                     // warp uniform
+            if (!((row | left) & kEdgeZero)) L[k] = __ldg(table + (row + left));
+            if (!((row | right) & kEdgeZero)) R[k] = __ldg(table + (row + right));
+        }
     }
+    double box[kStripRows];
+#pragma unroll
+    for (int k = 0; k < kStripRows; ++k)    // >= 0: the table is non-negative, edges are monotone
+        box[k] = (double)((R[k + 1] - L[k + 1]) - (R[k] - L[k]));
+    unit_add(a, rows, ws, box);
 }
 
 template <typename OutT>
 __global__ void __launch_bounds__(kMaxWarps * 32, 2)
-render_strips_kernel(Geo g, const Unit *__restrict__ units, const uint16_t *__restrict__ edges,
+render_strips_kernel(Geo g, const Unit *__restrict__ units, const uint32_t *__restrict__ edges,
                      const int *__restrict__ tile_start, int *__restrict__ next_tile,
                      const unsigned long long *__restrict__ wmax_bits, int64_t n_spots,
                      OutT *__restrict__ out, int accumulate) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    // per-warp carve: accumulators | TMA ring | unit batch | mbarriers
     long long *acc = reinterpret_cast<long long *>(smem_raw) + warp * (kStripRows * kStripCols);
-    Unit *meta = reinterpret_cast<Unit *>(smem_raw + (size_t)n_warps * kStripRows * kStripCols * 8) + warp * kBatch;
+    double *ring = reinterpret_cast<double *>(smem_raw) + n_warps * (kStripRows * kStripCols) +
+                   warp * (kStages * kStageEntries);
+    Unit *meta = reinterpret_cast<Unit *>(reinterpret_cast<long long *>(smem_raw) +
+                                          n_warps * (kStripRows * kStripCols + kStages * kStageEntries)) + warp * kBatch;
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(
+        reinterpret_cast<Unit *>(reinterpret_cast<long long *>(smem_raw) +
+                                 n_warps * (kStripRows * kStripCols + kStages * kStageEntries)) + n_warps * kBatch) +
+        warp * kStages;
 
     const int n_tiles = g.nti * g.ntj;
-    const uint32_t pitch = (uint32_t)g.pitch * 8u;
+    const uint32_t row_bytes = (uint32_t)g.slots * 8u;
     const double lsb = scalbn(1.0, -accumulator_shift(*wmax_bits, n_spots));
 
     for (int i = lane; i < kStripRows * kStripCols; i += 32) acc[i] = 0;
-    long long LA[kEdges] = {}, RA[kEdges] = {}, LB[kEdges] = {}, RB[kEdges] = {};   // corner registers of two units
+    for (int i = lane; i < kStages * kStageEntries; i += 32) ring[i] = 0.0;    // rows past a unit's last are read (and dropped)
+    if (lane == 0) {
+        for (int st = 0; st < kStages; ++st) mbar_init(&bars[st], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // zeroed ring visible to the async proxy
+    __syncwarp();
+    uint32_t produced = 0, consumed = 0;     // fast units staged / used so far (ring position and parity)
 
     for (;;) {
         int tile = 0;
@@ -192,18 +257,23 @@ render_strips_kernel(Geo g, const Unit *__restrict__ units, const uint16_t *__re
             }
             __syncwarp();
 
-            // software pipeline: edges two units ahead, corner loads one unit ahead
-            LaneEdges e0 = unit_edges(meta, 0, lane, edges), e1 = e0;
-            unit_gather(meta, 0, e0, pitch, LA, RA);
-            if (nb > 1) e1 = unit_edges(meta, 1, lane, edges);
-            for (int u = 0; u < nb; u += 2) {
-                if (u + 1 < nb) unit_gather(meta, u + 1, e1, pitch, LB, RB);
-                if (u + 2 < nb) e0 = unit_edges(meta, u + 2, lane, edges);
-                unit_accumulate(meta, u, lane, acc, LA, RA);
-                if (u + 1 < nb) {
-                    if (u + 2 < nb) unit_gather(meta, u + 2, e0, pitch, LA, RA);
-                    if (u + 3 < nb) e1 = unit_edges(meta, u + 3, lane, edges);
-                    unit_accumulate(meta, u + 1, lane, acc, LB, RB);
+            auto stage_unit = [&](int u) {
+                if (meta[u].extra & kUnitFast) {
+                    const uint32_t st = produced % kStages;
+                    unit_stage(meta, u, lane, ring + st * kStageEntries, &bars[st], row_bytes);
+                    ++produced;
+                }
+            };
+            for (int u = 0; u < min(nb, kStages - 1); ++u) stage_unit(u);
+            for (int u = 0; u < nb; ++u) {
+                if (u + kStages - 1 < nb) stage_unit(u + kStages - 1);
+                if (meta[u].extra & kUnitFast) {
+                    const uint32_t st = consumed % kStages;
+                    mbar_wait(&bars[st], (consumed / kStages) & 1u);
+                    unit_accumulate_fast(meta, u, lane, acc, ring + st * kStageEntries, g.slots);
+                    ++consumed;
+                } else {
+                    unit_accumulate_gather(meta, u, lane, acc, edges);
                 }
             }
         }
@@ -268,6 +338,9 @@ extern "C" int scb_profile_end(double *total_ms, int64_t *launches) {
     return 0;
 }
 
+constexpr size_t kWarpSmemBytes = (kStripRows * kStripCols + kStages * kStageEntries) * 8 + kBatch * sizeof(Unit) + kStages * 8;
+static_assert(2 * kMaxWarps * kWarpSmemBytes + 2048 <= 232448, "two CTAs per SM must fit in shared memory");
+
 static Geo strip_geo(const scb_geometry *geom) {
     Geo g = make_geo(geom, kStripRows, kStripCols, kUnitCols);
     g.special_edges = 1;
@@ -291,11 +364,11 @@ static int launch_render(const Geo &g, const Workspace &w, int64_t n_spots, OutT
     warps = warps < 1 ? 1 : (warps > kMaxWarps ? kMaxWarps : warps);
     int ctas = (n_tiles + warps - 1) / warps;
     if (ctas > slots) ctas = slots;
-    const size_t smem = (size_t)warps * (kStripRows * kStripCols * 8 + kBatch * sizeof(Unit));
+    const size_t smem = (size_t)warps * kWarpSmemBytes;
     static bool configured = false;     // per template instance
     if (!configured) {
         SCB_CUDA(cudaFuncSetAttribute(render_strips_kernel<OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)(kMaxWarps * (kStripRows * kStripCols * 8 + kBatch * sizeof(Unit)))));
+                                      (int)(kMaxWarps * kWarpSmemBytes)));
         configured = true;
     }
     render_strips_kernel<OutT><<<ctas, warps * 32, smem, s>>>(g, (const Unit *)w.pair_spot, w.edges, w.tile_start,
@@ -305,7 +378,7 @@ static int launch_render(const Geo &g, const Workspace &w, int64_t n_spots, OutT
 
 extern "C" int scb_render_expected(const scb_geometry *geom, int64_t n_spots, const double *d_depth,
                                    const double *d_x, const double *d_y, const double *d_weight,
-                                   const int64_t *d_sat, const double *d_inv_scale,
+                                   const int64_t *d_sat, const double *d_box, const double *d_inv_scale,
                                    const int32_t *d_slot_of_key, void *d_out, int out_type,
                                    int accumulate, void *d_workspace, size_t workspace_bytes,
                                    int32_t *d_errors, void *stream) {
@@ -320,7 +393,6 @@ extern "C" int scb_render_expected(const scb_geometry *geom, int64_t n_spots, co
     Workspace w = carve(g, n_spots, d_workspace, sizeof(Unit));
     SCB_REQUIRE(workspace_bytes >= w.bytes, SCB_E_WORKSPACE, "scb_render_expected: workspace %zu < %zu",
                 workspace_bytes, w.bytes);
-    SCB_REQUIRE(g.pitch <= 32768, SCB_E_UNSUPPORTED, "scb_render_expected: SAT row pitch %d > 32768 entries", g.pitch);
     SCB_REQUIRE((double)n_spots * 2.0 * w.edge_cap < 4294967296.0, SCB_E_UNSUPPORTED,
                 "scb_render_expected: %lld spots x %d pixel edges exceed the 32-bit edge index",
                 (long long)n_spots, 2 * w.edge_cap);
@@ -349,7 +421,7 @@ extern "C" int scb_render_expected(const scb_geometry *geom, int64_t n_spots, co
     }
     tile_scan_kernel<<<kScanCtas, 1024, 0, s>>>(n_tiles, g.stripes, w.tile_count, w.tile_start);
     if (n_spots > 0) {
-        strip_fill_kernel<<<scb_grid_for(n_spots, 256), 256, 0, s>>>(g, n_spots, w.spots, w.edge_cap, d_sat,
+        strip_fill_kernel<<<scb_grid_for(n_spots, 256), 256, 0, s>>>(g, n_spots, w.spots, w.edge_cap, d_sat, d_box,
                                                                     w.tile_start, w.tile_cursor, w.wmax_bits,
                                                                     (Unit *)w.pair_spot);
     }

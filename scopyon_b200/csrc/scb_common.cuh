@@ -129,15 +129,30 @@ __device__ __forceinline__ void box_muller(uint32_t r0, uint32_t r1, float &n0, 
     n1 = radius * s;
 }
 
-// SAT column layout shared by the builder (psf.cu) and the renderers: with M = sat_modulus,
-// column b of a table row lives at (b % M) * blocks + b / M.  `blocks` leaves at least one
-// spare slot per phase block (the builder stores the row's last column there, so the
-// clamped closing edge of a footprint is read from the same cache lines as its interior
-// edges) and is rounded up to 16 entries so that a phase block starts on a 128-byte line.
-static inline int scb_sat_blocks(int cols, int modulus) {
-    const int used = (cols + modulus - 1) / modulus;
-    const int padded = (used + 1 + 15) & ~15;
-    return ((int64_t)padded * modulus <= 32768) ? padded : used + 1;
+// SAT block layout shared by the builder (psf.cu) and the renderers.  With M = sat_modulus
+// (the pixel pitch in table samples) the pixel edges of one footprint are M samples apart on
+// both axes, i.e. they share one residue ("phase") mod M per axis.  Entry S[a][b] therefore
+// lives in block (a % M, b % M) at slot (a / M, b / M):
+//     index(pr, pc, ir, ic) = ((pr * M + pc) * B + ir) * B + ic,    value = S[min(ir*M+pr, side)][min(ic*M+pc, side)]
+// where B slots per phase leave at least one slot past the last sample: those slots repeat
+// the last row / column, so the clamped closing edge of a footprint is simply the next slot.
+// All corners a footprint needs are then one dense (rows+1) x (cols+1) rectangle of one
+// B x B block -- contiguous B*8-byte rows that a TMA bulk copy moves as they are.  B is a
+// multiple of 16 (128-byte lines) unless that would waste more than a quarter of the table.
+struct SatLayout {
+    int modulus, slots, side;
+    __host__ __device__ long long block_entries() const { return (long long)slots * slots; }
+    __host__ __device__ long long table_entries() const { return (long long)modulus * modulus * slots * slots; }
+};
+
+static inline SatLayout scb_sat_layout(int n_radial, int modulus) {
+    SatLayout L;
+    L.modulus = modulus < 1 ? 1 : modulus;
+    L.side = 2 * (n_radial - 1) + 1;
+    const int used = (L.side + 1 + L.modulus - 1) / L.modulus;
+    const int b16 = (used + 1 + 15) & ~15, b2 = (used + 1 + 1) & ~1;
+    L.slots = (b16 * 4 <= (used + 1) * 5) ? b16 : b2;
+    return L;
 }
 
 static inline unsigned int scb_grid_for(int64_t n, int block, int per_thread = 1) {

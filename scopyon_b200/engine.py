@@ -89,7 +89,8 @@ class SatStore:
     def shared(cls, engine):
         cfg = engine.configs
         key = (str(engine.device), engine.psf_type, float(cfg.psf_wavelength), cfg.psf_radial_width,
-               engine.geom.n_radial, engine.geom.n_depth_keys, float(cfg.depth_cutoff), engine.geom.sat_modulus)
+               engine.geom.n_radial, engine.geom.n_depth_keys, float(cfg.depth_cutoff), engine.geom.sat_modulus,
+               cls.wants_box(engine))
         store = cls._shared.get(key)
         if store is None:
             store = cls._shared[key] = cls(engine)
@@ -98,6 +99,14 @@ class SatStore:
     @classmethod
     def clear_shared(cls):
         cls._shared.clear()
+
+    @staticmethod
+    def wants_box(engine):
+        """Box tables (the per-pixel integrals the TMA render path reads) only pay off when the
+        pixel pitch is a whole number of table samples: otherwise no footprint has evenly
+        spaced edges and every spot is summed from the SAT corners."""
+        ratio = float(engine.geom.pixel_length) / float(engine.geom.resolution)
+        return abs(ratio - round(ratio)) < 1e-6 * ratio
 
     def __init__(self, engine):
         cfg = engine.configs
@@ -111,8 +120,11 @@ class SatStore:
         self.n_depth_keys = int(engine.geom.n_depth_keys)
         self.modulus = int(engine.geom.sat_modulus)
         self.rows = 2 * (self.n_radial - 1) + 2
-        self.pitch = int(self.lib.scb_psf_sat_pitch(self.n_radial, self.modulus))
+        self.slots = int(self.lib.scb_psf_sat_slots(self.n_radial, self.modulus))
+        self.table_entries = int(self.lib.scb_psf_sat_table_entries(self.n_radial, self.modulus))
+        self.with_box = self.wants_box(engine)
         self.sat = None
+        self.box = None
         self.inv_scale = None
         self.n_tables = 0
         self.last_radial = None
@@ -123,12 +135,17 @@ class SatStore:
         """Depth a table is evaluated at (``_epifm.py:80-84``)."""
         return float(key) * RESOLUTION if key < self.n_depth_keys else self.depth_cutoff
 
+    def index_of(self, a, b):
+        """Position of ``S[a][b]`` inside a stored table (the block layout of
+        ``csrc/scb_common.cuh``): block ``(a % M, b % M)``, slot ``(a // M, b // M)``."""
+        m, s = self.modulus, self.slots
+        return (((a % m) * m + (b % m)) * s + a // m) * s + b // m
+
     def plain(self, slot):
-        """Table ``slot`` on the host in plain ``S[a][b]`` order (undoes the column interleave)."""
+        """Table ``slot`` on the host in plain ``S[a][b]`` order (undoes the block layout)."""
         stored = self.sat[slot].cpu().numpy()
-        b = numpy.arange(self.rows)
-        blocks = self.pitch // self.modulus
-        return stored[:, (b % self.modulus) * blocks + b // self.modulus]
+        a = numpy.arange(self.rows)
+        return stored[self.index_of(a[:, None], a[None, :])]
 
     def all_resident(self):
         return self.n_tables > 0 and bool((self.slot_host >= 0).all())
@@ -159,12 +176,16 @@ class SatStore:
         capacity = 0 if self.sat is None else self.sat.shape[0]
         if need > capacity:
             new_cap = max(min(max(need, 2 * capacity, 1), self.n_depth_keys + 1), need)
-            sat = torch.empty((new_cap, self.rows, self.pitch), dtype=torch.int64, device=self.device)
+            sat = torch.empty((new_cap, self.table_entries), dtype=torch.int64, device=self.device)
+            box = torch.empty((new_cap, self.table_entries), dtype=torch.float64, device=self.device) \
+                if self.with_box else None
             inv = torch.zeros(new_cap, dtype=torch.float64, device=self.device)
             if self.n_tables:
                 sat[:self.n_tables].copy_(self.sat[:self.n_tables])
                 inv[:self.n_tables].copy_(self.inv_scale[:self.n_tables])
-            self.sat, self.inv_scale = sat, inv
+                if box is not None:
+                    box[:self.n_tables].copy_(self.box[:self.n_tables])
+            self.sat, self.box, self.inv_scale = sat, box, inv
         if radial is None:
             depths = torch.tensor([self.table_depth(k) for k in keys], dtype=torch.float64).to(self.device)
             radial = torch.empty((n_new, self.n_radial), dtype=torch.float64, device=self.device)
@@ -176,6 +197,7 @@ class SatStore:
         first = self.n_tables
         _native.check(self.lib.scb_psf_sat_build(
             _native.ptr(radial), self.n_radial, n_new, self.modulus, ctypes.c_void_p(self.sat[first].data_ptr()),
+            None if self.box is None else ctypes.c_void_p(self.box[first].data_ptr()),
             ctypes.c_void_p(self.inv_scale[first:].data_ptr()), _native.ptr(work), work_bytes, stream),
             "scb_psf_sat_build")
         self.n_tables = need
@@ -244,9 +266,8 @@ class DeviceEngine:
             # (the analytic Gaussian: 7e-6) and has no bias in dense fields.
             self.ensure_tables([0])
             side = self.tables.rows - 1
-            blocks = self.tables.pitch // self.tables.modulus
-            column = (side % self.tables.modulus) * blocks + side // self.tables.modulus
-            cumulative = self.tables.sat[0][:, column].to(torch.float64) * self.tables.inv_scale[0] * (RESOLUTION ** 2)
+            last_column = torch.from_numpy(self.tables.index_of(numpy.arange(side + 1), side)).to(self.device)
+            cumulative = self.tables.sat[0][last_column].to(torch.float64) * self.tables.inv_scale[0] * (RESOLUTION ** 2)
             self.gaussian_prefix = (cumulative / torch.sqrt(cumulative[-1])).contiguous()
 
         # detector-side constants
@@ -319,6 +340,7 @@ class DeviceEngine:
 
     # ------------------------------------------------------------------ PSF tables
     sat = property(lambda self: self.tables.sat)
+    box = property(lambda self: self.tables.box)
     inv_scale = property(lambda self: self.tables.inv_scale)
     slot_of_key = property(lambda self: self.tables.slot_of_key)
     slot_host = property(lambda self: self.tables.slot_host)
@@ -460,7 +482,7 @@ class DeviceEngine:
         self._call(
             "scb_render_expected", ctypes.byref(self.geom), total,
             _native.ptr(soa[0]), _native.ptr(soa[1]), _native.ptr(soa[2]), _native.ptr(weight),
-            _native.ptr(self.sat), _native.ptr(self.inv_scale), _native.ptr(self.slot_of_key),
+            _native.ptr(self.sat), _native.ptr(self.box), _native.ptr(self.inv_scale), _native.ptr(self.slot_of_key),
             _native.ptr(out), _native.F32 if out.dtype == torch.float32 else _native.F64, 0,
             _native.ptr(work), work.numel(), _native.ptr(self.errors), stream)
 

@@ -106,10 +106,22 @@ default:
     data[:, 2] = rng.uniform(-520 * pl, 520 * pl, n)
     data[:3000, 1] = rng.normal(100 * pl, 2 * pl, 3000)
     data[:3000, 2] = rng.normal(-200 * pl, 2 * pl, 3000)
+    # spots on exact pixel centres / corners / whole nanometres: every edge expression lands on an
+    # integer, where rounding decides the sample index (the unevenly spaced footprints of the SAT path)
+    data[3000:3200, 1] = (rng.randint(-400, 400, 200) + 0.5 * rng.randint(0, 2, 200)) * pl
+    data[3000:3200, 2] = (rng.randint(-400, 400, 200) + 0.5 * rng.randint(0, 2, 200)) * pl
+    data[3200:3400, 1] = rng.randint(-20000, 20000, 200) * 1e-9
+    data[3200:3400, 2] = rng.randint(-20000, 20000, 200) * 1e-9
     data[:, 3] = numpy.arange(n)
     data[:, 4] = (rng.uniform(size=n) > 0.1)                 # 10 % dark molecules
     sats, inv, slot = oracle_tables(params, engine, [0])
     got = render(engine, data)
+    # 65 nm pixels: evenly spaced footprints come from the box table by TMA; without the box
+    # table every footprint is summed from SAT corners -- the two paths agree bit for bit
+    assert engine.box is not None
+    box, engine.tables.box = engine.tables.box, None
+    assert numpy.array_equal(render(engine, data), got)
+    engine.tables.box = box
     dev_w = device_weights(engine, data, 0.033)
     assert (dev_w[data[:, 4] == 0] == 0).all()
     want = c_oracle.render_sat(c_oracle.geometry(params), data[:, 0], data[:, 1], data[:, 2], dev_w, sats, inv, slot)

@@ -41,7 +41,7 @@ else:
     work = eng._render_workspace(n)
     for k in range(iters):
         eng._call("scb_render_expected", ctypes.byref(eng.geom), n, _native.ptr(soa[0]), _native.ptr(soa[1]),
-                  _native.ptr(soa[2]), _native.ptr(w), _native.ptr(eng.sat), _native.ptr(eng.inv_scale),
+                  _native.ptr(soa[2]), _native.ptr(w), _native.ptr(eng.sat), _native.ptr(eng.box), _native.ptr(eng.inv_scale),
                   _native.ptr(eng.slot_of_key), _native.ptr(out), _native.F32, 0, _native.ptr(work), work.numel(),
                   _native.ptr(eng.errors), eng._stream())
 torch.cuda.synchronize()
