@@ -233,6 +233,21 @@ int scb_render_expected(const scb_geometry *geom, int64_t n_spots,
                         void *d_workspace, size_t workspace_bytes,
                         int32_t *d_errors, void *stream);
 
+/* The same two calls on particle ROWS as the host API holds them -- (n, 5) float64 rows
+ * (depth, x, y, molecule id, p_state), the output of EPIFMSimulator.__format_data
+ * (base.py:61-110) -- read in place, no transposition: what the particle loop of
+ * _EPIFMSimulator.output_frame (_epifm.py:1183-1202, 1262-1264) becomes for one
+ * (unit_time, particles) snapshot.  The budget RNG key is the id column. */
+int scb_emit_bleach_rows(uint64_t budget_seed, int64_t n, const double *d_rows,
+                         const int32_t *d_mol_slot, double unit_time, double focal_depth,
+                         const scb_photophysics *phys, double *d_budget, double *d_weight,
+                         double *d_true_data, void *stream);
+int scb_render_expected_rows(const scb_geometry *geom, int64_t n, const double *d_rows,
+                             const double *d_weight, const int64_t *d_sat, const double *d_box,
+                             const double *d_inv_scale, const int32_t *d_slot_of_key, void *d_out,
+                             int out_type, int accumulate, void *d_workspace, size_t workspace_bytes,
+                             int32_t *d_errors, void *stream);
+
 /* Tensor-core variant of scb_render_expected for the separable Gaussian PSF
  * (fluorophore.type == 'Gaussian', _epifm.py:133-134): a 128 x 128 screen tile is the
  * contraction D[i][j] = sum_s (w_s Ex_s(i)) Ey_s(j) over the spots binned to it, issued as

@@ -32,6 +32,46 @@ class EnvironSettings:
         self.processes = config.processes
 
 
+class ParticleRows(numpy.ndarray):
+    """``(N, 5)`` rows ``[depth, x, y, molecule id, p_state]`` as ``__format_data`` returns them --
+    a plain float64 array that additionally carries the molecule ids as a contiguous int64
+    column (``ids``), and lives in page-locked memory when a GPU is present so the device
+    can fetch it with one DMA.  Views and copies are ordinary arrays (``ids`` is dropped)."""
+
+    ids = None
+
+    def __array_finalize__(self, obj):
+        self.ids = None
+
+
+class _PinnedBudget:
+    """Bytes of page-locked input rows alive at once (they are freed with their arrays)."""
+    limit = 2 << 30
+    used = 0
+
+    @classmethod
+    def release(cls, nbytes):
+        cls.used -= nbytes
+
+
+def _new_rows(n):
+    """Zeroed (n, 5) float64 rows, page-locked when that is possible and affordable."""
+    nbytes = n * 5 * 8
+    if nbytes and _PinnedBudget.used + nbytes <= _PinnedBudget.limit:
+        try:
+            import torch
+            if torch.cuda.is_available():
+                import weakref
+                host = torch.zeros((n, 5), dtype=torch.float64, pin_memory=True)
+                rows = host.numpy().view(ParticleRows)     # keeps `host` alive through .base
+                _PinnedBudget.used += nbytes
+                weakref.finalize(host, _PinnedBudget.release, nbytes)
+                return rows
+        except (ImportError, RuntimeError):
+            pass
+    return numpy.zeros((n, 5)).view(ParticleRows)
+
+
 def _project(points, pre):
     """3-D world coordinates -> (depth, x, y) in the camera frame (base.py:76-91)."""
     data = points * pre.scale - numpy.array(pre.origin)
@@ -77,7 +117,7 @@ class EPIFMSimulator(object):
             raise ValueError("The given 'inputs' has wrong dimension.")
         pre = self.__config.preprocessing
         n, width = inputs.shape
-        data = numpy.zeros((n, 5))
+        data = _new_rows(n)
         if width in (2, 4):     # points on the focal plane
             data[:, 1:3] = inputs[:, :2] * pre.scale
         elif width in (3, 5):
@@ -89,6 +129,7 @@ class EPIFMSimulator(object):
             data[:, 4] = 1.0                # photon state
         else:
             data[:, 3:5] = inputs[:, width - 2:]
+        data.ids = numpy.ascontiguousarray(data[:, 3]).astype(numpy.int64)
         return data
 
     def __format_inputs(self, inputs):

@@ -69,7 +69,7 @@ __device__ __forceinline__ int stripe_of(const Geo &g, int64_t spot) { return (i
 
 // One thread per spot: footprint, depth key, tile census.
 __global__ void __launch_bounds__(256)
-spot_prepare_kernel(Geo g, int64_t n, const double *__restrict__ depth, const double *__restrict__ x,
+spot_prepare_kernel(Geo g, int64_t n, int64_t stride, const double *__restrict__ depth, const double *__restrict__ x,
                     const double *__restrict__ y, const double *__restrict__ weight,
                     const double *__restrict__ inv_scale, const int32_t *__restrict__ slot_of_key,
                     SpotRec *__restrict__ spots, int *__restrict__ tile_count,
@@ -84,9 +84,9 @@ spot_prepare_kernel(Geo g, int64_t n, const double *__restrict__ depth, const do
     double w_seen = 0.0;
     if (s < n) {
         const double w = weight[s];
-        const double xi = __dsub_rn(x[s], g.f1);
-        const double yi = __dsub_rn(y[s], g.f2);
-        const double dz = depth ? fabs(__dsub_rn(depth[s], g.f0)) : 0.0;
+        const double xi = __dsub_rn(x[s * stride], g.f1);
+        const double yi = __dsub_rn(y[s * stride], g.f2);
+        const double dz = depth ? fabs(__dsub_rn(depth[s * stride], g.f0)) : 0.0;
         if (w > 0.0 && isfinite(xi) && isfinite(yi) && isfinite(dz)) {   // _epifm.py:217-218
             // depth key, _epifm.py:76-84
             int key;

@@ -376,7 +376,7 @@ static int launch_render(const Geo &g, const Workspace &w, int64_t n_spots, OutT
     return 0;
 }
 
-extern "C" int scb_render_expected(const scb_geometry *geom, int64_t n_spots, const double *d_depth,
+static int render_expected_strided(const scb_geometry *geom, int64_t n_spots, int64_t stride, const double *d_depth,
                                    const double *d_x, const double *d_y, const double *d_weight,
                                    const int64_t *d_sat, const double *d_box, const double *d_inv_scale,
                                    const int32_t *d_slot_of_key, void *d_out, int out_type,
@@ -398,22 +398,11 @@ extern "C" int scb_render_expected(const scb_geometry *geom, int64_t n_spots, co
                 (long long)n_spots, 2 * w.edge_cap);
     cudaStream_t s = (cudaStream_t)stream;
     const int n_tiles = g.nti * g.ntj;
-    {
-        // The corner gathers use 8 bytes of every sector they touch; ask the L2 to fetch 32-byte
-        // sectors from HBM instead of 128-byte lines (measured 4 sectors per miss by default).
-        // Purely a performance hint, set once.
-        static bool hinted = false;
-        if (!hinted) {
-            cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
-            cudaGetLastError();
-            hinted = true;
-        }
-    }
     // census, cursors, weight maximum and the strip queue are adjacent 256-aligned blocks: clear them all
     SCB_CUDA(cudaMemsetAsync(w.tile_count, 0, (size_t)((char *)w.tile_start - (char *)w.tile_count), s));
     if (n_spots > 0) {
         spot_prepare_kernel<<<scb_grid_for(n_spots, 256), 256, 0, s>>>(
-            g, n_spots, d_depth, d_x, d_y, d_weight, d_inv_scale, d_slot_of_key, w.spots, w.tile_count,
+            g, n_spots, stride, d_depth, d_x, d_y, d_weight, d_inv_scale, d_slot_of_key, w.spots, w.tile_count,
             w.wmax_bits, d_errors);
         dim3 egrid, eblock;
         edges_launch_shape(w.edge_cap, n_spots, egrid, eblock);
@@ -433,4 +422,38 @@ extern "C" int scb_render_expected(const scb_geometry *geom, int64_t n_spots, co
     if (timed) cudaEventRecord(g_profile.stop[g_profile.used++], s);
     SCB_CUDA_LAUNCH_CHECK("scb_render_expected");
     return 0;
+}
+
+extern "C" int scb_render_expected(const scb_geometry *geom, int64_t n_spots, const double *d_depth,
+                                   const double *d_x, const double *d_y, const double *d_weight,
+                                   const int64_t *d_sat, const double *d_box, const double *d_inv_scale,
+                                   const int32_t *d_slot_of_key, void *d_out, int out_type,
+                                   int accumulate, void *d_workspace, size_t workspace_bytes,
+                                   int32_t *d_errors, void *stream) {
+    return render_expected_strided(geom, n_spots, 1, d_depth, d_x, d_y, d_weight, d_sat, d_box, d_inv_scale,
+                                   d_slot_of_key, d_out, out_type, accumulate, d_workspace, workspace_bytes, d_errors,
+                                   stream);
+}
+
+// ---- particle rows as the host API holds them: (n, 5) float64 rows (depth, x, y, molecule id,
+// p_state), the output of EPIFMSimulator.__format_data (base.py:61-110), read in place
+extern "C" int scb_emit_bleach_rows(uint64_t budget_seed, int64_t n, const double *d_rows,
+                                    const int32_t *d_mol_slot, double unit_time, double focal_depth,
+                                    const scb_photophysics *phys, double *d_budget, double *d_weight,
+                                    double *d_true_data, void *stream) {
+    SCB_REQUIRE(n == 0 || d_rows, SCB_E_NULL, "scb_emit_bleach_rows: NULL rows");
+    return scb_emit_bleach_strided(budget_seed, n, d_rows, d_rows + 1, d_rows + 2, d_rows + 4, d_mol_slot, nullptr,
+                                   d_rows + 3, 5, unit_time, focal_depth, phys, d_budget, d_weight, d_true_data,
+                                   stream);
+}
+
+extern "C" int scb_render_expected_rows(const scb_geometry *geom, int64_t n, const double *d_rows,
+                                        const double *d_weight, const int64_t *d_sat, const double *d_box,
+                                        const double *d_inv_scale, const int32_t *d_slot_of_key, void *d_out,
+                                        int out_type, int accumulate, void *d_workspace, size_t workspace_bytes,
+                                        int32_t *d_errors, void *stream) {
+    SCB_REQUIRE(n == 0 || d_rows, SCB_E_NULL, "scb_render_expected_rows: NULL rows");
+    return render_expected_strided(geom, n, 5, d_rows, d_rows + 1, d_rows + 2, d_weight, d_sat, d_box, d_inv_scale,
+                                   d_slot_of_key, d_out, out_type, accumulate, d_workspace, workspace_bytes, d_errors,
+                                   stream);
 }

@@ -10,6 +10,13 @@
 
 void scb_set_error(const char *fmt, ...);
 
+// particles.cu: emission / bleaching over coordinate arrays (stride 1) or particle rows (stride 5)
+int scb_emit_bleach_strided(uint64_t seed, int64_t n, const double *d_depth, const double *d_x, const double *d_y,
+                            const double *d_p_state, const int32_t *d_mol_slot, const int64_t *d_mol_id,
+                            const double *d_mol_id_column, int64_t stride, double unit_time, double focal_depth,
+                            const scb_photophysics *phys, double *d_budget, double *d_weight,
+                            double *d_true_data, void *stream);
+
 #define SCB_REQUIRE(cond, code, ...)            \
     do {                                        \
         if (!(cond)) {                          \

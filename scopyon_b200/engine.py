@@ -388,8 +388,7 @@ class DeviceEngine:
         stream = self._stream()
         focal = cfg.detector_focal_point
         true_dev, true_ids = None, None
-        soa = torch.empty((4, total), dtype=torch.float64, device=self.device)     # depth, x, y, p_state
-        rows_dev = torch.empty((total, 5), dtype=torch.float64, device=self.device)
+        rows_dev = torch.empty((total, 5), dtype=torch.float64, device=self.device)   # particle rows as given
         weight = torch.empty(total, dtype=torch.float64, device=self.device)
         self._stage_turn = getattr(self, "_stage_turn", 0) ^ 1     # this frame's staging area (see _h2d_stage)
         all_ids = self._ids_of(snapshots)
@@ -409,40 +408,46 @@ class DeviceEngine:
         for (unit_time, particles), n in zip(snapshots, sizes):
             if n == 0:
                 continue
-            particles = numpy.asarray(particles, dtype=numpy.float64)
             ids = all_ids[offset: offset + n]
-            order, rounds, slots_dev, ids_dev = None, [(0, n)], None, None
+            order, rounds, slots_dev = None, [(0, n)], None
             if table_ids is not None:
-                order, rounds, slots_dev, ids_dev = self._molecule_slots(table_ids, ids)
+                order, rounds, slots_dev, _ = self._molecule_slots(table_ids, ids)
+            # rows go up as they are: straight from the caller's array when that is page-locked
+            # (base.__format_data allocates it so), else through a pinned staging copy
+            host = None
+            if order is None and isinstance(particles, numpy.ndarray) and particles.dtype == numpy.float64 \
+                    and particles.flags.c_contiguous:
+                host = torch.from_numpy(particles.view(numpy.ndarray))
+                if not host.is_pinned():
+                    host = None
+            if host is None:
+                particles = numpy.asarray(particles, dtype=numpy.float64)
                 if order is not None:
                     particles = particles[order]
-            # rows go up as they are (one memcpy into pinned memory, one DMA); the transpose to
-            # SoA (depth, x, y, p_state) happens on the device
-            stage = self._h2d_stage(total)
-            numpy.copyto(stage.numpy()[offset: offset + n], particles)
-            rows_dev[offset: offset + n].copy_(stage[offset: offset + n], non_blocking=True)
+                host = self._h2d_stage(total)[offset: offset + n]
+                numpy.copyto(host.numpy(), particles)
+            rows_dev[offset: offset + n].copy_(host, non_blocking=True)
             if not all_resident:
-                keys.append(depth_keys_of(particles[:, 0] - focal[0], cfg.depth_cutoff, self.geom.n_depth_keys))
-            soa[:, offset: offset + n].copy_(rows_dev[offset: offset + n, self._soa_cols].t())
+                keys.append(depth_keys_of(numpy.asarray(particles)[:, 0] - focal[0], cfg.depth_cutoff,
+                                          self.geom.n_depth_keys))
             for lo, hi in rounds:
-                sl = slice(offset + lo, offset + hi)
                 self._call(
-                    "scb_emit_bleach", states.seed if states is not None else 0, hi - lo,
-                    _native.ptr(soa[0, sl]), _native.ptr(soa[1, sl]), _native.ptr(soa[2, sl]),
-                    _native.ptr(soa[3, sl]),
+                    "scb_emit_bleach_rows", states.seed if states is not None else 0, hi - lo,
+                    _native.ptr(rows_dev[offset + lo: offset + hi]),
                     None if slots_dev is None else _native.ptr(slots_dev[lo:hi]),
-                    None if ids_dev is None else _native.ptr(ids_dev[lo:hi]),
                     float(unit_time), float(focal[0]), ctypes.byref(self.phys),
                     None if states is None else _native.ptr(states.budget),
-                    _native.ptr(weight[sl]), None if true_dev is None else _native.ptr(true_dev), stream)
+                    _native.ptr(weight[offset + lo: offset + hi]),
+                    None if true_dev is None else _native.ptr(true_dev), stream)
             offset += n
 
         if self.gaussian_tc:
             need = self.lib.scb_gaussian_tc_workspace_bytes(ctypes.byref(self.geom), total)
             if self._workspace is None or self._workspace.numel() < need:
                 self._workspace = torch.empty(int(need * 1.25) + 256, dtype=torch.uint8, device=self.device)
+            xy = rows_dev[:, 1:3].t().contiguous()
             self._call(
-                "scb_render_gaussian_tc", ctypes.byref(self.geom), total, _native.ptr(soa[1]), _native.ptr(soa[2]),
+                "scb_render_gaussian_tc", ctypes.byref(self.geom), total, _native.ptr(xy[0]), _native.ptr(xy[1]),
                 _native.ptr(weight), _native.ptr(self.gaussian_prefix), _native.ptr(out),
                 _native.F32 if out.dtype == torch.float32 else _native.F64, 0, _native.ptr(self._workspace),
                 self._workspace.numel(), _native.ptr(self.errors), stream)
@@ -455,8 +460,12 @@ class DeviceEngine:
             else:
                 self.ensure_tables(needed)
         if not self.gaussian_tc:
-            self._render_sat(soa, weight, total, out, stream)
-
+            work = self._render_workspace(total)
+            self._call(
+                "scb_render_expected_rows", ctypes.byref(self.geom), total, _native.ptr(rows_dev), _native.ptr(weight),
+                _native.ptr(self.sat), _native.ptr(self.box), _native.ptr(self.inv_scale), _native.ptr(self.slot_of_key),
+                _native.ptr(out), _native.F32 if out.dtype == torch.float32 else _native.F64, 0,
+                _native.ptr(work), work.numel(), _native.ptr(self.errors), stream)
 
         if self._defer_true_data:
             return out, (true_dev, true_ids) if want_true_data else None
@@ -466,15 +475,21 @@ class DeviceEngine:
         return out, true_data
 
     def _ids_of(self, snapshots):
-        """int64 molecule ids of all snapshot rows; reuses the previous frame's conversion when
-        the (float) id columns are unchanged."""
-        cols = [numpy.asarray(p)[:, 3] for _, p in snapshots]
+        """int64 molecule ids of all snapshot rows.  Rows formatted by the facade carry them as a
+        contiguous column (``ParticleRows.ids``); consecutive frames usually show the same ids, in
+        which case the previous frame's array object is handed out again (the slot cache keys on it)."""
+        cols = []
+        for _, p in snapshots:
+            ids = getattr(p, "ids", None)
+            if ids is None or len(ids) != len(p):
+                ids = numpy.ascontiguousarray(numpy.asarray(p)[:, 3]).astype(numpy.int64)
+            cols.append(ids)
         cache = getattr(self, "_ids_cache", None)
         if cache is not None and len(cache[0]) == len(cols) and all(
-                a.shape == b.shape and numpy.array_equal(a, b) for a, b in zip(cache[0], cols)):
+                a is b or (a.shape == b.shape and numpy.array_equal(a, b)) for a, b in zip(cache[0], cols)):
             return cache[1]
-        ids = numpy.concatenate([c.astype(numpy.int64) for c in cols]) if cols else numpy.zeros(0, numpy.int64)
-        self._ids_cache = ([c.copy() for c in cols], ids)
+        ids = numpy.concatenate(cols) if cols else numpy.zeros(0, numpy.int64)
+        self._ids_cache = (cols, ids)
         return ids
 
     def _render_sat(self, soa, weight, total, out, stream):
