@@ -6,9 +6,9 @@ Workload (config.workload = "C4"): EPI 3-D movie, 1e5 molecules diffusing in
 16-bit ADC, offset 100, full well 30 000, column FPN 2 counts), photobleaching on,
 one snapshot per 33 ms frame.
 
-One "step" = one block of --frames-per-step frames: emission/bleaching -> tile binning
+One "step" = one block of --frames-per-step frames: emission/bleaching -> strip binning
 -> PSF render -> detector/ADC -> Brownian step, everything resident in HBM (9 kernels per
-frame: emit_bleach, spot_prepare, spot_edges, tile_scan, tile_fill, render_tiles,
+frame: emit_bleach, spot_prepare, spot_edges, tile_scan, strip_fill, render_strips,
 detector_fast, detector_slow, diffuse).  With N GPUs
 the movie is partitioned by frame blocks (weak scaling: every rank renders the same
 number of frames per step; a rank first replays the trajectory prefix of the frames
@@ -52,7 +52,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--frames-per-step", type=int, default=8)
+    ap.add_argument("--frames-per-step", type=int, default=32)
     ap.add_argument("--molecules", type=int, default=100000)
     ap.add_argument("--size", type=int, default=2048)
     ap.add_argument("--e2e-frames", type=int, default=24)
@@ -76,7 +76,9 @@ def box(size):
 
 # --------------------------------------------------------------------------- clocks
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled during the timed region."""
+    """SM clock + throttle reasons sampled DURING the timed region: NVML polled every few
+    milliseconds from a thread (the timed region lasts tens of milliseconds, too short for
+    `nvidia-smi -lms`); `nvidia-smi` is the fallback when NVML cannot be loaded."""
 
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -84,25 +86,71 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index = index
-        self.rows = []
+        self.samples = []          # (sm_mhz, reasons bitmask)
+        self.sm_max = None
         self.proc = None
+        self.thread = None
+        self.running = False
+        self.nvml = None
 
     def start(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            # torch's device index follows CUDA_VISIBLE_DEVICES; resolve it through the PCI bus id
+            import torch
+            bus = torch.cuda.get_device_properties(self.index).pci_bus_id
+            dom = torch.cuda.get_device_properties(self.index).pci_domain_id
+            dev = torch.cuda.get_device_properties(self.index).pci_device_id
+            handle = pynvml.nvmlDeviceGetHandleByPciBusId("{:08x}:{:02x}:{:02x}.0".format(dom, bus, dev).encode())
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = (pynvml, handle)
+            self.running = True
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:      # noqa: BLE001 -- any NVML problem: fall back to the CLI
+            self.nvml = None
+        try:
+            self.rows = []
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
         except OSError:
             self.proc = None
 
+    def _poll(self):
+        pynvml, handle = self.nvml
+        while self.running:
+            try:
+                sm = float(pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM))
+                try:
+                    reasons = int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(handle))
+                except AttributeError:
+                    reasons = int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(handle))
+                self.samples.append((sm, reasons))
+            except Exception:      # noqa: BLE001
+                pass
+            time.sleep(0.002)
+
     def _pump(self):
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
     def stop(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        if self.nvml is not None:
+            self.running = False
+            self.thread.join(timeout=2)
+            pynvml, _ = self.nvml
+            bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+            reasons = sorted(n for n in names if any(r & bits[n] for _, r in self.samples))
+            sm = [v for v, _ in self.samples]
+            return {"sm_mhz": float(numpy.median(sm)) if sm else None, "sm_max_mhz": self.sm_max,
+                    "samples": len(sm), "reasons": reasons, "source": "nvml, 2 ms period over the timed region"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -111,7 +159,6 @@ class ClockSampler:
         except subprocess.TimeoutExpired:
             self.proc.kill()
         sm, smax, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for row in self.rows:
             cells = [c.strip() for c in row.split(",")]
             if len(cells) < 7:
@@ -126,7 +173,7 @@ class ClockSampler:
                     reasons.add(name)
         return {"sm_mhz": float(numpy.median(sm)) if sm else None,
                 "sm_max_mhz": float(max(smax)) if smax else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi -lms 20"}
 
 
 # --------------------------------------------------------------------------- work counting
@@ -240,7 +287,8 @@ def workload_config(args):
                         "photobleaching on, 1 snapshot/frame".format(args.molecules, args.size, args.size),
             "frames_per_step": args.frames_per_step, "molecules": args.molecules,
             "image_size": [args.size, args.size], "parallelism": "frame-blocks x{}".format(args.gpus),
-            "cache": "per-frame working set (32 GB of PSF tables, random gathers) exceeds the 126 MB L2"}
+            "cache": "per-frame working set (35 GB of PSF box tables read at random, ~0.8 GB per frame) "
+                     "exceeds the 126 MB L2"}
 
 
 # --------------------------------------------------------------------------- GPU arm
@@ -323,8 +371,10 @@ def run_ours(args):
         traffic = None
         traffic_path = os.path.join(ROOT, "profiles", "traffic_r1.json")
         if os.path.exists(traffic_path) and args.molecules == 100000 and args.size == 2048:
-            traffic = json.load(open(traffic_path)).get("render_tiles_kernel<float>", {}).get("dram_bytes_per_launch")
-        achieved = evals * 8.5 / (per_launch_ms * 1e-3) / 1e9
+            traffic = json.load(open(traffic_path)).get("render_strips_kernel<float>", {}).get("dram_bytes_per_launch")
+        # algorithmic bytes: one 8-byte box-table value per spot-pixel eval
+        bytes_per_eval = 8.0
+        achieved = evals * bytes_per_eval / (per_launch_ms * 1e-3) / 1e9
         line = {
             "metric": "frames/sec (2048^2 sCMOS, 1e5 spots)", "value": value, "unit": "frames/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": elapsed_ms / K,
@@ -332,10 +382,11 @@ def run_ours(args):
             "data": "synthetic", "config": workload_config(args),
             "clocks": clocks, "e2e": e2e, "gpu_launches": 9 * F * K,
             "roofline": {
-                "kernel": "render_tiles_kernel<float>", "bound": "hbm", "achieved": achieved, "peak": peak,
+                "kernel": "render_strips_kernel<float>", "bound": "hbm", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
-                "algorithmic_bytes_per_launch": evals * 8.5, "spot_pixel_evals_per_launch": evals,
+                "algorithmic_bytes_per_launch": evals * bytes_per_eval, "bytes_per_spot_pixel_eval": bytes_per_eval,
+                "spot_pixel_evals_per_launch": evals,
                 "spot_pixel_evals_per_s": evals / (per_launch_ms * 1e-3), "ms_per_launch": per_launch_ms,
                 "share_of_step": render_ms.value / elapsed_ms,
             },

@@ -19,7 +19,7 @@ struct __align__(16) SpotRec {
     // along an axis share one phase and occupy consecutive slots, edge e at slot0 + e (slot -1 =
     // the zero sample before the table).  phase | (slot0 + 1) << 16, or -1 when irregular.
     int row_run, col_run;
-    int pad;
+    int walk;           // 1: spot_edges_kernel must walk this footprint's edges (irregular, or no box-table path)
 };
 
 struct Geo {
@@ -29,6 +29,7 @@ struct Geo {
     int stripes;        // copies of the per-tile counters (power of two): spreads the census atomics
     uint32_t modulus_magic;   // ceil(2^32 / modulus): b / modulus == umulhi(b, magic) for b < 2^16
     int special_edges;  // 1: column edges carry kEdgeZero / last-column codes (SAT render); 0: plain
+    int quick_runs;     // 1: spot_prepare may prove an axis regular from its two end edges (box-table path available)
     int side;           // table samples per axis (2*(n_radial-1)+1)
     int n_depth_keys;
     int modulus, slots;           // SAT block layout (scb_common.cuh): phases per axis, slots per phase
@@ -65,6 +66,44 @@ __device__ __forceinline__ int overlap_entries(const Geo &g, int jmin, int jmax,
     return (c_hi - c_lo + g.chunk - 1) / g.chunk;
 }
 
+// Unclamped ceil((i*pl - o)/res) when it is safely away from a rounding decision (|distance to
+// an integer| > 1e-9 samples, far above the ~1e-12 the evaluation order can move it); false otherwise.
+__device__ __forceinline__ bool safe_edge(int i, double o, const Geo &g, int &c) {
+    const double q = __dmul_rn(__dsub_rn(__dmul_rn((double)i, g.pl), o), g.inv_res);
+    const double up = ceil(q);
+    c = (int)up;
+    return fabs(q) < 1.0e6 && up - q > 1e-9 && q - (up - 1.0) > 1e-9;
+}
+
+// Regularity of one axis from its two end edges.  The exact edge positions are linear in the
+// pixel index, (i*pl - o)/res = q0 + k*(pl/res), so if the ceilings of the first and the last
+// edge differ by exactly (n-1)*M -- both evaluated safely away from an integer -- every edge in
+// between has ceiling c0 + k*M (the fractional parts move monotonically between the two ends).
+// Returns the run code (phase | (slot0 + 1) << 16) or -1 when the edges must be walked.
+__device__ __forceinline__ int quick_run(int first, int last, double o, const Geo &g) {
+    const int n = last - first + 1;                 // edges
+    int c0, cl;
+    if (n < 2 || !safe_edge(first, o, g, c0) || !safe_edge(last, o, g, cl)) return -1;
+    if (cl - c0 != (n - 1) * g.modulus) return -1;
+    // interior edges only between an optional opening edge at sample 0 and an optional closing edge at `side`
+    int lead = c0;                                  // first edge that lies inside the table
+    int slot_shift = 0;
+    if (c0 <= 0) {
+        lead = c0 + g.modulus;
+        slot_shift = 1;
+        if (lead <= 0) return -1;
+    }
+    if (lead >= g.side) return -1;                  // nothing interior
+    const int before_last = c0 + (n - 2) * g.modulus;
+    if (cl >= g.side && (before_last >= g.side || before_last <= 0)) return -1;   // closing edge needs an interior predecessor
+    if (before_last >= g.side) return -1;
+    const int slot = g.modulus > 1 ? (int)__umulhi((uint32_t)lead, g.modulus_magic) : lead;
+    const int phase = lead - slot * g.modulus;
+    const int slot0 = slot - slot_shift;            // slot of edge 0 (-1: the zero sample before the table)
+    if (slot0 + n - 1 >= g.slots) return -1;
+    return phase | (slot0 + 1) << 16;
+}
+
 __device__ __forceinline__ int stripe_of(const Geo &g, int64_t spot) { return (int)(spot >> 5) & (g.stripes - 1); }
 
 // One thread per spot: footprint, depth key, tile census.
@@ -79,7 +118,7 @@ spot_prepare_kernel(Geo g, int64_t n, int64_t stride, const double *__restrict__
     rec.slot = -1;
     rec.imin = rec.imax = rec.jmin = rec.jmax = 0;
     rec.ox = rec.oy = rec.w = 0.0;
-    rec.pad = 0;
+    rec.walk = 0;
     rec.row_run = rec.col_run = -1;
     double w_seen = 0.0;
     if (s < n) {
@@ -114,6 +153,11 @@ spot_prepare_kernel(Geo g, int64_t n, int64_t stride, const double *__restrict__
                     rec.slot = slot;
                     rec.w = inv_scale ? w * (g.res * g.res) * inv_scale[slot] : w;
                     w_seen = w;
+                    if (g.quick_runs) {
+                        rec.row_run = quick_run(rec.imin, rec.imax, rec.ox, g);
+                        rec.col_run = quick_run(rec.jmin, rec.jmax, rec.oy, g);
+                    }
+                    rec.walk = rec.row_run < 0 || rec.col_run < 0;
                     // census: the counters exist in `stripes` copies (one per group of 32 spots,
                     // round robin) so that the atomics of a frame spread over more L2 sectors
                     int *count = tile_count + (size_t)stripe_of(g, s) * g.nti * g.ntj;
@@ -159,7 +203,7 @@ spot_edges_kernel(Geo g, int64_t n, SpotRec *__restrict__ spots, uint32_t *__res
     const int axis = (int)(t & 1);
     if (s >= n) return;
     const SpotRec rec = spots[s];
-    if (rec.slot < 0) return;
+    if (rec.slot < 0 || !rec.walk) return;
     const int first = axis ? rec.jmin : rec.imin, last = axis ? rec.jmax : rec.imax;
     const double o = axis ? rec.oy : rec.ox;
     uint32_t *out = edges + (s * 2 + axis) * edge_cap;
@@ -233,10 +277,18 @@ tile_scan_kernel(int n_tiles, int stripes, const int *__restrict__ tile_count, i
     const int share = rounds * 1024;
     const int first = (int)cluster.block_rank() * share;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int carry = 0;
-    for (int r = 0; r < rounds; ++r) {
+    // all of this thread's entries are fetched first (independent loads): up to kScanRounds rounds
+    // live in registers, longer lists fall back to loading round by round
+    constexpr int kScanRounds = 8;
+    int held[kScanRounds];
+#pragma unroll
+    for (int r = 0; r < kScanRounds; ++r) {
         const int j = first + r * 1024 + threadIdx.x;
-        const int v = j < n ? tile_count[(size_t)(j & mask) * n_tiles + (j >> shift)] : 0;
+        held[r] = (r < rounds && j < n) ? tile_count[(size_t)(j & mask) * n_tiles + (j >> shift)] : 0;
+    }
+    int carry = 0;
+    auto scan_round = [&](int r, int v) {
+        const int j = first + r * 1024 + threadIdx.x;
         int incl = v;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -255,6 +307,13 @@ tile_scan_kernel(int n_tiles, int stripes, const int *__restrict__ tile_count, i
         if (j < n) tile_start[j] = carry + before + incl - v;
         carry += all;
         __syncthreads();
+    };
+#pragma unroll
+    for (int r = 0; r < kScanRounds; ++r)
+        if (r < rounds) scan_round(r, held[r]);
+    for (int r = kScanRounds; r < rounds; ++r) {
+        const int j = first + r * 1024 + threadIdx.x;
+        scan_round(r, j < n ? tile_count[(size_t)(j & mask) * n_tiles + (j >> shift)] : 0);
     }
     if (threadIdx.x == 0) cta_total = carry;
     cluster.sync();
@@ -308,6 +367,7 @@ inline size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
 Geo make_geo(const scb_geometry *geom, int tile_h, int tile_w, int chunk = 0) {
     Geo g;
     g.special_edges = 0;
+    g.quick_runs = 0;
     g.tile_h = tile_h; g.tile_w = tile_w; g.chunk = chunk;
     g.n_w = geom->n_w; g.n_h = geom->n_h;
     g.nti = (geom->n_w + tile_h - 1) / tile_h;

@@ -341,15 +341,17 @@ extern "C" int scb_profile_end(double *total_ms, int64_t *launches) {
 constexpr size_t kWarpSmemBytes = (kStripRows * kStripCols + kStages * kStageEntries) * 8 + kBatch * sizeof(Unit) + kStages * 8;
 static_assert(2 * kMaxWarps * kWarpSmemBytes + 2048 <= 232448, "two CTAs per SM must fit in shared memory");
 
-static Geo strip_geo(const scb_geometry *geom) {
+static Geo strip_geo(const scb_geometry *geom, bool have_box) {
     Geo g = make_geo(geom, kStripRows, kStripCols, kUnitCols);
     g.special_edges = 1;
+    // with a box table and block rows the TMA ring can hold, evenly spaced footprints never read their edges
+    g.quick_runs = have_box && g.slots <= kFastSlots;
     return g;
 }
 
 extern "C" size_t scb_render_workspace_bytes(const scb_geometry *geom, int64_t n_spots) {
     if (check_geometry(geom) != 0 || n_spots < 0) return 0;
-    Geo g = strip_geo(geom);
+    Geo g = strip_geo(geom, false);
     return carve(g, n_spots, nullptr, sizeof(Unit)).bytes;
 }
 
@@ -389,7 +391,7 @@ static int render_expected_strided(const scb_geometry *geom, int64_t n_spots, in
     SCB_REQUIRE(n_spots == 0 || (d_depth && d_x && d_y && d_weight && d_sat && d_inv_scale && d_slot_of_key),
                 SCB_E_NULL, "scb_render_expected: NULL spot/table pointer");
     SCB_REQUIRE(out_type == SCB_F32 || out_type == SCB_F64, SCB_E_INVALID, "out_type=%d", out_type);
-    Geo g = strip_geo(geom);
+    Geo g = strip_geo(geom, d_box != nullptr);
     Workspace w = carve(g, n_spots, d_workspace, sizeof(Unit));
     SCB_REQUIRE(workspace_bytes >= w.bytes, SCB_E_WORKSPACE, "scb_render_expected: workspace %zu < %zu",
                 workspace_bytes, w.bytes);

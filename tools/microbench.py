@@ -4,7 +4,7 @@
 
 Prints one JSON object per measurement: achieved GB/s against the algorithmic bytes of
 SURVEY.md section 8(d) (8 B per pixel-frame for noise+ADC, 48 B per particle-step fp64
-diffusion, 8.5 B per spot-pixel eval for the SAT render)."""
+diffusion, 8 B per spot-pixel eval for the render)."""
 import ctypes
 import json
 import os
@@ -119,7 +119,7 @@ def bench_render():
         evals = count_spot_pixel_evals(data, size, pl)
         print(json.dumps({"kernel": "scb_render_expected (prepare+scan+fill+render)", "size": size, "spots": n,
                           "3d": three_d, "ms": ms, "ms_best": best, "evals": evals, "evals/s": evals / (ms * 1e-3),
-                          "GB/s_algorithmic": evals * 8.5 / (ms * 1e-3) / 1e9, "tables": eng.n_tables,
+                          "GB/s_algorithmic": evals * 8.0 / (ms * 1e-3) / 1e9, "tables": eng.n_tables,
                           "table_build_s": build_s, "errors": int(eng.errors.item())}))
 
 
