@@ -135,15 +135,17 @@ size_t scb_psf_sat_workspace_bytes(int n_radial, int n_keys);
  * one B x B block: contiguous B*8-byte rows (two 128-byte lines for B = 32) that the render
  * kernel moves with TMA bulk copies (M = 1 is the plain row-major layout).
  * d_sat[n_keys][scb_psf_sat_table_entries()] (int64), d_inv_scale[n_keys] = 1/scale_k.
- * d_box (optional, same shape, fp64): the "box table" -- entry (r, c) of block (pr, pc) is
- * (double) of the box sum between slots (r-1, r) x (c-1, c) of that block (slot -1 = 0), i.e. the
- * integrated PSF of one pixel for a footprint whose pixel edges have phases (pr, pc).  The
- * render kernel reads it for footprints with evenly spaced edges (whole-nanometre pixel pitch);
- * all other footprints are summed from d_sat.  Both give bit-identical pixel values. */
+ * d_box (optional, same shape, box_type SCB_F64 or SCB_F32): the "box table" -- entry (r, c) of
+ * block (pr, pc) is the box sum between slots (r-1, r) x (c-1, c) of that block (slot -1 = 0)
+ * rounded to box_type, i.e. the integrated PSF of one pixel for a footprint whose pixel edges
+ * have phases (pr, pc).  The render kernel reads it for footprints with evenly spaced edges
+ * (whole-nanometre pixel pitch); all other footprints are summed from d_sat and rounded the
+ * same way, so both give bit-identical pixel values.  SCB_F32 halves the table and the DRAM
+ * traffic of the render at 6e-8 relative accuracy per pixel (meant for SCB_F32 frames). */
 int64_t scb_psf_sat_table_entries(int n_radial, int sat_modulus);
 int scb_psf_sat_slots(int n_radial, int sat_modulus);
 int scb_psf_sat_build(const double *d_radial, int n_radial, int n_keys, int sat_modulus,
-                      int64_t *d_sat, double *d_box, double *d_inv_scale,
+                      int64_t *d_sat, void *d_box, int box_type, double *d_inv_scale,
                       void *d_workspace, size_t workspace_bytes, void *stream);
 
 /* ---- particles --------------------------------------------------------------- */
@@ -227,7 +229,7 @@ size_t scb_render_workspace_bytes(const scb_geometry *geom, int64_t n_spots);
 int scb_render_expected(const scb_geometry *geom, int64_t n_spots,
                         const double *d_depth, const double *d_x, const double *d_y,
                         const double *d_weight,
-                        const int64_t *d_sat, const double *d_box, const double *d_inv_scale,
+                        const int64_t *d_sat, const void *d_box, int box_type, const double *d_inv_scale,
                         const int32_t *d_slot_of_key,
                         void *d_out, int out_type, int accumulate,
                         void *d_workspace, size_t workspace_bytes,
@@ -243,7 +245,7 @@ int scb_emit_bleach_rows(uint64_t budget_seed, int64_t n, const double *d_rows,
                          const scb_photophysics *phys, double *d_budget, double *d_weight,
                          double *d_true_data, void *stream);
 int scb_render_expected_rows(const scb_geometry *geom, int64_t n, const double *d_rows,
-                             const double *d_weight, const int64_t *d_sat, const double *d_box,
+                             const double *d_weight, const int64_t *d_sat, const void *d_box, int box_type,
                              const double *d_inv_scale, const int32_t *d_slot_of_key, void *d_out,
                              int out_type, int accumulate, void *d_workspace, size_t workspace_bytes,
                              int32_t *d_errors, void *stream);

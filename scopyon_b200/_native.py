@@ -66,7 +66,8 @@ SIGNATURES = {
     "scb_psf_sat_table_entries": (ctypes.c_int64, [ctypes.c_int, ctypes.c_int]),
     "scb_psf_sat_slots": (ctypes.c_int, [ctypes.c_int, ctypes.c_int]),
     "scb_psf_sat_build": (ctypes.c_int, [
-        c_ptr, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_ptr, c_ptr, c_ptr, c_ptr, ctypes.c_size_t, c_ptr]),
+        c_ptr, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_ptr, c_ptr, ctypes.c_int, c_ptr, c_ptr, ctypes.c_size_t,
+        c_ptr]),
     "scb_diffuse": (ctypes.c_int, [
         ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int, ctypes.c_int64, ctypes.c_int64,
         c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, ctypes.POINTER(ctypes.c_double),
@@ -86,13 +87,13 @@ SIGNATURES = {
         ctypes.POINTER(Photophysics), c_ptr, c_ptr]),
     "scb_render_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(Geometry), ctypes.c_int64]),
     "scb_render_expected": (ctypes.c_int, [
-        ctypes.POINTER(Geometry), ctypes.c_int64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
+        ctypes.POINTER(Geometry), ctypes.c_int64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, ctypes.c_int, c_ptr, c_ptr,
         c_ptr, ctypes.c_int, ctypes.c_int, c_ptr, ctypes.c_size_t, c_ptr, c_ptr]),
     "scb_emit_bleach_rows": (ctypes.c_int, [
         ctypes.c_uint64, ctypes.c_int64, c_ptr, c_ptr, ctypes.c_double, ctypes.c_double,
         ctypes.POINTER(Photophysics), c_ptr, c_ptr, c_ptr, c_ptr]),
     "scb_render_expected_rows": (ctypes.c_int, [
-        ctypes.POINTER(Geometry), ctypes.c_int64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
+        ctypes.POINTER(Geometry), ctypes.c_int64, c_ptr, c_ptr, c_ptr, c_ptr, ctypes.c_int, c_ptr, c_ptr, c_ptr,
         ctypes.c_int, ctypes.c_int, c_ptr, ctypes.c_size_t, c_ptr, c_ptr]),
     "scb_gaussian_tc_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(Geometry), ctypes.c_int64]),
     "scb_render_gaussian_tc": (ctypes.c_int, [

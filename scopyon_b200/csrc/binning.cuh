@@ -286,7 +286,28 @@ tile_scan_kernel(int n_tiles, int stripes, const int *__restrict__ tile_count, i
         const int j = first + r * 1024 + threadIdx.x;
         held[r] = (r < rounds && j < n) ? tile_count[(size_t)(j & mask) * n_tiles + (j >> shift)] : 0;
     }
+    // CTA total first (one block reduction), so that every CTA knows its offset before it writes
+    int mine = 0;
+#pragma unroll
+    for (int r = 0; r < kScanRounds; ++r) mine += held[r];
+    for (int r = kScanRounds; r < rounds; ++r) {
+        const int j = first + r * 1024 + threadIdx.x;
+        if (j < n) mine += tile_count[(size_t)(j & mask) * n_tiles + (j >> shift)];
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, d);
+    if (lane == 0) warp_tot[warp] = mine;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < 32; ++w) t += warp_tot[w];
+        cta_total = t;
+    }
+    cluster.sync();
     int carry = 0;
+    for (unsigned c = 0; c < cluster.block_rank(); ++c) carry += *cluster.map_shared_rank(&cta_total, c);
+    if (cluster.block_rank() == kScanCtas - 1 && threadIdx.x == 0) tile_start[n] = carry + cta_total;
+
     auto scan_round = [&](int r, int v) {
         const int j = first + r * 1024 + threadIdx.x;
         int incl = v;
@@ -295,6 +316,7 @@ tile_scan_kernel(int n_tiles, int stripes, const int *__restrict__ tile_count, i
             const int up = __shfl_up_sync(0xffffffffu, incl, d);
             if (lane >= d) incl += up;
         }
+        __syncthreads();                      // warp_tot of the previous round (or of the reduction) has been read
         if (lane == 31) warp_tot[warp] = incl;
         __syncthreads();
         int before = 0, all = 0;
@@ -306,7 +328,6 @@ tile_scan_kernel(int n_tiles, int stripes, const int *__restrict__ tile_count, i
         }
         if (j < n) tile_start[j] = carry + before + incl - v;
         carry += all;
-        __syncthreads();
     };
 #pragma unroll
     for (int r = 0; r < kScanRounds; ++r)
@@ -315,16 +336,6 @@ tile_scan_kernel(int n_tiles, int stripes, const int *__restrict__ tile_count, i
         const int j = first + r * 1024 + threadIdx.x;
         scan_round(r, j < n ? tile_count[(size_t)(j & mask) * n_tiles + (j >> shift)] : 0);
     }
-    if (threadIdx.x == 0) cta_total = carry;
-    cluster.sync();
-    int offset = 0;
-    for (unsigned c = 0; c < cluster.block_rank(); ++c) offset += *cluster.map_shared_rank(&cta_total, c);
-    if (offset)
-        for (int r = 0; r < rounds; ++r) {
-            const int j = first + r * 1024 + threadIdx.x;
-            if (j < n) tile_start[j] += offset;
-        }
-    if (cluster.block_rank() == kScanCtas - 1 && threadIdx.x == 0) tile_start[n] = offset + carry;
     cluster.sync();      // keep cta_total alive until every CTA has read it
 }
 

@@ -248,8 +248,8 @@ __global__ void sat_cols_kernel(int cols, int n_keys, int64_t *__restrict__ plai
 // edge phases (pr, pc) multiplies by its weight.  A footprint whose edges are evenly spaced
 // reads one dense rectangle of one box block and never touches the SAT itself.
 __global__ void __launch_bounds__(256)
-sat_blocks_kernel(const int64_t *__restrict__ plain, int64_t *__restrict__ sat, double *__restrict__ box,
-                  SatLayout L) {
+sat_blocks_kernel(const int64_t *__restrict__ plain, int64_t *__restrict__ sat, void *__restrict__ box,
+                  int box_type, SatLayout L) {
     const int cols = L.side + 1;
     const int block = blockIdx.x, key = blockIdx.y;
     const int pr = block / L.modulus, pc = block - pr * L.modulus;
@@ -265,7 +265,11 @@ sat_blocks_kernel(const int64_t *__restrict__ plain, int64_t *__restrict__ sat, 
         const int ir = e / L.slots, ic = e - ir * L.slots;
         const int64_t here = value(ir, ic);
         sat[at + e] = here;
-        if (box) box[at + e] = (double)((here - value(ir - 1, ic)) - (value(ir, ic - 1) - value(ir - 1, ic - 1)));
+        if (box) {
+            const int64_t sum = (here - value(ir - 1, ic)) - (value(ir, ic - 1) - value(ir - 1, ic - 1));
+            if (box_type == SCB_F32) static_cast<float *>(box)[at + e] = __ll2float_rn(sum);
+            else static_cast<double *>(box)[at + e] = __ll2double_rn(sum);
+        }
     }
 }
 
@@ -287,8 +291,10 @@ extern "C" size_t scb_psf_sat_workspace_bytes(int n_radial, int n_keys) {
 }
 
 extern "C" int scb_psf_sat_build(const double *d_radial, int n_radial, int n_keys, int sat_modulus,
-                                 int64_t *d_sat, double *d_box, double *d_inv_scale, void *d_workspace,
+                                 int64_t *d_sat, void *d_box, int box_type, double *d_inv_scale, void *d_workspace,
                                  size_t workspace_bytes, void *stream) {
+    SCB_REQUIRE(!d_box || box_type == SCB_F32 || box_type == SCB_F64, SCB_E_INVALID, "scb_psf_sat_build: box_type=%d",
+                box_type);
     SCB_REQUIRE(d_radial && d_sat && d_inv_scale && d_workspace, SCB_E_NULL,
                 "scb_psf_sat_build: NULL pointer");
     SCB_REQUIRE(n_radial >= 2 && n_radial <= 2048 && n_keys >= 1, SCB_E_INVALID,
@@ -316,7 +322,8 @@ extern "C" int scb_psf_sat_build(const double *d_radial, int n_radial, int n_key
         sat_cols_kernel<<<dim3((cols + 127) / 128, nb), 128, 0, s>>>(cols, nb, plain);
         sat_blocks_kernel<<<dim3(L.modulus * L.modulus, nb), 256, 0, s>>>(
             plain, d_sat + (size_t)first * L.table_entries(),
-            d_box ? d_box + (size_t)first * L.table_entries() : nullptr, L);
+            d_box ? (void *)((char *)d_box + (size_t)first * L.table_entries() * (box_type == SCB_F32 ? 4 : 8)) : nullptr,
+            box_type, L);
     }
     SCB_CUDA_LAUNCH_CHECK("scb_psf_sat_build");
     return 0;

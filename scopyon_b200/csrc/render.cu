@@ -9,8 +9,8 @@
 //     operations in the same order (explicit __d*_rn intrinsics: never contracted to FMA);
 //   * each slice sum is S[i1][j1] - S[i0][j1] - S[i1][j0] + S[i0][j0] on the int64 SAT
 //     built by scb_psf_sat_build -- exact, so results do not depend on how a footprint is cut;
-//   * one WARP owns one 8 x 128-pixel strip of the image and keeps its 1024 accumulators in
-//     shared memory.  The strip's work list holds one 32-byte unit per (spot, <=8 rows,
+//   * one WARP owns one 8 x 64-pixel strip of the image and keeps its 512 accumulators in
+//     shared memory (28 strips in flight per SM).  The strip's work list holds one 32-byte unit per (spot, <=8 rows,
 //     <=32 columns) overlap.  For a footprint whose pixel edges are evenly spaced (whole
 //     number of table samples per pixel) the box sums of all its pixels are one dense
 //     rectangle of one block of the "box table" (psf.cu), so a unit's (<= 8) x 32 values arrive
@@ -30,14 +30,17 @@
 namespace {
 
 constexpr int kStripRows = 8;         // pixel rows per strip
-constexpr int kStripCols = 128;       // pixel columns per strip
+constexpr int kStripCols = 64;        // pixel columns per strip
 constexpr int kUnitCols = 32;         // columns per unit = lanes
 constexpr int kMaxWarps = 7;          // warps (= strips in flight) per CTA
 constexpr int kBatch = 16;            // units fetched per round (one per lane of a half warp)
 constexpr int kEdges = kStripRows + 1;
-constexpr int kStages = 3;            // TMA ring depth
 constexpr int kFastSlots = 32;        // widest box-table block row the ring holds
 constexpr int kStageEntries = kStripRows * kFastSlots;
+// TMA ring depth: three stages (2 KB each of fp64 box values, 1 KB of fp32 ones)
+template <typename BoxT> constexpr int ring_stages() { return 3; }
+// CTAs per SM: shared memory per warp is 4 KB of accumulators + the ring + 0.5 KB of units
+template <typename BoxT> constexpr int ctas_per_sm() { return sizeof(BoxT) == 4 ? 4 : 3; }
 constexpr uint32_t kUnitFast = 0x80000000u;
 
 // One work-list entry: the overlap of a spot with (<= 8 rows) x (<= 32 columns) of a strip.
@@ -63,7 +66,7 @@ __device__ __forceinline__ int accumulator_shift(unsigned long long wmax_bits, i
 // One thread per spot: write the spot's units into the strips' list segments.
 __global__ void __launch_bounds__(256)
 strip_fill_kernel(Geo g, int64_t n, const SpotRec *__restrict__ spots, int edge_cap,
-                  const int64_t *__restrict__ sat, const double *__restrict__ box_table,
+                  const int64_t *__restrict__ sat, const void *__restrict__ box_table, int box_bytes,
                   const int *__restrict__ tile_start,
                   int *__restrict__ tile_cursor, const unsigned long long *__restrict__ wmax_bits,
                   Unit *__restrict__ units) {
@@ -74,12 +77,13 @@ strip_fill_kernel(Geo g, int64_t n, const SpotRec *__restrict__ spots, int edge_
     Unit u;
     u.ws = scalbn(rec.w, accumulator_shift(*wmax_bits, n));
     const size_t table_at = (size_t)rec.slot * ((size_t)g.modulus * g.modulus * g.slots * g.slots);
-    const bool fast = box_table && rec.row_run >= 0 && rec.col_run >= 0 && g.slots <= kFastSlots;
+    const bool fast = g.quick_runs && rec.row_run >= 0 && rec.col_run >= 0;   // quick_runs: a usable box table exists
     // edge e of a regular axis sits at slot slot0 + e (>= -1); the pixel between edges e and e + 1
     // is box-table row / column slot0 + e + 1
     const int row_slot0 = (rec.row_run >> 16) - 1, col_slot0 = (rec.col_run >> 16) - 1;
-    const double *block = box_table + table_at +
-                          ((size_t)(rec.row_run & 0xffff) * g.modulus + (rec.col_run & 0xffff)) * (size_t)(g.slots * g.slots);
+    const char *block = static_cast<const char *>(box_table) +
+                        (table_at + ((size_t)(rec.row_run & 0xffff) * g.modulus + (rec.col_run & 0xffff)) *
+                                        (size_t)(g.slots * g.slots)) * (size_t)box_bytes;
     const uint32_t ebase = (uint32_t)s * 2u * (uint32_t)edge_cap;
     const int stripe = stripe_of(g, s);
     int *cursor = tile_cursor + (size_t)stripe * g.nti * g.ntj;
@@ -101,7 +105,7 @@ strip_fill_kernel(Geo g, int64_t n, const SpotRec *__restrict__ spots, int edge_
                 u.shape = (uint32_t)rows | (uint32_t)min(g.chunk, c_hi - c) << 8 |
                           (uint32_t)(r_lo - ti * g.tile_h) << 16 | (uint32_t)(c - tj * g.tile_w) << 24;
                 if (fast) {
-                    u.src = block + (size_t)first_box_row * g.slots;
+                    u.src = block + (size_t)first_box_row * g.slots * (size_t)box_bytes;
                     u.extra = kUnitFast | (uint32_t)(col_slot0 + (c - rec.jmin) + 1);
                 } else {
                     u.src = sat + table_at;
@@ -141,7 +145,7 @@ __device__ __forceinline__ void tma_row(void *dst, const void *src, uint32_t byt
 }
 
 // Fast unit, producer side: one bulk copy of the unit's box-table rows (contiguous in the block).
-__device__ __forceinline__ void unit_stage(const Unit *meta, int u, int lane, double *stage, void *bar,
+__device__ __forceinline__ void unit_stage(const Unit *meta, int u, int lane, void *stage, void *bar,
                                            uint32_t row_bytes) {
     if (lane == 0) {
         const uint32_t bytes = (meta[u].shape & 0xffu) * row_bytes;
@@ -150,35 +154,43 @@ __device__ __forceinline__ void unit_stage(const Unit *meta, int u, int lane, do
     }
 }
 
+// box * weight -> accumulator LSBs, in the precision of the box table
+__device__ __forceinline__ long long to_fixed(double box, double ws) { return __double2ll_rn(__dmul_rn(box, ws)); }
+__device__ __forceinline__ long long to_fixed(float box, float ws) { return __float2ll_rn(__fmul_rn(box, ws)); }
+
 // Accumulator update shared by both paths.  Rows beyond the unit's last carry stale values:
 // their products are computed and dropped (only the update is predicated), which keeps the
 // loop branch free.  _epifm.py:280-282 (`if photons > 0` needs no branch: adding zero changes nothing)
-__device__ __forceinline__ void unit_add(long long *a, int rows, double ws, const double (&box)[kStripRows]) {
+template <typename BoxT>
+__device__ __forceinline__ void unit_add(long long *a, int rows, BoxT ws, const BoxT (&box)[kStripRows]) {
 #pragma unroll
     for (int k = 0; k < kStripRows; ++k) {
-        const long long q = __double2ll_rn(__dmul_rn(box[k], ws));
+        const long long q = to_fixed(box[k], ws);
         if (k < rows) a[k * kStripCols] += q;
     }
 }
 
 // Fast unit, consumer side: lane l reads its column of the staged box rows.
+template <typename BoxT, int SLOTS>
 __device__ __forceinline__ void unit_accumulate_fast(const Unit *meta, int u, int lane, long long *acc,
-                                                     const double *stage, int slots) {
-    const double ws = meta[u].ws;
+                                                     const BoxT *stage, int runtime_slots) {
+    const int slots = SLOTS ? SLOTS : runtime_slots;
+    const BoxT ws = (BoxT)meta[u].ws;
     const uint32_t shape = meta[u].shape;
     const int rows = (lane < (int)((shape >> 8) & 0xff)) ? (int)(shape & 0xff) : 0;   // idle lanes: no rows
     long long *a = acc + ((shape >> 16) & 0xff) * kStripCols + (shape >> 24) + lane;
-    const double *st = stage + min((int)(meta[u].extra & 0xffu) + lane, slots - 1);   // idle lanes stay inside the row
-    double box[kStripRows];
+    const BoxT *st = stage + min((int)(meta[u].extra & 0xffu) + lane, slots - 1);   // idle lanes stay inside the row
+    BoxT box[kStripRows];
 #pragma unroll
     for (int k = 0; k < kStripRows; ++k) box[k] = st[k * slots];
-    unit_add(a, rows, ws, box);
+    unit_add<BoxT>(a, rows, ws, box);
 }
 
 // Gather unit: per-edge table offsets from `edges`, corners straight from global memory.
+template <typename BoxT>
 __device__ __forceinline__ void unit_accumulate_gather(const Unit *meta, int u, int lane, long long *acc,
                                                        const uint32_t *__restrict__ edges) {
-    const double ws = meta[u].ws;
+    const BoxT ws = (BoxT)meta[u].ws;
     const uint32_t shape = meta[u].shape;
     const int n_rows = shape & 0xff, n_cols = (shape >> 8) & 0xff;
     const int rows = lane < n_cols ? n_rows : 0;
@@ -197,45 +209,52 @@ __device__ __forceinline__ void unit_accumulate_gather(const Unit *meta, int u, 
             if (!((row | right) & kEdgeZero)) R[k] = __ldg(table + (row + right));
         }
     }
-    double box[kStripRows];
+    BoxT box[kStripRows];
 #pragma unroll
-    for (int k = 0; k < kStripRows; ++k)    // >= 0: the table is non-negative, edges are monotone
-        box[k] = (double)((R[k + 1] - L[k + 1]) - (R[k] - L[k]));
-    unit_add(a, rows, ws, box);
+    for (int k = 0; k < kStripRows; ++k)    // >= 0: the table is non-negative, edges are monotone; rounded as the box table is
+        box[k] = (BoxT)((R[k + 1] - L[k + 1]) - (R[k] - L[k]));
+    unit_add<BoxT>(a, rows, ws, box);
 }
 
-template <typename OutT>
-__global__ void __launch_bounds__(kMaxWarps * 32, 2)
+template <typename BoxT>
+constexpr size_t warp_smem_bytes() {
+    return kStripRows * kStripCols * 8 + ring_stages<BoxT>() * kStageEntries * sizeof(BoxT) + kBatch * sizeof(Unit) + 32;
+}
+static_assert(ctas_per_sm<double>() * (kMaxWarps * warp_smem_bytes<double>() + 1024) <= 232448 &&
+                  ctas_per_sm<float>() * (kMaxWarps * warp_smem_bytes<float>() + 1024) <= 232448,
+              "the CTAs of one SM must fit in shared memory");
+
+template <typename OutT, typename BoxT, int SLOTS>
+__global__ void __launch_bounds__(kMaxWarps * 32, ctas_per_sm<BoxT>())
 render_strips_kernel(Geo g, const Unit *__restrict__ units, const uint32_t *__restrict__ edges,
                      const int *__restrict__ tile_start, int *__restrict__ next_tile,
                      const unsigned long long *__restrict__ wmax_bits, int64_t n_spots,
                      OutT *__restrict__ out, int accumulate) {
+    constexpr int kStages = ring_stages<BoxT>();
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // per-warp carve: accumulators | TMA ring | unit batch | mbarriers
-    long long *acc = reinterpret_cast<long long *>(smem_raw) + warp * (kStripRows * kStripCols);
-    double *ring = reinterpret_cast<double *>(smem_raw) + n_warps * (kStripRows * kStripCols) +
-                   warp * (kStages * kStageEntries);
-    Unit *meta = reinterpret_cast<Unit *>(reinterpret_cast<long long *>(smem_raw) +
-                                          n_warps * (kStripRows * kStripCols + kStages * kStageEntries)) + warp * kBatch;
-    unsigned long long *bars = reinterpret_cast<unsigned long long *>(
-        reinterpret_cast<Unit *>(reinterpret_cast<long long *>(smem_raw) +
-                                 n_warps * (kStripRows * kStripCols + kStages * kStageEntries)) + n_warps * kBatch) +
-        warp * kStages;
+    unsigned char *mine = smem_raw + warp * warp_smem_bytes<BoxT>();
+    long long *acc = reinterpret_cast<long long *>(mine);
+    BoxT *ring = reinterpret_cast<BoxT *>(mine + kStripRows * kStripCols * 8);
+    Unit *meta = reinterpret_cast<Unit *>(mine + kStripRows * kStripCols * 8 + kStages * kStageEntries * sizeof(BoxT));
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(meta + kBatch);
 
     const int n_tiles = g.nti * g.ntj;
-    const uint32_t row_bytes = (uint32_t)g.slots * 8u;
+    const int slots = SLOTS ? SLOTS : g.slots;
+    const uint32_t row_bytes = (uint32_t)slots * (uint32_t)sizeof(BoxT);
     const double lsb = scalbn(1.0, -accumulator_shift(*wmax_bits, n_spots));
 
     for (int i = lane; i < kStripRows * kStripCols; i += 32) acc[i] = 0;
-    for (int i = lane; i < kStages * kStageEntries; i += 32) ring[i] = 0.0;    // rows past a unit's last are read (and dropped)
+    for (int i = lane; i < kStages * kStageEntries; i += 32) ring[i] = (BoxT)0;   // rows past a unit's last are read (and dropped)
     if (lane == 0) {
         for (int st = 0; st < kStages; ++st) mbar_init(&bars[st], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // zeroed ring visible to the async proxy
     __syncwarp();
-    uint32_t produced = 0, consumed = 0;     // fast units staged / used so far (ring position and parity)
+    int p_stage = 0, c_stage = 0;            // ring positions of the producer and the consumer (fast units only)
+    uint32_t c_parity = 0;
 
     for (;;) {
         int tile = 0;
@@ -259,21 +278,19 @@ render_strips_kernel(Geo g, const Unit *__restrict__ units, const uint32_t *__re
 
             auto stage_unit = [&](int u) {
                 if (meta[u].extra & kUnitFast) {
-                    const uint32_t st = produced % kStages;
-                    unit_stage(meta, u, lane, ring + st * kStageEntries, &bars[st], row_bytes);
-                    ++produced;
+                    unit_stage(meta, u, lane, ring + p_stage * kStageEntries, &bars[p_stage], row_bytes);
+                    if (++p_stage == kStages) p_stage = 0;
                 }
             };
             for (int u = 0; u < min(nb, kStages - 1); ++u) stage_unit(u);
             for (int u = 0; u < nb; ++u) {
                 if (u + kStages - 1 < nb) stage_unit(u + kStages - 1);
                 if (meta[u].extra & kUnitFast) {
-                    const uint32_t st = consumed % kStages;
-                    mbar_wait(&bars[st], (consumed / kStages) & 1u);
-                    unit_accumulate_fast(meta, u, lane, acc, ring + st * kStageEntries, g.slots);
-                    ++consumed;
+                    mbar_wait(&bars[c_stage], c_parity);
+                    unit_accumulate_fast<BoxT, SLOTS>(meta, u, lane, acc, ring + c_stage * kStageEntries, slots);
+                    if (++c_stage == kStages) { c_stage = 0; c_parity ^= 1u; }
                 } else {
-                    unit_accumulate_gather(meta, u, lane, acc, edges);
+                    unit_accumulate_gather<BoxT>(meta, u, lane, acc, edges);
                 }
             }
         }
@@ -338,49 +355,57 @@ extern "C" int scb_profile_end(double *total_ms, int64_t *launches) {
     return 0;
 }
 
-constexpr size_t kWarpSmemBytes = (kStripRows * kStripCols + kStages * kStageEntries) * 8 + kBatch * sizeof(Unit) + kStages * 8;
-static_assert(2 * kMaxWarps * kWarpSmemBytes + 2048 <= 232448, "two CTAs per SM must fit in shared memory");
-
-static Geo strip_geo(const scb_geometry *geom, bool have_box) {
+static Geo strip_geo(const scb_geometry *geom, bool have_box, int box_bytes) {
     Geo g = make_geo(geom, kStripRows, kStripCols, kUnitCols);
     g.special_edges = 1;
-    // with a box table and block rows the TMA ring can hold, evenly spaced footprints never read their edges
-    g.quick_runs = have_box && g.slots <= kFastSlots;
+    // with a box table whose block rows the TMA ring can hold (and copy: multiples of 16 bytes),
+    // evenly spaced footprints never read their edges
+    g.quick_runs = have_box && g.slots <= kFastSlots && (g.slots * box_bytes) % 16 == 0;
     return g;
 }
 
 extern "C" size_t scb_render_workspace_bytes(const scb_geometry *geom, int64_t n_spots) {
     if (check_geometry(geom) != 0 || n_spots < 0) return 0;
-    Geo g = strip_geo(geom, false);
+    Geo g = strip_geo(geom, false, 8);
     return carve(g, n_spots, nullptr, sizeof(Unit)).bytes;
 }
 
-template <typename OutT>
-static int launch_render(const Geo &g, const Workspace &w, int64_t n_spots, OutT *out, int accumulate,
-                         cudaStream_t s) {
+template <typename OutT, typename BoxT, int SLOTS>
+static int launch_render_as(const Geo &g, const Workspace &w, int64_t n_spots, OutT *out, int accumulate,
+                            cudaStream_t s) {
     const int n_tiles = g.nti * g.ntj;
     // persistent grid: two CTAs per SM, each warp pulls strips from a queue; small images get
     // narrower CTAs so that the strips still spread over all SMs
-    const int slots = 2 * SCB_SM_COUNT;
+    const int slots = ctas_per_sm<BoxT>() * SCB_SM_COUNT;
     int warps = (n_tiles + slots - 1) / slots;
     warps = warps < 1 ? 1 : (warps > kMaxWarps ? kMaxWarps : warps);
     int ctas = (n_tiles + warps - 1) / warps;
     if (ctas > slots) ctas = slots;
-    const size_t smem = (size_t)warps * kWarpSmemBytes;
+    const size_t smem = (size_t)warps * warp_smem_bytes<BoxT>();
     static bool configured = false;     // per template instance
     if (!configured) {
-        SCB_CUDA(cudaFuncSetAttribute(render_strips_kernel<OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)(kMaxWarps * kWarpSmemBytes)));
+        SCB_CUDA(cudaFuncSetAttribute(render_strips_kernel<OutT, BoxT, SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(kMaxWarps * warp_smem_bytes<BoxT>())));
         configured = true;
     }
-    render_strips_kernel<OutT><<<ctas, warps * 32, smem, s>>>(g, (const Unit *)w.pair_spot, w.edges, w.tile_start,
-                                                            w.next_tile, w.wmax_bits, n_spots, out, accumulate);
+    render_strips_kernel<OutT, BoxT, SLOTS><<<ctas, warps * 32, smem, s>>>(
+        g, (const Unit *)w.pair_spot, w.edges, w.tile_start, w.next_tile, w.wmax_bits, n_spots, out, accumulate);
     return 0;
+}
+
+template <typename OutT>
+static int launch_render(const Geo &g, const Workspace &w, int64_t n_spots, OutT *out, int accumulate, int box_type,
+                         cudaStream_t s) {
+    if (box_type == SCB_F32)
+        return g.slots == 32 ? launch_render_as<OutT, float, 32>(g, w, n_spots, out, accumulate, s)
+                             : launch_render_as<OutT, float, 0>(g, w, n_spots, out, accumulate, s);
+    return g.slots == 32 ? launch_render_as<OutT, double, 32>(g, w, n_spots, out, accumulate, s)
+                         : launch_render_as<OutT, double, 0>(g, w, n_spots, out, accumulate, s);
 }
 
 static int render_expected_strided(const scb_geometry *geom, int64_t n_spots, int64_t stride, const double *d_depth,
                                    const double *d_x, const double *d_y, const double *d_weight,
-                                   const int64_t *d_sat, const double *d_box, const double *d_inv_scale,
+                                   const int64_t *d_sat, const void *d_box, int box_type, const double *d_inv_scale,
                                    const int32_t *d_slot_of_key, void *d_out, int out_type,
                                    int accumulate, void *d_workspace, size_t workspace_bytes,
                                    int32_t *d_errors, void *stream) {
@@ -391,7 +416,9 @@ static int render_expected_strided(const scb_geometry *geom, int64_t n_spots, in
     SCB_REQUIRE(n_spots == 0 || (d_depth && d_x && d_y && d_weight && d_sat && d_inv_scale && d_slot_of_key),
                 SCB_E_NULL, "scb_render_expected: NULL spot/table pointer");
     SCB_REQUIRE(out_type == SCB_F32 || out_type == SCB_F64, SCB_E_INVALID, "out_type=%d", out_type);
-    Geo g = strip_geo(geom, d_box != nullptr);
+    SCB_REQUIRE(box_type == SCB_F32 || box_type == SCB_F64, SCB_E_INVALID, "box_type=%d", box_type);
+    const int box_bytes = box_type == SCB_F32 ? 4 : 8;
+    Geo g = strip_geo(geom, d_box != nullptr, box_bytes);
     Workspace w = carve(g, n_spots, d_workspace, sizeof(Unit));
     SCB_REQUIRE(workspace_bytes >= w.bytes, SCB_E_WORKSPACE, "scb_render_expected: workspace %zu < %zu",
                 workspace_bytes, w.bytes);
@@ -413,13 +440,13 @@ static int render_expected_strided(const scb_geometry *geom, int64_t n_spots, in
     tile_scan_kernel<<<kScanCtas, 1024, 0, s>>>(n_tiles, g.stripes, w.tile_count, w.tile_start);
     if (n_spots > 0) {
         strip_fill_kernel<<<scb_grid_for(n_spots, 256), 256, 0, s>>>(g, n_spots, w.spots, w.edge_cap, d_sat, d_box,
-                                                                    w.tile_start, w.tile_cursor, w.wmax_bits,
-                                                                    (Unit *)w.pair_spot);
+                                                                    box_bytes, w.tile_start, w.tile_cursor,
+                                                                    w.wmax_bits, (Unit *)w.pair_spot);
     }
     const bool timed = g_profile.enabled && g_profile.used < g_profile.capacity;
     if (timed) cudaEventRecord(g_profile.start[g_profile.used], s);
-    if (out_type == SCB_F32) rc = launch_render<float>(g, w, n_spots, (float *)d_out, accumulate, s);
-    else rc = launch_render<double>(g, w, n_spots, (double *)d_out, accumulate, s);
+    if (out_type == SCB_F32) rc = launch_render<float>(g, w, n_spots, (float *)d_out, accumulate, box_type, s);
+    else rc = launch_render<double>(g, w, n_spots, (double *)d_out, accumulate, box_type, s);
     if (rc) return rc;
     if (timed) cudaEventRecord(g_profile.stop[g_profile.used++], s);
     SCB_CUDA_LAUNCH_CHECK("scb_render_expected");
@@ -428,11 +455,11 @@ static int render_expected_strided(const scb_geometry *geom, int64_t n_spots, in
 
 extern "C" int scb_render_expected(const scb_geometry *geom, int64_t n_spots, const double *d_depth,
                                    const double *d_x, const double *d_y, const double *d_weight,
-                                   const int64_t *d_sat, const double *d_box, const double *d_inv_scale,
+                                   const int64_t *d_sat, const void *d_box, int box_type, const double *d_inv_scale,
                                    const int32_t *d_slot_of_key, void *d_out, int out_type,
                                    int accumulate, void *d_workspace, size_t workspace_bytes,
                                    int32_t *d_errors, void *stream) {
-    return render_expected_strided(geom, n_spots, 1, d_depth, d_x, d_y, d_weight, d_sat, d_box, d_inv_scale,
+    return render_expected_strided(geom, n_spots, 1, d_depth, d_x, d_y, d_weight, d_sat, d_box, box_type, d_inv_scale,
                                    d_slot_of_key, d_out, out_type, accumulate, d_workspace, workspace_bytes, d_errors,
                                    stream);
 }
@@ -450,12 +477,12 @@ extern "C" int scb_emit_bleach_rows(uint64_t budget_seed, int64_t n, const doubl
 }
 
 extern "C" int scb_render_expected_rows(const scb_geometry *geom, int64_t n, const double *d_rows,
-                                        const double *d_weight, const int64_t *d_sat, const double *d_box,
+                                        const double *d_weight, const int64_t *d_sat, const void *d_box, int box_type,
                                         const double *d_inv_scale, const int32_t *d_slot_of_key, void *d_out,
                                         int out_type, int accumulate, void *d_workspace, size_t workspace_bytes,
                                         int32_t *d_errors, void *stream) {
     SCB_REQUIRE(n == 0 || d_rows, SCB_E_NULL, "scb_render_expected_rows: NULL rows");
-    return render_expected_strided(geom, n, 5, d_rows, d_rows + 1, d_rows + 2, d_weight, d_sat, d_box, d_inv_scale,
+    return render_expected_strided(geom, n, 5, d_rows, d_rows + 1, d_rows + 2, d_weight, d_sat, d_box, box_type, d_inv_scale,
                                    d_slot_of_key, d_out, out_type, accumulate, d_workspace, workspace_bytes, d_errors,
                                    stream);
 }

@@ -105,7 +105,7 @@ class DeviceMovie:
             _native.ptr(self.weight), None, stream), "scb_emit_bleach")
         _native.check(eng.lib.scb_render_expected(
             ctypes.byref(eng.geom), self.n, self._p(2), self._p(0), self._p(1), _native.ptr(self.weight),
-            _native.ptr(eng.sat), _native.ptr(eng.box), _native.ptr(eng.inv_scale), _native.ptr(eng.slot_of_key),
+            _native.ptr(eng.sat), _native.ptr(eng.box), eng.box_type, _native.ptr(eng.inv_scale), _native.ptr(eng.slot_of_key),
             _native.ptr(self.photons), eng.elem_type, 0, _native.ptr(self.work), self.work.numel(),
             _native.ptr(eng.errors), stream), "scb_render_expected")
         eng.detect(self.photons, self.frame, self.noise_seed, adc=adc_out, expectation=expectation_out)

@@ -139,6 +139,18 @@ default:
     assert abs(only.sum() - dev_w[interior].sum() * 0.9788254597277128) / only.sum() < 1e-11
     # run-to-run reproducibility (no atomics on the image)
     assert numpy.array_equal(render(engine, data[3000:]), render(engine, data[3000:]))
+    # fp32 frames use an fp32 box table: 6e-8 per pixel and weight, and again both paths agree bit for bit
+    _, _, _, engine32 = gpu_engine("""
+default:
+    detector: {type: CMOS, image_size: [1024, 1000], pixel_length: {value: 6.5e-6, units: m}, exposure_time: 0.033}
+    magnification: 100
+""", precision="f32")
+    got32 = render(engine32, data, dtype=torch.float32)
+    assert engine32.box.dtype == torch.float32
+    assert rel_err(got32.astype(numpy.float64), got) < 3e-7
+    box, engine32.tables.box = engine32.tables.box, None
+    assert numpy.array_equal(render(engine32, data, dtype=torch.float32), got32)
+    engine32.tables.box = box
 
 
 def test_empty_and_all_dark_inputs():

@@ -92,7 +92,7 @@ def bench_render():
     sys.path.insert(0, ROOT)
     from bench import C4_YAML, count_spot_pixel_evals
     for size, n, three_d in ((2048, 100000, False), (2048, 100000, True), (512, 1000, False)):
-        configs, eng = engine_for(C4_YAML % (size, size))
+        configs, eng = engine_for(C4_YAML % (size, size, 2.5))
         pl = configs.pixel_length
         rng = numpy.random.RandomState(1)
         data = numpy.zeros((n, 5))
@@ -112,7 +112,7 @@ def bench_render():
 
         def go():
             eng._call("scb_render_expected", ctypes.byref(eng.geom), n, _native.ptr(soa[0]), _native.ptr(soa[1]),
-                      _native.ptr(soa[2]), _native.ptr(w), _native.ptr(eng.sat), _native.ptr(eng.box), _native.ptr(eng.inv_scale),
+                      _native.ptr(soa[2]), _native.ptr(w), _native.ptr(eng.sat), _native.ptr(eng.box), eng.box_type, _native.ptr(eng.inv_scale),
                       _native.ptr(eng.slot_of_key), _native.ptr(out), _native.F32, 0, _native.ptr(work), work.numel(),
                       _native.ptr(eng.errors), eng._stream())
         ms, best = timed(go)

@@ -18,14 +18,14 @@ what = sys.argv[1]
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 6
 if what == "detector":
     size = 4096
-    configs, eng = engine_for(C4_YAML % (size, size))
+    configs, eng = engine_for(C4_YAML % (size, size, 2.5))
     photons = torch.full((size, size), 0.6, dtype=torch.float32, device="cuda")
     adc = torch.empty_like(photons)
     for k in range(iters):
         eng.detect(photons, k, 42, adc=adc)
 else:
     size, n = 2048, 100000
-    configs, eng = engine_for(C4_YAML % (size, size))
+    configs, eng = engine_for(C4_YAML % (size, size, 2.5))
     pl = configs.pixel_length
     rng = numpy.random.RandomState(1)
     data = numpy.zeros((n, 5))
@@ -41,7 +41,7 @@ else:
     work = eng._render_workspace(n)
     for k in range(iters):
         eng._call("scb_render_expected", ctypes.byref(eng.geom), n, _native.ptr(soa[0]), _native.ptr(soa[1]),
-                  _native.ptr(soa[2]), _native.ptr(w), _native.ptr(eng.sat), _native.ptr(eng.box), _native.ptr(eng.inv_scale),
+                  _native.ptr(soa[2]), _native.ptr(w), _native.ptr(eng.sat), _native.ptr(eng.box), eng.box_type, _native.ptr(eng.inv_scale),
                   _native.ptr(eng.slot_of_key), _native.ptr(out), _native.F32, 0, _native.ptr(work), work.numel(),
                   _native.ptr(eng.errors), eng._stream())
 torch.cuda.synchronize()
