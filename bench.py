@@ -345,8 +345,10 @@ def run_ours(args):
     torch.cuda.synchronize()
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     start.record()
+    t_enqueue = time.perf_counter()
     for _ in range(K):
         movie.render_block(block)
+    t_enqueue = time.perf_counter() - t_enqueue        # host time to enqueue the timed frames
     stop.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -400,6 +402,7 @@ def run_ours(args):
                 "share_of_step": render_ms.value / elapsed_ms,
             },
             "emitting_fraction": [emitting_start, emitting_end],
+            "host_enqueue_ms_per_frame": t_enqueue * 1e3 / (K * F),
             "replay_ms": replay_ms, "setup_s": setup_s, "frame_checksum_mean_adc": checksum, "table_errors": n_err,
         }
         if world == 1 and not args.no_cpu_baseline:
