@@ -389,7 +389,8 @@ def run_ours(args):
         line = {
             "metric": "frames/sec (2048^2 sCMOS, 1e5 spots)", "value": value, "unit": "frames/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": elapsed_ms / K,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64 accumulate / f32 frames",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 box tables and frames, 64-bit fixed-point accumulation (edge arithmetic f64)",
             "data": "synthetic", "config": workload_config(args),
             "clocks": clocks, "e2e": e2e, "gpu_launches": 9 * F * K,
             "roofline": {

@@ -144,14 +144,11 @@ __device__ __forceinline__ void tma_row(void *dst, const void *src, uint32_t byt
                  : "memory");
 }
 
-// Fast unit, producer side: one bulk copy of the unit's box-table rows (contiguous in the block).
-__device__ __forceinline__ void unit_stage(const Unit *meta, int u, int lane, void *stage, void *bar,
-                                           uint32_t row_bytes) {
-    if (lane == 0) {
-        const uint32_t bytes = (meta[u].shape & 0xffu) * row_bytes;
-        mbar_expect_tx(bar, bytes);
-        tma_row(stage, meta[u].src, bytes, bar);
-    }
+// Fast unit, producer side: one bulk copy of the unit's box-table rows (contiguous in the block),
+// issued by the lane that fetched the unit (it still holds source and size in registers).
+__device__ __forceinline__ void unit_stage(const void *src, uint32_t bytes, void *stage, void *bar) {
+    mbar_expect_tx(bar, bytes);
+    tma_row(stage, src, bytes, bar);
 }
 
 // box * weight -> accumulator LSBs, in the precision of the box table
@@ -161,29 +158,38 @@ __device__ __forceinline__ long long to_fixed(float box, float ws) { return __fl
 // Accumulator update shared by both paths.  Rows beyond the unit's last carry stale values:
 // their products are computed and dropped (only the update is predicated), which keeps the
 // loop branch free.  _epifm.py:280-282 (`if photons > 0` needs no branch: adding zero changes nothing)
-template <typename BoxT>
+template <typename BoxT, int ROWS>
 __device__ __forceinline__ void unit_add(long long *a, int rows, BoxT ws, const BoxT (&box)[kStripRows]) {
 #pragma unroll
-    for (int k = 0; k < kStripRows; ++k) {
+    for (int k = 0; k < ROWS; ++k) {
         const long long q = to_fixed(box[k], ws);
         if (k < rows) a[k * kStripCols] += q;
     }
 }
 
-// Fast unit, consumer side: lane l reads its column of the staged box rows.
+// Fast unit, consumer side: lane l reads its column of the staged box rows.  Units of at most
+// four rows (the top and bottom of most footprints) run a half-height copy of the loop.
 template <typename BoxT, int SLOTS>
 __device__ __forceinline__ void unit_accumulate_fast(const Unit *meta, int u, int lane, long long *acc,
                                                      const BoxT *stage, int runtime_slots) {
     const int slots = SLOTS ? SLOTS : runtime_slots;
     const BoxT ws = (BoxT)meta[u].ws;
     const uint32_t shape = meta[u].shape;
-    const int rows = (lane < (int)((shape >> 8) & 0xff)) ? (int)(shape & 0xff) : 0;   // idle lanes: no rows
+    const int n_rows = shape & 0xff;
+    int rows = (lane < (int)((shape >> 8) & 0xff)) ? n_rows : 0;   // idle lanes: no rows
+    asm volatile("" : "+r"(rows));       // keep it one value: one compare per row below instead of two
     long long *a = acc + ((shape >> 16) & 0xff) * kStripCols + (shape >> 24) + lane;
     const BoxT *st = stage + min((int)(meta[u].extra & 0xffu) + lane, slots - 1);   // idle lanes stay inside the row
     BoxT box[kStripRows];
+    if (n_rows <= kStripRows / 2) {         // warp uniform
 #pragma unroll
-    for (int k = 0; k < kStripRows; ++k) box[k] = st[k * slots];
-    unit_add<BoxT>(a, rows, ws, box);
+        for (int k = 0; k < kStripRows / 2; ++k) box[k] = st[k * slots];
+        unit_add<BoxT, kStripRows / 2>(a, rows, ws, box);
+    } else {
+#pragma unroll
+        for (int k = 0; k < kStripRows; ++k) box[k] = st[k * slots];
+        unit_add<BoxT, kStripRows>(a, rows, ws, box);
+    }
 }
 
 // Gather unit: per-edge table offsets from `edges`, corners straight from global memory.
@@ -213,7 +219,7 @@ __device__ __forceinline__ void unit_accumulate_gather(const Unit *meta, int u, 
 #pragma unroll
     for (int k = 0; k < kStripRows; ++k)    // >= 0: the table is non-negative, edges are monotone; rounded as the box table is
         box[k] = (BoxT)((R[k + 1] - L[k + 1]) - (R[k] - L[k]));
-    unit_add<BoxT>(a, rows, ws, box);
+    unit_add<BoxT, kStripRows>(a, rows, ws, box);
 }
 
 template <typename BoxT>
@@ -268,24 +274,34 @@ render_strips_kernel(Geo g, const Unit *__restrict__ units, const uint32_t *__re
         for (int base = seg_begin; base < seg_end; base += kBatch) {
             const int nb = min(kBatch, seg_end - base);
             __syncwarp();
+            // lane u fetches unit u of the batch, publishes it in shared memory and keeps what its
+            // TMA copy needs
+            const void *my_src = nullptr;
+            uint32_t my_bytes = 0;
+            bool my_fast = false;
             if (lane < nb) {
                 const uint4 *src = reinterpret_cast<const uint4 *>(units + base + lane);
                 uint4 *dst = reinterpret_cast<uint4 *>(meta + lane);
-                dst[0] = __ldg(src);
-                dst[1] = __ldg(src + 1);
+                const uint4 head = __ldg(src), tail = __ldg(src + 1);      // {ws, src} {erow, ecol, shape, extra}
+                dst[0] = head;
+                dst[1] = tail;
+                my_src = reinterpret_cast<const void *>(((unsigned long long)head.w << 32) | head.z);
+                my_bytes = (tail.z & 0xffu) * row_bytes;
+                my_fast = (tail.w & kUnitFast) != 0;
             }
+            const uint32_t fast_mask = __ballot_sync(0xffffffffu, my_fast);
             __syncwarp();
 
             auto stage_unit = [&](int u) {
-                if (meta[u].extra & kUnitFast) {
-                    unit_stage(meta, u, lane, ring + p_stage * kStageEntries, &bars[p_stage], row_bytes);
+                if ((fast_mask >> u) & 1u) {          // warp uniform
+                    if (lane == u) unit_stage(my_src, my_bytes, ring + p_stage * kStageEntries, &bars[p_stage]);
                     if (++p_stage == kStages) p_stage = 0;
                 }
             };
             for (int u = 0; u < min(nb, kStages - 1); ++u) stage_unit(u);
             for (int u = 0; u < nb; ++u) {
                 if (u + kStages - 1 < nb) stage_unit(u + kStages - 1);
-                if (meta[u].extra & kUnitFast) {
+                if ((fast_mask >> u) & 1u) {
                     mbar_wait(&bars[c_stage], c_parity);
                     unit_accumulate_fast<BoxT, SLOTS>(meta, u, lane, acc, ring + c_stage * kStageEntries, slots);
                     if (++c_stage == kStages) { c_stage = 0; c_parity ^= 1u; }
