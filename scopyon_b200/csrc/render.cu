@@ -301,6 +301,7 @@ render_strips_kernel(Geo g, const Unit *__restrict__ units, const uint32_t *__re
             for (int u = 0; u < min(nb, kStages - 1); ++u) stage_unit(u);
             for (int u = 0; u < nb; ++u) {
                 if (u + kStages - 1 < nb) stage_unit(u + kStages - 1);
+                __syncwarp();       // the previous unit's accumulator updates (other lanes, other columns) are visible
                 if ((fast_mask >> u) & 1u) {
                     mbar_wait(&bars[c_stage], c_parity);
                     unit_accumulate_fast<BoxT, SLOTS>(meta, u, lane, acc, ring + c_stage * kStageEntries, slots);

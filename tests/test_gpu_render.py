@@ -179,3 +179,47 @@ def test_motion_blur_sums_snapshots():
     assert set(true_data) == set(want_true)
     for m in want_true:
         assert numpy.allclose(true_data[m], want_true[m], rtol=1e-13, atol=0)
+
+
+@pytest.mark.parametrize("pixel_nm, magnification", [
+    (44.0, 100),      # 48 slots per phase: wider than the TMA ring -> every footprint gathers SAT corners
+    (65.0, 100),      # 32 slots: the box-table / TMA path at its compile-time width
+    (100.0, 100),     # 22 slots: box-table path at run-time width (fp64 rows are 16-byte multiples, fp32 rows are not)
+    (160.0, 100),     # 16 slots, 14-pixel footprints: mostly idle lanes
+    (250.0, 40),      # 10 slots, 9-pixel footprints
+    (66.39, 241),     # default magnification: no whole number of samples per pixel, SAT path only
+])
+def test_pixel_pitches_against_c_oracle(pixel_nm, magnification):
+    """Every table layout / kernel variant the pixel pitch selects gives the C oracle's image."""
+    yaml = """
+default:
+    detector: {type: CMOS, image_size: [150, 210], pixel_length: {value: %.9e, units: m}, exposure_time: 0.033}
+    magnification: %d
+""" % (pixel_nm * 1e-9 * magnification, magnification)
+    config, configs, params, engine = gpu_engine(yaml)
+    pl = configs.pixel_length
+    assert abs(pl / 1e-9 - pixel_nm) < 1e-6
+    rng = numpy.random.RandomState(int(pixel_nm))
+    n = 400
+    data = numpy.zeros((n, 5))
+    data[:, 0] = rng.uniform(0, 3, n).astype(int) * 150e-9             # three depth keys
+    data[:, 1] = rng.uniform(-80 * pl, 80 * pl, n)
+    data[:, 2] = rng.uniform(-110 * pl, 110 * pl, n)
+    data[:40, 1:3] = numpy.round(data[:40, 1:3] / pl) * pl              # exact pixel centres
+    data[:, 3] = numpy.arange(n)
+    data[:, 4] = 1
+    keys = numpy.unique(engine_keys(engine, configs, data))
+    sats, inv, slot = oracle_tables(params, engine, keys)
+    got = render(engine, data)
+    dev_w = device_weights(engine, data, 0.033)
+    want = c_oracle.render_sat(c_oracle.geometry(params), data[:, 0], data[:, 1], data[:, 2], dev_w, sats, inv, slot)
+    assert rel_err(got, want) < FIXED
+    assert ((got > 0) == (want > 0)).all()
+    if engine.box is not None:       # and the SAT-corner path alone gives the same bits
+        box, engine.tables.box = engine.tables.box, None
+        assert numpy.array_equal(render(engine, data), got)
+        engine.tables.box = box
+    _, _, _, engine32 = gpu_engine(yaml, precision="f32")
+    engine32.ensure_tables(keys)
+    got32 = render(engine32, data, dtype=torch.float32)
+    assert rel_err(got32.astype(numpy.float64), want) < 3e-7
