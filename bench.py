@@ -383,8 +383,9 @@ def run_ours(args):
         traffic_path = os.path.join(ROOT, "profiles", "traffic_r1.json")
         if os.path.exists(traffic_path) and args.molecules == 100000 and args.size == 2048:
             traffic = json.load(open(traffic_path)).get("render_strips_kernel<float>", {}).get("dram_bytes_per_launch")
-        # algorithmic bytes: one 8-byte box-table value per spot-pixel eval
-        bytes_per_eval = 8.0
+        # algorithmic bytes: one box-table value per spot-pixel eval -- 4 bytes with
+        # the fp32 tables that fp32 frames use, 8 with fp64 tables
+        bytes_per_eval = 4.0 if movie.engine.box is not None and movie.engine.box.dtype == torch.float32 else 8.0
         achieved = evals * bytes_per_eval / (per_launch_ms * 1e-3) / 1e9
         line = {
             "metric": "frames/sec (2048^2 sCMOS, 1e5 spots)", "value": value, "unit": "frames/s",
