@@ -210,6 +210,17 @@ int scb_replay_frames(uint64_t diffuse_seed, uint64_t budget_seed, uint64_t firs
                       const double sigma_dxy[3], double unit_time, double focal_depth,
                       const scb_photophysics *phys, double *d_budget, void *stream);
 
+/* scb_replay_frames that also records what every frame is rendered from: per frame the
+ * positions before that frame's Brownian step and the PSF weight of every molecule (as
+ * scb_emit_bleach computes it), in [n_frames][n] arrays.  Feeds scb_render_expected_frames. */
+int scb_movie_frames(uint64_t diffuse_seed, uint64_t budget_seed, uint64_t first_frame, int64_t n_frames,
+                     int64_t n, int64_t first_particle,
+                     double *d_depth, double *d_x, double *d_y,
+                     const double sigma_dxy[3], double unit_time, double focal_depth,
+                     const scb_photophysics *phys, double *d_budget,
+                     double *d_out_depth, double *d_out_x, double *d_out_y, double *d_out_weight,
+                     void *stream);
+
 /* ---- rendering --------------------------------------------------------------- */
 
 /* Upper bound of scratch bytes scb_render_expected needs for n_spots spots. */
@@ -249,6 +260,17 @@ int scb_render_expected_rows(const scb_geometry *geom, int64_t n, const double *
                              const double *d_inv_scale, const int32_t *d_slot_of_key, void *d_out,
                              int out_type, int accumulate, void *d_workspace, size_t workspace_bytes,
                              int32_t *d_errors, void *stream);
+
+/* A block of n_frames images in one call: frame f is rendered from spots
+ * [f * n_per_frame, (f + 1) * n_per_frame) of the arrays into image f of d_out
+ * ([n_frames][n_w][n_h]).  Every kernel of the pipeline runs once for the whole block. */
+size_t scb_render_frames_workspace_bytes(const scb_geometry *geom, int64_t n_per_frame, int n_frames);
+int scb_render_expected_frames(const scb_geometry *geom, int64_t n_per_frame, int n_frames,
+                               const double *d_depth, const double *d_x, const double *d_y,
+                               const double *d_weight, const int64_t *d_sat, const void *d_box,
+                               int box_type, const double *d_inv_scale, const int32_t *d_slot_of_key,
+                               void *d_out, int out_type, void *d_workspace, size_t workspace_bytes,
+                               int32_t *d_errors, void *stream);
 
 /* Tensor-core variant of scb_render_expected for the separable Gaussian PSF
  * (fluorophore.type == 'Gaussian', _epifm.py:133-134): a 128 x 128 screen tile is the
@@ -311,6 +333,15 @@ int scb_detector_adc(uint64_t seed, uint64_t frame, const scb_detector *det,
                      void *d_out_signal, void *d_out_noise,
                      void *d_workspace, size_t workspace_bytes,
                      void *stream);
+
+/* Frames first_frame .. first_frame + n_frames - 1 of a movie in one pair of launches: fp32 images
+ * [n_frames][n_w][n_h] in and out (no taps), n_frames * scb_detector_workspace_bytes() of scratch.
+ * The draws of frame f are those scb_detector_adc makes for that frame. */
+int scb_detector_adc_frames(uint64_t seed, uint64_t first_frame, int n_frames, const scb_detector *det,
+                            int32_t n_w, int32_t n_h, int elem_type,
+                            const void *d_photons, const void *d_offset,
+                            const scb_alias_entry *d_cmos_alias, int n_alias,
+                            void *d_adc, void *d_workspace, size_t workspace_bytes, void *stream);
 
 #ifdef __cplusplus
 }

@@ -95,6 +95,14 @@ SIGNATURES = {
     "scb_render_expected_rows": (ctypes.c_int, [
         ctypes.POINTER(Geometry), ctypes.c_int64, c_ptr, c_ptr, c_ptr, c_ptr, ctypes.c_int, c_ptr, c_ptr, c_ptr,
         ctypes.c_int, ctypes.c_int, c_ptr, ctypes.c_size_t, c_ptr, c_ptr]),
+    "scb_movie_frames": (ctypes.c_int, [
+        ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+        c_ptr, c_ptr, c_ptr, ctypes.POINTER(ctypes.c_double), ctypes.c_double, ctypes.c_double,
+        ctypes.POINTER(Photophysics), c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
+    "scb_render_frames_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(Geometry), ctypes.c_int64, ctypes.c_int]),
+    "scb_render_expected_frames": (ctypes.c_int, [
+        ctypes.POINTER(Geometry), ctypes.c_int64, ctypes.c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
+        ctypes.c_int, c_ptr, c_ptr, c_ptr, ctypes.c_int, c_ptr, ctypes.c_size_t, c_ptr, c_ptr]),
     "scb_gaussian_tc_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(Geometry), ctypes.c_int64]),
     "scb_render_gaussian_tc": (ctypes.c_int, [
         ctypes.POINTER(Geometry), ctypes.c_int64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, ctypes.c_int, ctypes.c_int,
@@ -107,6 +115,9 @@ SIGNATURES = {
         ctypes.c_uint64, ctypes.c_uint64, ctypes.POINTER(Detector), ctypes.c_int32, ctypes.c_int32,
         ctypes.c_int, c_ptr, c_ptr, c_ptr, ctypes.c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
         c_ptr, ctypes.c_size_t, c_ptr]),
+    "scb_detector_adc_frames": (ctypes.c_int, [
+        ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int, ctypes.POINTER(Detector), ctypes.c_int32, ctypes.c_int32,
+        ctypes.c_int, c_ptr, c_ptr, c_ptr, ctypes.c_int, c_ptr, c_ptr, ctypes.c_size_t, c_ptr]),
     "scb_detector_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int32, ctypes.c_int32]),
 }
 

@@ -20,10 +20,14 @@ struct __align__(16) SpotRec {
     // the zero sample before the table).  phase | (slot0 + 1) << 16, or -1 when irregular.
     int row_run, col_run;
     int walk;           // 1: spot_edges_kernel must walk this footprint's edges (irregular, or no box-table path)
+    int frame;          // image of a multi-frame call the spot belongs to
+    int pad;
 };
 
 struct Geo {
     int n_w, n_h, nti, ntj;
+    int frames;         // images rendered by one call (a block of movie frames); strips of frame f follow those of f - 1
+    int64_t spots_per_frame;
     int tile_h, tile_w; // screen tile in pixels (8 x 128: SAT render strips, 128 x 128: Gaussian tensor-core render)
     int chunk;          // >0: a (spot, tile) pair is listed once per `chunk` columns of the overlap
     int stripes;        // copies of the per-tile counters (power of two): spreads the census atomics
@@ -113,15 +117,21 @@ spot_prepare_kernel(Geo g, int64_t n, int64_t stride, const double *__restrict__
                     const double *__restrict__ inv_scale, const int32_t *__restrict__ slot_of_key,
                     SpotRec *__restrict__ spots, int *__restrict__ tile_count,
                     unsigned long long *__restrict__ wmax_bits, int32_t *__restrict__ errors) {
-    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // grid: x over the spots of one frame, y over frames
+    const int64_t in_frame = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int frame = blockIdx.y;
+    const int64_t s = g.frames > 1 ? (int64_t)frame * g.spots_per_frame + in_frame : in_frame;
+    const int64_t n_here = g.frames > 1 ? ((int64_t)(frame + 1) * g.spots_per_frame < n ? (int64_t)(frame + 1) * g.spots_per_frame : n) : n;
     SpotRec rec;
     rec.slot = -1;
+    rec.frame = frame;
+    rec.pad = 0;
     rec.imin = rec.imax = rec.jmin = rec.jmax = 0;
     rec.ox = rec.oy = rec.w = 0.0;
     rec.walk = 0;
     rec.row_run = rec.col_run = -1;
     double w_seen = 0.0;
-    if (s < n) {
+    if (s < n_here) {
         const double w = weight[s];
         const double xi = __dsub_rn(x[s * stride], g.f1);
         const double yi = __dsub_rn(y[s * stride], g.f2);
@@ -160,7 +170,7 @@ spot_prepare_kernel(Geo g, int64_t n, int64_t stride, const double *__restrict__
                     rec.walk = rec.row_run < 0 || rec.col_run < 0;
                     // census: the counters exist in `stripes` copies (one per group of 32 spots,
                     // round robin) so that the atomics of a frame spread over more L2 sectors
-                    int *count = tile_count + (size_t)stripe_of(g, s) * g.nti * g.ntj;
+                    int *count = tile_count + ((size_t)stripe_of(g, s) * g.frames + frame) * g.nti * g.ntj;
                     const int t0 = rec.imin / g.tile_h, t1 = (rec.imax - 1) / g.tile_h;
                     const int u0 = rec.jmin / g.tile_w, u1 = (rec.jmax - 1) / g.tile_w;
                     for (int tj = u0; tj <= u1; ++tj) {
@@ -375,12 +385,13 @@ struct Workspace {
 
 inline size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
 
-Geo make_geo(const scb_geometry *geom, int tile_h, int tile_w, int chunk = 0) {
+Geo make_geo(const scb_geometry *geom, int tile_h, int tile_w, int chunk = 0, int frames = 1) {
     Geo g;
     g.special_edges = 0;
     g.quick_runs = 0;
     g.tile_h = tile_h; g.tile_w = tile_w; g.chunk = chunk;
     g.n_w = geom->n_w; g.n_h = geom->n_h;
+    g.frames = frames < 1 ? 1 : frames; g.spots_per_frame = 0;
     g.nti = (geom->n_w + tile_h - 1) / tile_h;
     g.ntj = (geom->n_h + tile_w - 1) / tile_w;
     g.side = 2 * (geom->n_radial - 1) + 1;
@@ -396,7 +407,7 @@ Geo make_geo(const scb_geometry *geom, int tile_h, int tile_w, int chunk = 0) {
     g.modulus_magic = (uint32_t)((((uint64_t)1 << 32) + g.modulus - 1) / g.modulus);
     // counter copies: as many as keep the scan's register-resident path (<= 32768 entries), at most 8
     g.stripes = 1;
-    while (g.stripes < 8 && (int64_t)g.nti * g.ntj * g.stripes * 2 <= 32768) g.stripes *= 2;
+    while (g.stripes < 8 && (int64_t)g.frames * g.nti * g.ntj * g.stripes * 2 <= 32768) g.stripes *= 2;
     g.f0 = geom->focal[0]; g.f1 = geom->focal[1]; g.f2 = geom->focal[2];
     return g;
 }
@@ -414,7 +425,7 @@ int64_t max_tiles_per_spot(const Geo &g) {
 
 Workspace carve(const Geo &g, int64_t n, void *base, size_t entry_bytes = sizeof(int)) {
     Workspace w;
-    const size_t n_tiles = (size_t)g.nti * g.ntj;
+    const size_t n_tiles = (size_t)g.frames * g.nti * g.ntj;
     w.pair_capacity = (n > 0 ? n : 1) * max_tiles_per_spot(g);
     char *p = (char *)base;
     size_t off = 0;

@@ -150,7 +150,22 @@ struct DetArgs {
     void *out_signal, *out_noise;
     uint32_t *slow_list;       // pixels that left the fast path (bright, or EMCCD with electrons)
     uint32_t *slow_count;
+    // a block of frames in one launch (blockIdx.y = frame): images and worklists of consecutive
+    // frames lie frame_bytes / slow_words apart; 0 for a single frame
+    size_t frame_bytes, slow_words;
 };
+
+// Arguments of frame blockIdx.y of a multi-frame launch.
+__device__ __forceinline__ DetArgs frame_args(const DetArgs &a) {
+    DetArgs f = a;
+    const size_t y = blockIdx.y;
+    f.frame = a.frame + y;
+    f.photons = (const char *)a.photons + y * a.frame_bytes;
+    f.adc = (char *)a.adc + y * a.frame_bytes;
+    f.slow_list = a.slow_list + y * a.slow_words;
+    f.slow_count = a.slow_count + y * a.slow_words;
+    return f;
+}
 
 // ADC, _epifm.py:1472-1484 with gain = fullwell / (2^bit - offset), _epifm.py:958.
 __device__ __forceinline__ double adc_convert(double pe, double offset, const DetArgs &a) {
@@ -333,7 +348,8 @@ detector_kernel(const __grid_constant__ DetArgs a) {
 // incrementally -- the pass is instruction bound by the two Philox4x32-10 blocks per quad.
 template <int DET, int FPN>
 __global__ void __launch_bounds__(kThreads, 4)
-detector_fast_kernel(const __grid_constant__ DetArgs a) {
+detector_fast_kernel(const __grid_constant__ DetArgs launch) {
+    const DetArgs a = frame_args(launch);
     __shared__ scb_alias_entry s_alias[DET == SCB_DET_CMOS ? kMaxAlias : 1];
     if (DET == SCB_DET_CMOS) {
         for (int i = threadIdx.x; i < a.n_alias; i += kThreads) s_alias[i] = a.alias[i];
@@ -417,7 +433,8 @@ detector_fast_kernel(const __grid_constant__ DetArgs a) {
 // here is the one the streaming kernel drew.
 template <typename T, int DET>
 __global__ void __launch_bounds__(kThreads)
-detector_slow_kernel(const __grid_constant__ DetArgs a) {
+detector_slow_kernel(const __grid_constant__ DetArgs launch) {
+    const DetArgs a = frame_args(launch);
     const uint32_t n = *a.slow_count;
     const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
     const uint32_t f_lo = (uint32_t)a.frame, f_hi = (uint32_t)(a.frame >> 32);
@@ -471,25 +488,33 @@ adc_offsets_kernel(uint64_t seed, int64_t n, double adc0, double fpn_count, T *_
     offset[i] = (T)rint(adc0 + fpn_count * (double)n0);   // numpy.rint(rng.normal(ADC0, count)), _epifm.py:946,950-952
 }
 
+bool fast_path_ok(const DetArgs &a, size_t elem_bytes) {
+    return elem_bytes == 4 && !a.in_signal && !a.in_noise && !a.out_signal && !a.out_noise &&
+           !a.expectation && (a.n_pix & 3) == 0 && a.n_pix < ((int64_t)1 << 31) &&
+           (a.det.fpn_type != SCB_FPN_COLUMN || (a.n_h & 3) == 0);
+}
+
 template <typename T, int DET>
-void launch_detector(const DetArgs &a, cudaStream_t s) {
+void launch_detector(const DetArgs &a, int n_frames, cudaStream_t s) {
     const int64_t n_quads = (a.n_pix + 3) >> 2;
     int64_t blocks = (n_quads + kThreads - 1) / kThreads;
     const int64_t cap = (int64_t)SCB_SM_COUNT * 4 * 2;   // two waves of 4 resident CTAs (256 threads) per SM
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    cudaMemsetAsync(a.slow_count, 0, sizeof(uint32_t), s);
-    const bool fast = sizeof(T) == 4 && !a.in_signal && !a.in_noise && !a.out_signal && !a.out_noise &&
-                      !a.expectation && (a.n_pix & 3) == 0 && a.n_pix < ((int64_t)1 << 31) &&
-                      (a.det.fpn_type != SCB_FPN_COLUMN || (a.n_h & 3) == 0);
-    if (fast) {
-        if (a.det.fpn_type == SCB_FPN_NONE) detector_fast_kernel<DET, SCB_FPN_NONE><<<(unsigned)blocks, kThreads, 0, s>>>(a);
-        else if (a.det.fpn_type == SCB_FPN_PIXEL) detector_fast_kernel<DET, SCB_FPN_PIXEL><<<(unsigned)blocks, kThreads, 0, s>>>(a);
-        else detector_fast_kernel<DET, SCB_FPN_COLUMN><<<(unsigned)blocks, kThreads, 0, s>>>(a);
+    if (n_frames > 1)      // one counter per frame, a.slow_words apart
+        cudaMemset2DAsync(a.slow_count, a.slow_words * sizeof(uint32_t), 0, sizeof(uint32_t), (size_t)n_frames, s);
+    else
+        cudaMemsetAsync(a.slow_count, 0, sizeof(uint32_t), s);
+    const dim3 grid((unsigned)blocks, (unsigned)n_frames);
+    if (fast_path_ok(a, sizeof(T))) {
+        if (a.det.fpn_type == SCB_FPN_NONE) detector_fast_kernel<DET, SCB_FPN_NONE><<<grid, kThreads, 0, s>>>(a);
+        else if (a.det.fpn_type == SCB_FPN_PIXEL) detector_fast_kernel<DET, SCB_FPN_PIXEL><<<grid, kThreads, 0, s>>>(a);
+        else detector_fast_kernel<DET, SCB_FPN_COLUMN><<<grid, kThreads, 0, s>>>(a);
     } else {
-        detector_kernel<T, DET><<<(unsigned)blocks, kThreads, 0, s>>>(a);
+        detector_kernel<T, DET><<<(unsigned)blocks, kThreads, 0, s>>>(a);     // single frame only
     }
-    if (a.in_signal == nullptr) detector_slow_kernel<T, DET><<<SCB_SM_COUNT * 2, kThreads, 0, s>>>(a);
+    if (a.in_signal == nullptr)
+        detector_slow_kernel<T, DET><<<dim3(SCB_SM_COUNT * 2, (unsigned)n_frames), kThreads, 0, s>>>(a);
 }
 
 }  // namespace
@@ -514,12 +539,12 @@ extern "C" size_t scb_detector_workspace_bytes(int32_t n_w, int32_t n_h) {
     return 256 + (size_t)n_w * n_h * sizeof(uint32_t);   // counter + worst-case pixel list
 }
 
-extern "C" int scb_detector_adc(uint64_t seed, uint64_t frame, const scb_detector *det, int32_t n_w, int32_t n_h,
-                                int elem_type, const void *d_photons, const void *d_offset,
-                                const scb_alias_entry *d_cmos_alias, int n_alias, void *d_adc,
-                                void *d_expectation, const void *d_in_signal, const void *d_in_noise,
-                                void *d_out_signal, void *d_out_noise, void *d_workspace,
-                                size_t workspace_bytes, void *stream) {
+static int detector_adc(uint64_t seed, uint64_t frame, int n_frames, const scb_detector *det, int32_t n_w, int32_t n_h,
+                        int elem_type, const void *d_photons, const void *d_offset,
+                        const scb_alias_entry *d_cmos_alias, int n_alias, void *d_adc,
+                        void *d_expectation, const void *d_in_signal, const void *d_in_noise,
+                        void *d_out_signal, void *d_out_noise, void *d_workspace,
+                        size_t workspace_bytes, void *stream) {
     SCB_REQUIRE(det && d_photons && d_adc, SCB_E_NULL, "scb_detector_adc: NULL pointer");
     SCB_REQUIRE(n_w > 0 && n_h > 0, SCB_E_INVALID, "scb_detector_adc: image %d x %d", n_w, n_h);
     SCB_REQUIRE(elem_type == SCB_F32 || elem_type == SCB_F64, SCB_E_INVALID, "elem_type=%d", elem_type);
@@ -537,9 +562,13 @@ extern "C" int scb_detector_adc(uint64_t seed, uint64_t frame, const scb_detecto
     SCB_REQUIRE(((uintptr_t)d_photons % align) == 0 && ((uintptr_t)d_adc % align) == 0, SCB_E_INVALID,
                 "scb_detector_adc: image buffers must be 16-byte aligned");
     SCB_REQUIRE((int64_t)n_w * n_h < ((int64_t)1 << 32), SCB_E_INVALID, "scb_detector_adc: image too large");
-    SCB_REQUIRE(d_workspace && workspace_bytes >= scb_detector_workspace_bytes(n_w, n_h), SCB_E_WORKSPACE,
-                "scb_detector_adc: workspace %zu < %zu", workspace_bytes, scb_detector_workspace_bytes(n_w, n_h));
+    const size_t frame_work = scb_detector_workspace_bytes(n_w, n_h);
+    SCB_REQUIRE(n_frames >= 1 && n_frames <= 65535, SCB_E_INVALID, "scb_detector_adc: n_frames=%d", n_frames);
+    SCB_REQUIRE(d_workspace && workspace_bytes >= frame_work * (size_t)n_frames, SCB_E_WORKSPACE,
+                "scb_detector_adc: workspace %zu < %zu", workspace_bytes, frame_work * (size_t)n_frames);
     DetArgs a;
+    a.frame_bytes = n_frames > 1 ? (size_t)n_w * n_h * (elem_type == SCB_F32 ? 4 : 8) : 0;
+    a.slow_words = n_frames > 1 ? frame_work / sizeof(uint32_t) : 0;
     a.slow_count = (uint32_t *)d_workspace;
     a.slow_list = (uint32_t *)((char *)d_workspace + 256);
     a.seed = seed; a.frame = frame; a.det = *det;
@@ -554,15 +583,39 @@ extern "C" int scb_detector_adc(uint64_t seed, uint64_t frame, const scb_detecto
     a.in_signal = d_in_signal; a.in_noise = d_in_noise;
     a.out_signal = d_out_signal; a.out_noise = d_out_noise;
     cudaStream_t s = (cudaStream_t)stream;
+    SCB_REQUIRE(n_frames == 1 || fast_path_ok(a, elem_type == SCB_F32 ? 4 : 8), SCB_E_UNSUPPORTED,
+                "scb_detector_adc_frames: a block of frames needs fp32 images of a multiple of 4 pixels and no taps");
     if (elem_type == SCB_F32) {
-        if (det->type == SCB_DET_CMOS) launch_detector<float, SCB_DET_CMOS>(a, s);
-        else if (det->type == SCB_DET_EMCCD) launch_detector<float, SCB_DET_EMCCD>(a, s);
-        else launch_detector<float, SCB_DET_CCD>(a, s);
+        if (det->type == SCB_DET_CMOS) launch_detector<float, SCB_DET_CMOS>(a, n_frames, s);
+        else if (det->type == SCB_DET_EMCCD) launch_detector<float, SCB_DET_EMCCD>(a, n_frames, s);
+        else launch_detector<float, SCB_DET_CCD>(a, n_frames, s);
     } else {
-        if (det->type == SCB_DET_CMOS) launch_detector<double, SCB_DET_CMOS>(a, s);
-        else if (det->type == SCB_DET_EMCCD) launch_detector<double, SCB_DET_EMCCD>(a, s);
-        else launch_detector<double, SCB_DET_CCD>(a, s);
+        if (det->type == SCB_DET_CMOS) launch_detector<double, SCB_DET_CMOS>(a, n_frames, s);
+        else if (det->type == SCB_DET_EMCCD) launch_detector<double, SCB_DET_EMCCD>(a, n_frames, s);
+        else launch_detector<double, SCB_DET_CCD>(a, n_frames, s);
     }
     SCB_CUDA_LAUNCH_CHECK("scb_detector_adc");
     return 0;
+}
+
+extern "C" int scb_detector_adc(uint64_t seed, uint64_t frame, const scb_detector *det, int32_t n_w, int32_t n_h,
+                                int elem_type, const void *d_photons, const void *d_offset,
+                                const scb_alias_entry *d_cmos_alias, int n_alias, void *d_adc,
+                                void *d_expectation, const void *d_in_signal, const void *d_in_noise,
+                                void *d_out_signal, void *d_out_noise, void *d_workspace,
+                                size_t workspace_bytes, void *stream) {
+    return detector_adc(seed, frame, 1, det, n_w, n_h, elem_type, d_photons, d_offset, d_cmos_alias, n_alias, d_adc,
+                        d_expectation, d_in_signal, d_in_noise, d_out_signal, d_out_noise, d_workspace,
+                        workspace_bytes, stream);
+}
+
+// Frames first_frame .. first_frame + n_frames - 1 of a movie in one pair of launches: images
+// [n_frames][n_w][n_h] in and out (fp32, no taps), scb_detector_workspace_bytes() of scratch per frame.
+extern "C" int scb_detector_adc_frames(uint64_t seed, uint64_t first_frame, int n_frames, const scb_detector *det,
+                                       int32_t n_w, int32_t n_h, int elem_type, const void *d_photons,
+                                       const void *d_offset, const scb_alias_entry *d_cmos_alias, int n_alias,
+                                       void *d_adc, void *d_workspace, size_t workspace_bytes, void *stream) {
+    return detector_adc(seed, first_frame, n_frames, det, n_w, n_h, elem_type, d_photons, d_offset, d_cmos_alias,
+                        n_alias, d_adc, nullptr, nullptr, nullptr, nullptr, nullptr, d_workspace, workspace_bytes,
+                        stream);
 }

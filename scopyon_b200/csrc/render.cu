@@ -86,7 +86,8 @@ strip_fill_kernel(Geo g, int64_t n, const SpotRec *__restrict__ spots, int edge_
                                         (size_t)(g.slots * g.slots)) * (size_t)box_bytes;
     const uint32_t ebase = (uint32_t)s * 2u * (uint32_t)edge_cap;
     const int stripe = stripe_of(g, s);
-    int *cursor = tile_cursor + (size_t)stripe * g.nti * g.ntj;
+    const int frame_tile0 = rec.frame * g.nti * g.ntj;     // first strip of the spot's frame
+    int *cursor = tile_cursor + (size_t)stripe * g.frames * g.nti * g.ntj;
     const int t0 = rec.imin / g.tile_h, t1 = (rec.imax - 1) / g.tile_h;
     const int u0 = rec.jmin / g.tile_w, u1 = (rec.jmax - 1) / g.tile_w;
     for (int tj = u0; tj <= u1; ++tj) {
@@ -94,7 +95,7 @@ strip_fill_kernel(Geo g, int64_t n, const SpotRec *__restrict__ spots, int edge_
         const int entries = (c_hi - c_lo + g.chunk - 1) / g.chunk;
         for (int ti = t0; ti <= t1; ++ti) {
             const int r_lo = max(rec.imin, ti * g.tile_h), r_hi = min(rec.imax, (ti + 1) * g.tile_h);
-            const int tile = ti * g.ntj + tj;
+            const int tile = frame_tile0 + ti * g.ntj + tj;
             Unit *dst = units + tile_start[tile * g.stripes + stripe] + atomicAdd(&cursor[tile], entries);
             const int rows = r_hi - r_lo;
             u.erow = ebase + (uint32_t)(r_lo - rec.imin);
@@ -246,7 +247,7 @@ render_strips_kernel(Geo g, const Unit *__restrict__ units, const uint32_t *__re
     Unit *meta = reinterpret_cast<Unit *>(mine + kStripRows * kStripCols * 8 + kStages * kStageEntries * sizeof(BoxT));
     unsigned long long *bars = reinterpret_cast<unsigned long long *>(meta + kBatch);
 
-    const int n_tiles = g.nti * g.ntj;
+    const int frame_tiles = g.nti * g.ntj, n_tiles = g.frames * frame_tiles;
     const int slots = SLOTS ? SLOTS : g.slots;
     const uint32_t row_bytes = (uint32_t)slots * (uint32_t)sizeof(BoxT);
     const double lsb = scalbn(1.0, -accumulator_shift(*wmax_bits, n_spots));
@@ -267,8 +268,10 @@ render_strips_kernel(Geo g, const Unit *__restrict__ units, const uint32_t *__re
         if (lane == 0) tile = atomicAdd(next_tile, 1);
         tile = __shfl_sync(0xffffffffu, tile, 0);
         if (tile >= n_tiles) break;
-        const int ti = tile / g.ntj, tj = tile - ti * g.ntj;
+        const int frame = tile / frame_tiles, in_frame = tile - frame * frame_tiles;
+        const int ti = in_frame / g.ntj, tj = in_frame - ti * g.ntj;
         const int row0 = ti * kStripRows, col0 = tj * kStripCols;
+        OutT *image = out + (size_t)frame * g.n_w * g.n_h;
         const int seg_begin = tile_start[tile * g.stripes], seg_end = tile_start[(tile + 1) * g.stripes];
 
         for (int base = seg_begin; base < seg_end; base += kBatch) {
@@ -324,8 +327,8 @@ render_strips_kernel(Geo g, const Unit *__restrict__ units, const uint32_t *__re
                 acc[r * kStripCols + cc] = 0;
                 if (i < g.n_w && j < g.n_h) {
                     const size_t o = (size_t)i * g.n_h + j;
-                    if (accumulate) out[o] = (OutT)((double)out[o] + v);
-                    else out[o] = (OutT)v;
+                    if (accumulate) image[o] = (OutT)((double)image[o] + v);
+                    else image[o] = (OutT)v;
                 }
             }
         }
@@ -372,8 +375,9 @@ extern "C" int scb_profile_end(double *total_ms, int64_t *launches) {
     return 0;
 }
 
-static Geo strip_geo(const scb_geometry *geom, bool have_box, int box_bytes) {
-    Geo g = make_geo(geom, kStripRows, kStripCols, kUnitCols);
+static Geo strip_geo(const scb_geometry *geom, bool have_box, int box_bytes, int frames = 1, int64_t spots_per_frame = 0) {
+    Geo g = make_geo(geom, kStripRows, kStripCols, kUnitCols, frames);
+    g.spots_per_frame = spots_per_frame;
     g.special_edges = 1;
     // with a box table whose block rows the TMA ring can hold (and copy: multiples of 16 bytes),
     // evenly spaced footprints never read their edges
@@ -387,10 +391,16 @@ extern "C" size_t scb_render_workspace_bytes(const scb_geometry *geom, int64_t n
     return carve(g, n_spots, nullptr, sizeof(Unit)).bytes;
 }
 
+extern "C" size_t scb_render_frames_workspace_bytes(const scb_geometry *geom, int64_t n_per_frame, int n_frames) {
+    if (check_geometry(geom) != 0 || n_per_frame < 0 || n_frames < 1) return 0;
+    Geo g = strip_geo(geom, false, 8, n_frames, n_per_frame);
+    return carve(g, n_per_frame * n_frames, nullptr, sizeof(Unit)).bytes;
+}
+
 template <typename OutT, typename BoxT, int SLOTS>
 static int launch_render_as(const Geo &g, const Workspace &w, int64_t n_spots, OutT *out, int accumulate,
                             cudaStream_t s) {
-    const int n_tiles = g.nti * g.ntj;
+    const int n_tiles = g.frames * g.nti * g.ntj;
     // persistent grid: two CTAs per SM, each warp pulls strips from a queue; small images get
     // narrower CTAs so that the strips still spread over all SMs
     const int slots = ctas_per_sm<BoxT>() * SCB_SM_COUNT;
@@ -420,7 +430,7 @@ static int launch_render(const Geo &g, const Workspace &w, int64_t n_spots, OutT
                          : launch_render_as<OutT, double, 0>(g, w, n_spots, out, accumulate, s);
 }
 
-static int render_expected_strided(const scb_geometry *geom, int64_t n_spots, int64_t stride, const double *d_depth,
+static int render_expected_strided(const scb_geometry *geom, int64_t n_spots, int frames, int64_t stride, const double *d_depth,
                                    const double *d_x, const double *d_y, const double *d_weight,
                                    const int64_t *d_sat, const void *d_box, int box_type, const double *d_inv_scale,
                                    const int32_t *d_slot_of_key, void *d_out, int out_type,
@@ -435,7 +445,9 @@ static int render_expected_strided(const scb_geometry *geom, int64_t n_spots, in
     SCB_REQUIRE(out_type == SCB_F32 || out_type == SCB_F64, SCB_E_INVALID, "out_type=%d", out_type);
     SCB_REQUIRE(box_type == SCB_F32 || box_type == SCB_F64, SCB_E_INVALID, "box_type=%d", box_type);
     const int box_bytes = box_type == SCB_F32 ? 4 : 8;
-    Geo g = strip_geo(geom, d_box != nullptr, box_bytes);
+    SCB_REQUIRE(frames >= 1 && frames <= 4096 && n_spots % frames == 0, SCB_E_INVALID,
+                "scb_render_expected: %lld spots do not split into %d frames", (long long)n_spots, frames);
+    Geo g = strip_geo(geom, d_box != nullptr, box_bytes, frames, n_spots / frames);
     Workspace w = carve(g, n_spots, d_workspace, sizeof(Unit));
     SCB_REQUIRE(workspace_bytes >= w.bytes, SCB_E_WORKSPACE, "scb_render_expected: workspace %zu < %zu",
                 workspace_bytes, w.bytes);
@@ -443,11 +455,11 @@ static int render_expected_strided(const scb_geometry *geom, int64_t n_spots, in
                 "scb_render_expected: %lld spots x %d pixel edges exceed the 32-bit edge index",
                 (long long)n_spots, 2 * w.edge_cap);
     cudaStream_t s = (cudaStream_t)stream;
-    const int n_tiles = g.nti * g.ntj;
+    const int n_tiles = g.frames * g.nti * g.ntj;
     // census, cursors, weight maximum and the strip queue are adjacent 256-aligned blocks: clear them all
     SCB_CUDA(cudaMemsetAsync(w.tile_count, 0, (size_t)((char *)w.tile_start - (char *)w.tile_count), s));
     if (n_spots > 0) {
-        spot_prepare_kernel<<<scb_grid_for(n_spots, 256), 256, 0, s>>>(
+        spot_prepare_kernel<<<dim3(scb_grid_for(n_spots / frames, 256), frames), 256, 0, s>>>(
             g, n_spots, stride, d_depth, d_x, d_y, d_weight, d_inv_scale, d_slot_of_key, w.spots, w.tile_count,
             w.wmax_bits, d_errors);
         dim3 egrid, eblock;
@@ -476,7 +488,7 @@ extern "C" int scb_render_expected(const scb_geometry *geom, int64_t n_spots, co
                                    const int32_t *d_slot_of_key, void *d_out, int out_type,
                                    int accumulate, void *d_workspace, size_t workspace_bytes,
                                    int32_t *d_errors, void *stream) {
-    return render_expected_strided(geom, n_spots, 1, d_depth, d_x, d_y, d_weight, d_sat, d_box, box_type, d_inv_scale,
+    return render_expected_strided(geom, n_spots, 1, 1, d_depth, d_x, d_y, d_weight, d_sat, d_box, box_type, d_inv_scale,
                                    d_slot_of_key, d_out, out_type, accumulate, d_workspace, workspace_bytes, d_errors,
                                    stream);
 }
@@ -499,7 +511,23 @@ extern "C" int scb_render_expected_rows(const scb_geometry *geom, int64_t n, con
                                         int out_type, int accumulate, void *d_workspace, size_t workspace_bytes,
                                         int32_t *d_errors, void *stream) {
     SCB_REQUIRE(n == 0 || d_rows, SCB_E_NULL, "scb_render_expected_rows: NULL rows");
-    return render_expected_strided(geom, n, 5, d_rows, d_rows + 1, d_rows + 2, d_weight, d_sat, d_box, box_type, d_inv_scale,
+    return render_expected_strided(geom, n, 1, 5, d_rows, d_rows + 1, d_rows + 2, d_weight, d_sat, d_box, box_type, d_inv_scale,
                                    d_slot_of_key, d_out, out_type, accumulate, d_workspace, workspace_bytes, d_errors,
                                    stream);
+}
+
+// A block of movie frames in one call: frame f takes spots [f * n_per_frame, (f + 1) * n_per_frame)
+// of the arrays and image f of d_out.  Every kernel of the pipeline runs once for the whole block
+// (the binning kernels are latency bound, so a block costs little more than a frame).
+extern "C" int scb_render_expected_frames(const scb_geometry *geom, int64_t n_per_frame, int n_frames,
+                                          const double *d_depth, const double *d_x, const double *d_y,
+                                          const double *d_weight, const int64_t *d_sat, const void *d_box,
+                                          int box_type, const double *d_inv_scale, const int32_t *d_slot_of_key,
+                                          void *d_out, int out_type, void *d_workspace, size_t workspace_bytes,
+                                          int32_t *d_errors, void *stream) {
+    SCB_REQUIRE(n_per_frame >= 0 && n_frames >= 1, SCB_E_INVALID, "scb_render_expected_frames: n=%lld frames=%d",
+                (long long)n_per_frame, n_frames);
+    return render_expected_strided(geom, n_per_frame * n_frames, n_frames, 1, d_depth, d_x, d_y, d_weight, d_sat, d_box,
+                                   box_type, d_inv_scale, d_slot_of_key, d_out, out_type, 0, d_workspace,
+                                   workspace_bytes, d_errors, stream);
 }

@@ -114,11 +114,68 @@ class DeviceMovie:
             None, None, None, _native.vec3(self.sigma_xyd), None, None, 0, 0, None, None, stream), "scb_diffuse")
         self.frame += 1
 
+    #: frames binned and rendered per launch by ``render_block`` (the binning kernels are
+    #: latency bound, so a block of frames costs little more than one frame)
+    frames_per_launch = 8
+
     def render_block(self, out):
-        """Fill ``out`` (device tensor (B, Nw, Nh)) with the next B frames."""
-        for k in range(out.shape[0]):
-            self.render_next(out[k])
+        """Fill ``out`` (device tensor (B, Nw, Nh)) with the next B frames.  Bit-identical to B
+        calls of ``render_next``; the frames are processed ``frames_per_launch`` at a time:
+        one launch advances the molecules through those frames and records positions and
+        weights, one pipeline of launches bins and renders all of them, the detector runs per frame."""
+        total = out.shape[0]
+        k = 0
+        while k < total:
+            nf = min(self.frames_per_launch, total - k)
+            if nf == 1:
+                self.render_next(out[k])
+            else:
+                self._render_frames(out[k: k + nf])
+            k += nf
         return out
+
+    def _render_frames(self, out):
+        eng = self.engine
+        nf = out.shape[0]
+        stream = eng._stream()
+        focal = float(self.configs.detector_focal_point[0])
+        cache = getattr(self, "_block", None)
+        if cache is None or cache["nf"] < nf:
+            need = eng.lib.scb_render_frames_workspace_bytes(ctypes.byref(eng.geom), self.n, nf)
+            cache = self._block = dict(
+                nf=nf,
+                state=torch.empty((4, nf, self.n), dtype=torch.float64, device=eng.device),   # depth, x, y, weight
+                photons=torch.empty((nf, eng.n_w, eng.n_h), dtype=eng.dtype, device=eng.device),
+                work=torch.empty(int(need) + 256, dtype=torch.uint8, device=eng.device),
+                det_work=torch.empty(nf * eng.lib.scb_detector_workspace_bytes(eng.n_w, eng.n_h), dtype=torch.uint8,
+                                     device=eng.device))
+        state, photons, work = cache["state"], cache["photons"], cache["work"]
+        sigma_dxy = _native.vec3([self.sigma_xyd[2], self.sigma_xyd[0], self.sigma_xyd[1]])
+        _native.check(eng.lib.scb_movie_frames(
+            self.diffuse_seed, self.budget_seed, self.frame, nf, self.n, 0,
+            self._p(2), self._p(0), self._p(1), sigma_dxy, self.exposure, focal, ctypes.byref(eng.phys),
+            _native.ptr(self.budget), _native.ptr(state[0]), _native.ptr(state[1]), _native.ptr(state[2]),
+            _native.ptr(state[3]), stream), "scb_movie_frames")
+        _native.check(eng.lib.scb_render_expected_frames(
+            ctypes.byref(eng.geom), self.n, nf, _native.ptr(state[0]), _native.ptr(state[1]), _native.ptr(state[2]),
+            _native.ptr(state[3]), _native.ptr(eng.sat), _native.ptr(eng.box), eng.box_type,
+            _native.ptr(eng.inv_scale), _native.ptr(eng.slot_of_key), _native.ptr(photons), eng.elem_type,
+            _native.ptr(work), work.numel(), _native.ptr(eng.errors), stream), "scb_render_expected_frames")
+        batched = (eng.dtype == torch.float32 and out.dtype == torch.float32 and out.is_contiguous()
+                   and (eng.n_w * eng.n_h) % 4 == 0
+                   and (self.configs.ADConverter_fpn_type != 'column' or eng.n_h % 4 == 0))
+        if batched:
+            offset = eng.offset
+            _native.check(eng.lib.scb_detector_adc_frames(
+                int(self.noise_seed), int(self.frame), nf, ctypes.byref(eng.det), eng.n_w, eng.n_h, _native.F32,
+                _native.ptr(photons), _native.ptr(offset), _native.ptr(eng.alias),
+                0 if eng.alias is None else int(eng.alias.shape[0]), _native.ptr(out),
+                _native.ptr(cache["det_work"]), cache["det_work"].numel(), stream), "scb_detector_adc_frames")
+        else:
+            for f in range(nf):
+                eng.detect(photons[f], self.frame + f, self.noise_seed, adc=out[f])
+        self.weight = state[3, nf - 1]
+        self.frame += nf
 
     def positions(self):
         """Current ``(N, 5)`` rows ``[depth, x, y, id, p_state]`` on the host (for parity checks)."""
