@@ -8,8 +8,8 @@ one snapshot per 33 ms frame.
 
 One "step" = one block of --frames-per-step frames: emission/bleaching + Brownian steps
 -> strip binning -> PSF render -> detector/ADC, everything resident in HBM.  Frames are
-processed eight per launch (movie_frames, spot_prepare, spot_edges, tile_scan, strip_fill,
-render_strips, detector_fast, detector_slow once per eight frames).  With N GPUs
+processed sixteen per launch (movie_frames, spot_prepare, spot_edges, tile_scan, strip_fill,
+render_strips, detector_fast, detector_slow once per sixteen frames).  With N GPUs
 the movie is partitioned by frame blocks (weak scaling: every rank renders the same
 number of frames per step; a rank first replays the trajectory prefix of the frames
 before its block, reported as replay_ms, outside the timed steps).
@@ -318,6 +318,8 @@ def run_ours(args):
     lower, upper = box(args.size)
     t0 = time.perf_counter()
     movie = DeviceMovie(config, args.molecules, lower, upper, D_COEFF, SEED, device=device, precision="f32")
+    if os.environ.get("SCB_FRAMES_PER_LAUNCH"):
+        movie.frames_per_launch = int(os.environ["SCB_FRAMES_PER_LAUNCH"])
     torch.cuda.synchronize()
     setup_s = time.perf_counter() - t0
 
@@ -396,7 +398,7 @@ def run_ours(args):
             "dtype": "f32 box tables and frames, 64-bit fixed-point accumulation (edge arithmetic f64)",
             "data": "synthetic", "config": workload_config(args),
             "clocks": clocks, "e2e": e2e,
-            # per block of eight frames: movie_frames, spot_prepare, spot_edges, tile_scan, strip_fill,
+            # per block of sixteen frames: movie_frames, spot_prepare, spot_edges, tile_scan, strip_fill,
             # render_strips, detector_fast, detector_slow
             "gpu_launches": int(8 * render_launches.value),
             "roofline": {

@@ -115,8 +115,9 @@ class DeviceMovie:
         self.frame += 1
 
     #: frames binned and rendered per launch by ``render_block`` (the binning kernels are
-    #: latency bound, so a block of frames costs little more than one frame)
-    frames_per_launch = 8
+    #: latency bound and the render kernel balances better over more strips: 16 frames per
+    #: launch run 1.45x faster than 16 single frames; about 150 MB of scratch per frame at C4)
+    frames_per_launch = 16
 
     def render_block(self, out):
         """Fill ``out`` (device tensor (B, Nw, Nh)) with the next B frames.  Bit-identical to B
