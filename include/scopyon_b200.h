@@ -343,6 +343,19 @@ int scb_detector_adc_frames(uint64_t seed, uint64_t first_frame, int n_frames, c
                             const scb_alias_entry *d_cmos_alias, int n_alias,
                             void *d_adc, void *d_workspace, size_t workspace_bytes, void *stream);
 
+/* ---- finished frames ------------------------------------------------------------ */
+
+/* 8-bit scaling of a frame stack, Image.__as_8bit (image.py:98-123; "same as
+ * scipy.misc.bytescale") with the common limits Video.save uses for a movie (image.py:261-264):
+ *   out = uint8( ((data - cmin) * (high - low) / (cmax - cmin) + low).clip(low, high) + 0.5 ),
+ * low where cmax == cmin; fp64 arithmetic in the reference's order.  scb_frames_minmax reduces n
+ * elements to d_minmax[2] = (min, max) (16 bytes of workspace); scb_frames_to_8bit takes the
+ * limits from d_limits[2] on the device when given, else from cmin / cmax. */
+int scb_frames_minmax(const void *d_frames, int64_t n, int elem_type, double *d_minmax, void *d_workspace,
+                      void *stream);
+int scb_frames_to_8bit(const void *d_frames, int64_t n, int elem_type, const double *d_limits,
+                       double cmin, double cmax, double low, double high, uint8_t *d_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -119,6 +119,10 @@ SIGNATURES = {
         ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int, ctypes.POINTER(Detector), ctypes.c_int32, ctypes.c_int32,
         ctypes.c_int, c_ptr, c_ptr, c_ptr, ctypes.c_int, c_ptr, c_ptr, ctypes.c_size_t, c_ptr]),
     "scb_detector_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int32, ctypes.c_int32]),
+    "scb_frames_minmax": (ctypes.c_int, [c_ptr, ctypes.c_int64, ctypes.c_int, c_ptr, c_ptr, c_ptr]),
+    "scb_frames_to_8bit": (ctypes.c_int, [
+        c_ptr, ctypes.c_int64, ctypes.c_int, c_ptr, ctypes.c_double, ctypes.c_double, ctypes.c_double,
+        ctypes.c_double, c_ptr, c_ptr]),
 }
 
 # not part of the public header: host-side known-answer hook for the Philox generator

@@ -226,3 +226,33 @@ def assemble_channels(channel, group=None):
     planes = [torch.empty_like(channel) for _ in range(world)]
     dist.all_gather(planes, channel.contiguous(), group=group)
     return torch.stack(planes, dim=-1)
+
+
+def frames_to_8bit(frames, cmin=None, cmax=None, low=None, high=None):
+    """8-bit copy of a device frame stack ``(F, Nw, Nh)`` (or one frame), scaled like
+    ``Image.as_8bit`` with the limits ``Video.save`` uses: one common ``(cmin, cmax)`` --
+    by default the extrema over the whole stack (``image.py:98-123, 261-264``).  The result
+    stays on the device (a quarter of the fp32 bytes to download)."""
+    if not frames.is_cuda or frames.dtype not in (torch.float32, torch.float64):
+        raise TypeError("frames_to_8bit expects a float32/float64 CUDA tensor")
+    frames = frames.contiguous()
+    lib = _native.load()
+    stream = ctypes.c_void_p(torch.cuda.current_stream(frames.device).cuda_stream)
+    elem = _native.F32 if frames.dtype == torch.float32 else _native.F64
+    n = frames.numel()
+    limits = None
+    if cmin is None or cmax is None:
+        limits = torch.empty(2, dtype=torch.float64, device=frames.device)
+        scratch = torch.empty(2, dtype=torch.int64, device=frames.device)
+        _native.check(lib.scb_frames_minmax(_native.ptr(frames), n, elem, _native.ptr(limits), _native.ptr(scratch),
+                                            stream), "scb_frames_minmax")
+        if cmin is not None:
+            limits[0] = float(cmin)
+        if cmax is not None:
+            limits[1] = float(cmax)
+    out = torch.empty(frames.shape, dtype=torch.uint8, device=frames.device)
+    _native.check(lib.scb_frames_to_8bit(
+        _native.ptr(frames), n, elem, _native.ptr(limits), float(cmin or 0.0), float(cmax or 0.0),
+        float(0 if low is None else low), float(255 if high is None else high), _native.ptr(out), stream),
+        "scb_frames_to_8bit")
+    return out

@@ -107,3 +107,25 @@ def _nccl_worker(rank, world, port, out_dir):
     stack = gather_frames(block, 5)
     numpy.save(os.path.join(out_dir, "stack{}.npy".format(rank)), stack.cpu().numpy())
     dist.destroy_process_group()
+
+
+def test_frames_to_8bit_matches_image_as_8bit():
+    """Device-side 8-bit scaling of a frame stack = Image.as_8bit per frame with the common
+    limits Video.save uses (image.py:98-123, 261-264), bit for bit."""
+    import scopyon_b200
+    from scopyon_b200.movie import frames_to_8bit
+    rng = numpy.random.RandomState(11)
+    stack = (rng.gamma(2.0, 300.0, (3, 37, 53)) + 100).astype(numpy.float32)
+    stack[1, 5, 7] = 65535.0
+    dev = torch.from_numpy(stack).cuda()
+    for kwargs in ({}, {"cmin": 150.0, "cmax": 2000.0}, {"low": 10, "high": 200}, {"cmin": 0.0}):
+        got = frames_to_8bit(dev, **kwargs).cpu().numpy()
+        limits = dict(kwargs)
+        limits.setdefault("cmin", float(stack.min()))
+        limits.setdefault("cmax", float(stack.max()))
+        want = numpy.stack([scopyon_b200.Image(f.astype(numpy.float64)).as_8bit(**limits).as_array() for f in stack])
+        assert got.dtype == numpy.uint8 and numpy.array_equal(got, want)
+    flat = torch.full((2, 8, 8), 7.0, device="cuda")
+    assert (frames_to_8bit(flat, low=3).cpu().numpy() == 3).all()          # cmax == cmin -> low
+    f64 = torch.from_numpy(stack.astype(numpy.float64)).cuda()
+    assert numpy.array_equal(frames_to_8bit(f64).cpu().numpy(), frames_to_8bit(dev).cpu().numpy())
