@@ -14,7 +14,8 @@
  *     void*); calls are asynchronous with respect to the host.
  *   - return value: 0 = ok, <0 = invalid argument (SCB_E_*), >0 = cudaError_t.
  *     scb_last_error() returns a human-readable message for the calling thread.
- *   - no global state; thread-safe as long as streams and buffers differ.
+ *   - no global state apart from the measurement hook (scb_profile_begin / _end);
+ *     thread-safe as long as streams and buffers differ.
  *   - image axis 0 ("w", rows) is the particle's x, axis 1 ("h", columns,
  *     contiguous in memory) is y  (_epifm.py:225-231).
  */
