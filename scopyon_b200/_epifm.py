@@ -231,7 +231,7 @@ class EPIFMConfigs:
 
     def geometry(self):
         Nw, Nh = self.detector_image_size
-        # SAT column interleave = pixel pitch in table samples (see include/scopyon_b200.h)
+        # phase count of the SAT / box-table block layout = pixel pitch in table samples (see include/scopyon_b200.h)
         modulus = int(min(max(round(self.pixel_length / RESOLUTION), 1), 4096))
         g = _native.Geometry(
             n_w=int(Nw), n_h=int(Nh), n_radial=self.n_radial(), n_depth_keys=self.n_depth_keys(),

@@ -1,7 +1,8 @@
-// Spot -> screen-tile binning shared by the SAT render (render.cu, 16-pixel tiles) and the
-// Gaussian tensor-core render (gaussian_tc.cu, 128-pixel tiles): footprint + pixel-edge
-// arithmetic of overlay_signal_ (/root/reference/src/scopyon/_epifm.py:228-259), a tile
-// census, an exclusive scan and a scatter of spot indices (counting sort by tile).
+// Spot -> screen-tile binning shared by the box-table / SAT render (render.cu, 8 x 64-pixel
+// strips, one or many frames per call) and the Gaussian tensor-core render (gaussian_tc.cu,
+// 128-pixel tiles): footprint + pixel-edge arithmetic of overlay_signal_
+// (/root/reference/src/scopyon/_epifm.py:228-259), a tile census, an exclusive scan and a
+// scatter of list entries (counting sort by tile).
 #pragma once
 #include "scb_common.cuh"
 #include <cooperative_groups.h>

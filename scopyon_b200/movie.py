@@ -3,7 +3,7 @@
 The reference makes a movie by materialising the whole trajectory on the host
 (``sample_inputs``, ``sampling.py:154-162``) and rendering frames strictly in sequence
 (``generate_frames``, ``_epifm.py:1045-1049``).  Here particles live on the GPU: frame
-``f`` = [emission + photobleaching at the current positions -> tile-binned PSF render ->
+``f`` = [emission + photobleaching at the current positions -> strip-binned PSF render ->
 detector/ADC] followed by one Brownian step.  Every random draw is keyed by
 (seed; particle|pixel, frame), so rank ``r`` of ``G`` reproduces frames
 ``[r F/G, (r+1) F/G)`` exactly as a single GPU would: it replays the trajectory and the
