@@ -66,6 +66,9 @@ typedef struct scb_geometry {
     double resolution;       /* table sample pitch, 1e-9 m                            */
     double depth_cutoff;     /* fluorophore.depth_cutoff [m]                          */
     double focal[3];         /* detector.focal_point as (depth, x, y) [m]             */
+    double box_peak;         /* largest box-table entry * resolution^2 * inv_scale over the tables in use =  */
+                             /* largest fraction of a spot's photons on one pixel; sizes the 32-bit          */
+                             /* accumulators of the fp32 render (0 = unknown: treated as 1)                  */
 } scb_geometry;
 
 /* Photophysics scalars (_epifm.py:1281-1315, 1343-1360, 1486-1491); all config-only

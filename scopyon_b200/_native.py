@@ -32,6 +32,7 @@ class Geometry(ctypes.Structure):
         ("sat_modulus", ctypes.c_int32), ("reserved", ctypes.c_int32),
         ("pixel_length", ctypes.c_double), ("resolution", ctypes.c_double),
         ("depth_cutoff", ctypes.c_double), ("focal", ctypes.c_double * 3),
+        ("box_peak", ctypes.c_double),
     ]
 
 

@@ -39,6 +39,7 @@ struct Geo {
     int n_depth_keys;
     int modulus, slots;           // SAT block layout (scb_common.cuh): phases per axis, slots per phase
     double pl, res, inv_res, sw, half_w, half_h, depth_cutoff;
+    double box_peak;    // largest fraction of a spot's photons on one pixel (32-bit accumulators), 1 if unknown
     double f0, f1, f2;
 };
 
@@ -393,6 +394,7 @@ Geo make_geo(const scb_geometry *geom, int tile_h, int tile_w, int chunk = 0, in
     g.tile_h = tile_h; g.tile_w = tile_w; g.chunk = chunk;
     g.n_w = geom->n_w; g.n_h = geom->n_h;
     g.frames = frames < 1 ? 1 : frames; g.spots_per_frame = 0;
+    g.box_peak = 1.0;
     g.nti = (geom->n_w + tile_h - 1) / tile_h;
     g.ntj = (geom->n_h + tile_w - 1) / tile_w;
     g.side = 2 * (geom->n_radial - 1) + 1;

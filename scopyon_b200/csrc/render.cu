@@ -30,7 +30,13 @@
 namespace {
 
 constexpr int kStripRows = 8;         // pixel rows per strip
-constexpr int kStripCols = 64;        // pixel columns per strip
+// Accumulators and strip width by box-table precision.  fp64 tables (exact mode): 64-bit fixed
+// point, LSB chosen per call, 8 x 64-pixel strips.  fp32 tables (fp32 frames): 32-bit fixed point
+// with the LSB chosen per strip from its list length, 8 x 128-pixel strips -- the same 4 KB of
+// shared memory per warp, fewer and wider units, a cheaper conversion and add per pixel.
+template <typename BoxT> struct Mode;
+template <> struct Mode<double> { using Acc = long long; static constexpr int kCols = 64; };
+template <> struct Mode<float> { using Acc = int; static constexpr int kCols = 128; };
 constexpr int kUnitCols = 32;         // columns per unit = lanes
 constexpr int kMaxWarps = 7;          // warps (= strips in flight) per CTA
 constexpr int kBatch = 16;            // units fetched per round (one per lane of a half warp)
@@ -45,7 +51,7 @@ constexpr uint32_t kUnitFast = 0x80000000u;
 
 // One work-list entry: the overlap of a spot with (<= 8 rows) x (<= 32 columns) of a strip.
 struct __align__(16) Unit {
-    double ws;             // weight * res^2 / table scale * 2^K
+    double ws;             // weight * res^2 / table scale (the render scales it to accumulator LSBs)
     const void *src;       // fast: first box-table row of the unit (`rows` rows of `slots` doubles);  gather: the spot's SAT
     uint32_t erow, ecol;   // gather: first row / column edge of the overlap inside `edges`
     uint32_t shape;        // rows | cols << 8 | first strip row << 16 | first strip column << 24
@@ -63,6 +69,20 @@ __device__ __forceinline__ int accumulator_shift(unsigned long long wmax_bits, i
     return max(-900, min(62 - e, 900));
 }
 
+// 32-bit accumulators: a strip's pixels stay below (units in its list) * (largest weight) *
+// (largest fraction of a spot's photons one pixel can receive, box_peak); the factor 1.25 covers
+// the slightly wider pixels of unevenly spaced footprints and the half-LSB rounding of every
+// term, so with K = 31 - ceil(log2(bound)) every sum stays below 2^31 / 1.25.  The LSB is then
+// about (bound / actual maximum) * 2^-31 of the strip's brightest pixel: ~1e-7 of it for evenly
+// lit strips, a few 1e-6 where one strip holds both a dense cluster and faint background.
+__device__ __forceinline__ int strip_shift(int n_units, unsigned long long wmax_bits, double box_peak) {
+    const double wmax = __longlong_as_double((long long)wmax_bits);
+    if (!(wmax > 0.0) || n_units <= 0) return 0;
+    int e;
+    frexp(1.25 * (double)n_units * wmax * box_peak, &e);
+    return max(-900, min(31 - e, 900));
+}
+
 // One thread per spot: write the spot's units into the strips' list segments.
 __global__ void __launch_bounds__(256)
 strip_fill_kernel(Geo g, int64_t n, const SpotRec *__restrict__ spots, int edge_cap,
@@ -75,7 +95,7 @@ strip_fill_kernel(Geo g, int64_t n, const SpotRec *__restrict__ spots, int edge_
     const SpotRec rec = spots[s];
     if (rec.slot < 0) return;
     Unit u;
-    u.ws = scalbn(rec.w, accumulator_shift(*wmax_bits, n));
+    u.ws = rec.w;
     const size_t table_at = (size_t)rec.slot * ((size_t)g.modulus * g.modulus * g.slots * g.slots);
     const bool fast = g.quick_runs && rec.row_run >= 0 && rec.col_run >= 0;   // quick_runs: a usable box table exists
     // edge e of a regular axis sits at slot slot0 + e (>= -1); the pixel between edges e and e + 1
@@ -154,32 +174,32 @@ __device__ __forceinline__ void unit_stage(const void *src, uint32_t bytes, void
 
 // box * weight -> accumulator LSBs, in the precision of the box table
 __device__ __forceinline__ long long to_fixed(double box, double ws) { return __double2ll_rn(__dmul_rn(box, ws)); }
-__device__ __forceinline__ long long to_fixed(float box, float ws) { return __float2ll_rn(__fmul_rn(box, ws)); }
+__device__ __forceinline__ int to_fixed(float box, float ws) { return __float2int_rn(__fmul_rn(box, ws)); }
 
 // Accumulator update shared by both paths.  Rows beyond the unit's last carry stale values:
 // their products are computed and dropped (only the update is predicated), which keeps the
 // loop branch free.  _epifm.py:280-282 (`if photons > 0` needs no branch: adding zero changes nothing)
 template <typename BoxT, int ROWS>
-__device__ __forceinline__ void unit_add(long long *a, int rows, BoxT ws, const BoxT (&box)[kStripRows]) {
+__device__ __forceinline__ void unit_add(typename Mode<BoxT>::Acc *a, int rows, BoxT ws, const BoxT (&box)[kStripRows]) {
 #pragma unroll
     for (int k = 0; k < ROWS; ++k) {
-        const long long q = to_fixed(box[k], ws);
-        if (k < rows) a[k * kStripCols] += q;
+        const typename Mode<BoxT>::Acc q = to_fixed(box[k], ws);
+        if (k < rows) a[k * Mode<BoxT>::kCols] += q;
     }
 }
 
 // Fast unit, consumer side: lane l reads its column of the staged box rows.  Units of at most
 // four rows (the top and bottom of most footprints) run a half-height copy of the loop.
 template <typename BoxT, int SLOTS>
-__device__ __forceinline__ void unit_accumulate_fast(const Unit *meta, int u, int lane, long long *acc,
-                                                     const BoxT *stage, int runtime_slots) {
+__device__ __forceinline__ void unit_accumulate_fast(const Unit *meta, int u, int lane, typename Mode<BoxT>::Acc *acc,
+                                                     const BoxT *stage, int runtime_slots, double scale) {
     const int slots = SLOTS ? SLOTS : runtime_slots;
-    const BoxT ws = (BoxT)meta[u].ws;
+    const BoxT ws = (BoxT)(meta[u].ws * scale);
     const uint32_t shape = meta[u].shape;
     const int n_rows = shape & 0xff;
     int rows = (lane < (int)((shape >> 8) & 0xff)) ? n_rows : 0;   // idle lanes: no rows
     asm volatile("" : "+r"(rows));       // keep it one value: one compare per row below instead of two
-    long long *a = acc + ((shape >> 16) & 0xff) * kStripCols + (shape >> 24) + lane;
+    typename Mode<BoxT>::Acc *a = acc + ((shape >> 16) & 0xff) * Mode<BoxT>::kCols + (shape >> 24) + lane;
     const BoxT *st = stage + min((int)(meta[u].extra & 0xffu) + lane, slots - 1);   // idle lanes stay inside the row
     BoxT box[kStripRows];
     if (n_rows <= kStripRows / 2) {         // warp uniform
@@ -195,13 +215,13 @@ __device__ __forceinline__ void unit_accumulate_fast(const Unit *meta, int u, in
 
 // Gather unit: per-edge table offsets from `edges`, corners straight from global memory.
 template <typename BoxT>
-__device__ __forceinline__ void unit_accumulate_gather(const Unit *meta, int u, int lane, long long *acc,
-                                                       const uint32_t *__restrict__ edges) {
-    const BoxT ws = (BoxT)meta[u].ws;
+__device__ __forceinline__ void unit_accumulate_gather(const Unit *meta, int u, int lane, typename Mode<BoxT>::Acc *acc,
+                                                       const uint32_t *__restrict__ edges, double scale) {
+    const BoxT ws = (BoxT)(meta[u].ws * scale);
     const uint32_t shape = meta[u].shape;
     const int n_rows = shape & 0xff, n_cols = (shape >> 8) & 0xff;
     const int rows = lane < n_cols ? n_rows : 0;
-    long long *a = acc + ((shape >> 16) & 0xff) * kStripCols + (shape >> 24) + lane;
+    typename Mode<BoxT>::Acc *a = acc + ((shape >> 16) & 0xff) * Mode<BoxT>::kCols + (shape >> 24) + lane;
     const long long *table = static_cast<const long long *>(meta[u].src);
     const uint32_t c = meta[u].ecol + (uint32_t)min(lane, n_cols - 1);   // idle lanes repeat the last column
     const uint32_t left = __ldg(edges + c), right = __ldg(edges + c + 1);
@@ -225,7 +245,8 @@ __device__ __forceinline__ void unit_accumulate_gather(const Unit *meta, int u, 
 
 template <typename BoxT>
 constexpr size_t warp_smem_bytes() {
-    return kStripRows * kStripCols * 8 + ring_stages<BoxT>() * kStageEntries * sizeof(BoxT) + kBatch * sizeof(Unit) + 32;
+    return kStripRows * Mode<BoxT>::kCols * sizeof(typename Mode<BoxT>::Acc) + ring_stages<BoxT>() * kStageEntries * sizeof(BoxT) +
+           kBatch * sizeof(Unit) + 32;
 }
 static_assert(ctas_per_sm<double>() * (kMaxWarps * warp_smem_bytes<double>() + 1024) <= 232448 &&
                   ctas_per_sm<float>() * (kMaxWarps * warp_smem_bytes<float>() + 1024) <= 232448,
@@ -242,15 +263,19 @@ render_strips_kernel(Geo g, const Unit *__restrict__ units, const uint32_t *__re
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // per-warp carve: accumulators | TMA ring | unit batch | mbarriers
     unsigned char *mine = smem_raw + warp * warp_smem_bytes<BoxT>();
-    long long *acc = reinterpret_cast<long long *>(mine);
-    BoxT *ring = reinterpret_cast<BoxT *>(mine + kStripRows * kStripCols * 8);
-    Unit *meta = reinterpret_cast<Unit *>(mine + kStripRows * kStripCols * 8 + kStages * kStageEntries * sizeof(BoxT));
+    using Acc = typename Mode<BoxT>::Acc;
+    constexpr int kStripCols = Mode<BoxT>::kCols;
+    constexpr size_t kAccBytes = kStripRows * kStripCols * sizeof(Acc);
+    Acc *acc = reinterpret_cast<Acc *>(mine);
+    BoxT *ring = reinterpret_cast<BoxT *>(mine + kAccBytes);
+    Unit *meta = reinterpret_cast<Unit *>(mine + kAccBytes + kStages * kStageEntries * sizeof(BoxT));
     unsigned long long *bars = reinterpret_cast<unsigned long long *>(meta + kBatch);
 
     const int frame_tiles = g.nti * g.ntj, n_tiles = g.frames * frame_tiles;
     const int slots = SLOTS ? SLOTS : g.slots;
     const uint32_t row_bytes = (uint32_t)slots * (uint32_t)sizeof(BoxT);
-    const double lsb = scalbn(1.0, -accumulator_shift(*wmax_bits, n_spots));
+    const unsigned long long wmax = *wmax_bits;
+    const int call_shift = accumulator_shift(wmax, n_spots);      // 64-bit accumulators: one LSB per call
 
     for (int i = lane; i < kStripRows * kStripCols; i += 32) acc[i] = 0;
     for (int i = lane; i < kStages * kStageEntries; i += 32) ring[i] = (BoxT)0;   // rows past a unit's last are read (and dropped)
@@ -273,6 +298,8 @@ render_strips_kernel(Geo g, const Unit *__restrict__ units, const uint32_t *__re
         const int row0 = ti * kStripRows, col0 = tj * kStripCols;
         OutT *image = out + (size_t)frame * g.n_w * g.n_h;
         const int seg_begin = tile_start[tile * g.stripes], seg_end = tile_start[(tile + 1) * g.stripes];
+        const int shift = sizeof(Acc) == 4 ? strip_shift(seg_end - seg_begin, wmax, g.box_peak) : call_shift;
+        const double scale = scalbn(1.0, shift), lsb = scalbn(1.0, -shift);
 
         for (int base = seg_begin; base < seg_end; base += kBatch) {
             const int nb = min(kBatch, seg_end - base);
@@ -307,10 +334,10 @@ render_strips_kernel(Geo g, const Unit *__restrict__ units, const uint32_t *__re
                 __syncwarp();       // the previous unit's accumulator updates (other lanes, other columns) are visible
                 if ((fast_mask >> u) & 1u) {
                     mbar_wait(&bars[c_stage], c_parity);
-                    unit_accumulate_fast<BoxT, SLOTS>(meta, u, lane, acc, ring + c_stage * kStageEntries, slots);
+                    unit_accumulate_fast<BoxT, SLOTS>(meta, u, lane, acc, ring + c_stage * kStageEntries, slots, scale);
                     if (++c_stage == kStages) { c_stage = 0; c_parity ^= 1u; }
                 } else {
-                    unit_accumulate_gather<BoxT>(meta, u, lane, acc, edges);
+                    unit_accumulate_gather<BoxT>(meta, u, lane, acc, edges, scale);
                 }
             }
         }
@@ -376,12 +403,17 @@ extern "C" int scb_profile_end(double *total_ms, int64_t *launches) {
 }
 
 static Geo strip_geo(const scb_geometry *geom, bool have_box, int box_bytes, int frames = 1, int64_t spots_per_frame = 0) {
-    Geo g = make_geo(geom, kStripRows, kStripCols, kUnitCols, frames);
+    Geo g = make_geo(geom, kStripRows, box_bytes == 4 ? Mode<float>::kCols : Mode<double>::kCols, kUnitCols, frames);
     g.spots_per_frame = spots_per_frame;
+    g.box_peak = geom->box_peak > 0.0 && geom->box_peak <= 1.0 ? geom->box_peak : 1.0;
     g.special_edges = 1;
     // with a box table whose block rows the TMA ring can hold (and copy: multiples of 16 bytes),
     // evenly spaced footprints never read their edges
     g.quick_runs = have_box && g.slots <= kFastSlots && (g.slots * box_bytes) % 16 == 0;
+    // test hook: keep the table precision and accumulators but send every footprint down the SAT-corner path
+    if (const char *force = getenv("SCB_RENDER_FORCE_GATHER")) {
+        if (force[0] == '1') g.quick_runs = 0;
+    }
     return g;
 }
 
@@ -444,6 +476,7 @@ static int render_expected_strided(const scb_geometry *geom, int64_t n_spots, in
                 SCB_E_NULL, "scb_render_expected: NULL spot/table pointer");
     SCB_REQUIRE(out_type == SCB_F32 || out_type == SCB_F64, SCB_E_INVALID, "out_type=%d", out_type);
     SCB_REQUIRE(box_type == SCB_F32 || box_type == SCB_F64, SCB_E_INVALID, "box_type=%d", box_type);
+    if (!d_box) box_type = SCB_F64;       // no box table: every footprint is summed exactly from the SAT (64-bit accumulators)
     const int box_bytes = box_type == SCB_F32 ? 4 : 8;
     SCB_REQUIRE(frames >= 1 && frames <= 4096 && n_spots % frames == 0, SCB_E_INVALID,
                 "scb_render_expected: %lld spots do not split into %d frames", (long long)n_spots, frames);

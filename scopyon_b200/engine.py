@@ -129,6 +129,7 @@ class SatStore:
         self.box_type = _native.F32 if engine.precision == "f32" else _native.F64
         self.sat = None
         self.box = None
+        self.box_peak = 0.0      # largest fraction of a spot's photons one pixel receives (over the tables built so far)
         self.inv_scale = None
         self.n_tables = 0
         self.last_radial = None
@@ -204,6 +205,10 @@ class SatStore:
             None if self.box is None else ctypes.c_void_p(self.box[first].data_ptr()), self.box_type,
             ctypes.c_void_p(self.inv_scale[first:].data_ptr()), _native.ptr(work), work_bytes, stream),
             "scb_psf_sat_build")
+        if self.box is not None:
+            # sizes the 32-bit accumulators of the fp32 render (scb_geometry.box_peak)
+            peaks = self.box[first:need].amax(dim=1).to(torch.float64) * self.inv_scale[first:need] * (RESOLUTION ** 2)
+            self.box_peak = max(self.box_peak, float(peaks.max().item()))
         self.n_tables = need
         self.last_radial = radial
         return first
@@ -243,7 +248,7 @@ class DeviceEngine:
             raise ValueError("precision must be 'f32' or 'f64'")
         self.elem_type = _native.F32 if self.precision == "f32" else _native.F64
         self.dtype = torch.float32 if self.precision == "f32" else torch.float64
-        self.geom = configs.geometry()
+        self._geom = configs.geometry()
         self.phys = configs.photophysics()
         self.det = configs.detector_struct()
         self.psf_type = _native.PSF_GAUSSIAN if configs.fluorophore_type == 'Gaussian' else _native.PSF_BORN_WOLF
@@ -295,6 +300,14 @@ class DeviceEngine:
         self._expected = torch.zeros((self.n_w, self.n_h), dtype=self.dtype, device=self.device)
 
     # ------------------------------------------------------------------ plumbing
+    @property
+    def geom(self):
+        """The ``scb_geometry`` of this simulator; ``box_peak`` follows the shared table store
+        (tables may have been added by another simulator since the last call)."""
+        tables = getattr(self, "tables", None)
+        self._geom.box_peak = tables.box_peak if tables is not None else 0.0
+        return self._geom
+
     def _stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 

@@ -139,7 +139,10 @@ default:
     assert abs(only.sum() - dev_w[interior].sum() * 0.9788254597277128) / only.sum() < 1e-11
     # run-to-run reproducibility (no atomics on the image)
     assert numpy.array_equal(render(engine, data[3000:]), render(engine, data[3000:]))
-    # fp32 frames use an fp32 box table: 6e-8 per pixel and weight, and again both paths agree bit for bit
+    # fp32 frames use an fp32 box table and 32-bit fixed-point accumulators whose LSB is set per strip
+    # from the length of its list; this scene is the adverse case (a strip holding a 3 000-spot
+    # cluster and faint background): 1e-6 of the image maximum (north_star asks 1e-5 for fp32).
+    # Again both paths agree bit for bit
     _, _, _, engine32 = gpu_engine("""
 default:
     detector: {type: CMOS, image_size: [1024, 1000], pixel_length: {value: 6.5e-6, units: m}, exposure_time: 0.033}
@@ -147,9 +150,15 @@ default:
 """, precision="f32")
     got32 = render(engine32, data, dtype=torch.float32)
     assert engine32.box.dtype == torch.float32
-    assert rel_err(got32.astype(numpy.float64), got) < 3e-7
-    box, engine32.tables.box = engine32.tables.box, None
-    assert numpy.array_equal(render(engine32, data, dtype=torch.float32), got32)
+    assert rel_err(got32.astype(numpy.float64), got) < 3e-6
+    import os
+    os.environ["SCB_RENDER_FORCE_GATHER"] = "1"          # same tables and accumulators, SAT corners for every footprint
+    try:
+        assert numpy.array_equal(render(engine32, data, dtype=torch.float32), got32)
+    finally:
+        del os.environ["SCB_RENDER_FORCE_GATHER"]
+    box, engine32.tables.box = engine32.tables.box, None   # no box table at all: exact 64-bit accumulation
+    assert rel_err(render(engine32, data, dtype=torch.float32).astype(numpy.float64), got) < 3e-7
     engine32.tables.box = box
 
 
@@ -222,4 +231,5 @@ default:
     _, _, _, engine32 = gpu_engine(yaml, precision="f32")
     engine32.ensure_tables(keys)
     got32 = render(engine32, data, dtype=torch.float32)
-    assert rel_err(got32.astype(numpy.float64), want) < 3e-7
+    # 32-bit accumulators (box table present) or exact 64-bit ones (SAT only), fp32 output either way
+    assert rel_err(got32.astype(numpy.float64), want) < (1e-6 if engine32.box is not None else 3e-7)

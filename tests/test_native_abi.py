@@ -26,7 +26,7 @@ def test_library_builds_and_exports_header_symbols():
 
 def test_struct_layouts_match_header():
     # sizes implied by the header's field lists (natural alignment)
-    assert ctypes.sizeof(_native.Geometry) == 6 * 4 + 3 * 8 + 3 * 8
+    assert ctypes.sizeof(_native.Geometry) == 6 * 4 + 3 * 8 + 3 * 8 + 8      # + box_peak
     assert ctypes.sizeof(_native.Photophysics) == 7 * 8
     assert ctypes.sizeof(_native.Detector) == 4 * 4 + 7 * 8
 
