@@ -360,6 +360,45 @@ int scb_frames_minmax(const void *d_frames, int64_t n, int elem_type, double *d_
 int scb_frames_to_8bit(const void *d_frames, int64_t n, int elem_type, const double *d_limits,
                        double cmin, double cmax, double low, double high, uint8_t *d_out, void *stream);
 
+/* ---- spot detection (the step after image formation) ---------------------------- */
+
+/* Laplacian-of-Gaussian scale space of one image, the cube skimage.feature.blob_log builds for
+ * scopyon.analysis.blob_detection (analysis/spot_detection.py:14-47):
+ *   cube[s] = -scipy.ndimage.gaussian_laplace(image, sigma_s) * sigma_s^2,
+ * planes [n_sigma][n_w][n_h] fp64.  d_weights[n_sigma][2][weight_pitch] holds, per scale, the
+ * right half (taps 0..radius) of the Gaussian kernel and of its second derivative as
+ * scipy.ndimage.gaussian_filter1d computes them; d_radius[n_sigma] the radii, max_radius their
+ * maximum (<= scb_log_max_radius(), the shared-memory tile limit), d_sigma2[n_sigma] = sigma^2.
+ * Boundary mode 'reflect'.  The sums are formed in scipy's order without fused multiply-adds, so
+ * the cube equals scipy's bit for bit.  Workspace: scb_log_workspace_bytes(n_w, n_h, n_sigma);
+ * a caller short of memory builds the cube a few scales at a time. */
+size_t scb_log_workspace_bytes(int n_w, int n_h, int n_sigma);
+int scb_log_max_radius(void);
+int scb_log_scale_space(int n_w, int n_h, int n_sigma, const double *d_image, const int32_t *d_radius,
+                        int max_radius, const double *d_weights, int weight_pitch, const double *d_sigma2,
+                        double *d_cube, void *d_workspace, size_t workspace_bytes, void *stream);
+
+/* Scale-space peaks, skimage.feature.peak_local_max(cube, threshold_abs=threshold,
+ * footprint=ones((3,3,3)), exclude_border=False): voxels > threshold that no neighbour in the
+ * 3x3x3 box (edges replicated) exceeds.  Appends (i, j, scale index) to d_peaks[capacity][3] and
+ * the value to d_values[capacity] in no particular order; *d_count = number found (may exceed
+ * capacity: then only the first capacity were stored).  A count equal to the number of voxels
+ * means a flat cube, for which peak_local_max reports nothing. */
+int scb_log_peaks(int n_w, int n_h, int n_sigma, const double *d_cube, double threshold, int32_t *d_peaks,
+                  double *d_values, int64_t capacity, unsigned long long *d_count, void *stream);
+
+/* Per-blob background plane and Gaussian fit, scopyon.analysis.spot_detection's worker
+ * (analysis/spot_detection.py:110-137).  d_blobs[n_blobs][blob_stride] starts with (x, y); the ROI
+ * is rows int(x - roi_size) .. int(x + roi_size), columns likewise, clipped to the image
+ * (roi_size <= 15).  d_spots[n_blobs][6] = (center_x, center_y, intensity, bg, height, sigma)
+ * where d_status[blob] == 0; status 1 = no signal in the ROI, 2 = no background plane,
+ * 3 = fit did not converge within max_iterations, 4 = fitted centre outside the ROI: the blobs
+ * the reference skips.  The least-squares minimum is the one scipy.optimize.least_squares
+ * converges to from the same start; the two agree to the optimiser's tolerance, not bitwise. */
+int scb_spot_fit(int n_w, int n_h, const double *d_image, int64_t n_blobs, const double *d_blobs,
+                 int blob_stride, double roi_size, int max_iterations, double *d_spots, int32_t *d_status,
+                 void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -10,6 +10,7 @@ from .image import *
 from .sampling import *
 from .sampling2 import *
 from . import constants
+from . import analysis
 
 __all__ = [
     "EnvironSettings", "EPIFMSimulator",
@@ -19,6 +20,7 @@ __all__ = [
     "sample_inputs",
     "sample",
     "constants",
+    "analysis",
     ]
 
 __version__ = "0.1.0"

@@ -124,6 +124,16 @@ SIGNATURES = {
     "scb_frames_to_8bit": (ctypes.c_int, [
         c_ptr, ctypes.c_int64, ctypes.c_int, c_ptr, ctypes.c_double, ctypes.c_double, ctypes.c_double,
         ctypes.c_double, c_ptr, c_ptr]),
+    "scb_log_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    "scb_log_max_radius": (ctypes.c_int, []),
+    "scb_log_scale_space": (ctypes.c_int, [
+        ctypes.c_int, ctypes.c_int, ctypes.c_int, c_ptr, c_ptr, ctypes.c_int, c_ptr, ctypes.c_int, c_ptr, c_ptr,
+        c_ptr, ctypes.c_size_t, c_ptr]),
+    "scb_log_peaks": (ctypes.c_int, [
+        ctypes.c_int, ctypes.c_int, ctypes.c_int, c_ptr, ctypes.c_double, c_ptr, c_ptr, ctypes.c_int64, c_ptr, c_ptr]),
+    "scb_spot_fit": (ctypes.c_int, [
+        ctypes.c_int, ctypes.c_int, c_ptr, ctypes.c_int64, c_ptr, ctypes.c_int, ctypes.c_double, ctypes.c_int, c_ptr,
+        c_ptr, c_ptr]),
 }
 
 # not part of the public header: host-side known-answer hook for the Philox generator

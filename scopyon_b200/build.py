@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libscopyon_b200.so")
 OBJ_DIR = os.path.join(HERE, "_build")
-SOURCES = ["psf.cu", "render.cu", "particles.cu", "detector.cu", "gaussian_tc.cu", "frames.cu"]
+SOURCES = ["psf.cu", "render.cu", "particles.cu", "detector.cu", "gaussian_tc.cu", "frames.cu", "spots.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O3", "--expt-relaxed-constexpr",
