@@ -22,6 +22,8 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kMaxAlias = 256;
+constexpr int kFastCtasPerSm = 4;     // streaming kernel: 62 registers x 256 threads
+
 
 // Per-pixel overflow stream for rejection loops: Philox keyed (seed; pixel, frame), tag
 // EXTRA, block counter in the low bits of the tag word.
@@ -45,29 +47,141 @@ struct PixelRng {
     }
 };
 
-// Poisson by inversion for lambda < 12, on one 32-bit random word.  The word is compared
-// (as a float) against the cumulative probabilities scaled by 2^32; the first four terms
-// are unrolled and branch free, so a warp only diverges when a lane draws k >= 4.
+// Poisson by inversion for lambda < 12, on one 32-bit random word.  The word (converted
+// with round-toward-zero, so it stays below 2^32 and lambda = 0 can never count) is compared
+// against the cumulative probabilities scaled by 2^32.  The first four terms are unrolled and
+// branch free (poisson_head); a draw that passes all four continues in poisson_tail, which the
+// streaming kernel enters once per pixel quad.  Explicit _rn intrinsics keep the compiler
+// from contracting the recurrence differently in different kernels: every kernel draws the
+// same count from the same word.
 constexpr float kSmallLambda = 12.0f;
 
-__device__ __forceinline__ float poisson_small(float lambda, uint32_t r) {
-    const float rf = (float)r;                                              // [0, 2^32]
-    float p = exp2f(fmaf(lambda, -1.4426950408889634f, 32.0f));             // 2^32 * exp(-lambda)
+__device__ __forceinline__ float ex2_ftz(float x) {    // argument >= 14 here: no denormal handling needed
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+struct PoissonRun {   // state of the sequential search after the unrolled head
+    float p, s;
+};
+
+__device__ __forceinline__ float poisson_head(float lambda, float rf, PoissonRun &run) {
+    float p = ex2_ftz(fmaf(lambda, -1.4426950408889634f, 32.0f));            // 2^32 * exp(-lambda)
     float s = p;
-    int k = rf >= s;
-    p *= lambda;             s += p; k += rf >= s;
-    p *= lambda * 0.5f;      s += p; k += rf >= s;
-    p *= lambda * (1.0f / 3.0f); s += p; k += rf >= s;
-    if (k == 4) {
+    float k = rf >= s ? 1.0f : 0.0f;
+    p = __fmul_rn(p, lambda);                              s = __fadd_rn(s, p); k += rf >= s ? 1.0f : 0.0f;
+    p = __fmul_rn(p, __fmul_rn(lambda, 0.5f));             s = __fadd_rn(s, p); k += rf >= s ? 1.0f : 0.0f;
+    p = __fmul_rn(p, __fmul_rn(lambda, 1.0f / 3.0f));      s = __fadd_rn(s, p); k += rf >= s ? 1.0f : 0.0f;
+    run.p = p;
+    run.s = s;
+    return k;                                              // 0..4; 4 = not found yet
+}
+
+// Two pixels per instruction: Blackwell's packed fp32 arithmetic (add/mul/fma .f32x2 on a
+// 64-bit register pair).  Round-to-nearest, no flush: bit-identical to the scalar _rn forms.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float &lo, float &hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+
+// poisson_head for two pixels (same operations, same results).
+__device__ __forceinline__ void poisson_head2(float la, float lb, float rfa, float rfb, float &ka, float &kb,
+                                              PoissonRun &ra, PoissonRun &rb) {
+    const f32x2 lam = pack2(la, lb);
+    f32x2 p = pack2(ex2_ftz(fmaf(la, -1.4426950408889634f, 32.0f)), ex2_ftz(fmaf(lb, -1.4426950408889634f, 32.0f)));
+    f32x2 s = p;
+    float sa, sb;
+    unpack2(s, sa, sb);
+    f32x2 k = pack2(rfa >= sa ? 1.0f : 0.0f, rfb >= sb ? 1.0f : 0.0f);
+    p = mul2(p, lam);
+    s = add2(s, p); unpack2(s, sa, sb);
+    k = add2(k, pack2(rfa >= sa ? 1.0f : 0.0f, rfb >= sb ? 1.0f : 0.0f));
+    p = mul2(p, mul2(lam, pack2(0.5f, 0.5f)));
+    s = add2(s, p); unpack2(s, sa, sb);
+    k = add2(k, pack2(rfa >= sa ? 1.0f : 0.0f, rfb >= sb ? 1.0f : 0.0f));
+    p = mul2(p, mul2(lam, pack2(1.0f / 3.0f, 1.0f / 3.0f)));
+    s = add2(s, p); unpack2(s, sa, sb);
+    k = add2(k, pack2(rfa >= sa ? 1.0f : 0.0f, rfb >= sb ? 1.0f : 0.0f));
+    unpack2(k, ka, kb);
+    unpack2(p, ra.p, rb.p);
+    ra.s = sa;
+    rb.s = sb;
+}
+
+__device__ __noinline__ float poisson_tail(float lambda, float rf, float p, float s) {
+    int k = 4;
 #pragma unroll 1
-        while (k < 160) {
-            p *= __fdividef(lambda, (float)k);
-            s += p;
-            if (rf < s) break;
-            ++k;
-        }
+    while (k < 160) {
+        p = __fmul_rn(p, __fdividef(lambda, (float)k));
+        s = __fadd_rn(s, p);
+        if (rf < s) break;
+        ++k;
     }
-    return lambda > 0.0f ? (float)k : 0.0f;
+    return (float)k;
+}
+
+__device__ __forceinline__ float poisson_small(float lambda, uint32_t r) {
+    const float rf = __uint2float_rz(r);                                    // [0, 2^32)
+    PoissonRun run;
+    float k = poisson_head(lambda, rf, run);
+    if (k == 4.0f) k = poisson_tail(lambda, rf, run.p, run.s);
+    return k;
+}
+
+// CMOS read noise: Walker alias draw on one 32-bit word.  r * n = (entry index, 32-bit
+// fraction); the fraction is compared as an integer with the entry's threshold * 2^32.
+__device__ __forceinline__ uint32_t alias_threshold_bits(float threshold) {
+    return threshold >= 1.0f ? 0xffffffffu : __float2uint_rz(threshold * 4294967296.0f);
+}
+struct AliasSlot {    // shared-memory copy of scb_alias_entry with the threshold as 32-bit integer
+    float value, alias_value;
+    uint32_t threshold_bits, pad;
+};
+__device__ __forceinline__ float alias_draw(uint32_t r, uint32_t n_alias, const AliasSlot *slots) {
+    uint32_t idx, frac;
+    mulhilo32(r, n_alias, idx, frac);
+    const AliasSlot e = slots[idx];
+    return frac < e.threshold_bits ? e.value : e.alias_value;
+}
+__device__ __forceinline__ float alias_draw(uint32_t r, uint32_t n_alias, const scb_alias_entry *entries) {
+    uint32_t idx, frac;
+    mulhilo32(r, n_alias, idx, frac);
+    const scb_alias_entry e = entries[idx];
+    return frac < alias_threshold_bits(e.threshold) ? e.value : e.alias_value;
+}
+__device__ __forceinline__ void load_alias(AliasSlot *slots, const scb_alias_entry *entries, int n, int n_threads) {
+    for (int i = threadIdx.x; i < n; i += n_threads) {
+        const scb_alias_entry e = entries[i];
+        AliasSlot s = {e.value, e.alias_value, alias_threshold_bits(e.threshold), 0u};
+        slots[i] = s;
+    }
+    __syncthreads();
 }
 
 // PTRS, W. Hoermann, "The transformed rejection method for generating Poisson random
@@ -136,6 +250,7 @@ __device__ __noinline__ double emccd_signal(double E, double gain, uint32_t r, P
 }
 
 struct DetArgs {
+    PhiloxKeys keys;           // round keys of `seed`, filled on the host: constant-bank operands in the kernels
     uint64_t seed, frame;
     scb_detector det;
     int64_t n_pix;
@@ -143,6 +258,8 @@ struct DetArgs {
     int n_alias;
     double adc_max, pow2bit;
     float inv_fullwell, inv_nh;
+    // fp32 copies for the streaming kernel (no per-iteration double -> float conversions)
+    float qe_f, qe_bg_f, fullwell_f, pow2bit_f, adc_max_f, readout_f, adc_offset_f;
     const void *photons, *offset;
     const scb_alias_entry *alias;
     void *adc, *expectation;
@@ -200,15 +317,16 @@ struct PixelOut {
 // One pixel: expectation -> shot noise (+EM gain) -> readout noise -> ADC.
 // Scalars only (no local arrays), so everything stays in registers.
 template <typename T, int DET>
-__device__ __forceinline__ PixelOut<T> detect_pixel(const DetArgs &a, const scb_alias_entry *s_alias, int64_t pix,
+__device__ __forceinline__ PixelOut<T> detect_pixel(const DetArgs &a, const AliasSlot *s_alias, int64_t pix,
                                                     bool valid, T photons, T offset, uint32_t r_shot,
-                                                    uint32_t r_read, float normal, T qe, T bg) {
+                                                    uint32_t r_read, float normal, T qe, T bg, float qe_bg) {
     PixelOut<T> o;
     o.ex = qe * (photons + bg);                                           // _epifm.py:1438-1441
     if (a.in_signal) {
         o.sig = valid ? ((const T *)a.in_signal)[pix] : (T)0;
     } else {
-        const float lam = (float)o.ex;
+        // the Poisson mean as the streaming kernel forms it (one fma), so both draw the same count
+        const float lam = sizeof(T) == 4 ? fmaf((float)qe, (float)photons, qe_bg) : (float)o.ex;
         // fast path: small expectation; an EMCCD pixel with zero photoelectrons stays zero
         // (S = 0 lies inside the reference's support whenever E < 12)
         const float n_small = poisson_small(fminf(lam, kSmallLambda), r_shot);
@@ -219,10 +337,7 @@ __device__ __forceinline__ PixelOut<T> detect_pixel(const DetArgs &a, const scb_
     if (a.in_noise) {
         o.noi = valid ? ((const T *)a.in_noise)[pix] : (T)0;
     } else if (DET == SCB_DET_CMOS) {
-        const uint64_t prod = (uint64_t)r_read * (uint32_t)a.n_alias;
-        const scb_alias_entry e = s_alias[(uint32_t)(prod >> 32)];
-        const float frac = (float)(uint32_t)prod * 2.3283064365386963e-10f;
-        o.noi = (T)(frac < e.threshold ? e.value : e.alias_value);
+        o.noi = (T)alias_draw(r_read, (uint32_t)a.n_alias, s_alias);
     } else {
         o.noi = (T)a.det.readout_noise * (T)normal;                       // _epifm.py:360-362
     }
@@ -275,16 +390,14 @@ __device__ __forceinline__ void load_quad(const void *base, int64_t p0, int64_t 
 template <typename T, int DET>
 __global__ void __launch_bounds__(kThreads, 4)
 detector_kernel(const __grid_constant__ DetArgs a) {
-    __shared__ scb_alias_entry s_alias[DET == SCB_DET_CMOS ? kMaxAlias : 1];
-    if (DET == SCB_DET_CMOS) {
-        for (int i = threadIdx.x; i < a.n_alias; i += kThreads) s_alias[i] = a.alias[i];
-        __syncthreads();
-    }
+    __shared__ AliasSlot s_alias[DET == SCB_DET_CMOS ? kMaxAlias : 1];
+    if (DET == SCB_DET_CMOS) load_alias(s_alias, a.alias, a.n_alias, kThreads);
     const int64_t n_quads = (a.n_pix + 3) >> 2;
     const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
     const uint32_t f_lo = (uint32_t)a.frame, f_hi = (uint32_t)(a.frame >> 32);
     const T qe = (T)a.det.qe;
     const T bg = a.det.background_on ? (T)a.det.background : (T)0;
+    const float qe_bg = a.det.background_on ? (float)(a.det.qe * a.det.background) : 0.0f;
     const bool row_aligned = (a.n_h & 3) == 0;
     const bool gaussian_readout = DET != SCB_DET_CMOS && a.in_noise == nullptr && a.det.readout_noise > 0.0;
 
@@ -329,10 +442,10 @@ detector_kernel(const __grid_constant__ DetArgs a) {
             box_muller(rr.x, rr.y, n0, n1);
             box_muller(rr.z, rr.w, n2, n3);
         }
-        const PixelOut<T> o0 = detect_pixel<T, DET>(a, s_alias, p0 + 0, p0 + 0 < a.n_pix, ph0, of0, rs.x, rr.x, n0, qe, bg);
-        const PixelOut<T> o1 = detect_pixel<T, DET>(a, s_alias, p0 + 1, p0 + 1 < a.n_pix, ph1, of1, rs.y, rr.y, n1, qe, bg);
-        const PixelOut<T> o2 = detect_pixel<T, DET>(a, s_alias, p0 + 2, p0 + 2 < a.n_pix, ph2, of2, rs.z, rr.z, n2, qe, bg);
-        const PixelOut<T> o3 = detect_pixel<T, DET>(a, s_alias, p0 + 3, p0 + 3 < a.n_pix, ph3, of3, rs.w, rr.w, n3, qe, bg);
+        const PixelOut<T> o0 = detect_pixel<T, DET>(a, s_alias, p0 + 0, p0 + 0 < a.n_pix, ph0, of0, rs.x, rr.x, n0, qe, bg, qe_bg);
+        const PixelOut<T> o1 = detect_pixel<T, DET>(a, s_alias, p0 + 1, p0 + 1 < a.n_pix, ph1, of1, rs.y, rr.y, n1, qe, bg, qe_bg);
+        const PixelOut<T> o2 = detect_pixel<T, DET>(a, s_alias, p0 + 2, p0 + 2 < a.n_pix, ph2, of2, rs.z, rr.z, n2, qe, bg, qe_bg);
+        const PixelOut<T> o3 = detect_pixel<T, DET>(a, s_alias, p0 + 3, p0 + 3 < a.n_pix, ph3, of3, rs.w, rr.w, n3, qe, bg, qe_bg);
 
         store_quad<T>(a.adc, p0, a.n_pix, full, o0.adc, o1.adc, o2.adc, o3.adc);
         if (a.expectation) store_quad<T>(a.expectation, p0, a.n_pix, full, o0.ex, o1.ex, o2.ex, o3.ex);
@@ -343,40 +456,39 @@ detector_kernel(const __grid_constant__ DetArgs a) {
 
 // Streaming kernel specialised for the production configuration: fp32 frames, no injected
 // draws, no taps, n_pix a multiple of 4 and < 2^31.  Same arithmetic and the same random
-// streams as detector_kernel<float, DET> (checked against it in tests), but 32-bit
-// indexing, no per-pixel validity or tap branches, and the column index advanced
-// incrementally -- the pass is instruction bound by the two Philox4x32-10 blocks per quad.
+// streams as detector_kernel<float, DET> (tests/test_gpu_detector.py compares them bit for
+// bit), but 32-bit indexing, no per-pixel validity or tap branches, the column index
+// advanced incrementally, one slow-list test and one Poisson-tail test per pixel quad, the
+// Philox round keys read straight from the constant bank, and the Poisson recurrence and
+// the ADC on packed fp32 pairs.  What bounds it (ncu, profiles/): the 40 IMAD.WIDE of the
+// two Philox4x32-10 blocks issue at a quarter rate on the heavy FMA pipe
+// (tools/probes/imad_probe.cu), 160 of the ~250 issue cycles a warp spends per quad.
 template <int DET, int FPN>
-__global__ void __launch_bounds__(kThreads, 4)
+__global__ void __launch_bounds__(kThreads, kFastCtasPerSm)
 detector_fast_kernel(const __grid_constant__ DetArgs launch) {
     const DetArgs a = frame_args(launch);
-    __shared__ scb_alias_entry s_alias[DET == SCB_DET_CMOS ? kMaxAlias : 1];
-    if (DET == SCB_DET_CMOS) {
-        for (int i = threadIdx.x; i < a.n_alias; i += kThreads) s_alias[i] = a.alias[i];
-        __syncthreads();
-    }
+    __shared__ AliasSlot s_alias[DET == SCB_DET_CMOS ? kMaxAlias : 1];
+    if (DET == SCB_DET_CMOS) load_alias(s_alias, a.alias, a.n_alias, kThreads);
     const uint32_t n_quads = (uint32_t)(a.n_pix >> 2);
-    const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
     const uint32_t f_lo = (uint32_t)a.frame, t_shot = SCB_TAG_SHOT ^ (uint32_t)(a.frame >> 32),
                    t_read = SCB_TAG_READ ^ (uint32_t)(a.frame >> 32);
-    const float qe = (float)a.det.qe;
-    const float qe_bg = a.det.background_on ? (float)(a.det.qe * a.det.background) : 0.0f;
-    const float fullwell = (float)a.det.fullwell, pow2bit = (float)a.pow2bit, adc_max = (float)a.adc_max;
-    const float inv_fullwell = a.inv_fullwell, emgain_unused = 0.f; (void)emgain_unused;
-    const float rn = (float)a.det.readout_noise;
+    const float qe = launch.qe_f, qe_bg = launch.qe_bg_f;
+    const float fullwell = launch.fullwell_f, pow2bit = launch.pow2bit_f, adc_max = launch.adc_max_f;
+    const float inv_fullwell = launch.inv_fullwell;
+    const float rn = launch.readout_f;
     const float4 *photons = reinterpret_cast<const float4 *>(a.photons);
     float4 *adc = reinterpret_cast<float4 *>(a.adc);
     const float *offset = (const float *)a.offset;
     const uint32_t n_alias = (uint32_t)a.n_alias;
+    const uint32_t n_h = (uint32_t)a.n_h;
 
-    const PhiloxKeys keys = philox_round_keys(k0, k1);
     const uint32_t stride = gridDim.x * kThreads;
     uint32_t q = blockIdx.x * kThreads + threadIdx.x;
     // column of the quad's first pixel, advanced by (4*stride) mod n_h per iteration
     uint32_t j0 = 0, j_step = 0;
     if (FPN == SCB_FPN_COLUMN) {
-        j0 = (uint32_t)(((uint64_t)q << 2) % (uint32_t)a.n_h);
-        j_step = (uint32_t)(((uint64_t)stride << 2) % (uint32_t)a.n_h);
+        j0 = (uint32_t)(((uint64_t)q << 2) % n_h);
+        j_step = (uint32_t)(((uint64_t)stride << 2) % n_h);
     }
     float4 next = make_float4(0.f, 0.f, 0.f, 0.f);
     if (q < n_quads) next = __ldcs(photons + q);
@@ -385,44 +497,73 @@ detector_fast_kernel(const __grid_constant__ DetArgs launch) {
         if (q + stride < n_quads) next = __ldcs(photons + q + stride);
         float4 off;
         if (FPN == SCB_FPN_NONE) {
-            off.x = off.y = off.z = off.w = (float)a.det.adc_offset;
+            off.x = off.y = off.z = off.w = launch.adc_offset_f;
         } else if (FPN == SCB_FPN_PIXEL) {
             off = __ldcs(reinterpret_cast<const float4 *>(offset) + q);
         } else {
             off = __ldg(reinterpret_cast<const float4 *>(offset + j0));
             j0 += j_step;
-            if (j0 >= (uint32_t)a.n_h) j0 -= (uint32_t)a.n_h;
+            if (j0 >= n_h) j0 -= n_h;
         }
-        const Philox4 rs = philox4x32_10(q, 0u, f_lo, t_shot, keys);
+        const Philox4 rs = philox4x32_10(q, 0u, f_lo, t_shot, launch.keys);
         Philox4 rr = {0u, 0u, 0u, 0u};
-        if (DET == SCB_DET_CMOS || rn > 0.0f) rr = philox4x32_10(q, 0u, f_lo, t_read, keys);
-        float n0 = 0.f, n1 = 0.f, n2 = 0.f, n3 = 0.f;
-        if (DET != SCB_DET_CMOS && rn > 0.0f) {
+        if (DET == SCB_DET_CMOS || rn > 0.0f) rr = philox4x32_10(q, 0u, f_lo, t_read, launch.keys);
+        // shot noise: two packed branch-free heads, one test for the rare tails
+        const float l0 = fmaf(qe, ph.x, qe_bg), l1 = fmaf(qe, ph.y, qe_bg),
+                    l2 = fmaf(qe, ph.z, qe_bg), l3 = fmaf(qe, ph.w, qe_bg);
+        const float c0 = fminf(l0, kSmallLambda), c1 = fminf(l1, kSmallLambda),
+                    c2 = fminf(l2, kSmallLambda), c3 = fminf(l3, kSmallLambda);
+        const float f0 = __uint2float_rz(rs.x), f1 = __uint2float_rz(rs.y),
+                    f2 = __uint2float_rz(rs.z), f3 = __uint2float_rz(rs.w);
+        PoissonRun r0, r1, r2, r3;
+        float k0, k1, k2, k3;
+        poisson_head2(c0, c1, f0, f1, k0, k1, r0, r1);
+        poisson_head2(c2, c3, f2, f3, k2, k3, r2, r3);
+        if (fmaxf(fmaxf(k0, k1), fmaxf(k2, k3)) == 4.0f) {
+            if (k0 == 4.0f) k0 = poisson_tail(c0, f0, r0.p, r0.s);
+            if (k1 == 4.0f) k1 = poisson_tail(c1, f1, r1.p, r1.s);
+            if (k2 == 4.0f) k2 = poisson_tail(c2, f2, r2.p, r2.s);
+            if (k3 == 4.0f) k3 = poisson_tail(c3, f3, r3.p, r3.s);
+        }
+        // pixels for the general samplers (bright, NaN, or EMCCD with electrons)
+        bool slow = !(l0 < kSmallLambda && l1 < kSmallLambda && l2 < kSmallLambda && l3 < kSmallLambda);
+        if (DET == SCB_DET_EMCCD) slow = slow || (k0 + k1) + (k2 + k3) != 0.0f;
+        if (slow) {
+            auto enlist = [&](float lam, float k, uint32_t pix) {
+                if (!(lam < kSmallLambda) || (DET == SCB_DET_EMCCD && k != 0.0f))
+                    a.slow_list[atomicAdd(a.slow_count, 1u)] = pix;
+            };
+            enlist(l0, k0, (q << 2) + 0);
+            enlist(l1, k1, (q << 2) + 1);
+            enlist(l2, k2, (q << 2) + 2);
+            enlist(l3, k3, (q << 2) + 3);
+        }
+        float n0, n1, n2, n3;
+        if (DET == SCB_DET_CMOS) {
+            n0 = alias_draw(rr.x, n_alias, s_alias);
+            n1 = alias_draw(rr.y, n_alias, s_alias);
+            n2 = alias_draw(rr.z, n_alias, s_alias);
+            n3 = alias_draw(rr.w, n_alias, s_alias);
+        } else if (rn > 0.0f) {
             box_muller(rr.x, rr.y, n0, n1);
             box_muller(rr.z, rr.w, n2, n3);
+            n0 *= rn; n1 *= rn; n2 *= rn; n3 *= rn;
+        } else {
+            n0 = n1 = n2 = n3 = rn * 0.0f;
         }
-        auto pixel = [&](float photon, float off_i, uint32_t r_shot, uint32_t r_read, float normal,
-                         uint32_t pix) -> float {
-            const float lam = fmaf(qe, photon, qe_bg);
-            const float sig = poisson_small(fminf(lam, kSmallLambda), r_shot);
-            if (!(lam < kSmallLambda) || (DET == SCB_DET_EMCCD && sig != 0.0f))
-                a.slow_list[atomicAdd(a.slow_count, 1u)] = pix;
-            float noi;
-            if (DET == SCB_DET_CMOS) {
-                const uint64_t prod = (uint64_t)r_read * n_alias;
-                const scb_alias_entry e = s_alias[(uint32_t)(prod >> 32)];
-                noi = ((float)(uint32_t)prod * 2.3283064365386963e-10f) < e.threshold ? e.value : e.alias_value;
-            } else {
-                noi = rn * normal;
-            }
-            const float pe = fminf(sig + noi, fullwell);
-            return fminf(fmaxf(fmaf(pe, (pow2bit - off_i) * inv_fullwell, off_i), 0.0f), adc_max);
+        // full-well clip, gain, offset, clip to the ADC range: two pixels per instruction
+        auto convert2 = [&](float sa, float sb, float na, float nb, float oa, float ob, float &ua, float &ub) {
+            float pa, pb;
+            unpack2(add2(pack2(sa, sb), pack2(na, nb)), pa, pb);
+            const f32x2 off2 = pack2(oa, ob);
+            const f32x2 inv_gain = mul2(sub2(pack2(pow2bit, pow2bit), off2), pack2(inv_fullwell, inv_fullwell));
+            unpack2(fma2(pack2(fminf(pa, fullwell), fminf(pb, fullwell)), inv_gain, off2), ua, ub);
+            ua = fminf(fmaxf(ua, 0.0f), adc_max);
+            ub = fminf(fmaxf(ub, 0.0f), adc_max);
         };
         float4 out;
-        out.x = pixel(ph.x, off.x, rs.x, rr.x, n0, (q << 2) + 0);
-        out.y = pixel(ph.y, off.y, rs.y, rr.y, n1, (q << 2) + 1);
-        out.z = pixel(ph.z, off.z, rs.z, rr.z, n2, (q << 2) + 2);
-        out.w = pixel(ph.w, off.w, rs.w, rr.w, n3, (q << 2) + 3);
+        convert2(k0, k1, n0, n1, off.x, off.y, out.x, out.y);
+        convert2(k2, k3, n2, n3, off.z, off.w, out.z, out.w);
         __stcs(adc + q, out);
     }
 }
@@ -444,7 +585,10 @@ detector_slow_kernel(const __grid_constant__ DetArgs launch) {
         const int w = (int)(pix & 3);
         const T qe = (T)a.det.qe;
         const T bg = a.det.background_on ? (T)a.det.background : (T)0;
-        const T ex = qe * (((const T *)a.photons)[pix] + bg);
+        const T photon = ((const T *)a.photons)[pix];
+        const T ex = sizeof(T) == 4
+            ? (T)fmaf((float)qe, (float)photon, a.det.background_on ? (float)(a.det.qe * a.det.background) : 0.0f)
+            : qe * (photon + bg);
         T offset = (T)a.det.adc_offset;
         if (a.det.fpn_type == SCB_FPN_PIXEL) offset = ((const T *)a.offset)[pix];
         else if (a.det.fpn_type == SCB_FPN_COLUMN) offset = ((const T *)a.offset)[pix % a.n_h];
@@ -461,10 +605,7 @@ detector_slow_kernel(const __grid_constant__ DetArgs launch) {
             const Philox4 rr = philox4x32_10((uint32_t)q, (uint32_t)(q >> 32), f_lo, SCB_TAG_READ ^ f_hi, k0, k1);
             if (DET == SCB_DET_CMOS) {
                 const uint32_t r_read = w == 0 ? rr.x : w == 1 ? rr.y : w == 2 ? rr.z : rr.w;
-                const uint64_t prod = (uint64_t)r_read * (uint32_t)a.n_alias;
-                const scb_alias_entry e = a.alias[(uint32_t)(prod >> 32)];
-                const float frac = (float)(uint32_t)prod * 2.3283064365386963e-10f;
-                noi = (T)(frac < e.threshold ? e.value : e.alias_value);
+                noi = (T)alias_draw(r_read, (uint32_t)a.n_alias, a.alias);
             } else if (a.det.readout_noise > 0.0) {
                 float n0, n1;
                 if (w < 2) box_muller(rr.x, rr.y, n0, n1);
@@ -494,6 +635,20 @@ bool fast_path_ok(const DetArgs &a, size_t elem_bytes) {
            (a.det.fpn_type != SCB_FPN_COLUMN || (a.n_h & 3) == 0);
 }
 
+template <int DET>
+void launch_fast(const DetArgs &a, int n_frames, cudaStream_t s) {
+    // two waves of the resident CTAs per frame; blockIdx.y = frame of a block
+    const int64_t n_quads = a.n_pix >> 2;
+    int64_t blocks = (n_quads + kThreads - 1) / kThreads;
+    const int64_t cap = (int64_t)SCB_SM_COUNT * kFastCtasPerSm * 2;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    const dim3 grid((unsigned)blocks, (unsigned)n_frames);
+    if (a.det.fpn_type == SCB_FPN_NONE) detector_fast_kernel<DET, SCB_FPN_NONE><<<grid, kThreads, 0, s>>>(a);
+    else if (a.det.fpn_type == SCB_FPN_PIXEL) detector_fast_kernel<DET, SCB_FPN_PIXEL><<<grid, kThreads, 0, s>>>(a);
+    else detector_fast_kernel<DET, SCB_FPN_COLUMN><<<grid, kThreads, 0, s>>>(a);
+}
+
 template <typename T, int DET>
 void launch_detector(const DetArgs &a, int n_frames, cudaStream_t s) {
     const int64_t n_quads = (a.n_pix + 3) >> 2;
@@ -507,9 +662,7 @@ void launch_detector(const DetArgs &a, int n_frames, cudaStream_t s) {
         cudaMemsetAsync(a.slow_count, 0, sizeof(uint32_t), s);
     const dim3 grid((unsigned)blocks, (unsigned)n_frames);
     if (fast_path_ok(a, sizeof(T))) {
-        if (a.det.fpn_type == SCB_FPN_NONE) detector_fast_kernel<DET, SCB_FPN_NONE><<<grid, kThreads, 0, s>>>(a);
-        else if (a.det.fpn_type == SCB_FPN_PIXEL) detector_fast_kernel<DET, SCB_FPN_PIXEL><<<grid, kThreads, 0, s>>>(a);
-        else detector_fast_kernel<DET, SCB_FPN_COLUMN><<<grid, kThreads, 0, s>>>(a);
+        launch_fast<DET>(a, n_frames, s);
     } else {
         detector_kernel<T, DET><<<(unsigned)blocks, kThreads, 0, s>>>(a);     // single frame only
     }
@@ -572,12 +725,20 @@ static int detector_adc(uint64_t seed, uint64_t frame, int n_frames, const scb_d
     a.slow_count = (uint32_t *)d_workspace;
     a.slow_list = (uint32_t *)((char *)d_workspace + 256);
     a.seed = seed; a.frame = frame; a.det = *det;
+    a.keys = philox_round_keys((uint32_t)seed, (uint32_t)(seed >> 32));
     a.n_pix = (int64_t)n_w * n_h; a.n_h = n_h;
     a.n_alias = need_alias ? n_alias : 0;
     a.pow2bit = ldexp(1.0, det->bit);
     a.inv_fullwell = (float)(1.0 / det->fullwell);
     a.inv_nh = (float)(1.0 / (double)n_h);
+    a.qe_f = (float)det->qe;
+    a.qe_bg_f = det->background_on ? (float)(det->qe * det->background) : 0.0f;
+    a.fullwell_f = (float)det->fullwell;
+    a.pow2bit_f = (float)a.pow2bit;
+    a.readout_f = (float)det->readout_noise;
+    a.adc_offset_f = (float)det->adc_offset;
     a.adc_max = a.pow2bit - 1.0;
+    a.adc_max_f = (float)a.adc_max;
     a.photons = d_photons; a.offset = d_offset; a.alias = d_cmos_alias;
     a.adc = d_adc; a.expectation = d_expectation;
     a.in_signal = d_in_signal; a.in_noise = d_in_noise;
