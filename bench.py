@@ -60,7 +60,7 @@ def parse_args():
     ap.add_argument("--frames-per-step", type=int, default=128)
     ap.add_argument("--molecules", type=int, default=100000)
     ap.add_argument("--size", type=int, default=2048)
-    ap.add_argument("--e2e-frames", type=int, default=24)
+    ap.add_argument("--e2e-frames", type=int, default=48)
     ap.add_argument("--cpu-sample-spots", type=int, default=384)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -431,7 +431,8 @@ def run_ours(args):
 
 def run_e2e(args, config, movie, world, device):
     """The same metric through scopyon_b200.generate_images: per frame the (N, 5) float64
-    positions go host -> device from pinned memory and the float64 frame comes back."""
+    positions go host -> device from pinned memory and the frame comes back (float32 on the
+    wire, float64 in the caller's hands)."""
     import torch
     import torch.distributed as dist
     import scopyon_b200
@@ -472,7 +473,8 @@ def run_e2e(args, config, movie, world, device):
     DeviceEngine.trace = None
     return {"value": world * n_frames / dt, "unit": "frames/s", "host_ms_per_frame": breakdown,
             "h2d_bytes_per_step": int(args.molecules * (4 * 8 + 4 + 8)),
-            "d2h_bytes_per_step": int(args.size * args.size * 8),
+            "d2h_bytes_per_step": int(args.size * args.size * 4),
+            "d2h": "float32 frame into pinned staging memory, widened to the float64 array the API returns by host threads (scb_host_widen_*)",
             "frames_timed": n_frames, "per": "frame (one generate_images iteration)"}
 
 

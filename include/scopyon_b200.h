@@ -399,6 +399,21 @@ int scb_spot_fit(int n_w, int n_h, const double *d_image, int64_t n_blobs, const
                  int blob_stride, double roi_size, int max_iterations, double *d_spots, int32_t *d_status,
                  void *stream);
 
+/* ---- host side of the end-to-end path ---------------------------------------------------
+ * scopyon hands frames to the caller as float64 (Nw, Nh) arrays (image.py:12-36,
+ * _epifm.py:1177); the fp32 pipeline downloads them as float32 into pinned staging memory
+ * (half the PCIe bytes) and widens them here, on a small pool of host threads, while the next
+ * frames are in flight.  (double)float is exact: the result equals a device-side widening.
+ * scb_host_widen_start queues src[n] -> dst[n]; the work starts once `cuda_event` (the event
+ * recorded after the download on `device`; NULL = the source is ready) has completed.  Returns a
+ * ticket > 0 (or -1); tickets finish in order.  scb_host_widen_wait blocks until the ticket is
+ * done: 0, or the CUDA error the download ended with.  scb_host_widen_threads sets the number
+ * of worker threads (1..64, applied when the queue is idle) and returns the previous one.
+ * Pure host code: no kernel is launched. */
+int64_t scb_host_widen_start(const float *h_src, double *h_dst, int64_t n, void *cuda_event, int device);
+int scb_host_widen_wait(int64_t ticket);
+int scb_host_widen_threads(int n_threads);
+
 #ifdef __cplusplus
 }
 #endif

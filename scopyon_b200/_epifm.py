@@ -12,6 +12,7 @@ the user's ``rng`` only seeds counter-based Philox streams on the device (one 64
 seed per configs object and per frame sequence), so a seeded script is reproducible,
 but the streams differ from MT19937's (statistical parity).
 """
+import collections
 import copy
 import json
 import math
@@ -335,8 +336,9 @@ class _EPIFMSimulator:
             rng=None, processes=None, full_output=True):
         """Yield ``(camera, infodict)`` per frame (``_epifm.py:1017-1049``).  The photon
         budgets -- the only state carried from frame to frame -- stay on the device, and
-        frame f+1 is enqueued before frame f is awaited (one-frame lookahead), so the host
-        preparation of the next frame overlaps the device work and the download of this one."""
+        frames f+1 and f+2 are enqueued before frame f is awaited (two-frame lookahead), so the
+        host preparation of the next frames overlaps the device work, the float32 download and
+        the host-side widening to float64 of this one."""
         if rng is None:
             _log.info('A random number generator was initialized.')
             rng = numpy.random.RandomState()
@@ -368,14 +370,14 @@ class _EPIFMSimulator:
                 infodict['fluorescence_states'] = budgets
             return camera, infodict
 
-        pending = None
+        from . import engine as engine_module
+        in_flight = collections.deque()
         for frame_index in range(num_frames):
-            following = begin(frame_index)
-            if pending is not None:
-                yield finish(pending)
-            pending = following
-        if pending is not None:
-            yield finish(pending)
+            in_flight.append(begin(frame_index))
+            if len(in_flight) == engine_module.FRAMES_IN_FLIGHT:
+                yield finish(in_flight.popleft())
+        while in_flight:
+            yield finish(in_flight.popleft())
 
     def output_frame(
             self, input_data, frame_index=0, start_time=0.0, exposure_time=None,

@@ -134,6 +134,9 @@ SIGNATURES = {
     "scb_spot_fit": (ctypes.c_int, [
         ctypes.c_int, ctypes.c_int, c_ptr, ctypes.c_int64, c_ptr, ctypes.c_int, ctypes.c_double, ctypes.c_int, c_ptr,
         c_ptr, c_ptr]),
+    "scb_host_widen_start": (ctypes.c_int64, [c_ptr, c_ptr, ctypes.c_int64, c_ptr, ctypes.c_int]),
+    "scb_host_widen_wait": (ctypes.c_int, [ctypes.c_int64]),
+    "scb_host_widen_threads": (ctypes.c_int, [ctypes.c_int]),
 }
 
 # not part of the public header: host-side known-answer hook for the Philox generator

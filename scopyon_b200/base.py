@@ -141,7 +141,12 @@ class EPIFMSimulator(object):
                 if not (isinstance(elem, (tuple, list)) and len(elem) == 2
                         and isinstance(elem[0], numbers.Real) and isinstance(elem[1], numpy.ndarray)):
                     raise ValueError("The given 'inputs' has wrong type.")
-                data.append((elem[0], self.__format_data(elem[1])))
+                rows = self.__format_data(elem[1])
+                # consecutive snapshots usually show the same molecules in the same order: they then
+                # share one id column object, which the engine's per-frame caches recognise by identity
+                if data and rows.ids.shape == data[-1][1].ids.shape and numpy.array_equal(rows.ids, data[-1][1].ids):
+                    rows.ids = data[-1][1].ids
+                data.append((elem[0], rows))
             return data
         raise TypeError(
             "Invalid argument was given [{}]."

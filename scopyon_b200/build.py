@@ -15,7 +15,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libscopyon_b200.so")
 OBJ_DIR = os.path.join(HERE, "_build")
-SOURCES = ["psf.cu", "render.cu", "particles.cu", "detector.cu", "gaussian_tc.cu", "frames.cu", "spots.cu"]
+SOURCES = ["psf.cu", "render.cu", "particles.cu", "detector.cu", "gaussian_tc.cu", "frames.cu", "spots.cu",
+           "host_frames.cpp"]       # .cpp: host-only code (nvcc hands it to g++)
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O3", "--expt-relaxed-constexpr",
@@ -50,7 +51,7 @@ def build_library(force=False, verbose=False):
     sources = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
     jobs = []
     for src in sources:
-        obj = os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + ".o")
+        obj = os.path.join(OBJ_DIR, os.path.splitext(os.path.basename(src))[0] + ".o")
         stamp = obj + ".sha"
         digest = _digest(_deps(src))
         if not force and os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read() == digest:
@@ -72,7 +73,7 @@ def build_library(force=False, verbose=False):
             if verbose and log:
                 print(log, file=sys.stderr)
 
-    objs = [os.path.join(OBJ_DIR, os.path.basename(s)[:-3] + ".o") for s in sources]
+    objs = [os.path.join(OBJ_DIR, os.path.splitext(os.path.basename(s))[0] + ".o") for s in sources]
     if jobs or not os.path.exists(LIB):
         cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-lcuda"]
         res = subprocess.run(cmd, capture_output=True, text=True)

@@ -21,6 +21,26 @@ def require_cuda():
             "scopyon_b200 needs a CUDA device (built for NVIDIA B200, sm_100a); there is no CPU fallback")
 
 
+_libc = ctypes.CDLL(None)
+_libc.memcmp.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
+
+
+def same_array(a, b):
+    """``a`` and ``b`` hold the same values: identity, else one memcmp (no temporaries; an id
+    column is compared once per frame on the end-to-end path)."""
+    if a is b:
+        return True
+    if a.shape != b.shape or a.dtype != b.dtype:
+        return False
+    if not (a.flags.c_contiguous and b.flags.c_contiguous):
+        return bool(numpy.array_equal(a, b))
+    return _libc.memcmp(a.ctypes.data, b.ctypes.data, a.nbytes) == 0
+
+
+# Frames enqueued before the oldest is awaited (generate_frames) + 1: plane sets, staging areas.
+FRAMES_IN_FLIGHT = 3
+
+
 def walker_alias(values, weights):
     """Walker/Vose alias table of a categorical distribution -> (n, 4) float32 rows
     (value, alias_value, threshold, 0): the layout of ``scb_alias_entry``."""
@@ -309,6 +329,9 @@ class DeviceEngine:
         return self._geom
 
     def _stream(self):
+        cached = getattr(self, "_frame_stream", None)      # set for the duration of begin_frame
+        if cached is not None:
+            return cached
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def _call(self, name, *args):
@@ -321,12 +344,12 @@ class DeviceEngine:
         return host.pin_memory().to(self.device, non_blocking=True)
 
     def _h2d_stage(self, n):
-        """Pinned (capacity, 5) float64 staging area for particle uploads.  Two areas alternate
-        per frame: with the one-frame lookahead of ``generate_frames`` the upload of frame f may
-        still be queued while the host already fills the area for frame f+1."""
+        """Pinned (capacity, 5) float64 staging area for particle uploads.  ``FRAMES_IN_FLIGHT``
+        areas rotate: with the lookahead of ``generate_frames`` the uploads of the previous frames
+        may still be queued while the host already fills the area for the next one."""
         stages = getattr(self, "_stage_h2d", None)
         if stages is None:
-            stages = self._stage_h2d = [None, None]
+            stages = self._stage_h2d = [None] * FRAMES_IN_FLIGHT
         stage = stages[self._stage_turn]
         if stage is None or stage.shape[0] < n:
             capacity = max(n, 2 * (0 if stage is None else stage.shape[0]), 1024)
@@ -408,7 +431,7 @@ class DeviceEngine:
         true_dev, true_ids = None, None
         rows_dev = torch.empty((total, 5), dtype=torch.float64, device=self.device)   # particle rows as given
         weight = torch.empty(total, dtype=torch.float64, device=self.device)
-        self._stage_turn = getattr(self, "_stage_turn", 0) ^ 1     # this frame's staging area (see _h2d_stage)
+        self._stage_turn = (getattr(self, "_stage_turn", 0) + 1) % FRAMES_IN_FLIGHT   # this frame's staging area (see _h2d_stage)
         all_ids = self._ids_of(snapshots)
         if states is not None:
             table_ids = states.ids
@@ -426,7 +449,7 @@ class DeviceEngine:
         for (unit_time, particles), n in zip(snapshots, sizes):
             if n == 0:
                 continue
-            ids = all_ids[offset: offset + n]
+            ids = all_ids if n == total else all_ids[offset: offset + n]    # the cached object itself when it can be
             order, rounds, slots_dev = None, [(0, n)], None
             if table_ids is not None:
                 order, rounds, slots_dev, _ = self._molecule_slots(table_ids, ids)
@@ -503,8 +526,7 @@ class DeviceEngine:
                 ids = numpy.ascontiguousarray(numpy.asarray(p)[:, 3]).astype(numpy.int64)
             cols.append(ids)
         cache = getattr(self, "_ids_cache", None)
-        if cache is not None and len(cache[0]) == len(cols) and all(
-                a is b or (a.shape == b.shape and numpy.array_equal(a, b)) for a, b in zip(cache[0], cols)):
+        if cache is not None and len(cache[0]) == len(cols) and all(same_array(a, b) for a, b in zip(cache[0], cols)):
             return cache[1]
         ids = numpy.concatenate(cols) if cols else numpy.zeros(0, numpy.int64)
         self._ids_cache = (cols, ids)
@@ -525,8 +547,7 @@ class DeviceEngine:
         inside one snapshot the reference updates its budget row by row, so the rows are
         reordered into rounds (occurrence k launched after occurrence k-1)."""
         cache = getattr(self, "_slot_cache", None)
-        if cache is not None and cache[0] is table_ids and (cache[1] is ids or (
-                cache[1].shape == ids.shape and numpy.array_equal(cache[1], ids))):
+        if cache is not None and cache[0] is table_ids and same_array(cache[1], ids):
             return cache[2]
         n = len(ids)
         order, rounds = None, [(0, n)]
@@ -582,6 +603,16 @@ class DeviceEngine:
         handle without waiting for the device; ``finish_frame`` waits and hands out the arrays.
         Planes are widened to float64 on the device and written straight into pinned host
         arrays (one DMA per plane, no host-side conversion or copy)."""
+        main = torch.cuda.current_stream(self.device)
+        self._frame_stream = ctypes.c_void_p(main.cuda_stream)      # one stream lookup per frame
+        try:
+            return self._begin_frame(main, snapshots, frame_index, noise_seed, states, exposure_time, want_true_data,
+                                     want_expectation, snapshot_states)
+        finally:
+            self._frame_stream = None
+
+    def _begin_frame(self, main, snapshots, frame_index, noise_seed, states, exposure_time, want_true_data,
+                     want_expectation, snapshot_states):
         self._defer_true_data = True
         try:
             photons, true_pending = self.render_expected(
@@ -589,34 +620,55 @@ class DeviceEngine:
         finally:
             self._defer_true_data = False
         if getattr(self, "_planes32", None) is None:
-            # two plane sets alternate per frame: the download of frame f (copy stream) overlaps the
-            # kernels of frame f+1; generate_frames awaits frame f before it starts frame f+2
-            self._planes32 = torch.empty((2, 2, self.n_w, self.n_h), dtype=self.dtype, device=self.device)
-            self._planes64 = torch.empty((2, 2, self.n_w, self.n_h), dtype=torch.float64, device=self.device)
+            # FRAMES_IN_FLIGHT plane sets rotate: the download of frame f (copy stream) overlaps the
+            # kernels of the frames behind it; generate_frames awaits frame f before it starts
+            # frame f + FRAMES_IN_FLIGHT
+            self._planes32 = torch.empty((FRAMES_IN_FLIGHT, 2, self.n_w, self.n_h), dtype=self.dtype, device=self.device)
+            self._planes_free = [None] * FRAMES_IN_FLIGHT       # download of the set's previous frame
+            self._stage32 = None
+            self._stage_tickets = [[] for _ in range(FRAMES_IN_FLIGHT)]
+            if self.dtype == torch.float32:
+                # fp32 planes are downloaded as they are (half the PCIe bytes of float64) into pinned
+                # staging memory and widened by host threads (scb_host_widen_*): exact
+                self._stage32 = torch.empty((FRAMES_IN_FLIGHT, 2, self.n_w, self.n_h), dtype=torch.float32,
+                                            pin_memory=True)
             self._copy_stream = torch.cuda.Stream(device=self.device)
             self._plane_turn = 0
-        self._plane_turn ^= 1
-        p32, p64 = self._planes32[self._plane_turn], self._planes64[self._plane_turn]
+        turn = self._plane_turn = (self._plane_turn + 1) % FRAMES_IN_FLIGHT
+        if self._planes_free[turn] is not None:
+            main.wait_event(self._planes_free[turn])            # the set's previous frame has left the device
+        for ticket in self._stage_tickets[turn]:                # ... and its staging area has been read
+            _native.check(self.lib.scb_host_widen_wait(ticket), "scb_host_widen_wait")
+        self._stage_tickets[turn] = []
+        p32 = self._planes32[turn]
         self.detect(photons, frame_index, noise_seed, adc=p32[0], expectation=p32[1] if want_expectation else None)
         with _Trace(self, "host_alloc_planes"):
             hosts = [self._host_plane()[0] for _ in range(2 if want_expectation else 1)]
-        main = torch.cuda.current_stream(self.device)
+        tickets = []
         with _Trace(self, "enqueue_d2h"):
-            srcs = []
-            for k in range(len(hosts)):
-                src = p32[k]
-                if src.dtype != torch.float64:
-                    p64[k].copy_(src)
-                    src = p64[k]
-                srcs.append(src)
             ready = torch.cuda.Event()
             ready.record(main)
             self._copy_stream.wait_event(ready)
             with torch.cuda.stream(self._copy_stream):
-                for host, src in zip(hosts, srcs):
-                    host.copy_(src, non_blocking=True)
+                if self._stage32 is None:
+                    for k, host in enumerate(hosts):
+                        host.copy_(p32[k], non_blocking=True)      # float64 planes: straight into the caller's array
+                else:
+                    for k in range(len(hosts)):
+                        self._stage32[turn][k].copy_(p32[k], non_blocking=True)
                 planes_done = torch.cuda.Event()
                 planes_done.record(self._copy_stream)
+            self._planes_free[turn] = planes_done
+            if self._stage32 is not None:
+                device_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+                for k, host in enumerate(hosts):
+                    ticket = self.lib.scb_host_widen_start(
+                        self._stage32[turn][k].data_ptr(), host.data_ptr(), host.numel(),
+                        ctypes.c_void_p(planes_done.cuda_event), device_index)
+                    if ticket <= 0:
+                        raise _native.NativeError("scb_host_widen_start: " + self.lib.scb_last_error().decode())
+                    tickets.append(ticket)
+                self._stage_tickets[turn] = tickets
         true_host = None
         if isinstance(true_pending, tuple):
             true_host = (torch.empty(true_pending[0].shape, dtype=torch.float64, pin_memory=True), true_pending[1])
@@ -630,9 +682,9 @@ class DeviceEngine:
         errors_host = torch.empty(1, dtype=torch.int32, pin_memory=True)
         errors_host.copy_(self.errors, non_blocking=True)
         done = torch.cuda.Event()
-        done.record(torch.cuda.current_stream(self.device))
+        done.record(main)
         return dict(hosts=hosts, true=true_host, budget=budget_host, states=states, done=done, errors=errors_host,
-                    planes_done=planes_done,
+                    planes_done=planes_done, tickets=tickets,
                     exposure_time=exposure_time, want_expectation=want_expectation)
 
     def finish_frame(self, pending):
@@ -641,6 +693,8 @@ class DeviceEngine:
         with _Trace(self, "wait_device"):
             pending["done"].synchronize()
             pending["planes_done"].synchronize()
+            for ticket in pending["tickets"]:       # float64 planes widened on the host (releases the GIL)
+                _native.check(self.lib.scb_host_widen_wait(ticket), "scb_host_widen_wait")
         n_err = int(pending["errors"][0])      # read from pinned memory: no further device sync
         if n_err:
             self.errors.zero_()

@@ -61,3 +61,33 @@ def test_philox_known_answers():
         out = (ctypes.c_uint32 * 4)()
         lib.scb_philox4x32_10((ctypes.c_uint32 * 4)(*ctr), (ctypes.c_uint32 * 2)(*key), out)
         assert tuple(out) == want
+
+
+def test_host_widen_is_exact_and_ordered():
+    """scb_host_widen_*: the host-thread float32 -> float64 widening of downloaded frames
+    (pure host code).  Exact, leaves neighbouring memory alone, tickets complete in order."""
+    import numpy
+    from scopyon_b200 import _native
+    lib = _native.load()
+    rng = numpy.random.RandomState(0)
+    previous = lib.scb_host_widen_threads(3)
+    try:
+        for n in (0, 1, 7, 63, 64, 65, 1000, 300 * 301 + 5):
+            src = rng.standard_normal(n).astype(numpy.float32)
+            if n > 4:
+                src[:4] = [numpy.inf, -0.0, numpy.float32(1e-45), numpy.float32(3.4e38)]
+            dst = numpy.full(n + 3, -7.0)
+            ticket = lib.scb_host_widen_start(src.ctypes.data, dst[1:].ctypes.data, n, None, 0)   # 8-byte aligned only
+            assert ticket > 0 and lib.scb_host_widen_wait(ticket) == 0
+            assert numpy.array_equal(dst[1:n + 1], src.astype(numpy.float64))
+            assert dst[0] == -7.0 and (dst[n + 1:] == -7.0).all()
+        src = rng.standard_normal((6, 5000)).astype(numpy.float32)
+        dst = numpy.zeros((6, 5000))
+        tickets = [lib.scb_host_widen_start(src[k].ctypes.data, dst[k].ctypes.data, 5000, None, 0) for k in range(6)]
+        assert tickets == list(range(tickets[0], tickets[0] + 6))
+        assert lib.scb_host_widen_wait(tickets[-1]) == 0          # the last one done = all done
+        assert numpy.array_equal(dst, src.astype(numpy.float64))
+        assert lib.scb_host_widen_wait(tickets[-1] + 1000) != 0 and b"ticket" in lib.scb_last_error()
+        assert lib.scb_host_widen_start(None, dst.ctypes.data, 4, None, 0) == -1
+    finally:
+        lib.scb_host_widen_threads(previous)
