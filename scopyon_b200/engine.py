@@ -37,6 +37,10 @@ def same_array(a, b):
     return _libc.memcmp(a.ctypes.data, b.ctypes.data, a.nbytes) == 0
 
 
+# Planes of at least this many pixels take the float32-download + host-widening route (1024 x 1024:
+# below that the float64 download is a few tens of microseconds and the thread wake-up dominates).
+HOST_WIDEN_MIN_PIXELS = 1 << 20
+
 # Frames enqueued before the oldest is awaited (generate_frames) + 1: plane sets, staging areas.
 FRAMES_IN_FLIGHT = 3
 
@@ -625,13 +629,18 @@ class DeviceEngine:
             # frame f + FRAMES_IN_FLIGHT
             self._planes32 = torch.empty((FRAMES_IN_FLIGHT, 2, self.n_w, self.n_h), dtype=self.dtype, device=self.device)
             self._planes_free = [None] * FRAMES_IN_FLIGHT       # download of the set's previous frame
-            self._stage32 = None
+            self._stage32 = self._planes64 = None
             self._stage_tickets = [[] for _ in range(FRAMES_IN_FLIGHT)]
-            if self.dtype == torch.float32:
-                # fp32 planes are downloaded as they are (half the PCIe bytes of float64) into pinned
-                # staging memory and widened by host threads (scb_host_widen_*): exact
+            if self.dtype == torch.float32 and self.n_w * self.n_h >= HOST_WIDEN_MIN_PIXELS:
+                # large fp32 planes are downloaded as they are (half the PCIe bytes of float64) into
+                # pinned staging memory and widened by host threads (scb_host_widen_*): exact
                 self._stage32 = torch.empty((FRAMES_IN_FLIGHT, 2, self.n_w, self.n_h), dtype=torch.float32,
                                             pin_memory=True)
+            elif self.dtype == torch.float32:
+                # small ones (the wake-up of the host threads would cost more than the bytes saved)
+                # are widened on the device and downloaded as float64
+                self._planes64 = torch.empty((FRAMES_IN_FLIGHT, 2, self.n_w, self.n_h), dtype=torch.float64,
+                                             device=self.device)
             self._copy_stream = torch.cuda.Stream(device=self.device)
             self._plane_turn = 0
         turn = self._plane_turn = (self._plane_turn + 1) % FRAMES_IN_FLIGHT
@@ -646,13 +655,18 @@ class DeviceEngine:
             hosts = [self._host_plane()[0] for _ in range(2 if want_expectation else 1)]
         tickets = []
         with _Trace(self, "enqueue_d2h"):
+            sources = p32
+            if self._planes64 is not None:
+                sources = self._planes64[turn]
+                for k in range(len(hosts)):
+                    sources[k].copy_(p32[k])
             ready = torch.cuda.Event()
             ready.record(main)
             self._copy_stream.wait_event(ready)
             with torch.cuda.stream(self._copy_stream):
                 if self._stage32 is None:
                     for k, host in enumerate(hosts):
-                        host.copy_(p32[k], non_blocking=True)      # float64 planes: straight into the caller's array
+                        host.copy_(sources[k], non_blocking=True)  # float64 planes: straight into the caller's array
                 else:
                     for k in range(len(hosts)):
                         self._stage32[turn][k].copy_(p32[k], non_blocking=True)

@@ -154,3 +154,40 @@ def test_cmos_3d_epi_movie_against_oracle_expectation():
         assert "fluorescence_states" not in info
         adc = img.as_array()
         assert adc.min() >= 0 and abs(adc.mean() - (100 + (want.mean() + 1.9) / (30000 / (65536 - 100)))) < 3
+
+
+@pytest.mark.parametrize("full_output", [False, True])
+def test_large_frames_take_the_host_widening_route_and_equal_the_device_one(full_output, monkeypatch):
+    """Frames of >= 1024 x 1024 pixels leave the device as float32 and are widened to float64 by
+    host threads (scb_host_widen_*), three frames in flight; smaller ones are widened on the
+    device.  Same seeds, same kernels: the float64 arrays must be identical, frame for frame."""
+    from scopyon_b200 import engine as engine_module
+
+    def movie(min_pixels):
+        monkeypatch.setattr(engine_module, "HOST_WIDEN_MIN_PIXELS", min_pixels)
+        config = scopyon_b200.DefaultConfiguration()
+        config.update("""
+default:
+    magnification: 100
+    detector: {type: CMOS, image_size: [1024, 1040], pixel_length: {value: 6.5e-6, units: m}, QE: 0.73, exposure_time: 0.033}
+    analog_to_digital_converter: {bit: 16, offset: 100, fullwell: 30000, type: column, count: 2.0}
+""")
+        rng = numpy.random.RandomState(5)
+        pl = 6.5e-6 / 100
+        points = numpy.stack([rng.uniform(-500 * pl, 500 * pl, 400), rng.uniform(-500 * pl, 500 * pl, 400)], axis=1)
+        inputs = [(k * 0.033, points + k * 1e-8) for k in range(8)]
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            sim = scopyon_b200.create_simulator(config, rng=numpy.random.RandomState(9))
+            out = list(sim.generate_images(inputs, num_frames=7, full_output=full_output))
+        if full_output:
+            return [img.as_array().copy() for img, _ in out], [info["expectation"].copy() for _, info in out], sim
+        return [img.as_array().copy() for img in out], [], sim
+
+    host_frames, host_expect, sim_host = movie(1 << 20)
+    device_frames, device_expect, sim_device = movie(1 << 40)
+    assert len(host_frames) == 7 and host_frames[0].dtype == numpy.float64 and host_frames[0].shape == (1024, 1040)
+    for a, b in zip(host_frames + host_expect, device_frames + device_expect):
+        assert numpy.array_equal(a, b)
+    assert not numpy.array_equal(host_frames[0], host_frames[1])
+    assert 100 < host_frames[0].mean() < 120
