@@ -3,6 +3,7 @@ read-noise alias table, ADC offset map, scratch) and runs one frame through the
 C-ABI kernels.  PyTorch is used for device memory, streams and host<->device copies only.
 """
 import ctypes
+import os
 
 import numpy
 
@@ -636,6 +637,9 @@ class DeviceEngine:
                 # pinned staging memory and widened by host threads (scb_host_widen_*): exact
                 self._stage32 = torch.empty((FRAMES_IN_FLIGHT, 2, self.n_w, self.n_h), dtype=torch.float32,
                                             pin_memory=True)
+                ranks_here = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1)
+                if ranks_here > 1:      # one process per GPU: the ranks of a box share its host cores
+                    self.lib.scb_host_widen_threads(max(1, min(6, (os.cpu_count() or 8) // (2 * ranks_here))))
             elif self.dtype == torch.float32:
                 # small ones (the wake-up of the host threads would cost more than the bytes saved)
                 # are widened on the device and downloaded as float64
