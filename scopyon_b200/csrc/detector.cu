@@ -188,7 +188,8 @@ __device__ __forceinline__ void load_alias(AliasSlot *slots, const scb_alias_ent
 // variables" (1993); the same algorithm numpy uses for lam >= 10.
 __device__ __noinline__ double poisson_ptrs(double lambda, PixelRng &rng) {
     const double slam = sqrt(lambda);
-    const double loglam = log(lambda);
+    double loglam = 0.0;                   // log(lambda), only needed when the quick acceptance fails
+    bool have_log = false;
     const double b = 0.931 + 2.53 * slam;
     const double a = -0.059 + 0.02483 * b;
     const double invalpha = 1.1239 + 1.1328 / (b - 3.4);
@@ -200,6 +201,7 @@ __device__ __noinline__ double poisson_ptrs(double lambda, PixelRng &rng) {
         const double k = floor((2.0 * a / us + b) * U + lambda + 0.43);
         if (us >= 0.07 && V <= vr) return k;
         if (k < 0.0 || (us < 0.013 && V > us)) continue;
+        if (!have_log) { loglam = log(lambda); have_log = true; }
         if (log(V) + log(invalpha) - log(a / (us * us) + b) <= -lambda + k * loglam - lgamma(k + 1.0)) return k;
     }
     return floor(lambda);
@@ -490,16 +492,21 @@ detector_fast_kernel(const __grid_constant__ DetArgs launch) {
         j0 = (uint32_t)(((uint64_t)q << 2) % n_h);
         j_step = (uint32_t)(((uint64_t)stride << 2) % n_h);
     }
+    // The loop is warp uniform (a warp leaves it together: lanes past the end carry zero photons and store
+    // nothing), so the slow-pixel list can be appended to with warp-wide votes.
+    const uint32_t lane = threadIdx.x & 31u;
     float4 next = make_float4(0.f, 0.f, 0.f, 0.f);
     if (q < n_quads) next = __ldcs(photons + q);
-    for (; q < n_quads; q += stride) {
+    for (; q - lane < n_quads; q += stride) {
+        const bool valid = q < n_quads;
         const float4 ph = next;
+        next = make_float4(0.f, 0.f, 0.f, 0.f);
         if (q + stride < n_quads) next = __ldcs(photons + q + stride);
         float4 off;
         if (FPN == SCB_FPN_NONE) {
             off.x = off.y = off.z = off.w = launch.adc_offset_f;
         } else if (FPN == SCB_FPN_PIXEL) {
-            off = __ldcs(reinterpret_cast<const float4 *>(offset) + q);
+            off = valid ? __ldcs(reinterpret_cast<const float4 *>(offset) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
         } else {
             off = __ldg(reinterpret_cast<const float4 *>(offset + j0));
             j0 += j_step;
@@ -525,18 +532,27 @@ detector_fast_kernel(const __grid_constant__ DetArgs launch) {
             if (k2 == 4.0f) k2 = poisson_tail(c2, f2, r2.p, r2.s);
             if (k3 == 4.0f) k3 = poisson_tail(c3, f3, r3.p, r3.s);
         }
-        // pixels for the general samplers (bright, NaN, or EMCCD with electrons)
-        bool slow = !(l0 < kSmallLambda && l1 < kSmallLambda && l2 < kSmallLambda && l3 < kSmallLambda);
-        if (DET == SCB_DET_EMCCD) slow = slow || (k0 + k1) + (k2 + k3) != 0.0f;
-        if (slow) {
-            auto enlist = [&](float lam, float k, uint32_t pix) {
-                if (!(lam < kSmallLambda) || (DET == SCB_DET_EMCCD && k != 0.0f))
-                    a.slow_list[atomicAdd(a.slow_count, 1u)] = pix;
-            };
-            enlist(l0, k0, (q << 2) + 0);
-            enlist(l1, k1, (q << 2) + 1);
-            enlist(l2, k2, (q << 2) + 2);
-            enlist(l3, k3, (q << 2) + 3);
+        // pixels for the general samplers (bright, NaN, or EMCCD with electrons): one vote per quad; a warp
+        // that holds any claims its list space with a single atomic (a frame of bright pixels would otherwise
+        // serialise half a million atomics on one counter)
+        bool slow = valid && !(l0 < kSmallLambda && l1 < kSmallLambda && l2 < kSmallLambda && l3 < kSmallLambda);
+        if (DET == SCB_DET_EMCCD) slow = slow || (valid && (k0 + k1) + (k2 + k3) != 0.0f);
+        if (__any_sync(0xffffffffu, slow)) {
+            const bool s0 = slow && (!(l0 < kSmallLambda) || (DET == SCB_DET_EMCCD && k0 != 0.0f));
+            const bool s1 = slow && (!(l1 < kSmallLambda) || (DET == SCB_DET_EMCCD && k1 != 0.0f));
+            const bool s2 = slow && (!(l2 < kSmallLambda) || (DET == SCB_DET_EMCCD && k2 != 0.0f));
+            const bool s3 = slow && (!(l3 < kSmallLambda) || (DET == SCB_DET_EMCCD && k3 != 0.0f));
+            const uint32_t b0 = __ballot_sync(0xffffffffu, s0), b1 = __ballot_sync(0xffffffffu, s1),
+                           b2 = __ballot_sync(0xffffffffu, s2), b3 = __ballot_sync(0xffffffffu, s3);
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(a.slow_count, (uint32_t)(__popc(b0) + __popc(b1) + __popc(b2) + __popc(b3)));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            const uint32_t below = (1u << lane) - 1u;
+            uint32_t pos = base + __popc(b0 & below) + __popc(b1 & below) + __popc(b2 & below) + __popc(b3 & below);
+            if (s0) a.slow_list[pos++] = (q << 2) + 0;
+            if (s1) a.slow_list[pos++] = (q << 2) + 1;
+            if (s2) a.slow_list[pos++] = (q << 2) + 2;
+            if (s3) a.slow_list[pos++] = (q << 2) + 3;
         }
         float n0, n1, n2, n3;
         if (DET == SCB_DET_CMOS) {
@@ -564,7 +580,7 @@ detector_fast_kernel(const __grid_constant__ DetArgs launch) {
         float4 out;
         convert2(k0, k1, n0, n1, off.x, off.y, out.x, out.y);
         convert2(k2, k3, n2, n3, off.z, off.w, out.z, out.w);
-        __stcs(adc + q, out);
+        if (valid) __stcs(adc + q, out);
     }
 }
 
