@@ -372,12 +372,18 @@ class _EPIFMSimulator:
 
         from . import engine as engine_module
         in_flight = collections.deque()
-        for frame_index in range(num_frames):
-            in_flight.append(begin(frame_index))
-            if len(in_flight) == engine_module.FRAMES_IN_FLIGHT:
+        try:
+            for frame_index in range(num_frames):
+                in_flight.append(begin(frame_index))
+                if len(in_flight) == engine_module.FRAMES_IN_FLIGHT:
+                    yield finish(in_flight.popleft())
+            while in_flight:
                 yield finish(in_flight.popleft())
-        while in_flight:
-            yield finish(in_flight.popleft())
+        finally:
+            # the caller stopped early (or a frame failed): nothing may still be writing into the
+            # host arrays of the frames in flight when they are released
+            for pending in in_flight:
+                engine.abandon_frame(pending)
 
     def output_frame(
             self, input_data, frame_index=0, start_time=0.0, exposure_time=None,

@@ -730,6 +730,25 @@ class DeviceEngine:
             budgets = {int(i): float(b) for i, b in zip(pending["states"].ids[keep], host[keep])}
         return adc, expectation, true_data, budgets
 
+    def abandon_frame(self, pending):
+        """Wait until the device and the widening threads are done with a frame that will never be
+        handed out (``finish_frame`` was not called): its host arrays may be released afterwards."""
+        try:
+            pending["done"].synchronize()
+            pending["planes_done"].synchronize()
+        finally:
+            for ticket in pending["tickets"]:
+                self.lib.scb_host_widen_wait(ticket)
+
+    def __del__(self):
+        # staging memory must outlive the widening jobs that read it
+        try:
+            for tickets in getattr(self, "_stage_tickets", None) or []:
+                for ticket in tickets:
+                    self.lib.scb_host_widen_wait(ticket)
+        except Exception:       # interpreter shutdown: the library may be gone
+            pass
+
     def form_frame(self, snapshots, frame_index, noise_seed, states, exposure_time, want_true_data,
                    want_expectation=True):
         """One frame on the host: ``(adc (Nw, Nh) float64, expectation or None, true_data)``."""

@@ -191,3 +191,35 @@ default:
         assert numpy.array_equal(a, b)
     assert not numpy.array_equal(host_frames[0], host_frames[1])
     assert 100 < host_frames[0].mean() < 120
+
+
+def test_generator_abandoned_with_frames_in_flight():
+    """Breaking out of generate_images leaves two frames enqueued: closing the generator waits for
+    their downloads and widening jobs, and the next movie is unaffected (same seeds, same frames)."""
+    config = scopyon_b200.DefaultConfiguration()
+    config.update("""
+default:
+    magnification: 100
+    detector: {type: CMOS, image_size: [1024, 1024], pixel_length: {value: 6.5e-6, units: m}, QE: 0.73, exposure_time: 0.033}
+""")
+    rng = numpy.random.RandomState(2)
+    points = rng.uniform(-400 * 6.5e-8, 400 * 6.5e-8, (300, 2))
+    inputs = [(k * 0.033, points + k * 2e-8) for k in range(10)]
+
+    def first_frames(count, stop_after):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            sim = scopyon_b200.create_simulator(config, rng=numpy.random.RandomState(4))
+            frames = []
+            gen = sim.generate_images(inputs, num_frames=count)
+            for img in gen:
+                frames.append(img.as_array().copy())
+                if len(frames) == stop_after:
+                    break
+            gen.close()
+        return frames
+
+    short = first_frames(9, 2)            # frames 2 and 3 are in flight when the loop stops
+    full = first_frames(9, 9)
+    assert len(short) == 2 and len(full) == 9
+    assert numpy.array_equal(short[0], full[0]) and numpy.array_equal(short[1], full[1])
