@@ -118,7 +118,8 @@ spot_prepare_kernel(Geo g, int64_t n, int64_t stride, const double *__restrict__
                     const double *__restrict__ y, const double *__restrict__ weight,
                     const double *__restrict__ inv_scale, const int32_t *__restrict__ slot_of_key,
                     SpotRec *__restrict__ spots, int *__restrict__ tile_count,
-                    unsigned long long *__restrict__ wmax_bits, int32_t *__restrict__ errors) {
+                    unsigned long long *__restrict__ wmax_bits, int32_t *__restrict__ errors,
+                    int *__restrict__ ranks = nullptr, int rank_cap = 0) {
     // grid: x over the spots of one frame, y over frames
     const int64_t in_frame = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int frame = blockIdx.y;
@@ -175,9 +176,23 @@ spot_prepare_kernel(Geo g, int64_t n, int64_t stride, const double *__restrict__
                     int *count = tile_count + ((size_t)stripe_of(g, s) * g.frames + frame) * g.nti * g.ntj;
                     const int t0 = rec.imin / g.tile_h, t1 = (rec.imax - 1) / g.tile_h;
                     const int u0 = rec.jmin / g.tile_w, u1 = (rec.jmax - 1) / g.tile_w;
+                    // With `ranks` the census also hands every (spot, tile) its place in the tile's list
+                    // (the value the counter had), in the order the fill kernel walks the tiles: the
+                    // fill then needs no atomics of its own.
+                    int *my_rank = ranks ? ranks + (size_t)s * rank_cap : nullptr;
+                    int visited = 0;
                     for (int tj = u0; tj <= u1; ++tj) {
                         const int entries = overlap_entries(g, rec.jmin, rec.jmax, tj);
-                        for (int ti = t0; ti <= t1; ++ti) atomicAdd(&count[ti * g.ntj + tj], entries);
+                        for (int ti = t0; ti <= t1; ++ti) {
+                            if (my_rank) {
+                                const int r = atomicAdd(&count[ti * g.ntj + tj], entries);
+                                if (visited < rank_cap) my_rank[visited] = r;
+                                else atomicAdd(errors, 1);      // cannot happen: rank_cap bounds the tiles of a footprint
+                                ++visited;
+                            } else {
+                                atomicAdd(&count[ti * g.ntj + tj], entries);
+                            }
+                        }
                     }
                 }
             }
@@ -381,6 +396,8 @@ struct Workspace {
     unsigned long long *wmax_bits;   // bit pattern of the largest spot weight (cleared with the census)
     int *next_tile;                  // dynamic tile queue of the persistent render kernel (cleared likewise)
     int *pair_spot;                  // list entries: spot indices (entry_bytes = 4) or render units
+    int *ranks;                      // [n][rank_cap] list positions handed out by the census (render path)
+    int rank_cap;
     size_t bytes;
     int64_t pair_capacity;
 };
@@ -426,7 +443,17 @@ int64_t max_tiles_per_spot(const Geo &g) {
     return a * b;
 }
 
-Workspace carve(const Geo &g, int64_t n, void *base, size_t entry_bytes = sizeof(int)) {
+// tiles one footprint can touch (rows x columns of tiles)
+int tiles_per_spot_bound(const Geo &g) {
+    const double rows = ceil(g.sw / g.pl) + 2.0;
+    int64_t a = (int64_t)((rows + g.tile_h - 2) / g.tile_h) + 1;
+    int64_t b = (int64_t)((rows + g.tile_w - 2) / g.tile_w) + 1;
+    if (a > g.nti) a = g.nti;
+    if (b > g.ntj) b = g.ntj;
+    return (int)(a * b);
+}
+
+Workspace carve(const Geo &g, int64_t n, void *base, size_t entry_bytes = sizeof(int), bool with_ranks = false) {
     Workspace w;
     const size_t n_tiles = (size_t)g.frames * g.nti * g.ntj;
     w.pair_capacity = (n > 0 ? n : 1) * max_tiles_per_spot(g);
@@ -448,6 +475,12 @@ Workspace carve(const Geo &g, int64_t n, void *base, size_t entry_bytes = sizeof
     w.next_tile = (int *)(p + off + 8); off += 256;
     w.tile_start = (int *)(p + off); off += align_up((n_tiles * g.stripes + 1) * sizeof(int));
     w.pair_spot = (int *)(p + off); off += align_up((size_t)w.pair_capacity * entry_bytes);
+    w.ranks = nullptr;
+    w.rank_cap = 0;
+    if (with_ranks) {
+        w.rank_cap = tiles_per_spot_bound(g);
+        w.ranks = (int *)(p + off); off += align_up((size_t)(n > 0 ? n : 1) * w.rank_cap * sizeof(int));
+    }
     w.bytes = off;
     return w;
 }

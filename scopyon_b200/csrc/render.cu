@@ -83,12 +83,13 @@ __device__ __forceinline__ int strip_shift(int n_units, unsigned long long wmax_
     return max(-900, min(31 - e, 900));
 }
 
-// One thread per spot: write the spot's units into the strips' list segments.
+// One thread per spot: write the spot's units into the strips' list segments, at the places the
+// census handed out (`ranks`, in the same tile order) -- no atomics here.
 __global__ void __launch_bounds__(256)
 strip_fill_kernel(Geo g, int64_t n, const SpotRec *__restrict__ spots, int edge_cap,
+                  const int *__restrict__ ranks, int rank_cap,
                   const int64_t *__restrict__ sat, const void *__restrict__ box_table, int box_bytes,
-                  const int *__restrict__ tile_start,
-                  int *__restrict__ tile_cursor, const unsigned long long *__restrict__ wmax_bits,
+                  const int *__restrict__ tile_start, const unsigned long long *__restrict__ wmax_bits,
                   Unit *__restrict__ units) {
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
@@ -107,7 +108,8 @@ strip_fill_kernel(Geo g, int64_t n, const SpotRec *__restrict__ spots, int edge_
     const uint32_t ebase = (uint32_t)s * 2u * (uint32_t)edge_cap;
     const int stripe = stripe_of(g, s);
     const int frame_tile0 = rec.frame * g.nti * g.ntj;     // first strip of the spot's frame
-    int *cursor = tile_cursor + (size_t)stripe * g.frames * g.nti * g.ntj;
+    const int *my_rank = ranks + (size_t)s * rank_cap;
+    int visited = 0;
     const int t0 = rec.imin / g.tile_h, t1 = (rec.imax - 1) / g.tile_h;
     const int u0 = rec.jmin / g.tile_w, u1 = (rec.jmax - 1) / g.tile_w;
     for (int tj = u0; tj <= u1; ++tj) {
@@ -116,7 +118,8 @@ strip_fill_kernel(Geo g, int64_t n, const SpotRec *__restrict__ spots, int edge_
         for (int ti = t0; ti <= t1; ++ti) {
             const int r_lo = max(rec.imin, ti * g.tile_h), r_hi = min(rec.imax, (ti + 1) * g.tile_h);
             const int tile = frame_tile0 + ti * g.ntj + tj;
-            Unit *dst = units + tile_start[tile * g.stripes + stripe] + atomicAdd(&cursor[tile], entries);
+            Unit *dst = units + tile_start[tile * g.stripes + stripe] + __ldg(my_rank + visited);
+            ++visited;
             const int rows = r_hi - r_lo;
             u.erow = ebase + (uint32_t)(r_lo - rec.imin);
             const int first_box_row = row_slot0 + (r_lo - rec.imin) + 1;
@@ -420,13 +423,13 @@ static Geo strip_geo(const scb_geometry *geom, bool have_box, int box_bytes, int
 extern "C" size_t scb_render_workspace_bytes(const scb_geometry *geom, int64_t n_spots) {
     if (check_geometry(geom) != 0 || n_spots < 0) return 0;
     Geo g = strip_geo(geom, false, 8);
-    return carve(g, n_spots, nullptr, sizeof(Unit)).bytes;
+    return carve(g, n_spots, nullptr, sizeof(Unit), true).bytes;
 }
 
 extern "C" size_t scb_render_frames_workspace_bytes(const scb_geometry *geom, int64_t n_per_frame, int n_frames) {
     if (check_geometry(geom) != 0 || n_per_frame < 0 || n_frames < 1) return 0;
     Geo g = strip_geo(geom, false, 8, n_frames, n_per_frame);
-    return carve(g, n_per_frame * n_frames, nullptr, sizeof(Unit)).bytes;
+    return carve(g, n_per_frame * n_frames, nullptr, sizeof(Unit), true).bytes;
 }
 
 template <typename OutT, typename BoxT, int SLOTS>
@@ -481,7 +484,7 @@ static int render_expected_strided(const scb_geometry *geom, int64_t n_spots, in
     SCB_REQUIRE(frames >= 1 && frames <= 4096 && n_spots % frames == 0, SCB_E_INVALID,
                 "scb_render_expected: %lld spots do not split into %d frames", (long long)n_spots, frames);
     Geo g = strip_geo(geom, d_box != nullptr, box_bytes, frames, n_spots / frames);
-    Workspace w = carve(g, n_spots, d_workspace, sizeof(Unit));
+    Workspace w = carve(g, n_spots, d_workspace, sizeof(Unit), true);
     SCB_REQUIRE(workspace_bytes >= w.bytes, SCB_E_WORKSPACE, "scb_render_expected: workspace %zu < %zu",
                 workspace_bytes, w.bytes);
     SCB_REQUIRE((double)n_spots * 2.0 * w.edge_cap < 4294967296.0, SCB_E_UNSUPPORTED,
@@ -494,15 +497,15 @@ static int render_expected_strided(const scb_geometry *geom, int64_t n_spots, in
     if (n_spots > 0) {
         spot_prepare_kernel<<<dim3(scb_grid_for(n_spots / frames, 256), frames), 256, 0, s>>>(
             g, n_spots, stride, d_depth, d_x, d_y, d_weight, d_inv_scale, d_slot_of_key, w.spots, w.tile_count,
-            w.wmax_bits, d_errors);
+            w.wmax_bits, d_errors, w.ranks, w.rank_cap);
         dim3 egrid, eblock;
         edges_launch_shape(w.edge_cap, n_spots, egrid, eblock);
         spot_edges_kernel<<<egrid, eblock, 0, s>>>(g, n_spots, w.spots, w.edges, w.edge_cap);
     }
     tile_scan_kernel<<<kScanCtas, 1024, 0, s>>>(n_tiles, g.stripes, w.tile_count, w.tile_start);
     if (n_spots > 0) {
-        strip_fill_kernel<<<scb_grid_for(n_spots, 256), 256, 0, s>>>(g, n_spots, w.spots, w.edge_cap, d_sat, d_box,
-                                                                    box_bytes, w.tile_start, w.tile_cursor,
+        strip_fill_kernel<<<scb_grid_for(n_spots, 256), 256, 0, s>>>(g, n_spots, w.spots, w.edge_cap, w.ranks, w.rank_cap,
+                                                                    d_sat, d_box, box_bytes, w.tile_start,
                                                                     w.wmax_bits, (Unit *)w.pair_spot);
     }
     const bool timed = g_profile.enabled && g_profile.used < g_profile.capacity;
