@@ -9,22 +9,25 @@
 //     operations in the same order (explicit __d*_rn intrinsics: never contracted to FMA);
 //   * each slice sum is S[i1][j1] - S[i0][j1] - S[i1][j0] + S[i0][j0] on the int64 SAT
 //     built by scb_psf_sat_build -- exact, so results do not depend on how a footprint is cut;
-//   * one WARP owns one 8 x 64-pixel strip of the image and keeps its 512 accumulators in
-//     shared memory (28 strips in flight per SM).  The strip's work list holds one 32-byte unit per (spot, <=8 rows,
-//     <=32 columns) overlap.  For a footprint whose pixel edges are evenly spaced (whole
-//     number of table samples per pixel) the box sums of all its pixels are one dense
-//     rectangle of one block of the "box table" (psf.cu), so a unit's (<= 8) x 32 values arrive
-//     by TMA: one bulk copy of up to 2 KB into a three-stage shared-memory ring, completion
-//     on an mbarrier, two units ahead of the arithmetic.  Lane l owns column l of the unit and
-//     adds `box * weight` to its accumulators: one shared-memory load, one multiply and one
-//     conversion per pixel.  Every lane of a unit carries a footprint pixel, there is no
-//     block-wide barrier and no atomic on the image.  Footprints whose edges are not evenly
-//     spaced (pixel pitch not a whole number of samples, or a rounding step in the edge
-//     arithmetic) gather the four SAT corners per pixel through per-edge offsets -- same
-//     integer box sums, bit-identical result;
-//   * accumulators are 64-bit fixed point (LSB 2^-K photons, K chosen per call from the
-//     largest spot weight so that the sum cannot overflow): integer addition is associative,
-//     so the image is bitwise reproducible whatever order the work list was filled in.
+//   * one WARP owns one strip of the image -- 8 x 128 pixels with 32-bit accumulators (fp32 box
+//     tables, the default) or 8 x 64 with 64-bit ones (fp64 tables, exact mode) -- and keeps its
+//     accumulators in 4 KB of shared memory (28 strips in flight per SM).  The strip's work list holds
+//     one 32-byte unit per (spot, <= 8 rows, <= 32 columns) overlap; the census of spot_prepare hands
+//     every (spot, strip) its place in the list, so the lists are filled without atomics.  For a
+//     footprint whose pixel edges are evenly spaced (whole number of table samples per pixel) the box
+//     sums of all its pixels are one dense rectangle of one block of the "box table" (psf.cu), so a
+//     unit's (<= 8) x 32 values arrive by TMA: one bulk copy of up to 1 KB (2 KB in fp64) into a
+//     three-stage shared-memory ring, completion on an mbarrier, two units ahead of the arithmetic.
+//     Lane l owns column l of the unit and adds `box * weight` to its accumulators: one shared-memory
+//     load, one multiply and one conversion per pixel.  Every lane of a unit carries a footprint pixel,
+//     there is no block-wide barrier and no atomic on the image.  Footprints whose edges are not evenly
+//     spaced (pixel pitch not a whole number of samples, or a rounding step in the edge arithmetic)
+//     gather the four SAT corners per pixel through per-edge offsets -- same integer box sums,
+//     bit-identical result;
+//   * accumulators are fixed point: 64-bit with the LSB 2^-K photons chosen per call from the largest
+//     spot weight (exact mode), 32-bit with the LSB chosen per strip from its list length (fp32 mode),
+//     in both cases so that no sum can overflow.  Integer addition is associative, so the image is
+//     bitwise reproducible whatever order the work list was filled in.
 #include "binning.cuh"
 
 namespace {
