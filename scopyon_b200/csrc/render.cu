@@ -200,7 +200,9 @@ template <typename BoxT, int SLOTS>
 __device__ __forceinline__ void unit_accumulate_fast(const Unit *meta, int u, int lane, typename Mode<BoxT>::Acc *acc,
                                                      const BoxT *stage, int runtime_slots, double scale) {
     const int slots = SLOTS ? SLOTS : runtime_slots;
-    const BoxT ws = (BoxT)(meta[u].ws * scale);
+    BoxT ws;
+    if constexpr (sizeof(BoxT) == 4) ws = *reinterpret_cast<const float *>(&meta[u].ws);   // scaled at fetch time
+    else ws = (BoxT)(meta[u].ws * scale);
     const uint32_t shape = meta[u].shape;
     const int n_rows = shape & 0xff;
     int rows = (lane < (int)((shape >> 8) & 0xff)) ? n_rows : 0;   // idle lanes: no rows
@@ -223,7 +225,9 @@ __device__ __forceinline__ void unit_accumulate_fast(const Unit *meta, int u, in
 template <typename BoxT>
 __device__ __forceinline__ void unit_accumulate_gather(const Unit *meta, int u, int lane, typename Mode<BoxT>::Acc *acc,
                                                        const uint32_t *__restrict__ edges, double scale) {
-    const BoxT ws = (BoxT)(meta[u].ws * scale);
+    BoxT ws;
+    if constexpr (sizeof(BoxT) == 4) ws = *reinterpret_cast<const float *>(&meta[u].ws);   // scaled at fetch time
+    else ws = (BoxT)(meta[u].ws * scale);
     const uint32_t shape = meta[u].shape;
     const int n_rows = shape & 0xff, n_cols = (shape >> 8) & 0xff;
     const int rows = lane < n_cols ? n_rows : 0;
@@ -318,7 +322,14 @@ render_strips_kernel(Geo g, const Unit *__restrict__ units, const uint32_t *__re
             if (lane < nb) {
                 const uint4 *src = reinterpret_cast<const uint4 *>(units + base + lane);
                 uint4 *dst = reinterpret_cast<uint4 *>(meta + lane);
-                const uint4 head = __ldg(src), tail = __ldg(src + 1);      // {ws, src} {erow, ecol, shape, extra}
+                uint4 head = __ldg(src);                                    // {ws, src}
+                const uint4 tail = __ldg(src + 1);                          // {erow, ecol, shape, extra}
+                if constexpr (sizeof(BoxT) == 4) {
+                    // fp32 mode: the unit's weight in accumulator LSBs is formed once, by the fetching lane
+                    // (the same double product and conversion the 32 consumer lanes would each repeat)
+                    const double ws = __longlong_as_double(((long long)head.y << 32) | head.x);
+                    head.x = __float_as_uint((float)(ws * scale));
+                }
                 dst[0] = head;
                 dst[1] = tail;
                 my_src = reinterpret_cast<const void *>(((unsigned long long)head.w << 32) | head.z);
