@@ -201,14 +201,27 @@ __device__ __forceinline__ void unit_accumulate_fast(const Unit *meta, int u, in
                                                      const BoxT *stage, int runtime_slots, double scale) {
     const int slots = SLOTS ? SLOTS : runtime_slots;
     BoxT ws;
-    if constexpr (sizeof(BoxT) == 4) ws = *reinterpret_cast<const float *>(&meta[u].ws);   // scaled at fetch time
-    else ws = (BoxT)(meta[u].ws * scale);
-    const uint32_t shape = meta[u].shape;
-    const int n_rows = shape & 0xff;
-    int rows = (lane < (int)((shape >> 8) & 0xff)) ? n_rows : 0;   // idle lanes: no rows
+    int n_rows, n_cols, acc_at, box_col;
+    if constexpr (sizeof(BoxT) == 4) {
+        // fp32 mode: the fetching lane has unpacked the unit (see the fetch below): one 16-byte load
+        const uint4 packed = *reinterpret_cast<const uint4 *>(meta + u);
+        ws = __uint_as_float(packed.x);
+        acc_at = (int)packed.y;
+        box_col = (int)packed.z;
+        n_rows = (int)(packed.w & 0xffu);
+        n_cols = (int)(packed.w >> 8);
+    } else {
+        ws = (BoxT)(meta[u].ws * scale);
+        const uint32_t shape = meta[u].shape;
+        n_rows = shape & 0xff;
+        n_cols = (shape >> 8) & 0xff;
+        acc_at = ((shape >> 16) & 0xff) * Mode<BoxT>::kCols + (shape >> 24);
+        box_col = (int)(meta[u].extra & 0xffu);
+    }
+    int rows = lane < n_cols ? n_rows : 0;   // idle lanes: no rows
     asm volatile("" : "+r"(rows));       // keep it one value: one compare per row below instead of two
-    typename Mode<BoxT>::Acc *a = acc + ((shape >> 16) & 0xff) * Mode<BoxT>::kCols + (shape >> 24) + lane;
-    const BoxT *st = stage + min((int)(meta[u].extra & 0xffu) + lane, slots - 1);   // idle lanes stay inside the row
+    typename Mode<BoxT>::Acc *a = acc + acc_at + lane;
+    const BoxT *st = stage + min(box_col + lane, slots - 1);   // idle lanes stay inside the row
     BoxT box[kStripRows];
     if (n_rows <= kStripRows / 2) {         // warp uniform
 #pragma unroll
@@ -324,15 +337,22 @@ render_strips_kernel(Geo g, const Unit *__restrict__ units, const uint32_t *__re
                 uint4 *dst = reinterpret_cast<uint4 *>(meta + lane);
                 uint4 head = __ldg(src);                                    // {ws, src}
                 const uint4 tail = __ldg(src + 1);                          // {erow, ecol, shape, extra}
+                my_src = reinterpret_cast<const void *>(((unsigned long long)head.w << 32) | head.z);
                 if constexpr (sizeof(BoxT) == 4) {
-                    // fp32 mode: the unit's weight in accumulator LSBs is formed once, by the fetching lane
-                    // (the same double product and conversion the 32 consumer lanes would each repeat)
+                    // fp32 mode: the fetching lane forms the unit's weight in accumulator LSBs once (the same
+                    // double product and conversion the 32 consumer lanes would each repeat) and, for a
+                    // box-table unit, unpacks shape and column into the words the consumers use directly:
+                    // {weight, accumulator offset, box-table column, rows | columns << 8}
                     const double ws = __longlong_as_double(((long long)head.y << 32) | head.x);
                     head.x = __float_as_uint((float)(ws * scale));
+                    if (tail.w & kUnitFast) {
+                        head.y = ((tail.z >> 16) & 0xffu) * Mode<BoxT>::kCols + (tail.z >> 24);
+                        head.z = tail.w & 0xffu;
+                        head.w = tail.z & 0xffffu;
+                    }
                 }
                 dst[0] = head;
                 dst[1] = tail;
-                my_src = reinterpret_cast<const void *>(((unsigned long long)head.w << 32) | head.z);
                 my_bytes = (tail.z & 0xffu) * row_bytes;
                 my_fast = (tail.w & kUnitFast) != 0;
             }
