@@ -76,6 +76,7 @@ class WidenPool {
 
     // Takes effect when the queue is idle; returns the previous setting.
     int set_threads(int n) {
+        std::lock_guard<std::mutex> control(control_);     // no submit() while the pool is rebuilt
         std::unique_lock<std::mutex> lock(mu_);
         const int old = n_workers_;
         if (n >= 1 && n <= 64 && n != n_workers_) {
@@ -89,6 +90,7 @@ class WidenPool {
     }
 
     int64_t submit(const float *src, double *dst, size_t n, cudaEvent_t event, int device) {
+        std::lock_guard<std::mutex> control(control_);
         std::lock_guard<std::mutex> lock(mu_);
         if (!running_) start_locked();
         Job job = {src, dst, n, event, device, next_ticket_++};
@@ -185,6 +187,7 @@ class WidenPool {
         }
     }
 
+    std::mutex control_;     // serialises submit() and set_threads()
     std::mutex mu_;
     std::condition_variable queue_cv_, work_cv_, parts_cv_, done_cv_;
     std::deque<Job> queue_;
