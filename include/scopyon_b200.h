@@ -357,6 +357,10 @@ int scb_detector_adc_frames(uint64_t seed, uint64_t first_frame, int n_frames, c
  * limits from d_limits[2] on the device when given, else from cmin / cmax. */
 int scb_frames_minmax(const void *d_frames, int64_t n, int elem_type, double *d_minmax, void *d_workspace,
                       void *stream);
+/* 16-bit camera counts of a frame stack for export: out = uint16(rint(clip(v, 0, 65535))), NaN -> 0
+ * (what `img.as_array().round().clip(0, 65535).astype(uint16)` gives; the reference's ADC does not
+ * quantise, _epifm.py:1472-1484, so this is an export format, not the API's return type). */
+int scb_frames_to_u16(const void *d_frames, int64_t n, int elem_type, uint16_t *d_out, void *stream);
 int scb_frames_to_8bit(const void *d_frames, int64_t n, int elem_type, const double *d_limits,
                        double cmin, double cmax, double low, double high, uint8_t *d_out, void *stream);
 
@@ -413,6 +417,25 @@ int scb_spot_fit(int n_w, int n_h, const double *d_image, int64_t n_blobs, const
 int64_t scb_host_widen_start(const float *h_src, double *h_dst, int64_t n, void *cuda_event, int device);
 int scb_host_widen_wait(int64_t ticket);
 int scb_host_widen_threads(int n_threads);
+/* Pins worker w to cpus[w % n_cpus] (n_cpus = 0: no pinning), applied when the queue is idle: the ranks
+ * of one box (one process per GPU) give their workers disjoint cores next to their GPU. */
+int scb_host_widen_affinity(const int *cpus, int n_cpus);
+/* Host memory bandwidth with the access patterns of this path, n_threads threads on private buffers,
+ * best of `repeats`: mode 0 = copy with streaming stores (read b + write b), mode 1 = the float32 ->
+ * float64 widening above (read b + write 2b).  *bytes_per_s = bytes read + written per second: the
+ * bound the end-to-end frame rate of a box is reported against (bench.py).  Pure host code. */
+int scb_host_bandwidth(int mode, int64_t bytes_per_thread, int n_threads, int repeats, double *bytes_per_s);
+
+/* ---- device properties / test hooks ------------------------------------------------------ */
+
+/* Multiprocessors of the current device (grids of the persistent kernels are sized from it). */
+int scb_device_sm_count(void);
+/* Known-answer hooks for the tests; not used by the product path.  scb_philox4x32_10: the counter-based
+ * generator on the host (Random123 vectors).  scb_test_poisson_inversion: the detector's inversion
+ * sampler (expectation < 12 photoelectrons) on n given (expectation, 32-bit word) pairs -> counts. */
+void scb_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+int scb_test_poisson_inversion(int64_t n, const float *d_lambda, const uint32_t *d_word, float *d_count,
+                               void *stream);
 
 #ifdef __cplusplus
 }

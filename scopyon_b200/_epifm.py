@@ -316,6 +316,11 @@ def frame_windows(times, frame_index, start_time, exposure_time, configs):
     return windows, t, exposure_time
 
 
+def _payload(plane):
+    """The array to copy a finished plane from: itself, or the float32 payload of a ``HostPlane``."""
+    return getattr(plane, "f32", plane)
+
+
 class _EPIFMSimulator:
     """Frame generator with the reference's interface (``_epifm.py:998-1225``)."""
 
@@ -361,10 +366,10 @@ class _EPIFMSimulator:
         def finish(pending):
             adc, expectation, true_data, budgets = engine.finish_frame(pending)
             if not full_output:
-                return adc, dict(true_data={})
+                return adc, dict(true_data={})      # the bare ADC plane: an array, or a float32 HostPlane
             camera = numpy.empty(adc.shape + (2,), dtype=numpy.float64)   # _epifm.py:1177
-            camera[:, :, 0] = expectation
-            camera[:, :, 1] = adc
+            camera[:, :, 0] = _payload(expectation)   # float32 payloads are widened by the assignment (exact)
+            camera[:, :, 1] = _payload(adc)
             infodict = dict(true_data=true_data if true_data is not None else {})
             if budgets is not None:
                 infodict['fluorescence_states'] = budgets
@@ -417,13 +422,13 @@ class _EPIFMSimulator:
         snapshots = [(unit_time, input_data[k][1]) for k, unit_time in windows]
         adc, expectation, true_data = engine.form_frame(
             snapshots, frame_index=frame_index, noise_seed=noise_seed, states=states,
-            exposure_time=exposure_time, want_true_data=_full_output, want_expectation=not _planes)
+            exposure_time=exposure_time, want_true_data=_full_output, want_expectation=not _planes, lazy=True)
         if _planes:
             camera = adc
         else:
             camera = numpy.empty(adc.shape + (2,), dtype=numpy.float64)   # _epifm.py:1177
-            camera[:, :, 0] = expectation
-            camera[:, :, 1] = adc
+            camera[:, :, 0] = _payload(expectation)
+            camera[:, :, 1] = _payload(adc)
 
         infodict = dict(true_data=true_data if true_data is not None else {})
         if fluorescence_states is not None:

@@ -137,12 +137,17 @@ SIGNATURES = {
     "scb_host_widen_start": (ctypes.c_int64, [c_ptr, c_ptr, ctypes.c_int64, c_ptr, ctypes.c_int]),
     "scb_host_widen_wait": (ctypes.c_int, [ctypes.c_int64]),
     "scb_host_widen_threads": (ctypes.c_int, [ctypes.c_int]),
+    "scb_host_widen_affinity": (ctypes.c_int, [ctypes.POINTER(ctypes.c_int), ctypes.c_int]),
+    "scb_host_bandwidth": (ctypes.c_int, [
+        ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]),
+    "scb_frames_to_u16": (ctypes.c_int, [c_ptr, ctypes.c_int64, ctypes.c_int, c_ptr, c_ptr]),
+    "scb_device_sm_count": (ctypes.c_int, []),
+    # known-answer hooks for the tests
+    "scb_philox4x32_10": (None, [ctypes.POINTER(ctypes.c_uint32)] * 3),
+    "scb_test_poisson_inversion": (ctypes.c_int, [ctypes.c_int64, c_ptr, c_ptr, c_ptr, c_ptr]),
 }
 
-# not part of the public header: host-side known-answer hook for the Philox generator
-_EXTRA = {
-    "scb_philox4x32_10": (None, [ctypes.POINTER(ctypes.c_uint32)] * 3),
-}
+_EXTRA = {}
 
 _lib = None
 

@@ -134,13 +134,18 @@ __device__ __forceinline__ void poisson_head2(float la, float lb, float rfa, flo
     rb.s = sb;
 }
 
+// The running sum is fp32 against a word scaled by 2^32: once a term falls below half an ulp of the sum
+// (128-256 near 2^32) the sum stops moving, possibly a few hundred below the largest words.  The terms only
+// shrink from there on (a lost term lies past the mode), so the search ends at that count: the top ~2^-23 of
+// the word range is folded into the last count that could still be told apart, never into the loop bound.
 __device__ __noinline__ float poisson_tail(float lambda, float rf, float p, float s) {
     int k = 4;
 #pragma unroll 1
     while (k < 160) {
         p = __fmul_rn(p, __fdividef(lambda, (float)k));
-        s = __fadd_rn(s, p);
-        if (rf < s) break;
+        const float next = __fadd_rn(s, p);
+        if (rf < next || next == s) break;
+        s = next;
         ++k;
     }
     return (float)k;
@@ -634,6 +639,14 @@ detector_slow_kernel(const __grid_constant__ DetArgs launch) {
     }
 }
 
+// test hook: the inversion sampler on given (lambda, word) pairs
+__global__ void __launch_bounds__(kThreads)
+poisson_inversion_probe_kernel(int64_t n, const float *__restrict__ lambda, const uint32_t *__restrict__ word,
+                               float *__restrict__ count) {
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i < n) count[i] = poisson_small(fminf(lambda[i], kSmallLambda), word[i]);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 adc_offsets_kernel(uint64_t seed, int64_t n, double adc0, double fpn_count, T *__restrict__ offset) {
@@ -687,6 +700,16 @@ void launch_detector(const DetArgs &a, int n_frames, cudaStream_t s) {
 }
 
 }  // namespace
+
+extern "C" int scb_test_poisson_inversion(int64_t n, const float *d_lambda, const uint32_t *d_word, float *d_count,
+                                          void *stream) {
+    SCB_REQUIRE(n >= 0 && (n == 0 || (d_lambda && d_word && d_count)), SCB_E_NULL, "scb_test_poisson_inversion: NULL pointer");
+    if (n == 0) return 0;
+    poisson_inversion_probe_kernel<<<scb_grid_for(n, kThreads), kThreads, 0, (cudaStream_t)stream>>>(n, d_lambda, d_word,
+                                                                                                  d_count);
+    SCB_CUDA_LAUNCH_CHECK("scb_test_poisson_inversion");
+    return 0;
+}
 
 extern "C" int scb_adc_offsets(uint64_t seed, int64_t n, double adc0, double fpn_count, void *d_offset,
                                int elem_type, void *stream) {

@@ -89,7 +89,47 @@ to_8bit_kernel(const T *__restrict__ data, int64_t n, const double *__restrict__
     }
 }
 
+// 16-bit camera counts: uint16(rint(clip(v, 0, 65535))), NaN -> 0.  Eight pixels per thread: one 16-byte store.
+template <typename T>
+__global__ void __launch_bounds__(256)
+to_u16_kernel(const T *__restrict__ data, int64_t n, uint16_t *__restrict__ out) {
+    const int64_t octs = (n + 7) >> 3;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < octs; q += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int64_t i = (q << 3) + k;
+            uint32_t v = 0;
+            if (i < n) {
+                const double x = (double)data[i];
+                v = (uint32_t)__double2int_rn(fmin(fmax(x, 0.0), 65535.0));     // fmax(NaN, 0) = 0
+            }
+            w[k >> 1] |= v << (16 * (k & 1));
+        }
+        if ((q << 3) + 7 < n) {
+            reinterpret_cast<uint4 *>(out)[q] = make_uint4(w[0], w[1], w[2], w[3]);
+        } else {
+            for (int k = 0; k < 8 && (q << 3) + k < n; ++k) out[(q << 3) + k] = (uint16_t)(w[k >> 1] >> (16 * (k & 1)));
+        }
+    }
+}
+
 }  // namespace
+
+extern "C" int scb_frames_to_u16(const void *d_frames, int64_t n, int elem_type, uint16_t *d_out, void *stream) {
+    SCB_REQUIRE(d_frames && d_out, SCB_E_NULL, "scb_frames_to_u16: NULL pointer");
+    SCB_REQUIRE(n > 0, SCB_E_INVALID, "scb_frames_to_u16: n=%lld", (long long)n);
+    SCB_REQUIRE(elem_type == SCB_F32 || elem_type == SCB_F64, SCB_E_INVALID, "elem_type=%d", elem_type);
+    SCB_REQUIRE(((uintptr_t)d_out & 15) == 0, SCB_E_INVALID, "scb_frames_to_u16: output must be 16-byte aligned");
+    cudaStream_t s = (cudaStream_t)stream;
+    const unsigned int want = scb_grid_for((n + 7) >> 3, 256, 2);
+    const unsigned int cap = (unsigned int)SCB_SM_COUNT * 16;
+    const unsigned int grid = want < cap ? want : cap;
+    if (elem_type == SCB_F32) to_u16_kernel<float><<<grid, 256, 0, s>>>((const float *)d_frames, n, d_out);
+    else to_u16_kernel<double><<<grid, 256, 0, s>>>((const double *)d_frames, n, d_out);
+    SCB_CUDA_LAUNCH_CHECK("scb_frames_to_u16");
+    return 0;
+}
 
 extern "C" int scb_frames_minmax(const void *d_frames, int64_t n, int elem_type, double *d_minmax, void *d_workspace,
                                  void *stream) {
@@ -99,7 +139,7 @@ extern "C" int scb_frames_minmax(const void *d_frames, int64_t n, int elem_type,
     cudaStream_t s = (cudaStream_t)stream;
     unsigned long long *keys = (unsigned long long *)d_workspace;       // 16 bytes
     minmax_init_kernel<<<1, 1, 0, s>>>(keys);
-    const unsigned int grid = scb_grid_for(n, 256, 16) < SCB_SM_COUNT * 8 ? scb_grid_for(n, 256, 16) : SCB_SM_COUNT * 8;
+    const unsigned int grid = scb_grid_for(n, 256, 16) < (unsigned int)SCB_SM_COUNT * 8 ? scb_grid_for(n, 256, 16) : (unsigned int)SCB_SM_COUNT * 8;
     if (elem_type == SCB_F32) minmax_kernel<float><<<grid, 256, 0, s>>>((const float *)d_frames, n, keys);
     else minmax_kernel<double><<<grid, 256, 0, s>>>((const double *)d_frames, n, keys);
     minmax_finish_kernel<<<1, 1, 0, s>>>(keys, d_minmax);
@@ -115,7 +155,7 @@ extern "C" int scb_frames_to_8bit(const void *d_frames, int64_t n, int elem_type
     SCB_REQUIRE(((uintptr_t)d_out & 3) == 0, SCB_E_INVALID, "scb_frames_to_8bit: output must be 4-byte aligned");
     cudaStream_t s = (cudaStream_t)stream;
     const unsigned int want = scb_grid_for((n + 3) >> 2, 256, 4);
-    const unsigned int grid = want < SCB_SM_COUNT * 16 ? want : SCB_SM_COUNT * 16;
+    const unsigned int grid = want < (unsigned int)SCB_SM_COUNT * 16 ? want : (unsigned int)SCB_SM_COUNT * 16;
     if (elem_type == SCB_F32)
         to_8bit_kernel<float><<<grid, 256, 0, s>>>((const float *)d_frames, n, d_limits, cmin, cmax, low, high, d_out);
     else

@@ -17,7 +17,13 @@
 #include <condition_variable>
 #include <deque>
 #include <mutex>
+#include <pthread.h>
+#include <sched.h>
+#include <string.h>
+
+#include <chrono>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/scopyon_b200.h"
@@ -99,19 +105,43 @@ class WidenPool {
         return job.ticket;
     }
 
-    // 0, or the CUDA error the download of that (or an earlier) ticket ended with
+    // 0, or the CUDA error the download of THIS ticket ended with (reported once, then forgotten:
+    // one failed download does not poison later frames, engines or devices)
     int wait(int64_t ticket) {
         std::unique_lock<std::mutex> lock(mu_);
         if (ticket < 1 || ticket >= next_ticket_) return -1;
         done_cv_.wait(lock, [&] { return done_ticket_ >= ticket; });
-        return (int)error_;
+        const auto it = errors_.find(ticket);
+        if (it == errors_.end()) return 0;
+        const int err = (int)it->second;
+        errors_.erase(it);
+        return err;
+    }
+
+    // Worker w runs on cpus[w % n] from the next start of the pool (n = 0: no pinning).
+    void set_affinity(const int *cpus, int n) {
+        std::lock_guard<std::mutex> control(control_);
+        std::unique_lock<std::mutex> lock(mu_);
+        done_cv_.wait(lock, [&] { return done_ticket_ == next_ticket_ - 1; });
+        lock.unlock();
+        stop();
+        lock.lock();
+        cpus_.assign(cpus, cpus + (n > 0 ? n : 0));
     }
 
   private:
     void start_locked() {
         quit_ = false;
         running_ = true;
-        for (int w = 0; w < n_workers_; ++w) workers_.emplace_back([this, w, g = generation_] { worker(w, g); });
+        for (int w = 0; w < n_workers_; ++w) {
+            workers_.emplace_back([this, w, g = generation_] { worker(w, g); });
+            if (!cpus_.empty()) {
+                cpu_set_t set;
+                CPU_ZERO(&set);
+                CPU_SET(cpus_[w % cpus_.size()], &set);
+                pthread_setaffinity_np(workers_.back().native_handle(), sizeof(set), &set);    // best effort
+            }
+        }
         dispatcher_ = std::thread([this] { dispatch(); });
     }
 
@@ -156,7 +186,10 @@ class WidenPool {
             }
             {
                 std::lock_guard<std::mutex> lock(mu_);
-                if (err != cudaSuccess) error_ = err;
+                if (err != cudaSuccess) {
+                    if (errors_.size() >= 1024) errors_.clear();    // never awaited: do not grow without bound
+                    errors_[job.ticket] = err;
+                }
                 done_ticket_ = job.ticket;
                 done_cv_.notify_all();
             }
@@ -199,7 +232,8 @@ class WidenPool {
     int n_workers_ = 0;
     bool running_ = false, quit_ = false;
     int64_t next_ticket_ = 1, done_ticket_ = 0;
-    cudaError_t error_ = cudaSuccess;
+    std::unordered_map<int64_t, cudaError_t> errors_;     // failed downloads by ticket, until waited for
+    std::vector<int> cpus_;                                // worker affinity (empty: none)
 
   public:
     WidenPool() {
@@ -218,6 +252,92 @@ WidenPool &pool() {
 }  // namespace
 
 extern "C" int scb_host_widen_threads(int n_threads) { return pool().set_threads(n_threads); }
+
+extern "C" int scb_host_widen_affinity(const int *cpus, int n_cpus) {
+    if (n_cpus < 0 || n_cpus > 1024 || (n_cpus > 0 && !cpus)) {
+        scb_set_error("scb_host_widen_affinity: cpus=%p n_cpus=%d", (const void *)cpus, n_cpus);
+        return SCB_E_INVALID;
+    }
+    for (int i = 0; i < n_cpus; ++i)
+        if (cpus[i] < 0 || cpus[i] >= CPU_SETSIZE) {
+            scb_set_error("scb_host_widen_affinity: cpu %d out of range", cpus[i]);
+            return SCB_E_INVALID;
+        }
+    pool().set_affinity(cpus, n_cpus);
+    return 0;
+}
+
+// Host memory bandwidth with the access patterns of the end-to-end path, on `n_threads` threads
+// over private buffers (first touched by the thread that uses them): best of `repeats` passes.
+//   mode 0  copy, streaming stores: read b + write b per byte of source  (STREAM "copy")
+//   mode 1  float32 -> float64 widening as scb_host_widen_* does it: read b + write 2 b
+// Returns bytes moved per second (reads + writes) in *bytes_per_s.
+extern "C" int scb_host_bandwidth(int mode, int64_t bytes_per_thread, int n_threads, int repeats, double *bytes_per_s) {
+    if ((mode != 0 && mode != 1) || bytes_per_thread < 4096 || n_threads < 1 || n_threads > 256 || repeats < 1 ||
+        !bytes_per_s) {
+        scb_set_error("scb_host_bandwidth: mode=%d bytes=%lld threads=%d repeats=%d", mode, (long long)bytes_per_thread,
+                      n_threads, repeats);
+        return SCB_E_INVALID;
+    }
+    const size_t n = (size_t)bytes_per_thread / 4;              // float32 elements of source per thread
+    const size_t dst_bytes = mode == 1 ? n * 8 : n * 4;
+    std::vector<float *> src(n_threads, nullptr);
+    std::vector<void *> dst(n_threads, nullptr);
+    std::atomic<int> ready{0}, failed{0};
+    std::atomic<int> go{0};
+    std::vector<double> seconds((size_t)n_threads * repeats, 0.0);
+    std::vector<std::thread> threads;
+    for (int t = 0; t < n_threads; ++t) {
+        threads.emplace_back([&, t] {
+            if (posix_memalign((void **)&src[t], 64, n * 4) || posix_memalign(&dst[t], 64, dst_bytes)) {
+                failed.fetch_add(1);
+            } else {
+                for (size_t i = 0; i < n; ++i) src[t][i] = (float)(i & 1023);
+                memset(dst[t], 0, dst_bytes);
+            }
+            ready.fetch_add(1);
+            for (int r = 0; r < repeats; ++r) {
+                while (go.load(std::memory_order_acquire) <= r) std::this_thread::yield();
+                if (failed.load()) continue;
+                const auto t0 = std::chrono::steady_clock::now();
+                if (mode == 1) {
+                    widen_range(src[t], (double *)dst[t], n);
+                } else {
+                    // the same streaming-store path, float for float
+                    const float *s = src[t];
+                    float *d = (float *)dst[t];
+                    for (size_t i = 0; i + 4 <= n; i += 4) _mm_stream_ps(d + i, _mm_load_ps(s + i));
+                    _mm_sfence();
+                }
+                seconds[(size_t)t * repeats + r] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            }
+        });
+    }
+    while (ready.load() < n_threads) std::this_thread::yield();
+    double best = 0.0;
+    for (int r = 0; r < repeats; ++r) {
+        const auto t0 = std::chrono::steady_clock::now();
+        go.store(r + 1, std::memory_order_release);
+        // a pass ends when the slowest thread has finished: wait by joining on the last repeat, by polling before
+        for (;;) {
+            bool all = true;
+            for (int t = 0; t < n_threads; ++t) all = all && (seconds[(size_t)t * repeats + r] > 0.0 || failed.load());
+            if (all) break;
+            std::this_thread::yield();
+        }
+        const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        const double moved = (double)n_threads * ((double)n * 4 + (double)dst_bytes);
+        if (wall > 0.0 && moved / wall > best) best = moved / wall;
+    }
+    for (auto &th : threads) th.join();
+    for (int t = 0; t < n_threads; ++t) { free(src[t]); free(dst[t]); }
+    if (failed.load()) {
+        scb_set_error("scb_host_bandwidth: out of memory");
+        return SCB_E_INVALID;
+    }
+    *bytes_per_s = best;
+    return 0;
+}
 
 extern "C" int64_t scb_host_widen_start(const float *h_src, double *h_dst, int64_t n, void *cuda_event, int device) {
     if (!h_src || !h_dst || n < 0) {

@@ -10,6 +10,8 @@
 
 #include <stdarg.h>
 
+#include <atomic>
+
 // ------------------------------------------------------------------ error plumbing
 static thread_local char g_scb_error[512] = "";
 
@@ -22,6 +24,20 @@ void scb_set_error(const char *fmt, ...) {
 
 extern "C" const char *scb_last_error(void) { return g_scb_error; }
 extern "C" int scb_version(void) { return SCB_VERSION; }
+
+// Multiprocessor count of the current device, cached per device ordinal.
+int scb_sm_count() {
+    static std::atomic<int> cached[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    int n = cached[dev].load(std::memory_order_relaxed);
+    if (n <= 0) {
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev].store(n, std::memory_order_relaxed);
+    }
+    return n;
+}
+extern "C" int scb_device_sm_count(void) { return scb_sm_count(); }
 
 // Host-callable Philox for known-answer tests of the counter-based generator.
 extern "C" void scb_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {

@@ -30,6 +30,9 @@
 //     bitwise reproducible whatever order the work list was filled in.
 #include "binning.cuh"
 
+#include <atomic>
+#include <mutex>
+
 namespace {
 
 constexpr int kStripRows = 8;         // pixel rows per strip
@@ -367,8 +370,10 @@ render_strips_kernel(Geo g, const Unit *__restrict__ units, const uint32_t *__re
             };
             for (int u = 0; u < min(nb, kStages - 1); ++u) stage_unit(u);
             for (int u = 0; u < nb; ++u) {
+                // the previous unit's accumulator updates (other lanes, other columns) are visible, and every
+                // lane has finished reading the ring stage the next copy overwrites (the one unit u - 1 used)
+                __syncwarp();
                 if (u + kStages - 1 < nb) stage_unit(u + kStages - 1);
-                __syncwarp();       // the previous unit's accumulator updates (other lanes, other columns) are visible
                 if ((fast_mask >> u) & 1u) {
                     mbar_wait(&bars[c_stage], c_parity);
                     unit_accumulate_fast<BoxT, SLOTS>(meta, u, lane, acc, ring + c_stage * kStageEntries, slots, scale);
@@ -401,6 +406,7 @@ render_strips_kernel(Geo g, const Unit *__restrict__ units, const uint32_t *__re
 
 // ---- measurement hook -----------------------------------------------------------
 struct ProfilePool {
+    std::mutex mu;         // begin / end / the launches that record may come from different threads
     cudaEvent_t *start = nullptr, *stop = nullptr;
     int capacity = 0, used = 0;
     bool enabled = false;
@@ -410,6 +416,7 @@ struct ProfilePool {
 
 extern "C" int scb_profile_begin(int max_launches) {
     SCB_REQUIRE(max_launches > 0 && max_launches <= (1 << 20), SCB_E_INVALID, "scb_profile_begin: max_launches=%d", max_launches);
+    std::lock_guard<std::mutex> lock(g_profile.mu);
     if (g_profile.capacity < max_launches) {
         for (int i = 0; i < g_profile.capacity; ++i) { cudaEventDestroy(g_profile.start[i]); cudaEventDestroy(g_profile.stop[i]); }
         free(g_profile.start); free(g_profile.stop);
@@ -425,6 +432,7 @@ extern "C" int scb_profile_begin(int max_launches) {
 
 extern "C" int scb_profile_end(double *total_ms, int64_t *launches) {
     SCB_REQUIRE(total_ms && launches, SCB_E_NULL, "scb_profile_end: NULL pointer");
+    std::lock_guard<std::mutex> lock(g_profile.mu);
     g_profile.enabled = false;
     double sum = 0.0;
     for (int i = 0; i < g_profile.used; ++i) {
@@ -478,11 +486,15 @@ static int launch_render_as(const Geo &g, const Workspace &w, int64_t n_spots, O
     int ctas = (n_tiles + warps - 1) / warps;
     if (ctas > slots) ctas = slots;
     const size_t smem = (size_t)warps * warp_smem_bytes<BoxT>();
-    static bool configured = false;     // per template instance
-    if (!configured) {
+    // the attribute is per device: remembered per template instance and device ordinal
+    static std::atomic<unsigned long long> configured{0};
+    int dev = 0;
+    SCB_CUDA(cudaGetDevice(&dev));
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (!(configured.load(std::memory_order_acquire) & bit)) {
         SCB_CUDA(cudaFuncSetAttribute(render_strips_kernel<OutT, BoxT, SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)(kMaxWarps * warp_smem_bytes<BoxT>())));
-        configured = true;
+        configured.fetch_or(bit, std::memory_order_release);
     }
     render_strips_kernel<OutT, BoxT, SLOTS><<<ctas, warps * 32, smem, s>>>(
         g, (const Unit *)w.pair_spot, w.edges, w.tile_start, w.next_tile, w.wmax_bits, n_spots, out, accumulate);
@@ -542,12 +554,16 @@ static int render_expected_strided(const scb_geometry *geom, int64_t n_spots, in
                                                                     d_sat, d_box, box_bytes, w.tile_start,
                                                                     w.wmax_bits, (Unit *)w.pair_spot);
     }
-    const bool timed = g_profile.enabled && g_profile.used < g_profile.capacity;
-    if (timed) cudaEventRecord(g_profile.start[g_profile.used], s);
+    int timed = -1;        // slot of this launch in the measurement hook's event pool
+    if (g_profile.enabled) {
+        std::lock_guard<std::mutex> lock(g_profile.mu);
+        if (g_profile.enabled && g_profile.used < g_profile.capacity) timed = g_profile.used++;
+    }
+    if (timed >= 0) cudaEventRecord(g_profile.start[timed], s);
     if (out_type == SCB_F32) rc = launch_render<float>(g, w, n_spots, (float *)d_out, accumulate, box_type, s);
     else rc = launch_render<double>(g, w, n_spots, (double *)d_out, accumulate, box_type, s);
+    if (timed >= 0) cudaEventRecord(g_profile.stop[timed], s);
     if (rc) return rc;
-    if (timed) cudaEventRecord(g_profile.stop[g_profile.used++], s);
     SCB_CUDA_LAUNCH_CHECK("scb_render_expected");
     return 0;
 }

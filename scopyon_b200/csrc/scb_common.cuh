@@ -6,7 +6,10 @@
 #include <math.h>
 #include "../../include/scopyon_b200.h"
 
-#define SCB_SM_COUNT 148  // B200: 2 dies x 74 SMs
+// Multiprocessors of the current device (B200: 148 = 2 dies x 74), queried once per device
+// (psf.cu); grids of persistent / capped kernels are sized from it.
+int scb_sm_count();
+#define SCB_SM_COUNT scb_sm_count()
 
 void scb_set_error(const char *fmt, ...);
 

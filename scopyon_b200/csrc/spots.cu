@@ -560,7 +560,7 @@ extern "C" int scb_log_peaks(int n_w, int n_h, int n_sigma, const double *d_cube
     SCB_CUDA(cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), s));
     const int64_t total = (int64_t)n_sigma * n_w * n_h;
     const unsigned int want = scb_grid_for(total, 256, 4);
-    const unsigned int grid = want < SCB_SM_COUNT * 16 ? want : SCB_SM_COUNT * 16;
+    const unsigned int grid = want < (unsigned int)SCB_SM_COUNT * 16 ? want : (unsigned int)SCB_SM_COUNT * 16;
     log_peaks_kernel<<<grid, 256, 0, s>>>(d_cube, n_w, n_h, n_sigma, threshold, d_peaks, d_values, capacity, d_count);
     SCB_CUDA_LAUNCH_CHECK("scb_log_peaks");
     return 0;

@@ -45,6 +45,11 @@ HOST_WIDEN_MIN_PIXELS = 1 << 20
 # Frames enqueued before the oldest is awaited (generate_frames) + 1: plane sets, staging areas.
 FRAMES_IN_FLIGHT = 3
 
+# Large float32 frames are handed out as they arrive (image.HostPlane: page-locked float32 payload, float64
+# array materialised on demand) while fewer than this many bytes of such payloads are alive; a caller that
+# retains more frames than that gets eagerly widened float64 arrays in pageable memory instead.
+LAZY_PINNED_BYTES = 1 << 30
+
 
 def walker_alias(values, weights):
     """Walker/Vose alias table of a categorical distribution -> (n, 4) float32 rows
@@ -340,7 +345,9 @@ class DeviceEngine:
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def _call(self, name, *args):
-        _native.check(getattr(self.lib, name)(*args), name)
+        # the library launches on the current CUDA device: make it this engine's for the call
+        with torch.cuda.device(self.device):
+            _native.check(getattr(self.lib, name)(*args), name)
 
     def _to_device(self, array, dtype=None):
         host = torch.from_numpy(numpy.ascontiguousarray(array))
@@ -361,19 +368,20 @@ class DeviceEngine:
             stage = stages[self._stage_turn] = torch.empty((capacity, 5), dtype=torch.float64).pin_memory()
         return stage
 
-    def _host_plane(self):
+    def _host_plane(self, shape=None):
         """A float64 (Nw, Nh) host array for one returned plane.  While few planes are alive
         (streaming use) it is pinned memory the device writes directly, so no host copy
         is needed; when the caller retains many frames it falls back to pageable memory."""
         import weakref
+        shape = (self.n_w, self.n_h) if shape is None else tuple(shape)
         live = getattr(self, "_live_planes", None)
         if live is None:
             live = self._live_planes = weakref.WeakSet()
         if len(live) < self.max_pinned_planes:
-            t = torch.empty((self.n_w, self.n_h), dtype=torch.float64, pin_memory=True)
+            t = torch.empty(shape, dtype=torch.float64, pin_memory=True)
             live.add(t)
             return t, True
-        return torch.empty((self.n_w, self.n_h), dtype=torch.float64), False
+        return torch.empty(shape, dtype=torch.float64), False
 
     def _render_workspace(self, n_spots):
         need = self.lib.scb_render_workspace_bytes(ctypes.byref(self.geom), n_spots)
@@ -566,7 +574,12 @@ class DeviceEngine:
             bounds = numpy.concatenate([[0], numpy.cumsum(numpy.bincount(rank))])
             rounds = [(int(bounds[i]), int(bounds[i + 1])) for i in range(len(bounds) - 1)]
         ordered = ids if order is None else ids[order]
-        slots = numpy.searchsorted(table_ids, ordered).astype(numpy.int32)
+        slots = numpy.searchsorted(table_ids, ordered)
+        # an id outside the table would alias another molecule's budget (or write past the end)
+        if n and (len(table_ids) == 0 or not numpy.array_equal(
+                table_ids[numpy.minimum(slots, len(table_ids) - 1)], ordered)):
+            raise ValueError("a molecule id absent from the fluorescence states / input data was given")
+        slots = slots.astype(numpy.int32)
         result = (order, rounds, self._to_device(slots), self._to_device(ordered))
         self._slot_cache = (table_ids, ids, result)
         return result
@@ -603,21 +616,69 @@ class DeviceEngine:
         return adc
 
     def begin_frame(self, snapshots, frame_index, noise_seed, states, exposure_time, want_true_data,
-                    want_expectation=True, snapshot_states=False):
+                    want_expectation=True, snapshot_states=False, lazy=True):
         """Enqueue one frame (upload, kernels, download into pinned host planes) and return a
         handle without waiting for the device; ``finish_frame`` waits and hands out the arrays.
-        Planes are widened to float64 on the device and written straight into pinned host
-        arrays (one DMA per plane, no host-side conversion or copy)."""
-        main = torch.cuda.current_stream(self.device)
-        self._frame_stream = ctypes.c_void_p(main.cuda_stream)      # one stream lookup per frame
+        Small planes are widened to float64 on the device and written straight into pinned host
+        arrays (one DMA per plane); large float32 planes are downloaded as they are -- into the
+        page-locked payload of an ``image.HostPlane`` when ``lazy`` (the float64 array is then made
+        on demand), else into staging memory that host threads widen while the next frames run."""
+        with torch.cuda.device(self.device):        # kernels launch on the current device: make it ours
+            main = torch.cuda.current_stream(self.device)
+            self._frame_stream = ctypes.c_void_p(main.cuda_stream)      # one stream lookup per frame
+            try:
+                return self._begin_frame(main, snapshots, frame_index, noise_seed, states, exposure_time,
+                                         want_true_data, want_expectation, snapshot_states, lazy)
+            finally:
+                self._frame_stream = None
+
+    def _widen_setup(self):
+        """Worker threads of the widening pool: the ranks of one box (one process per GPU) share its host
+        cores, so each takes its share of them and pins its workers there."""
+        if getattr(self, "_widen_ready", False):
+            return
+        self._widen_ready = True
+        ranks_here = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1)
+        if ranks_here <= 1:
+            return
+        local = int(os.environ.get("LOCAL_RANK", "0") or 0)
         try:
-            return self._begin_frame(main, snapshots, frame_index, noise_seed, states, exposure_time, want_true_data,
-                                     want_expectation, snapshot_states)
-        finally:
-            self._frame_stream = None
+            cpus = sorted(os.sched_getaffinity(0))
+        except AttributeError:      # pragma: no cover
+            cpus = list(range(os.cpu_count() or 1))
+        share = max(1, len(cpus) // ranks_here)
+        mine = cpus[local * share: (local + 1) * share] or cpus
+        # leave one core of the share to the interpreter thread when there is a choice
+        workers = mine[1:] if len(mine) > 2 else mine
+        self.lib.scb_host_widen_threads(max(1, min(6, len(workers))))
+        self.lib.scb_host_widen_affinity((ctypes.c_int * len(workers))(*workers), len(workers))
+
+    def widen_host(self, f32):
+        """float32 host array -> the float64 array of the API, on the widening pool (exact)."""
+        self._widen_setup()
+        dst, _ = self._host_plane(shape=f32.shape)
+        src = numpy.ascontiguousarray(f32)
+        ticket = self.lib.scb_host_widen_start(src.ctypes.data, dst.data_ptr(), src.size, None, 0)
+        if ticket <= 0:
+            raise _native.NativeError("scb_host_widen_start: " + self.lib.scb_last_error().decode())
+        _native.check(self.lib.scb_host_widen_wait(ticket), "scb_host_widen_wait")
+        return dst.numpy()
+
+    def _lazy_plane(self):
+        """A page-locked float32 (Nw, Nh) payload for one frame, or None when the caller already holds
+        ``LAZY_PINNED_BYTES`` of them (torch's caching host allocator recycles released ones)."""
+        import weakref
+        live = getattr(self, "_live_lazy", None)
+        if live is None:
+            live = self._live_lazy = weakref.WeakSet()
+        if (len(live) + 1) * self.n_w * self.n_h * 4 > LAZY_PINNED_BYTES:
+            return None
+        t = torch.empty((self.n_w, self.n_h), dtype=torch.float32, pin_memory=True)
+        live.add(t)
+        return t
 
     def _begin_frame(self, main, snapshots, frame_index, noise_seed, states, exposure_time, want_true_data,
-                     want_expectation, snapshot_states):
+                     want_expectation, snapshot_states, lazy=True):
         self._defer_true_data = True
         try:
             photons, true_pending = self.render_expected(
@@ -632,16 +693,9 @@ class DeviceEngine:
             self._planes_free = [None] * FRAMES_IN_FLIGHT       # download of the set's previous frame
             self._stage32 = self._planes64 = None
             self._stage_tickets = [[] for _ in range(FRAMES_IN_FLIGHT)]
-            if self.dtype == torch.float32 and self.n_w * self.n_h >= HOST_WIDEN_MIN_PIXELS:
-                # large fp32 planes are downloaded as they are (half the PCIe bytes of float64) into
-                # pinned staging memory and widened by host threads (scb_host_widen_*): exact
-                self._stage32 = torch.empty((FRAMES_IN_FLIGHT, 2, self.n_w, self.n_h), dtype=torch.float32,
-                                            pin_memory=True)
-                ranks_here = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1)
-                if ranks_here > 1:      # one process per GPU: the ranks of a box share its host cores
-                    self.lib.scb_host_widen_threads(max(1, min(6, (os.cpu_count() or 8) // (2 * ranks_here))))
-            elif self.dtype == torch.float32:
-                # small ones (the wake-up of the host threads would cost more than the bytes saved)
+            self._large32 = self.dtype == torch.float32 and self.n_w * self.n_h >= HOST_WIDEN_MIN_PIXELS
+            if self.dtype == torch.float32 and not self._large32:
+                # small planes (the wake-up of the host threads would cost more than the bytes saved)
                 # are widened on the device and downloaded as float64
                 self._planes64 = torch.empty((FRAMES_IN_FLIGHT, 2, self.n_w, self.n_h), dtype=torch.float64,
                                              device=self.device)
@@ -655,29 +709,44 @@ class DeviceEngine:
         self._stage_tickets[turn] = []
         p32 = self._planes32[turn]
         self.detect(photons, frame_index, noise_seed, adc=p32[0], expectation=p32[1] if want_expectation else None)
+        n_planes = 2 if want_expectation else 1
+        payloads = None
         with _Trace(self, "host_alloc_planes"):
-            hosts = [self._host_plane()[0] for _ in range(2 if want_expectation else 1)]
+            if self._large32 and lazy:
+                payloads = [self._lazy_plane() for _ in range(n_planes)]
+                if any(p is None for p in payloads):
+                    payloads = None
+            if payloads is None:
+                hosts = [self._host_plane()[0] for _ in range(n_planes)]
+        staged = self._large32 and payloads is None
+        if staged and self._stage32 is None:
+            # eager route for large float32 planes: pinned staging memory, widened by host threads
+            self._stage32 = torch.empty((FRAMES_IN_FLIGHT, 2, self.n_w, self.n_h), dtype=torch.float32, pin_memory=True)
+            self._widen_setup()
         tickets = []
         with _Trace(self, "enqueue_d2h"):
             sources = p32
             if self._planes64 is not None:
                 sources = self._planes64[turn]
-                for k in range(len(hosts)):
+                for k in range(n_planes):
                     sources[k].copy_(p32[k])
             ready = torch.cuda.Event()
             ready.record(main)
             self._copy_stream.wait_event(ready)
             with torch.cuda.stream(self._copy_stream):
-                if self._stage32 is None:
+                if payloads is not None:
+                    for k, host in enumerate(payloads):
+                        host.copy_(p32[k], non_blocking=True)       # float32 planes: the frame's own payload
+                elif not staged:
                     for k, host in enumerate(hosts):
                         host.copy_(sources[k], non_blocking=True)  # float64 planes: straight into the caller's array
                 else:
-                    for k in range(len(hosts)):
+                    for k in range(n_planes):
                         self._stage32[turn][k].copy_(p32[k], non_blocking=True)
                 planes_done = torch.cuda.Event()
                 planes_done.record(self._copy_stream)
             self._planes_free[turn] = planes_done
-            if self._stage32 is not None:
+            if staged:
                 device_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
                 for k, host in enumerate(hosts):
                     ticket = self.lib.scb_host_widen_start(
@@ -697,17 +766,22 @@ class DeviceEngine:
         if snapshot_states and states is not None:
             budget_host = torch.empty(states.budget.shape, dtype=torch.float64, pin_memory=True)
             budget_host.copy_(states.budget, non_blocking=True)
+        # this frame's count of spots without a PSF table; the counter restarts for the next frame, so one
+        # failed frame is reported once and not again by the frames already in flight behind it
         errors_host = torch.empty(1, dtype=torch.int32, pin_memory=True)
         errors_host.copy_(self.errors, non_blocking=True)
+        self.errors.zero_()
         done = torch.cuda.Event()
         done.record(main)
-        return dict(hosts=hosts, true=true_host, budget=budget_host, states=states, done=done, errors=errors_host,
+        return dict(hosts=payloads if payloads is not None else hosts, lazy=payloads is not None,
+                    true=true_host, budget=budget_host, states=states, done=done, errors=errors_host,
                     planes_done=planes_done, tickets=tickets,
                     exposure_time=exposure_time, want_expectation=want_expectation)
 
     def finish_frame(self, pending):
         """Wait for a frame started by ``begin_frame``: ``(adc, expectation or None, true_data,
-        budgets dict or None)``."""
+        budgets dict or None)``.  ``adc`` / ``expectation`` are float64 arrays, or ``image.HostPlane``
+        objects (float32 payload, float64 on demand) for large frames begun with ``lazy``."""
         with _Trace(self, "wait_device"):
             pending["done"].synchronize()
             pending["planes_done"].synchronize()
@@ -715,11 +789,15 @@ class DeviceEngine:
                 _native.check(self.lib.scb_host_widen_wait(ticket), "scb_host_widen_wait")
         n_err = int(pending["errors"][0])      # read from pinned memory: no further device sync
         if n_err:
-            self.errors.zero_()
             raise _native.NativeError("{} spots referenced a PSF table that was not built".format(n_err))
         hosts = pending["hosts"]
-        adc = hosts[0].numpy()
-        expectation = hosts[1].numpy() if pending["want_expectation"] else None
+        if pending["lazy"]:
+            from .image import HostPlane
+            planes = [HostPlane(h.numpy(), widen=self.widen_host, keep=h) for h in hosts]
+        else:
+            planes = [h.numpy() for h in hosts]
+        adc = planes[0]
+        expectation = planes[1] if pending["want_expectation"] else None
         true_data = pending["true"]
         if isinstance(true_data, tuple):
             true_data = self._finish_true_data(true_data[0].numpy().copy(), true_data[1], pending["exposure_time"])
@@ -750,8 +828,8 @@ class DeviceEngine:
             pass
 
     def form_frame(self, snapshots, frame_index, noise_seed, states, exposure_time, want_true_data,
-                   want_expectation=True):
+                   want_expectation=True, lazy=False):
         """One frame on the host: ``(adc (Nw, Nh) float64, expectation or None, true_data)``."""
         adc, expectation, true_data, _ = self.finish_frame(self.begin_frame(
-            snapshots, frame_index, noise_seed, states, exposure_time, want_true_data, want_expectation))
+            snapshots, frame_index, noise_seed, states, exposure_time, want_true_data, want_expectation, lazy=lazy))
         return adc, expectation, true_data

@@ -12,6 +12,40 @@ import numpy
 __all__ = ["Image", "Video"]
 
 
+class HostPlane(object):
+    """A frame that came off the GPU as float32 (page-locked host memory) and stands for the float64
+    ``(Nw, Nh)`` array scopyon hands out (``_epifm.py:1177``, ``base.py:159``).  ``(double)float`` is
+    exact, so the float64 array is a pure function of the payload and is only materialised when
+    somebody asks for it (``Image.as_array()``, ``numpy.asarray(plane)``): a movie that is scaled to
+    8 bit, written to disk or merely counted never pays the 2 x 4 bytes per pixel of host memory
+    traffic the widening costs.  ``widen(src, dst)`` is the engine's multi-threaded converter."""
+
+    ndim = 2
+    dtype = numpy.dtype(numpy.float64)
+
+    def __init__(self, f32, widen=None, keep=None):
+        assert f32.ndim == 2 and f32.dtype == numpy.float32
+        self.f32 = f32
+        self._widen = widen
+        self._keep = keep          # owner of the payload's memory
+        self._wide = None
+
+    shape = property(lambda self: self.f32.shape)
+    size = property(lambda self: self.f32.size)
+
+    def widen(self):
+        if self._wide is None:
+            if self._widen is not None:
+                self._wide = self._widen(self.f32)
+            else:
+                self._wide = self.f32.astype(numpy.float64)
+        return self._wide
+
+    def __array__(self, dtype=None, copy=None):
+        wide = self.widen()
+        return wide if dtype is None or numpy.dtype(dtype) == wide.dtype else wide.astype(dtype)
+
+
 def _bytescale(data, cmin=None, cmax=None, low=None, high=None):
     """Linear map of [cmin, cmax] onto [low, high] as uint8 (``image.py:98-123``)."""
     cmin = data.min() if cmin is None else cmin
@@ -29,7 +63,11 @@ class Image(object):
 
     def __init__(self, data):
         assert data.ndim == 2 or (data.ndim == 3 and data.shape[2] == 3)
-        self.__data = data
+        self.__payload = data      # an ndarray, or a HostPlane until the float64 array is asked for
+
+    @property
+    def __data(self):
+        return self.as_array()
 
     @staticmethod
     def load(file):
@@ -60,13 +98,25 @@ class Image(object):
             rgb[:, :, i] = channel.as_array() if isinstance(channel, Image) else channel
         return Image(rgb)
 
-    def as_array(self):
-        return self.__data
+    def as_array(self, dtype=None):
+        """The image as an ndarray (the reference's ``Image.as_array()``, ``image.py:70-71``).
 
-    dtype = property(lambda self: self.__data.dtype)
-    ndim = property(lambda self: self.__data.ndim)
-    size = property(lambda self: self.__data.size)
-    shape = property(lambda self: self.__data.shape)
+        Frames formed on the GPU in float32 are widened to the float64 array of the reference on the
+        first call (exact; the array is then kept).  ``as_array(numpy.float32)`` -- an extension --
+        returns the float32 payload itself without widening when the frame still holds one."""
+        data = self.__payload
+        if isinstance(data, HostPlane):
+            if dtype is not None and numpy.dtype(dtype) == numpy.float32:
+                return data.f32
+            data = self.__payload = data.widen()       # the float32 payload (pinned memory) is released
+        if dtype is not None and numpy.dtype(dtype) != data.dtype:
+            return data.astype(dtype)
+        return data
+
+    dtype = property(lambda self: self.__payload.dtype)
+    ndim = property(lambda self: self.__payload.ndim)
+    size = property(lambda self: self.__payload.size)
+    shape = property(lambda self: self.__payload.shape)
 
     def as_8bit(self, cmin=None, cmax=None, low=None, high=None):
         if self.dtype == numpy.uint8:

@@ -77,6 +77,10 @@ class DeviceMovie:
 
     def reset(self, first_frame=0):
         """Place the molecules and replay to ``first_frame`` (frames before it are not rendered)."""
+        with torch.cuda.device(self.engine.device):
+            self._reset(first_frame)
+
+    def _reset(self, first_frame):
         eng = self.engine
         _native.check(eng.lib.scb_place_uniform(
             self.place_seed, self.n, 0, self._p(0), self._p(1), self._p(2),
@@ -96,6 +100,10 @@ class DeviceMovie:
     # ------------------------------------------------------------------ one frame
     def render_next(self, adc_out, expectation_out=None):
         """Render frame ``self.frame`` into ``adc_out`` (device tensor (Nw, Nh)) and advance."""
+        with torch.cuda.device(self.engine.device):
+            self._render_next(adc_out, expectation_out)
+
+    def _render_next(self, adc_out, expectation_out=None):
         eng = self.engine
         stream = eng._stream()
         focal = self.configs.detector_focal_point
@@ -126,14 +134,117 @@ class DeviceMovie:
         weights, one pipeline of launches bins and renders all of them, the detector runs per frame."""
         total = out.shape[0]
         k = 0
-        while k < total:
-            nf = min(self.frames_per_launch, total - k)
-            if nf == 1:
-                self.render_next(out[k])
-            else:
-                self._render_frames(out[k: k + nf])
-            k += nf
+        with torch.cuda.device(self.engine.device):
+            while k < total:
+                nf = min(self.frames_per_launch, total - k)
+                if nf == 1:
+                    self._render_next(out[k])
+                else:
+                    self._render_frames(out[k: k + nf])
+                k += nf
         return out
+
+    # ------------------------------------------------------------------ frames out to the host
+    #: export formats of ``stream_frames``: what leaves the device per pixel
+    EXPORT_FORMATS = ("f32", "u16", "u8")
+
+    def _export_plan(self, fmt, ring):
+        """Buffers of ``stream_frames``: two device blocks (one renders while the other leaves the
+        device), their converted copies for the integer formats, ``ring`` page-locked host blocks."""
+        eng = self.engine
+        key = (fmt, int(ring), self.frames_per_launch)
+        plans = self.__dict__.setdefault("_export_plans", {})
+        plan = plans.get(key)
+        if plan is None:
+            nb = self.frames_per_launch
+            shape = (nb, eng.n_w, eng.n_h)
+            wire = {"f32": torch.float32, "u16": torch.uint16, "u8": torch.uint8}[fmt]
+            plan = plans[key] = dict(
+                block=torch.empty((2,) + shape, dtype=torch.float32, device=eng.device),
+                wire=None if fmt == "f32" else torch.empty((2,) + shape, dtype=wire, device=eng.device),
+                host=torch.empty((ring,) + shape, dtype=wire, pin_memory=True),
+                copy_stream=torch.cuda.Stream(device=eng.device))
+        return plan
+
+    def stream_frames(self, num_frames, fmt="f32", sink=None, limits=None, ring=3):
+        """Render the next ``num_frames`` frames and stream every finished block of
+        ``frames_per_launch`` frames to page-locked host memory -- the data plane of a sharded movie
+        (the reference yields every frame to its caller, ``_epifm.py:1045-1049``; a rank of a
+        frame-block partition exports its own block range, nothing is gathered on one GPU).
+
+        The download of block k (copy stream) overlaps the rendering of block k + 1.  ``fmt``:
+        ``"f32"`` the frames as computed (exact), ``"u16"`` rounded 16-bit camera counts
+        (``scb_frames_to_u16``), ``"u8"`` the 8-bit pictures ``Video.save`` makes
+        (``scb_frames_to_8bit``, ``image.py:98-123``) with the fixed ``limits=(cmin, cmax)``
+        (default: the ADC's range).  ``sink(first_frame, block)`` is called in frame order with a
+        numpy view ``(frames, Nw, Nh)`` of the host ring -- valid during the call only; ``ring`` host
+        blocks are in flight.  Returns the number of frames delivered."""
+        if fmt not in self.EXPORT_FORMATS:
+            raise ValueError("fmt must be one of {}".format(self.EXPORT_FORMATS))
+        eng = self.engine
+        if eng.dtype != torch.float32:
+            raise ValueError("stream_frames exports the float32 pipeline's frames (precision='f32')")
+        ring = max(2, int(ring))
+        nb = self.frames_per_launch
+        lib = eng.lib
+        with torch.cuda.device(eng.device):
+            plan = self._export_plan(fmt, ring)
+            main = torch.cuda.current_stream(eng.device)
+            copy = plan["copy_stream"]
+            stream = ctypes.c_void_p(main.cuda_stream)
+            if fmt == "u8":
+                cmin, cmax = limits if limits is not None else (0.0, float(2 ** int(self.configs.ADConverter_bit) - 1))
+            n_blocks = (int(num_frames) + nb - 1) // nb
+            in_flight = {}          # block -> (copied event, first frame, frames, host slot)
+            delivered = 0
+
+            def deliver(k):
+                nonlocal delivered
+                event, first, nf, slot = in_flight.pop(k)
+                event.synchronize()
+                if sink is not None:
+                    sink(first, plan["host"][slot, :nf].numpy())
+                delivered += nf
+
+            for k in range(n_blocks):
+                nf = min(nb, int(num_frames) - k * nb)
+                half, slot = k & 1, k % ring
+                if k - ring in in_flight:               # the host slot is handed back by its previous block
+                    deliver(k - ring)
+                previous = plan.get(("left", half))     # device block `half` has left the device (block k - 2)
+                if previous is not None:
+                    main.wait_event(previous)
+                first = self.frame
+                block = plan["block"][half, :nf]
+                if nf == 1:
+                    self._render_next(block[0])
+                else:
+                    self._render_frames(block)
+                source = block
+                if fmt != "f32":
+                    source = plan["wire"][half, :nf]
+                    n = block.numel()
+                    if fmt == "u16":
+                        _native.check(lib.scb_frames_to_u16(_native.ptr(block), n, _native.F32, _native.ptr(source),
+                                                            stream), "scb_frames_to_u16")
+                    else:
+                        _native.check(lib.scb_frames_to_8bit(_native.ptr(block), n, _native.F32, None, float(cmin),
+                                                             float(cmax), 0.0, 255.0, _native.ptr(source), stream),
+                                      "scb_frames_to_8bit")
+                rendered = torch.cuda.Event()
+                rendered.record(main)
+                copy.wait_event(rendered)
+                with torch.cuda.stream(copy):
+                    plan["host"][slot, :nf].copy_(source, non_blocking=True)
+                    copied = torch.cuda.Event()
+                    copied.record(copy)
+                plan[("left", half)] = copied
+                in_flight[k] = (copied, first, nf, slot)
+                if k - (ring - 1) in in_flight:         # keep the sink at most ring - 1 blocks behind
+                    deliver(k - (ring - 1))
+            for k in sorted(in_flight):
+                deliver(k)
+        return delivered
 
     def _render_frames(self, out):
         eng = self.engine
@@ -186,6 +297,63 @@ class DeviceMovie:
         data[:, 3] = numpy.arange(self.n)
         data[:, 4] = 1.0
         return data
+
+
+class NpyFrameWriter(object):
+    """Streaming ``.npy`` writer for a frame stack of known length: the header for the full
+    ``(num_frames, Nw, Nh)`` array is written first, blocks of frames are appended as they arrive
+    (``sink`` of ``DeviceMovie.stream_frames``), so a movie far larger than host memory goes to
+    disk block by block.  The file is what ``numpy.save`` of the whole stack would produce --
+    the ``.npy`` route of ``Image.save`` / ``Video.save`` (``image.py:125-140, 240-277``)."""
+
+    def __init__(self, filename, num_frames, frame_shape, dtype):
+        self.shape = (int(num_frames),) + tuple(int(v) for v in frame_shape)
+        self.dtype = numpy.dtype(dtype)
+        self.written = 0
+        self.file = open(str(filename), "wb")
+        header = {"descr": numpy.lib.format.dtype_to_descr(self.dtype), "fortran_order": False, "shape": self.shape}
+        numpy.lib.format.write_array_header_1_0(self.file, header)
+
+    def __call__(self, first_frame, block):
+        """Append ``block`` (frames, Nw, Nh); blocks must arrive in frame order."""
+        if block.dtype != self.dtype or tuple(block.shape[1:]) != self.shape[1:]:
+            raise ValueError("block of {} {} does not fit a {} {} stack".format(block.dtype, block.shape, self.dtype, self.shape))
+        if self.written + block.shape[0] > self.shape[0]:
+            raise ValueError("more frames than the header announced")
+        numpy.ascontiguousarray(block).tofile(self.file)
+        self.written += block.shape[0]
+
+    def close(self):
+        if self.file is not None:
+            self.file.close()
+            self.file = None
+            if self.written != self.shape[0]:
+                raise ValueError("{} of {} frames were written".format(self.written, self.shape[0]))
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, exc_type, exc, tb):
+        if exc_type is None:
+            self.close()
+        elif self.file is not None:
+            self.file.close()
+            self.file = None
+
+
+def save_movie(movie, filename, num_frames, fmt="f32", limits=None, as_float64=False):
+    """Render the next ``num_frames`` frames of ``movie`` (a ``DeviceMovie``) straight into a ``.npy``
+    stack on disk: float32 frames (or float64, widened on the host, with ``as_float64``), rounded
+    uint16 camera counts, or the uint8 pictures of ``Video.save(filename.npy, ...)`` with fixed
+    ``limits``.  Returns the number of frames written."""
+    eng = movie.engine
+    dtype = {"f32": numpy.float64 if as_float64 else numpy.float32, "u16": numpy.uint16, "u8": numpy.uint8}[fmt]
+    with NpyFrameWriter(filename, num_frames, (eng.n_w, eng.n_h), dtype) as writer:
+        if fmt == "f32" and as_float64:
+            sink = lambda first, block: writer(first, block.astype(numpy.float64))   # noqa: E731 -- exact
+        else:
+            sink = writer
+        return movie.stream_frames(num_frames, fmt=fmt, sink=sink, limits=limits)
 
 
 def gather_frames(local_frames, num_frames, group=None, dst=None):

@@ -157,14 +157,17 @@ def test_cmos_3d_epi_movie_against_oracle_expectation():
 
 
 @pytest.mark.parametrize("full_output", [False, True])
-def test_large_frames_take_the_host_widening_route_and_equal_the_device_one(full_output, monkeypatch):
-    """Frames of >= 1024 x 1024 pixels leave the device as float32 and are widened to float64 by
-    host threads (scb_host_widen_*), three frames in flight; smaller ones are widened on the
-    device.  Same seeds, same kernels: the float64 arrays must be identical, frame for frame."""
+def test_large_frames_leave_the_device_as_float32_and_equal_the_device_widened_ones(full_output, monkeypatch):
+    """Frames of >= 1024 x 1024 pixels leave the device as float32: into the page-locked payload of
+    the Image (float64 array made on demand, image.HostPlane) or -- when the caller already holds
+    LAZY_PINNED_BYTES of payloads -- into staging memory widened by host threads (scb_host_widen_*),
+    three frames in flight; smaller ones are widened on the device.  Same seeds, same kernels: the
+    float64 arrays must be identical, frame for frame, on all three routes."""
     from scopyon_b200 import engine as engine_module
 
-    def movie(min_pixels):
+    def movie(min_pixels, lazy_bytes):
         monkeypatch.setattr(engine_module, "HOST_WIDEN_MIN_PIXELS", min_pixels)
+        monkeypatch.setattr(engine_module, "LAZY_PINNED_BYTES", lazy_bytes)
         config = scopyon_b200.DefaultConfiguration()
         config.update("""
 default:
@@ -181,14 +184,23 @@ default:
             sim = scopyon_b200.create_simulator(config, rng=numpy.random.RandomState(9))
             out = list(sim.generate_images(inputs, num_frames=7, full_output=full_output))
         if full_output:
-            return [img.as_array().copy() for img, _ in out], [info["expectation"].copy() for _, info in out], sim
-        return [img.as_array().copy() for img in out], [], sim
+            return [img for img, _ in out], [info["expectation"].copy() for _, info in out]
+        return out, []
 
-    host_frames, host_expect, sim_host = movie(1 << 20)
-    device_frames, device_expect, sim_device = movie(1 << 40)
+    lazy_images, lazy_expect = movie(1 << 20, 1 << 30)
+    if not full_output:
+        # the Image carries the float32 frame; the float64 array appears on demand and is exact
+        payload = lazy_images[0].as_array(numpy.float32)
+        assert payload.dtype == numpy.float32 and lazy_images[0].dtype == numpy.float64
+        assert numpy.array_equal(lazy_images[0].as_array(), payload.astype(numpy.float64))
+    lazy_frames = [img.as_array().copy() for img in lazy_images]
+    host_images, host_expect = movie(1 << 20, 0)
+    host_frames = [img.as_array().copy() for img in host_images]
+    device_images, device_expect = movie(1 << 40, 1 << 30)
+    device_frames = [img.as_array().copy() for img in device_images]
     assert len(host_frames) == 7 and host_frames[0].dtype == numpy.float64 and host_frames[0].shape == (1024, 1040)
-    for a, b in zip(host_frames + host_expect, device_frames + device_expect):
-        assert numpy.array_equal(a, b)
+    for a, b, c in zip(host_frames + host_expect, device_frames + device_expect, lazy_frames + lazy_expect):
+        assert numpy.array_equal(a, b) and numpy.array_equal(a, c)
     assert not numpy.array_equal(host_frames[0], host_frames[1])
     assert 100 < host_frames[0].mean() < 120
 

@@ -196,3 +196,77 @@ default:
         torch.cuda.synchronize()
         assert numpy.array_equal(fast.cpu().numpy(), generic)
     assert sig.max() > 100 and sig.min() == 0
+
+
+def test_poisson_inversion_never_returns_the_loop_bound():
+    """The inversion sampler (expectation < 12 e-) compares a 32-bit word with an fp32 running sum that
+    stops moving a few hundred below 2^32; the largest words must map to the last count that could still
+    be told apart, not to the search bound (a 160 e- hot pixel with probability ~1e-7 per pixel).
+    The map word -> count is monotone and equals the exact quantile function away from its steps."""
+    from scopyon_b200 import _native
+    lib = _native.load()
+    lambdas = numpy.array([1e-6, 0.0092, 0.05, 0.3, 0.7, 1.0, 1.9, 2.5, 3.3, 4.0, 5.7, 7.7, 9.9, 11.0, 11.999],
+                          dtype=numpy.float32)
+    words = numpy.array([0xffffffff, 0xfffffffe, 0xffffff80, 0xffffff00, 0xfffffe80, 0xfffffe00, 0xfffffd00,
+                         0xfffff000, 0xffff0000, 0xff000000, 0x80000000, 0x1000, 0], dtype=numpy.uint32)
+    lam, wrd = [a.ravel() for a in numpy.meshgrid(lambdas, words, indexing="ij")]
+    # +- 1 ulp around every expectation as well (the saturation depends on the rounding of the sum)
+    lam = numpy.concatenate([lam, numpy.nextafter(lam, numpy.float32(0)), numpy.nextafter(lam, numpy.float32(100))])
+    wrd = numpy.concatenate([wrd, wrd, wrd])
+    d_lam = torch.from_numpy(numpy.ascontiguousarray(lam, dtype=numpy.float32)).cuda()
+    d_wrd = torch.from_numpy(wrd.astype(numpy.int64)).cuda().to(torch.uint32)
+    out = torch.empty(len(lam), dtype=torch.float32, device="cuda")
+    assert lib.scb_test_poisson_inversion(len(lam), d_lam.data_ptr(), d_wrd.data_ptr(), out.data_ptr(), None) == 0
+    torch.cuda.synchronize()
+    counts = out.cpu().numpy()
+    # a count beyond the 1 - 2^-33 quantile (+2) can only come from a stuck search
+    ceiling = scipy.stats.poisson.isf(2.0 ** -33, lam.astype(numpy.float64)) + 2
+    assert (counts <= ceiling).all(), (lam[counts > ceiling], wrd[counts > ceiling], counts[counts > ceiling])
+    assert counts.max() < 60
+    # the largest word gives the largest count of its expectation; word 0 gives 0 for every expectation
+    by_lambda = counts.reshape(3, len(lambdas), len(words))
+    assert (numpy.diff(by_lambda, axis=2) <= 0).all() and (by_lambda[:, :, -1] == 0).all()
+    # random words: the exact quantile function except within rounding distance of a step
+    rng = numpy.random.RandomState(1)
+    n = 1 << 20
+    lam = rng.choice(lambdas[1:], n).astype(numpy.float32)
+    wrd = rng.randint(0, 2 ** 32, n, dtype=numpy.uint64).astype(numpy.uint32)
+    d_lam = torch.from_numpy(lam).cuda()
+    d_wrd = torch.from_numpy(wrd.astype(numpy.int64)).cuda().to(torch.uint32)
+    out = torch.empty(n, dtype=torch.float32, device="cuda")
+    assert lib.scb_test_poisson_inversion(n, d_lam.data_ptr(), d_wrd.data_ptr(), out.data_ptr(), None) == 0
+    torch.cuda.synchronize()
+    u = (wrd.astype(numpy.float64) + 0.5) / 2.0 ** 32
+    want = scipy.stats.poisson.ppf(u, lam.astype(numpy.float64))
+    assert (out.cpu().numpy() != want).mean() < 5e-5
+
+
+@pytest.mark.parametrize("fpn", ["none", "column", "pixel"])
+def test_production_fp32_adc_against_oracle_on_its_own_draws(fpn):
+    """The streaming kernel (fp32, reciprocal-multiply ADC on packed pairs) against the oracle's ADC
+    formula (_epifm.py:1472-1484) evaluated in float64 on the SAME draws: signal and noise of every pixel
+    are tapped from the generic kernel, which draws them from the same Philox words, and the counts the
+    streaming kernel wrote must equal orc.adc_counts(signal + noise) to fp32 rounding."""
+    yaml = """
+default:
+    detector: {type: CMOS, image_size: [256, 192], QE: 0.73}
+    analog_to_digital_converter: {type: %s, count: 3.0, offset: 100, fullwell: 30000}
+""" % fpn
+    _, configs, params, engine = gpu_engine(yaml, precision="f32")
+    rng = numpy.random.RandomState(8)
+    photons = rng.exponential(3.0, (256, 192)).astype(numpy.float32)
+    photons[:4] = rng.uniform(20000, 60000, (4, 192))          # up to and beyond the full well
+    dev = torch.from_numpy(photons).to(engine.device)
+    fast = torch.empty_like(dev)
+    engine.detect(dev, 3, 2024, adc=fast)                       # production path: no taps
+    _, _, signal, noise = run_detector(engine, dev, frame=3, seed=2024)
+    torch.cuda.synchronize()
+    if fpn == "none":
+        offset, gain = orc.adc_params(params)
+    else:
+        offset, gain = orc.adc_params(params, engine.offset.cpu().numpy().astype(numpy.float64))
+    want = orc.adc_counts(signal.astype(numpy.float64) + noise.astype(numpy.float64), params["adc_fullwell"], gain,
+                          offset, params["adc_bit"])
+    got = fast.cpu().numpy().astype(numpy.float64)
+    assert abs(got - want).max() <= 4e-7 * want.max()           # a few fp32 ulps of the count
+    assert got.max() == 2 ** 16 - 1 and got.min() >= 0 and (signal > 12).sum() > 500

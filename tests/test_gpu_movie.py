@@ -129,3 +129,67 @@ def test_frames_to_8bit_matches_image_as_8bit():
     assert (frames_to_8bit(flat, low=3).cpu().numpy() == 3).all()          # cmax == cmin -> low
     f64 = torch.from_numpy(stack.astype(numpy.float64)).cuda()
     assert numpy.array_equal(frames_to_8bit(f64).cpu().numpy(), frames_to_8bit(dev).cpu().numpy())
+
+
+@pytest.mark.parametrize("frames_per_launch", [16, 3])
+def test_stream_frames_exports_the_movie_block_by_block(frames_per_launch, tmp_path):
+    """The data plane of a sharded movie: stream_frames hands every finished block to the host
+    (float32 exact; uint16 = rint/clip; uint8 = Image.as_8bit with fixed limits) and the frames are
+    the ones render_block produces, bit for bit; save_movie writes the same stack as a .npy file."""
+    import scopyon_b200
+    from scopyon_b200.movie import save_movie
+    n_frames = 23                                         # ragged last block
+    _, whole = make_movie("0.0", "true")
+    frames = torch.empty((n_frames, 96, 80), dtype=torch.float32, device=whole.engine.device)
+    whole.render_block(frames)
+    frames = frames.cpu().numpy()
+
+    def collect(fmt, **kwargs):
+        _, movie = make_movie("0.0", "true")
+        movie.frames_per_launch = frames_per_launch
+        got, firsts = [], []
+
+        def sink(first, block):
+            firsts.append(first)
+            got.append(block.copy())                      # the view is only valid during the call
+        assert movie.stream_frames(n_frames, fmt=fmt, sink=sink, ring=2, **kwargs) == n_frames
+        assert firsts == list(range(0, n_frames, frames_per_launch)) and movie.frame == n_frames
+        return numpy.concatenate(got)
+
+    f32 = collect("f32")
+    assert f32.dtype == numpy.float32 and numpy.array_equal(f32, frames)
+    u16 = collect("u16")
+    assert u16.dtype == numpy.uint16
+    assert numpy.array_equal(u16, numpy.rint(numpy.clip(frames.astype(numpy.float64), 0, 65535)).astype(numpy.uint16))
+    u8 = collect("u8", limits=(90.0, 140.0))
+    want = numpy.stack([scopyon_b200.Image(f.astype(numpy.float64)).as_8bit(cmin=90.0, cmax=140.0).as_array()
+                        for f in frames])
+    assert u8.dtype == numpy.uint8 and numpy.array_equal(u8, want)
+    # a second call continues the movie where the first stopped
+    _, movie = make_movie("0.0", "true")
+    movie.frames_per_launch = frames_per_launch
+    parts = []
+    movie.stream_frames(10, sink=lambda first, block: parts.append(block.copy()))
+    movie.stream_frames(n_frames - 10, sink=lambda first, block: parts.append(block.copy()))
+    assert numpy.array_equal(numpy.concatenate(parts), frames)
+    # straight to disk
+    _, movie = make_movie("0.0", "true")
+    assert save_movie(movie, tmp_path / "movie.npy", n_frames) == n_frames
+    assert numpy.array_equal(numpy.load(tmp_path / "movie.npy"), frames)
+    _, movie = make_movie("0.0", "true")
+    save_movie(movie, tmp_path / "movie16.npy", n_frames, fmt="u16")
+    assert numpy.array_equal(numpy.load(tmp_path / "movie16.npy"), u16)
+
+
+def test_frames_to_u16():
+    rng = numpy.random.RandomState(5)
+    stack = rng.uniform(-10, 70000, (2, 33, 41)).astype(numpy.float32)
+    stack[0, 0, :6] = [0.5, 1.5, 2.5, -0.0, 65535.4, numpy.nan]        # ties to even, clip, NaN -> 0
+    lib = scopyon_b200._native.load()
+    for dtype in (torch.float32, torch.float64):
+        dev = torch.from_numpy(stack).cuda().to(dtype)
+        out = torch.empty(stack.shape, dtype=torch.uint16, device="cuda")
+        assert lib.scb_frames_to_u16(dev.data_ptr(), dev.numel(), 0 if dtype == torch.float32 else 1, out.data_ptr(), None) == 0
+        torch.cuda.synchronize()
+        want = numpy.rint(numpy.clip(numpy.nan_to_num(stack.astype(numpy.float64), nan=0.0), 0, 65535)).astype(numpy.uint16)
+        assert numpy.array_equal(out.cpu().numpy(), want)

@@ -135,3 +135,48 @@ def test_product_never_imports_oracle():
             if name.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, name)).read()
                 assert "epifm_oracle" not in text and "c_oracle" not in text and "ref_shim" not in text, name
+
+
+def test_image_with_float32_payload_is_the_float64_image():
+    """Frames that came off the GPU as float32 (image.HostPlane) behave as the float64 arrays the
+    reference hands out: dtype, shape, as_array, 8-bit scaling, save; the payload is widened once."""
+    from scopyon_b200.image import HostPlane, Image
+    rng = numpy.random.RandomState(2)
+    f32 = (rng.standard_normal((12, 17)) * 100 + 100).astype(numpy.float32)
+    calls = []
+
+    def widen(src):
+        calls.append(1)
+        return src.astype(numpy.float64)
+
+    img = Image(HostPlane(f32, widen=widen))
+    plain = Image(f32.astype(numpy.float64))
+    assert img.dtype == numpy.float64 and img.shape == (12, 17) and img.ndim == 2 and img.size == 12 * 17
+    assert img.as_array(numpy.float32) is f32 and not calls          # no widening for the float32 payload
+    a = img.as_array()
+    assert a.dtype == numpy.float64 and numpy.array_equal(a, plain.as_array()) and len(calls) == 1
+    assert img.as_array() is a and len(calls) == 1                    # kept
+    assert numpy.array_equal(img.as_8bit().as_array(), plain.as_8bit().as_array())
+    rgb = Image.RGB(red=Image(HostPlane(f32)), green=plain)
+    assert rgb.shape == (12, 17, 3) and numpy.array_equal(rgb.as_array()[:, :, 0], rgb.as_array()[:, :, 1])
+    assert numpy.array_equal(numpy.asarray(HostPlane(f32)), plain.as_array())
+
+
+def test_streaming_npy_writer(tmp_path):
+    """NpyFrameWriter: blocks appended in order give the file numpy.save writes for the whole stack."""
+    from scopyon_b200.movie import NpyFrameWriter
+    rng = numpy.random.RandomState(4)
+    for dtype in (numpy.float32, numpy.uint16, numpy.uint8):
+        stack = (rng.uniform(0, 200, (11, 6, 9))).astype(dtype)
+        path = tmp_path / "movie_{}.npy".format(numpy.dtype(dtype).name)
+        with NpyFrameWriter(path, 11, (6, 9), dtype) as writer:
+            writer(0, stack[:4])
+            writer(4, stack[4:8])
+            writer(8, stack[8:])
+        assert numpy.array_equal(numpy.load(path), stack) and numpy.load(path).dtype == dtype
+    with pytest.raises(ValueError):
+        with NpyFrameWriter(tmp_path / "short.npy", 5, (6, 9), numpy.float32) as writer:
+            writer(0, numpy.zeros((3, 6, 9), numpy.float32))                 # 3 of 5 frames
+    with pytest.raises(ValueError):
+        with NpyFrameWriter(tmp_path / "wrong.npy", 5, (6, 9), numpy.float32) as writer:
+            writer(0, numpy.zeros((3, 6, 9), numpy.float64))                 # wrong dtype

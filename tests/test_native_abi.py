@@ -91,3 +91,25 @@ def test_host_widen_is_exact_and_ordered():
         assert lib.scb_host_widen_start(None, dst.ctypes.data, 4, None, 0) == -1
     finally:
         lib.scb_host_widen_threads(previous)
+
+
+def test_host_widen_affinity_and_bandwidth_probe():
+    """Worker pinning and the host-bandwidth probe bench.py reports the end-to-end rate against."""
+    import numpy
+    lib = _native.load()
+    cpus = sorted(os.sched_getaffinity(0))[:2]
+    assert lib.scb_host_widen_affinity((ctypes.c_int * len(cpus))(*cpus), len(cpus)) == 0
+    try:
+        src = numpy.arange(100000, dtype=numpy.float32)
+        dst = numpy.zeros(100000)
+        ticket = lib.scb_host_widen_start(src.ctypes.data, dst.ctypes.data, src.size, None, 0)
+        assert ticket > 0 and lib.scb_host_widen_wait(ticket) == 0
+        assert numpy.array_equal(dst, src.astype(numpy.float64))
+    finally:
+        assert lib.scb_host_widen_affinity(None, 0) == 0
+    assert lib.scb_host_widen_affinity((ctypes.c_int * 1)(-1), 1) != 0
+    for mode in (0, 1):
+        rate = ctypes.c_double(0.0)
+        assert lib.scb_host_bandwidth(mode, 1 << 20, 2, 2, ctypes.byref(rate)) == 0
+        assert rate.value > 1e8          # more than 0.1 GB/s on any machine
+    assert lib.scb_host_bandwidth(2, 1 << 20, 2, 2, ctypes.byref(rate)) != 0
