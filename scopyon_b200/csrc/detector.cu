@@ -267,6 +267,7 @@ struct DetArgs {
     float inv_fullwell, inv_nh;
     // fp32 copies for the streaming kernel (no per-iteration double -> float conversions)
     float qe_f, qe_bg_f, fullwell_f, pow2bit_f, adc_max_f, readout_f, adc_offset_f;
+    int rounds;                // Philox rounds of the per-quad shot / readout streams (10; see detector_rounds())
     const void *photons, *offset;
     const scb_alias_entry *alias;
     void *adc, *expectation;
@@ -441,9 +442,9 @@ detector_kernel(const __grid_constant__ DetArgs a) {
         }
         Philox4 rs = {0u, 0u, 0u, 0u}, rr = {0u, 0u, 0u, 0u};
         if (a.in_signal == nullptr)
-            rs = philox4x32_10((uint32_t)q, (uint32_t)(q >> 32), f_lo, SCB_TAG_SHOT ^ f_hi, k0, k1);
+            rs = philox4x32_n((uint32_t)q, (uint32_t)(q >> 32), f_lo, SCB_TAG_SHOT ^ f_hi, k0, k1, a.rounds);
         if (a.in_noise == nullptr && (DET == SCB_DET_CMOS || gaussian_readout))
-            rr = philox4x32_10((uint32_t)q, (uint32_t)(q >> 32), f_lo, SCB_TAG_READ ^ f_hi, k0, k1);
+            rr = philox4x32_n((uint32_t)q, (uint32_t)(q >> 32), f_lo, SCB_TAG_READ ^ f_hi, k0, k1, a.rounds);
         float n0 = 0.f, n1 = 0.f, n2 = 0.f, n3 = 0.f;
         if (gaussian_readout) {
             box_muller(rr.x, rr.y, n0, n1);
@@ -470,7 +471,7 @@ detector_kernel(const __grid_constant__ DetArgs a) {
 // the ADC on packed fp32 pairs.  What bounds it (ncu, profiles/): the 40 IMAD.WIDE of the
 // two Philox4x32-10 blocks issue at a quarter rate on the heavy FMA pipe
 // (tools/probes/imad_probe.cu), 160 of the ~250 issue cycles a warp spends per quad.
-template <int DET, int FPN>
+template <int DET, int FPN, int ROUNDS>
 __global__ void __launch_bounds__(kThreads, kFastCtasPerSm)
 detector_fast_kernel(const __grid_constant__ DetArgs launch) {
     const DetArgs a = frame_args(launch);
@@ -517,9 +518,9 @@ detector_fast_kernel(const __grid_constant__ DetArgs launch) {
             j0 += j_step;
             if (j0 >= n_h) j0 -= n_h;
         }
-        const Philox4 rs = philox4x32_10(q, 0u, f_lo, t_shot, launch.keys);
+        const Philox4 rs = philox4x32_r<ROUNDS>(q, 0u, f_lo, t_shot, launch.keys);
         Philox4 rr = {0u, 0u, 0u, 0u};
-        if (DET == SCB_DET_CMOS || rn > 0.0f) rr = philox4x32_10(q, 0u, f_lo, t_read, launch.keys);
+        if (DET == SCB_DET_CMOS || rn > 0.0f) rr = philox4x32_r<ROUNDS>(q, 0u, f_lo, t_read, launch.keys);
         // shot noise: two packed branch-free heads, one test for the rare tails
         const float l0 = fmaf(qe, ph.x, qe_bg), l1 = fmaf(qe, ph.y, qe_bg),
                     l2 = fmaf(qe, ph.z, qe_bg), l3 = fmaf(qe, ph.w, qe_bg);
@@ -613,7 +614,7 @@ detector_slow_kernel(const __grid_constant__ DetArgs launch) {
         T offset = (T)a.det.adc_offset;
         if (a.det.fpn_type == SCB_FPN_PIXEL) offset = ((const T *)a.offset)[pix];
         else if (a.det.fpn_type == SCB_FPN_COLUMN) offset = ((const T *)a.offset)[pix % a.n_h];
-        const Philox4 rs = philox4x32_10((uint32_t)q, (uint32_t)(q >> 32), f_lo, SCB_TAG_SHOT ^ f_hi, k0, k1);
+        const Philox4 rs = philox4x32_n((uint32_t)q, (uint32_t)(q >> 32), f_lo, SCB_TAG_SHOT ^ f_hi, k0, k1, a.rounds);
         const uint32_t r_shot = w == 0 ? rs.x : w == 1 ? rs.y : w == 2 ? rs.z : rs.w;
         PixelRng rng(a.seed, (uint64_t)pix, a.frame);
         double sig;
@@ -623,7 +624,7 @@ detector_slow_kernel(const __grid_constant__ DetArgs launch) {
         if (a.in_noise) {
             noi = ((const T *)a.in_noise)[pix];
         } else {
-            const Philox4 rr = philox4x32_10((uint32_t)q, (uint32_t)(q >> 32), f_lo, SCB_TAG_READ ^ f_hi, k0, k1);
+            const Philox4 rr = philox4x32_n((uint32_t)q, (uint32_t)(q >> 32), f_lo, SCB_TAG_READ ^ f_hi, k0, k1, a.rounds);
             if (DET == SCB_DET_CMOS) {
                 const uint32_t r_read = w == 0 ? rr.x : w == 1 ? rr.y : w == 2 ? rr.z : rr.w;
                 noi = (T)alias_draw(r_read, (uint32_t)a.n_alias, a.alias);
@@ -664,6 +665,26 @@ bool fast_path_ok(const DetArgs &a, size_t elem_bytes) {
            (a.det.fpn_type != SCB_FPN_COLUMN || (a.n_h & 3) == 0);
 }
 
+// Philox rounds of the detector's per-quad streams.  10 (the Random123 / cuRAND default) unless the
+// environment asks for a measured variant: SCB_DETECTOR_ROUNDS=7 is the smallest Crush-resistant count
+// (all kernels follow, so the statistical tests can be run under it); 1..6 only time the streaming
+// kernel with a cheaper generator -- the ceiling a free generator would give -- and are not samplers.
+int detector_rounds() {
+    static const int rounds = [] {
+        const char *env = getenv("SCB_DETECTOR_ROUNDS");
+        const int r = env ? atoi(env) : 10;
+        return r >= 1 && r <= 10 ? r : 10;
+    }();
+    return rounds;
+}
+
+template <int DET, int ROUNDS>
+void launch_fast_rounds(const DetArgs &a, const dim3 grid, cudaStream_t s) {
+    if (a.det.fpn_type == SCB_FPN_NONE) detector_fast_kernel<DET, SCB_FPN_NONE, ROUNDS><<<grid, kThreads, 0, s>>>(a);
+    else if (a.det.fpn_type == SCB_FPN_PIXEL) detector_fast_kernel<DET, SCB_FPN_PIXEL, ROUNDS><<<grid, kThreads, 0, s>>>(a);
+    else detector_fast_kernel<DET, SCB_FPN_COLUMN, ROUNDS><<<grid, kThreads, 0, s>>>(a);
+}
+
 template <int DET>
 void launch_fast(const DetArgs &a, int n_frames, cudaStream_t s) {
     // two waves of the resident CTAs per frame; blockIdx.y = frame of a block
@@ -673,9 +694,9 @@ void launch_fast(const DetArgs &a, int n_frames, cudaStream_t s) {
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     const dim3 grid((unsigned)blocks, (unsigned)n_frames);
-    if (a.det.fpn_type == SCB_FPN_NONE) detector_fast_kernel<DET, SCB_FPN_NONE><<<grid, kThreads, 0, s>>>(a);
-    else if (a.det.fpn_type == SCB_FPN_PIXEL) detector_fast_kernel<DET, SCB_FPN_PIXEL><<<grid, kThreads, 0, s>>>(a);
-    else detector_fast_kernel<DET, SCB_FPN_COLUMN><<<grid, kThreads, 0, s>>>(a);
+    if (a.rounds == 10) launch_fast_rounds<DET, 10>(a, grid, s);
+    else if (a.rounds == 7) launch_fast_rounds<DET, 7>(a, grid, s);
+    else launch_fast_rounds<DET, 1>(a, grid, s);          // timing ceiling only
 }
 
 template <typename T, int DET>
@@ -765,6 +786,7 @@ static int detector_adc(uint64_t seed, uint64_t frame, int n_frames, const scb_d
     a.slow_list = (uint32_t *)((char *)d_workspace + 256);
     a.seed = seed; a.frame = frame; a.det = *det;
     a.keys = philox_round_keys((uint32_t)seed, (uint32_t)(seed >> 32));
+    a.rounds = detector_rounds();
     a.n_pix = (int64_t)n_w * n_h; a.n_h = n_h;
     a.n_alias = need_alias ? n_alias : 0;
     a.pow2bit = ldexp(1.0, det->bit);

@@ -88,16 +88,41 @@ __host__ __device__ __forceinline__ PhiloxKeys philox_round_keys(uint32_t k0, ui
     }
     return k;
 }
-__host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
-                                                          const PhiloxKeys &k) {
+// ROUNDS = 10 is the generator every stream of this library uses.  7 is the smallest round count for which
+// Random123 reports Philox4x32 Crush-resistant; it exists for the detector's measured variants only
+// (detector.cu), as does any smaller count (timing ceilings, never a sampler).
+template <int ROUNDS>
+__host__ __device__ __forceinline__ Philox4 philox4x32_r(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                         const PhiloxKeys &k) {
+    static_assert(ROUNDS >= 1 && ROUNDS <= 10, "round keys are precomputed for ten rounds");
     const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
 #pragma unroll
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < ROUNDS; ++r) {
         uint32_t hi0, lo0, hi1, lo1;
         mulhilo32(M0, c0, hi0, lo0);
         mulhilo32(M1, c2, hi1, lo1);
         c0 = hi1 ^ c1 ^ k.a[r];
         c2 = hi0 ^ c3 ^ k.b[r];
+        c1 = lo1;
+        c3 = lo0;
+    }
+    Philox4 out = {c0, c1, c2, c3};
+    return out;
+}
+__host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                          const PhiloxKeys &k) {
+    return philox4x32_r<10>(c0, c1, c2, c3, k);
+}
+// round count chosen at run time (generic kernels, where the generator is not the bottleneck)
+__host__ __device__ __forceinline__ Philox4 philox4x32_n(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                         uint32_t k0, uint32_t k1, int rounds) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+    for (int r = 0; r < rounds; ++r) {
+        uint32_t hi0, lo0, hi1, lo1;
+        mulhilo32(M0, c0, hi0, lo0);
+        mulhilo32(M1, c2, hi1, lo1);
+        c0 = hi1 ^ c1 ^ (k0 + (uint32_t)r * 0x9E3779B9u);
+        c2 = hi0 ^ c3 ^ (k1 + (uint32_t)r * 0xBB67AE85u);
         c1 = lo1;
         c3 = lo0;
     }

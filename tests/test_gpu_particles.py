@@ -181,3 +181,56 @@ default:
     assert all(abs(after[m] - budgets[m]) <= 1e-12 * max(1.0, budgets[m]) for m in list(budgets)[:2000]
                if m in {int(i) for i in data[:2000, 3]})
     assert (got == 0).mean() > 0.03                          # a fair share has bleached after 4 x 33 ms at T1/2 = 0.2 s
+
+
+def test_multistate_sampler_against_the_sampling2_oracle():
+    """scopyon_b200.sample (GPU) against oracle/sampling2_oracle.py (the restated sampling2.py with
+    `side='left'`): per-state displacement variance 2 D[state] dt per axis and two-sample KS of the
+    displacements, periodic wrap into [lower, upper), and the one-step transition counts -- chi-square of
+    the GPU's count matrix against the oracle's one-step probabilities, and two-sample against the
+    oracle's own draw."""
+    import scipy.stats
+    import sampling2_oracle as s2
+    n_per = 4000
+    N = [n_per, n_per, n_per]
+    D = numpy.array([1e-12, 0.0, 2.5e-13])
+    dt = 0.05
+    lower, upper = numpy.zeros(2), numpy.ones(2) * 4e-6
+    transmat = numpy.array([[0.0, 2.0, 0.5], [1.0, 0.0, 0.0], [0.3, 4.0, 0.0]])
+    t = [0.0, dt]
+    # no transitions, no wrap: displacements per state
+    got = scopyon_b200.sample(t, N, lower=lower, upper=upper, D=D, ndim=2, rng=numpy.random.RandomState(1))
+    want = s2.sample(t, N, lower, upper, D, ndim=2, rng=numpy.random.RandomState(2))
+    for state in range(3):
+        sel = got[0][:, 2] == state
+        d_got = (got[1][sel, :2] - got[0][sel, :2]).ravel()
+        d_want = (want[1][want[0][:, 2] == state, :2] - want[0][want[0][:, 2] == state, :2]).ravel()
+        sigma = numpy.sqrt(2 * D[state] * dt)
+        if sigma == 0:
+            assert (d_got == 0).all() and (d_want == 0).all()
+            continue
+        assert abs(d_got.std() / sigma - 1) < 0.03 and abs(d_got.mean()) < 4 * sigma / numpy.sqrt(len(d_got))
+        assert scipy.stats.ks_2samp(d_got, d_want).pvalue > 0.01            # 8000 vs 8000 draws
+        assert scipy.stats.kstest(d_got / sigma, "norm").pvalue > 0.01
+    # periodic wrap: same rule as the oracle applied to the GPU's own unwrapped step
+    wrapped = scopyon_b200.sample(t, N, lower=lower, upper=upper, D=D * 400, ndim=2, periodic=True,
+                                  rng=numpy.random.RandomState(1))
+    free = scopyon_b200.sample(t, N, lower=lower, upper=upper, D=D * 400, ndim=2, periodic=False,
+                               rng=numpy.random.RandomState(1))
+    assert (free[1][:, :2] < 0).any() and (free[1][:, :2] > 4e-6).any()      # some molecules did leave the box
+    want_wrapped = (free[1][:, :2] - lower) % (upper - lower) + lower           # sampling2.py:47-48
+    assert numpy.allclose(wrapped[1][:, :2], want_wrapped, rtol=0, atol=1e-20)
+    assert wrapped[1][:, :2].min() >= 0 and wrapped[1][:, :2].max() < 4e-6
+    # transitions: one step from known states
+    got = scopyon_b200.sample(t, N, lower=lower, upper=upper, D=D, transmat=transmat, ndim=2,
+                              rng=numpy.random.RandomState(3))
+    want = s2.sample(t, N, lower, upper, D, transmat=transmat, ndim=2, rng=numpy.random.RandomState(4))
+    Pacc = s2.transition_probabilities(transmat, dt)
+    P = numpy.diff(numpy.concatenate([numpy.zeros((3, 1)), Pacc], axis=1), axis=1)
+    for state in range(3):
+        counts_got = numpy.bincount(got[1][got[0][:, 2] == state, 2].astype(int), minlength=3)
+        counts_want = numpy.bincount(want[1][want[0][:, 2] == state, 2].astype(int), minlength=3)
+        keep = P[state] > 0
+        assert counts_got[~keep].sum() == 0 and counts_want[~keep].sum() == 0
+        assert scipy.stats.chisquare(counts_got[keep], n_per * P[state][keep]).pvalue > 0.001
+        assert scipy.stats.chi2_contingency(numpy.stack([counts_got[keep], counts_want[keep]]))[1] > 0.001

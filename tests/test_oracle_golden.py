@@ -134,3 +134,19 @@ def test_emccd_pmf_matches_reference():
         assert numpy.array_equal(S[::step], g["S{}".format(i)])
         assert numpy.array_equal(cdf[::step], g["cdf{}".format(i)])
         assert (S * p).sum() == float(g["mean{}".format(i)])
+
+
+def test_sampling2_oracle_against_reference_golden():
+    """oracle/sampling2_oracle.py reproduces the reference's multi-state trajectories
+    (tests/golden/sampling2_case.npz, made by oracle/make_golden_sampling2.py from the live reference)
+    bit for bit on the same RandomState."""
+    import sampling2_oracle as s2
+    g = golden("sampling2_case.npz")
+    t = list(g["t"])
+    out = s2.sample(t, [40, 25, 10], g["lower"], g["upper"], g["D"], transmat=g["transmat"], ndim=3, periodic=True,
+                    rng=numpy.random.RandomState(2024))
+    assert numpy.array_equal(numpy.stack(out), g["periodic_switching"])
+    free = s2.sample(t, [30, 30], numpy.zeros(2), numpy.ones(2) * 1e-6, numpy.array([2e-13, 5e-12]), ndim=2,
+                     periodic=False, rng=numpy.random.RandomState(7))
+    assert numpy.array_equal(numpy.stack(free), g["free"])
+    assert len(numpy.unique(g["periodic_switching"][-1][:, 3])) == 3          # states did switch

@@ -106,3 +106,37 @@ def test_move_points_same_stream(ref):
     a = S.move_points(numpy.random.RandomState(4), pts, D=[1e-13, 2e-13, 0.0], dt=0.033, ndim=3)
     b = orc.move_points(numpy.random.RandomState(4), pts, D=[1e-13, 2e-13, 0.0], dt=0.033, ndim=3)
     assert numpy.allclose(a, b, rtol=1e-15, atol=0)
+
+
+def test_sampling2_bit_for_bit(ref, monkeypatch):
+    """oracle/sampling2_oracle.py against the live sampling2.py on the same RandomState: placement,
+    per-state Brownian step with periodic wrap, the whole `sample` loop -- and the transition step,
+    which the reference can only run once `side='leff'` (sampling2.py:66) is read as 'left'."""
+    import sampling2_oracle as s2
+    from scopyon import sampling2 as R
+    lower, upper = numpy.array([0.0, -1e-6, 2e-7]), numpy.array([1e-6, 1e-6, 2e-7])     # one degenerate axis
+    a = getattr(R, "__generate_points")(numpy.random.RandomState(1), N=[30, 0, 12], lower=lower, upper=upper, ndim=3)
+    b = s2.generate_points(numpy.random.RandomState(1), [30, 0, 12], lower, upper, 3)
+    assert numpy.array_equal(a, b) and a.shape == (42, 5)
+    D = numpy.array([1e-12, 0.0, 3e-13])
+    for periodic in (False, True):
+        ma = getattr(R, "__move_points")(numpy.random.RandomState(2), a, D=D, lower=lower, upper=upper, dt=0.05, ndim=3,
+                                         periodic=periodic)
+        mb = s2.move_points(numpy.random.RandomState(2), b, D, lower, upper, 0.05, 3, periodic)
+        assert numpy.array_equal(ma, mb)
+    assert (mb[:, 0] >= 0).all() and (mb[:, 0] < 1e-6).all() and (mb[:, 2] == 2e-7).all()
+    transmat = numpy.array([[0.0, 2.0, 0.5], [1.0, 0.0, 0.0], [0.3, 4.0, 0.0]])
+    with pytest.raises(ValueError):          # the reference as written
+        getattr(R, "__transition_states")(numpy.random.RandomState(3), a, transmat=transmat, dt=0.1, ndim=3)
+    real = numpy.searchsorted
+    monkeypatch.setattr(numpy, "searchsorted",
+                        lambda arr, v, side='left', sorter=None: real(arr, v, side='left' if side == 'leff' else side, sorter=sorter))
+    ta = getattr(R, "__transition_states")(numpy.random.RandomState(3), a, transmat=transmat, dt=0.1, ndim=3)
+    tb = s2.transition_states(numpy.random.RandomState(3), b, transmat, 0.1, 3)
+    assert numpy.array_equal(ta, tb) and len(numpy.unique(tb[:, 3])) == 3
+    t = [0.0, 0.1, 0.1, 0.25]
+    sa = R.sample(t, [20, 10, 5], lower=lower, upper=upper, D=D, transmat=transmat, ndim=3, periodic=True,
+                  rng=numpy.random.RandomState(4))
+    sb = s2.sample(t, [20, 10, 5], lower, upper, D, transmat=transmat, ndim=3, periodic=True,
+                   rng=numpy.random.RandomState(4))
+    assert len(sa) == len(sb) == 4 and all(numpy.array_equal(x, y) for x, y in zip(sa, sb))

@@ -79,6 +79,29 @@ def bench_detector():
                                   "frac_of_measured_hbm": gbs / PEAK, "frames/s": 1e3 / ms}))
 
 
+def bench_detector_block():
+    """The detector pass as the C4 step runs it: 16 frames of 2048^2 per launch (scb_detector_adc_frames),
+    CMOS + column FPN, C4-like signal.  SCB_DETECTOR_ROUNDS selects the measured generator variants."""
+    sys.path.insert(0, ROOT)
+    from bench import C4_YAML
+    size, nf = 2048, 16
+    configs, eng = engine_for(C4_YAML % (size, size, 2.5))
+    rng = numpy.random.RandomState(0)
+    photons = torch.from_numpy(rng.gamma(0.5, 1.2, (nf, size, size)).astype(numpy.float32)).cuda()   # mean 0.6 photons/px
+    adc = torch.empty_like(photons)
+    work = torch.empty(nf * eng.lib.scb_detector_workspace_bytes(size, size), dtype=torch.uint8, device="cuda")
+
+    def go():
+        eng._call("scb_detector_adc_frames", 42, 0, nf, ctypes.byref(eng.det), size, size, _native.F32,
+                  _native.ptr(photons), _native.ptr(eng.offset), _native.ptr(eng.alias), int(eng.alias.shape[0]),
+                  _native.ptr(adc), _native.ptr(work), work.numel(), eng._stream())
+    ms, best = timed(go, iters=10, warm=3)
+    gbs = nf * size * size * 8 / (ms * 1e-3) / 1e9
+    print(json.dumps({"kernel": "detector_fast_kernel<CMOS,column> + slow pass, 16 x 2048^2 per launch",
+                      "philox_rounds": int(os.environ.get("SCB_DETECTOR_ROUNDS", "10")), "ms": ms, "ms_best": best,
+                      "GB/s": gbs, "frac_of_measured_hbm": gbs / PEAK, "mean_adc": float(adc.mean().item())}))
+
+
 def bench_diffuse():
     for n in (100000, 10000000, 50000000):
         parts = DeviceParticles(n, 3)
@@ -185,6 +208,8 @@ if __name__ == "__main__":
     print(json.dumps({"gpu": torch.cuda.get_device_name(0), "hbm_peak_gbs": PEAK}))
     if "detector" in what:
         bench_detector()
+    if "detector_block" in what:
+        bench_detector_block()
     if "diffuse" in what:
         bench_diffuse()
     if "render" in what:
