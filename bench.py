@@ -84,6 +84,8 @@ def parse_args():
     ap.add_argument("--e2e-frames", type=int, default=48)
     ap.add_argument("--cpu-sample-spots", type=int, default=384)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--resident-only", action="store_true",
+                    help="kernel work only: skip export, end-to-end, host bounds, parity and CPU legs (variant sweeps)")
     ap.add_argument("--payload", default=None, help="(internal) parity payload of the cpu-check leg")
     args = ap.parse_args()
     if args.molecules is None:
@@ -632,6 +634,19 @@ def run_weak(args):
     checksum = float(block[-1].double().mean().item())
     elapsed_ms = max_over_ranks(elapsed_ms, world, device)
     value = world * K * F / (elapsed_ms * 1e-3)
+
+    if args.resident_only:
+        if rank == 0:
+            per_launch_ms = render_ms / max(1, render_launches)
+            print(json.dumps({"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": K,
+                              "warmup": W, "ms_per_step": elapsed_ms / K, "render_ms_per_launch": per_launch_ms,
+                              "render_share_of_step": render_ms / elapsed_ms,
+                              "variant": {k: v for k, v in os.environ.items() if k.startswith("SCB_")},
+                              "frame_checksum_mean_adc": checksum, "table_errors": n_err, "clocks": clocks}))
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
 
     # ---- the 2.5 s half-life of SURVEY.md section 8(d), beside the headline
     spec = None

@@ -348,6 +348,7 @@ class _EPIFMSimulator:
             _log.info('A random number generator was initialized.')
             rng = numpy.random.RandomState()
         engine = self.engine
+        engine._eager_float64 = False       # float32 payloads until the caller asks a frame for its float64 array
         states = None
         if self.configs.effects.photobleaching_switch:
             states = engine.new_budget_state(input_data, draw_seed(rng))

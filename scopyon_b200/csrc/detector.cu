@@ -54,7 +54,16 @@ struct PixelRng {
 // streaming kernel enters once per pixel quad.  Explicit _rn intrinsics keep the compiler
 // from contracting the recurrence differently in different kernels: every kernel draws the
 // same count from the same word.
+//
+// The running sum is fp32: it carries ~2^-21 of relative error (ex2.approx, one rounding per term) and
+// moves in steps of 256-512 near 2^32, so a sum scaled by exactly 2^32 can stall a few hundred BELOW the
+// largest words -- every count test then passes and the search would run to its bound.  The scale is
+// therefore 2^kPoissonScaleLog2 = 2^32 * (1 + 2.6e-6), the next fp32 exponent after 32: the converged sum
+// lies ~11 000 above 2^32, beyond any error the recurrence can accumulate (< 6 500), so every word is
+// passed while the terms are still far above the rounding step.  The price is the cumulative
+// distribution scaled by 1 + 2.6e-6 -- the accuracy an fp32 inversion has anyway.
 constexpr float kSmallLambda = 12.0f;
+constexpr float kPoissonScaleLog2 = 32.000003814697266f;     // nextafterf(32, 64)
 
 __device__ __forceinline__ float ex2_ftz(float x) {    // argument >= 14 here: no denormal handling needed
     float y;
@@ -67,7 +76,7 @@ struct PoissonRun {   // state of the sequential search after the unrolled head
 };
 
 __device__ __forceinline__ float poisson_head(float lambda, float rf, PoissonRun &run) {
-    float p = ex2_ftz(fmaf(lambda, -1.4426950408889634f, 32.0f));            // 2^32 * exp(-lambda)
+    float p = ex2_ftz(fmaf(lambda, -1.4426950408889634f, kPoissonScaleLog2));            // 2^32 * exp(-lambda)
     float s = p;
     float k = rf >= s ? 1.0f : 0.0f;
     p = __fmul_rn(p, lambda);                              s = __fadd_rn(s, p); k += rf >= s ? 1.0f : 0.0f;
@@ -114,7 +123,7 @@ __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
 __device__ __forceinline__ void poisson_head2(float la, float lb, float rfa, float rfb, float &ka, float &kb,
                                               PoissonRun &ra, PoissonRun &rb) {
     const f32x2 lam = pack2(la, lb);
-    f32x2 p = pack2(ex2_ftz(fmaf(la, -1.4426950408889634f, 32.0f)), ex2_ftz(fmaf(lb, -1.4426950408889634f, 32.0f)));
+    f32x2 p = pack2(ex2_ftz(fmaf(la, -1.4426950408889634f, kPoissonScaleLog2)), ex2_ftz(fmaf(lb, -1.4426950408889634f, kPoissonScaleLog2)));
     f32x2 s = p;
     float sa, sb;
     unpack2(s, sa, sb);
@@ -134,10 +143,9 @@ __device__ __forceinline__ void poisson_head2(float la, float lb, float rfa, flo
     rb.s = sb;
 }
 
-// The running sum is fp32 against a word scaled by 2^32: once a term falls below half an ulp of the sum
-// (128-256 near 2^32) the sum stops moving, possibly a few hundred below the largest words.  The terms only
-// shrink from there on (a lost term lies past the mode), so the search ends at that count: the top ~2^-23 of
-// the word range is folded into the last count that could still be told apart, never into the loop bound.
+// With the scale above the sum passes every word long before its terms reach the rounding step; should it
+// stop moving all the same (a lost term lies past the mode, later ones only shrink) the search ends at
+// that count and never at the loop bound.
 __device__ __noinline__ float poisson_tail(float lambda, float rf, float p, float s) {
     int k = 4;
 #pragma unroll 1

@@ -35,24 +35,36 @@
 
 namespace {
 
-constexpr int kStripRows = 8;         // pixel rows per strip
-// Accumulators and strip width by box-table precision.  fp64 tables (exact mode): 64-bit fixed
-// point, LSB chosen per call, 8 x 64-pixel strips.  fp32 tables (fp32 frames): 32-bit fixed point
-// with the LSB chosen per strip from its list length, 8 x 128-pixel strips -- the same 4 KB of
-// shared memory per warp, fewer and wider units, a cheaper conversion and add per pixel.
-template <typename BoxT> struct Mode;
-template <> struct Mode<double> { using Acc = long long; static constexpr int kCols = 64; };
-template <> struct Mode<float> { using Acc = int; static constexpr int kCols = 128; };
+// Accumulators and strip shape.  A strip's accumulators fill 4 KB of shared memory: 64-bit fixed point
+// (fp64 box tables, exact mode: LSB chosen per call) or 32-bit fixed point (fp32 tables, fp32 frames: LSB
+// chosen per strip from its list length).  ROWS x kCols pixels: 8 x 64 (exact mode), and for fp32 either
+// 8 x 128 or 16 x 64 -- taller strips cut a ~31 x 31 footprint into fewer units (4.3 instead of 7.0 per
+// spot: fewer census atomics, fewer unit records, less per-unit bookkeeping in the render) at the price
+// of 2 KB ring stages.
+template <typename BoxT> struct AccOf;
+template <> struct AccOf<double> { using type = long long; };
+template <> struct AccOf<float> { using type = int; };
+template <typename BoxT, int ROWS> struct Mode {
+    using Acc = typename AccOf<BoxT>::type;
+    static constexpr int kCols = 4096 / (ROWS * (int)sizeof(Acc));
+};
 constexpr int kUnitCols = 32;         // columns per unit = lanes
 constexpr int kMaxWarps = 7;          // warps (= strips in flight) per CTA
-constexpr int kBatch = 16;            // units fetched per round (one per lane of a half warp)
-constexpr int kEdges = kStripRows + 1;
+// units fetched per round (one per lane): 16, or 8 with 16-row strips, whose larger ring then still lets
+// 21 warps share an SM's shared memory
+template <int ROWS> constexpr int batch_units() { return ROWS == 16 ? 8 : 16; }
 constexpr int kFastSlots = 32;        // widest box-table block row the ring holds
-constexpr int kStageEntries = kStripRows * kFastSlots;
-// TMA ring depth: three stages (2 KB each of fp64 box values, 1 KB of fp32 ones)
-template <typename BoxT> constexpr int ring_stages() { return 3; }
-// CTAs per SM: shared memory per warp is 4 KB of accumulators + the ring + 0.5 KB of units
-template <typename BoxT> constexpr int ctas_per_sm() { return sizeof(BoxT) == 4 ? 4 : 3; }
+constexpr int kDefaultRows = 8;       // fp32 strip shape and copy engine unless the environment says otherwise
+constexpr int kDefaultCopy = 0;
+constexpr int kStages = 3;            // ring depth: the copy of unit u + 2 is issued while unit u is consumed
+template <typename BoxT, int ROWS> constexpr size_t warp_smem_bytes() {
+    return 4096 + kStages * ROWS * kFastSlots * sizeof(BoxT) + batch_units<ROWS>() * 32 + 32;
+}
+// CTAs per SM from the shared memory one warp needs (accumulators + ring + unit batch)
+template <typename BoxT, int ROWS> constexpr int ctas_per_sm() {
+    constexpr int fit = (int)(232448 / (kMaxWarps * warp_smem_bytes<BoxT, ROWS>() + 1024));
+    return fit > 4 ? 4 : fit;
+}
 constexpr uint32_t kUnitFast = 0x80000000u;
 
 // One work-list entry: the overlap of a spot with (<= 8 rows) x (<= 32 columns) of a strip.
@@ -185,23 +197,36 @@ __device__ __forceinline__ void unit_stage(const void *src, uint32_t bytes, void
 __device__ __forceinline__ long long to_fixed(double box, double ws) { return __double2ll_rn(__dmul_rn(box, ws)); }
 __device__ __forceinline__ int to_fixed(float box, float ws) { return __float2int_rn(__fmul_rn(box, ws)); }
 
-// Accumulator update shared by both paths.  Rows beyond the unit's last carry stale values:
-// their products are computed and dropped (only the update is predicated), which keeps the
-// loop branch free.  _epifm.py:280-282 (`if photons > 0` needs no branch: adding zero changes nothing)
-template <typename BoxT, int ROWS>
-__device__ __forceinline__ void unit_add(typename Mode<BoxT>::Acc *a, int rows, BoxT ws, const BoxT (&box)[kStripRows]) {
+// Per-lane cp.async (LDGSTS) staging: the alternative to the TMA bulk copy.  A unit's rows are one
+// contiguous run of the block (<= 2 KB), so lane l copies the 16-byte pieces l, l + 32, ... of it: no
+// elected lane, no uniform-register traffic, no mbarrier -- completion is this thread's cp.async group.
+__device__ __forceinline__ void cp_async16(void *dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// Accumulator update of four consecutive rows of a unit, shared by both paths.  Rows beyond the unit's
+// last carry stale values: their products are computed and dropped (only the update is predicated), which
+// keeps the body branch free.  _epifm.py:280-282 (`if photons > 0` needs no branch: adding zero changes nothing)
+template <typename Acc, typename BoxT, int COLS>
+__device__ __forceinline__ void rows4_add(Acc *a, int rows_left, BoxT ws, const BoxT (&box)[4]) {
 #pragma unroll
-    for (int k = 0; k < ROWS; ++k) {
-        const typename Mode<BoxT>::Acc q = to_fixed(box[k], ws);
-        if (k < rows) a[k * Mode<BoxT>::kCols] += q;
+    for (int k = 0; k < 4; ++k) {
+        const Acc q = to_fixed(box[k], ws);
+        if (k < rows_left) a[k * COLS] += q;
     }
 }
 
-// Fast unit, consumer side: lane l reads its column of the staged box rows.  Units of at most
-// four rows (the top and bottom of most footprints) run a half-height copy of the loop.
-template <typename BoxT, int SLOTS>
-__device__ __forceinline__ void unit_accumulate_fast(const Unit *meta, int u, int lane, typename Mode<BoxT>::Acc *acc,
-                                                     const BoxT *stage, int runtime_slots, double scale) {
+// Fast unit, consumer side: lane l reads its column of the staged box rows, four rows per round
+// (a unit has 1..ROWS rows; the round count is warp uniform).
+template <typename BoxT, int ROWS, int SLOTS>
+__device__ __forceinline__ void unit_accumulate_fast(const Unit *meta, int u, int lane,
+                                                     typename Mode<BoxT, ROWS>::Acc *acc, const BoxT *stage,
+                                                     int runtime_slots, double scale) {
+    using M = Mode<BoxT, ROWS>;
     const int slots = SLOTS ? SLOTS : runtime_slots;
     BoxT ws;
     int n_rows, n_cols, acc_at, box_col;
@@ -218,80 +243,91 @@ __device__ __forceinline__ void unit_accumulate_fast(const Unit *meta, int u, in
         const uint32_t shape = meta[u].shape;
         n_rows = shape & 0xff;
         n_cols = (shape >> 8) & 0xff;
-        acc_at = ((shape >> 16) & 0xff) * Mode<BoxT>::kCols + (shape >> 24);
+        acc_at = ((shape >> 16) & 0xff) * M::kCols + (shape >> 24);
         box_col = (int)(meta[u].extra & 0xffu);
     }
     int rows = lane < n_cols ? n_rows : 0;   // idle lanes: no rows
     asm volatile("" : "+r"(rows));       // keep it one value: one compare per row below instead of two
-    typename Mode<BoxT>::Acc *a = acc + acc_at + lane;
+    typename M::Acc *a = acc + acc_at + lane;
     const BoxT *st = stage + min(box_col + lane, slots - 1);   // idle lanes stay inside the row
-    BoxT box[kStripRows];
-    if (n_rows <= kStripRows / 2) {         // warp uniform
+#pragma unroll 1
+    for (int r0 = 0; r0 < n_rows; r0 += 4) {                   // warp uniform
+        BoxT box[4];
 #pragma unroll
-        for (int k = 0; k < kStripRows / 2; ++k) box[k] = st[k * slots];
-        unit_add<BoxT, kStripRows / 2>(a, rows, ws, box);
-    } else {
-#pragma unroll
-        for (int k = 0; k < kStripRows; ++k) box[k] = st[k * slots];
-        unit_add<BoxT, kStripRows>(a, rows, ws, box);
+        for (int k = 0; k < 4; ++k) box[k] = st[(r0 + k) * slots];
+        rows4_add<typename M::Acc, BoxT, M::kCols>(a + r0 * M::kCols, rows - r0, ws, box);
     }
 }
 
-// Gather unit: per-edge table offsets from `edges`, corners straight from global memory.
-template <typename BoxT>
-__device__ __forceinline__ void unit_accumulate_gather(const Unit *meta, int u, int lane, typename Mode<BoxT>::Acc *acc,
+// Gather unit: per-edge table offsets from `edges`, corners straight from global memory.  Neighbouring
+// lanes share a column edge (the right corners of lane l are the left corners of lane l + 1), so a lane
+// fetches its left corners only and takes the right ones from its neighbour by shuffle; the last active
+// lane fetches both.
+template <typename BoxT, int ROWS>
+__device__ __forceinline__ void unit_accumulate_gather(const Unit *meta, int u, int lane,
+                                                       typename Mode<BoxT, ROWS>::Acc *acc,
                                                        const uint32_t *__restrict__ edges, double scale) {
+    using M = Mode<BoxT, ROWS>;
     BoxT ws;
     if constexpr (sizeof(BoxT) == 4) ws = *reinterpret_cast<const float *>(&meta[u].ws);   // scaled at fetch time
     else ws = (BoxT)(meta[u].ws * scale);
     const uint32_t shape = meta[u].shape;
     const int n_rows = shape & 0xff, n_cols = (shape >> 8) & 0xff;
     const int rows = lane < n_cols ? n_rows : 0;
-    typename Mode<BoxT>::Acc *a = acc + ((shape >> 16) & 0xff) * Mode<BoxT>::kCols + (shape >> 24) + lane;
+    typename M::Acc *a = acc + ((shape >> 16) & 0xff) * M::kCols + (shape >> 24) + lane;
     const long long *table = static_cast<const long long *>(meta[u].src);
     const uint32_t c = meta[u].ecol + (uint32_t)min(lane, n_cols - 1);   // idle lanes repeat the last column
     const uint32_t left = __ldg(edges + c), right = __ldg(edges + c + 1);
-    const uint32_t my_row = __ldg(edges + meta[u].erow + (uint32_t)min(lane, n_rows));
-    long long L[kEdges], R[kEdges];
+    const bool last_lane = lane == n_cols - 1 || lane == 31;
+    const uint32_t erow = meta[u].erow;
+#pragma unroll 1
+    for (int r0 = 0; r0 < n_rows; r0 += 4) {                  // warp uniform; edges r0 .. r0 + 4
+        const uint32_t my_row = __ldg(edges + erow + (uint32_t)min(r0 + min(lane, 4), n_rows));
+        long long L[5], R[5];
 #pragma unroll
-    for (int k = 0; k < kEdges; ++k) {
-        const uint32_t row = __shfl_sync(0xffffffffu, my_row, k);
-        L[k] = 0; R[k] = 0;
-        if (k <= n_rows) {                     // warp uniform
-            if (!((row | left) & kEdgeZero)) L[k] = __ldg(table + (row + left));
-            if (!((row | right) & kEdgeZero)) R[k] = __ldg(table + (row + right));
+        for (int k = 0; k < 5; ++k) {
+            const uint32_t row = __shfl_sync(0xffffffffu, my_row, k);
+            L[k] = 0;
+            long long own_right = 0;
+            if (r0 + k <= n_rows) {                            // warp uniform
+                if (!((row | left) & kEdgeZero)) L[k] = __ldg(table + (row + left));
+                if (last_lane && !((row | right) & kEdgeZero)) own_right = __ldg(table + (row + right));
+            }
+            const long long from_neighbour = __shfl_down_sync(0xffffffffu, L[k], 1);
+            R[k] = last_lane ? own_right : from_neighbour;
         }
-    }
-    BoxT box[kStripRows];
+        BoxT box[4];
 #pragma unroll
-    for (int k = 0; k < kStripRows; ++k)    // >= 0: the table is non-negative, edges are monotone; rounded as the box table is
-        box[k] = (BoxT)((R[k + 1] - L[k + 1]) - (R[k] - L[k]));
-    unit_add<BoxT, kStripRows>(a, rows, ws, box);
+        for (int k = 0; k < 4; ++k)    // >= 0: the table is non-negative, edges are monotone; rounded as the box table is
+            box[k] = (BoxT)((R[k + 1] - L[k + 1]) - (R[k] - L[k]));
+        rows4_add<typename M::Acc, BoxT, M::kCols>(a + r0 * M::kCols, rows - r0, ws, box);
+    }
 }
 
-template <typename BoxT>
-constexpr size_t warp_smem_bytes() {
-    return kStripRows * Mode<BoxT>::kCols * sizeof(typename Mode<BoxT>::Acc) + ring_stages<BoxT>() * kStageEntries * sizeof(BoxT) +
-           kBatch * sizeof(Unit) + 32;
-}
-static_assert(ctas_per_sm<double>() * (kMaxWarps * warp_smem_bytes<double>() + 1024) <= 232448 &&
-                  ctas_per_sm<float>() * (kMaxWarps * warp_smem_bytes<float>() + 1024) <= 232448,
+static_assert(ctas_per_sm<double, 8>() * (kMaxWarps * warp_smem_bytes<double, 8>() + 1024) <= 232448 &&
+                  ctas_per_sm<float, 8>() * (kMaxWarps * warp_smem_bytes<float, 8>() + 1024) <= 232448 &&
+                  ctas_per_sm<float, 16>() * (kMaxWarps * warp_smem_bytes<float, 16>() + 1024) <= 232448,
               "the CTAs of one SM must fit in shared memory");
 
-template <typename OutT, typename BoxT, int SLOTS>
-__global__ void __launch_bounds__(kMaxWarps * 32, ctas_per_sm<BoxT>())
+// COPY: 0 = TMA bulk copy per unit (issued by the lane that fetched the unit, completion on an mbarrier),
+//       1 = per-lane cp.async pieces (completion by cp.async group).
+template <typename OutT, typename BoxT, int ROWS, int SLOTS, int COPY>
+__global__ void __launch_bounds__(kMaxWarps * 32, ctas_per_sm<BoxT, ROWS>())
 render_strips_kernel(Geo g, const Unit *__restrict__ units, const uint32_t *__restrict__ edges,
                      const int *__restrict__ tile_start, int *__restrict__ next_tile,
                      const unsigned long long *__restrict__ wmax_bits, int64_t n_spots,
                      OutT *__restrict__ out, int accumulate) {
-    constexpr int kStages = ring_stages<BoxT>();
+    using M = Mode<BoxT, ROWS>;
+    using Acc = typename M::Acc;
+    constexpr int kStripCols = M::kCols;
+    constexpr int kStageEntries = ROWS * kFastSlots;
+    constexpr size_t kAccBytes = ROWS * kStripCols * sizeof(Acc);
+    constexpr int kBatch = batch_units<ROWS>();
+    static_assert(kAccBytes == 4096, "accumulators of one strip");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // per-warp carve: accumulators | TMA ring | unit batch | mbarriers
-    unsigned char *mine = smem_raw + warp * warp_smem_bytes<BoxT>();
-    using Acc = typename Mode<BoxT>::Acc;
-    constexpr int kStripCols = Mode<BoxT>::kCols;
-    constexpr size_t kAccBytes = kStripRows * kStripCols * sizeof(Acc);
+    // per-warp carve: accumulators | copy ring | unit batch | mbarriers
+    unsigned char *mine = smem_raw + warp * warp_smem_bytes<BoxT, ROWS>();
     Acc *acc = reinterpret_cast<Acc *>(mine);
     BoxT *ring = reinterpret_cast<BoxT *>(mine + kAccBytes);
     Unit *meta = reinterpret_cast<Unit *>(mine + kAccBytes + kStages * kStageEntries * sizeof(BoxT));
@@ -303,13 +339,15 @@ render_strips_kernel(Geo g, const Unit *__restrict__ units, const uint32_t *__re
     const unsigned long long wmax = *wmax_bits;
     const int call_shift = accumulator_shift(wmax, n_spots);      // 64-bit accumulators: one LSB per call
 
-    for (int i = lane; i < kStripRows * kStripCols; i += 32) acc[i] = 0;
+    for (int i = lane; i < ROWS * kStripCols; i += 32) acc[i] = 0;
     for (int i = lane; i < kStages * kStageEntries; i += 32) ring[i] = (BoxT)0;   // rows past a unit's last are read (and dropped)
-    if (lane == 0) {
-        for (int st = 0; st < kStages; ++st) mbar_init(&bars[st], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (COPY == 0) {
+        if (lane == 0) {
+            for (int st = 0; st < kStages; ++st) mbar_init(&bars[st], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // zeroed ring visible to the async proxy
     }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // zeroed ring visible to the async proxy
     __syncwarp();
     int p_stage = 0, c_stage = 0;            // ring positions of the producer and the consumer (fast units only)
     uint32_t c_parity = 0;
@@ -321,7 +359,7 @@ render_strips_kernel(Geo g, const Unit *__restrict__ units, const uint32_t *__re
         if (tile >= n_tiles) break;
         const int frame = tile / frame_tiles, in_frame = tile - frame * frame_tiles;
         const int ti = in_frame / g.ntj, tj = in_frame - ti * g.ntj;
-        const int row0 = ti * kStripRows, col0 = tj * kStripCols;
+        const int row0 = ti * ROWS, col0 = tj * kStripCols;
         OutT *image = out + (size_t)frame * g.n_w * g.n_h;
         const int seg_begin = tile_start[tile * g.stripes], seg_end = tile_start[(tile + 1) * g.stripes];
         const int shift = sizeof(Acc) == 4 ? strip_shift(seg_end - seg_begin, wmax, g.box_peak) : call_shift;
@@ -339,33 +377,54 @@ render_strips_kernel(Geo g, const Unit *__restrict__ units, const uint32_t *__re
                 const uint4 *src = reinterpret_cast<const uint4 *>(units + base + lane);
                 uint4 *dst = reinterpret_cast<uint4 *>(meta + lane);
                 uint4 head = __ldg(src);                                    // {ws, src}
-                const uint4 tail = __ldg(src + 1);                          // {erow, ecol, shape, extra}
+                uint4 tail = __ldg(src + 1);                                // {erow, ecol, shape, extra}
                 my_src = reinterpret_cast<const void *>(((unsigned long long)head.w << 32) | head.z);
+                my_bytes = (tail.z & 0xffu) * row_bytes;
+                my_fast = (tail.w & kUnitFast) != 0;
                 if constexpr (sizeof(BoxT) == 4) {
                     // fp32 mode: the fetching lane forms the unit's weight in accumulator LSBs once (the same
                     // double product and conversion the 32 consumer lanes would each repeat) and, for a
                     // box-table unit, unpacks shape and column into the words the consumers use directly:
-                    // {weight, accumulator offset, box-table column, rows | columns << 8}
+                    // {weight, accumulator offset, box-table column, rows | columns << 8}, source pointer behind
                     const double ws = __longlong_as_double(((long long)head.y << 32) | head.x);
                     head.x = __float_as_uint((float)(ws * scale));
-                    if (tail.w & kUnitFast) {
-                        head.y = ((tail.z >> 16) & 0xffu) * Mode<BoxT>::kCols + (tail.z >> 24);
+                    if (my_fast) {
+                        tail.x = head.z;                                    // source pointer (edge indices are unused)
+                        tail.y = head.w;
+                        head.y = ((tail.z >> 16) & 0xffu) * M::kCols + (tail.z >> 24);
                         head.z = tail.w & 0xffu;
                         head.w = tail.z & 0xffffu;
                     }
                 }
                 dst[0] = head;
                 dst[1] = tail;
-                my_bytes = (tail.z & 0xffu) * row_bytes;
-                my_fast = (tail.w & kUnitFast) != 0;
             }
             const uint32_t fast_mask = __ballot_sync(0xffffffffu, my_fast);
             __syncwarp();
 
             auto stage_unit = [&](int u) {
-                if ((fast_mask >> u) & 1u) {          // warp uniform
-                    if (lane == u) unit_stage(my_src, my_bytes, ring + p_stage * kStageEntries, &bars[p_stage]);
-                    if (++p_stage == kStages) p_stage = 0;
+                if (COPY == 0) {
+                    if ((fast_mask >> u) & 1u) {          // warp uniform
+                        if (lane == u) unit_stage(my_src, my_bytes, ring + p_stage * kStageEntries, &bars[p_stage]);
+                        if (++p_stage == kStages) p_stage = 0;
+                    }
+                } else {
+                    if ((fast_mask >> u) & 1u) {
+                        const char *src;
+                        uint32_t bytes;
+                        if constexpr (sizeof(BoxT) == 4) {
+                            const uint2 where = *reinterpret_cast<const uint2 *>(&meta[u].erow);
+                            src = reinterpret_cast<const char *>(((unsigned long long)where.y << 32) | where.x);
+                            bytes = (*reinterpret_cast<const uint32_t *>(&meta[u].src + 1) & 0xffu) * row_bytes;
+                        } else {
+                            src = static_cast<const char *>(meta[u].src);
+                            bytes = (meta[u].shape & 0xffu) * row_bytes;
+                        }
+                        char *dst = reinterpret_cast<char *>(ring + p_stage * kStageEntries);
+                        for (uint32_t off = lane * 16u; off < bytes; off += 512u) cp_async16(dst + off, src + off);
+                        if (++p_stage == kStages) p_stage = 0;
+                    }
+                    cp_async_commit();                     // one group per unit, empty for gather units
                 }
             };
             for (int u = 0; u < min(nb, kStages - 1); ++u) stage_unit(u);
@@ -375,19 +434,29 @@ render_strips_kernel(Geo g, const Unit *__restrict__ units, const uint32_t *__re
                 __syncwarp();
                 if (u + kStages - 1 < nb) stage_unit(u + kStages - 1);
                 if ((fast_mask >> u) & 1u) {
-                    mbar_wait(&bars[c_stage], c_parity);
-                    unit_accumulate_fast<BoxT, SLOTS>(meta, u, lane, acc, ring + c_stage * kStageEntries, slots, scale);
+                    if (COPY == 0) {
+                        mbar_wait(&bars[c_stage], c_parity);
+                    } else {
+                        // groups committed after unit u's: min(nb - 1 - u, 2)
+                        const int ahead = min(nb - 1 - u, kStages - 1);
+                        if (ahead >= 2) cp_async_wait<2>();
+                        else if (ahead == 1) cp_async_wait<1>();
+                        else cp_async_wait<0>();
+                        __syncwarp();                      // the other lanes' pieces have landed too
+                    }
+                    unit_accumulate_fast<BoxT, ROWS, SLOTS>(meta, u, lane, acc, ring + c_stage * kStageEntries, slots, scale);
                     if (++c_stage == kStages) { c_stage = 0; c_parity ^= 1u; }
                 } else {
-                    unit_accumulate_gather<BoxT>(meta, u, lane, acc, edges, scale);
+                    unit_accumulate_gather<BoxT, ROWS>(meta, u, lane, acc, edges, scale);
                 }
             }
+            if (COPY == 1) cp_async_wait<0>();             // gather units at the end of a batch leave empty groups behind
         }
 
         // ---- write the strip (coalesced rows) and clear the accumulators for the next one
         __syncwarp();
 #pragma unroll
-        for (int r = 0; r < kStripRows; ++r) {
+        for (int r = 0; r < ROWS; ++r) {
             const int i = row0 + r;
 #pragma unroll
             for (int q = 0; q < kStripCols / 32; ++q) {
@@ -447,8 +516,26 @@ extern "C" int scb_profile_end(double *total_ms, int64_t *launches) {
     return 0;
 }
 
+// Measured variants of the fp32 render, chosen once per process from the environment:
+//   SCB_RENDER_ROWS = 8 | 16   strip shape 8 x 128 or 16 x 64 pixels
+//   SCB_RENDER_COPY = tma | ldgsts   one TMA bulk copy per unit, or per-lane cp.async pieces
+struct RenderVariant {
+    int rows, copy;
+};
+static RenderVariant render_variant() {
+    static const RenderVariant v = [] {
+        RenderVariant r = {kDefaultRows, kDefaultCopy};
+        if (const char *e = getenv("SCB_RENDER_ROWS")) r.rows = atoi(e) == 16 ? 16 : (atoi(e) == 8 ? 8 : r.rows);
+        if (const char *e = getenv("SCB_RENDER_COPY")) r.copy = e[0] == 'l' ? 1 : (e[0] == 't' ? 0 : r.copy);
+        return r;
+    }();
+    return v;
+}
+
 static Geo strip_geo(const scb_geometry *geom, bool have_box, int box_bytes, int frames = 1, int64_t spots_per_frame = 0) {
-    Geo g = make_geo(geom, kStripRows, box_bytes == 4 ? Mode<float>::kCols : Mode<double>::kCols, kUnitCols, frames);
+    const int rows = box_bytes == 4 ? render_variant().rows : 8;
+    const int cols = box_bytes == 4 ? (rows == 16 ? Mode<float, 16>::kCols : Mode<float, 8>::kCols) : Mode<double, 8>::kCols;
+    Geo g = make_geo(geom, rows, cols, kUnitCols, frames);
     g.spots_per_frame = spots_per_frame;
     g.box_peak = geom->box_peak > 0.0 && geom->box_peak <= 1.0 ? geom->box_peak : 1.0;
     g.special_edges = 1;
@@ -464,51 +551,68 @@ static Geo strip_geo(const scb_geometry *geom, bool have_box, int box_bytes, int
 
 extern "C" size_t scb_render_workspace_bytes(const scb_geometry *geom, int64_t n_spots) {
     if (check_geometry(geom) != 0 || n_spots < 0) return 0;
-    Geo g = strip_geo(geom, false, 8);
-    return carve(g, n_spots, nullptr, sizeof(Unit), true).bytes;
+    const size_t exact = carve(strip_geo(geom, false, 8), n_spots, nullptr, sizeof(Unit), true).bytes;
+    const size_t fp32 = carve(strip_geo(geom, false, 4), n_spots, nullptr, sizeof(Unit), true).bytes;
+    return exact > fp32 ? exact : fp32;
 }
 
 extern "C" size_t scb_render_frames_workspace_bytes(const scb_geometry *geom, int64_t n_per_frame, int n_frames) {
     if (check_geometry(geom) != 0 || n_per_frame < 0 || n_frames < 1) return 0;
-    Geo g = strip_geo(geom, false, 8, n_frames, n_per_frame);
-    return carve(g, n_per_frame * n_frames, nullptr, sizeof(Unit), true).bytes;
+    const size_t exact = carve(strip_geo(geom, false, 8, n_frames, n_per_frame), n_per_frame * n_frames, nullptr,
+                               sizeof(Unit), true).bytes;
+    const size_t fp32 = carve(strip_geo(geom, false, 4, n_frames, n_per_frame), n_per_frame * n_frames, nullptr,
+                              sizeof(Unit), true).bytes;
+    return exact > fp32 ? exact : fp32;
 }
 
-template <typename OutT, typename BoxT, int SLOTS>
+template <typename OutT, typename BoxT, int ROWS, int SLOTS, int COPY>
 static int launch_render_as(const Geo &g, const Workspace &w, int64_t n_spots, OutT *out, int accumulate,
                             cudaStream_t s) {
     const int n_tiles = g.frames * g.nti * g.ntj;
-    // persistent grid: two CTAs per SM, each warp pulls strips from a queue; small images get
+    // persistent grid: a few CTAs per SM, each warp pulls strips from a queue; small images get
     // narrower CTAs so that the strips still spread over all SMs
-    const int slots = ctas_per_sm<BoxT>() * SCB_SM_COUNT;
+    const int slots = ctas_per_sm<BoxT, ROWS>() * SCB_SM_COUNT;
     int warps = (n_tiles + slots - 1) / slots;
     warps = warps < 1 ? 1 : (warps > kMaxWarps ? kMaxWarps : warps);
     int ctas = (n_tiles + warps - 1) / warps;
     if (ctas > slots) ctas = slots;
-    const size_t smem = (size_t)warps * warp_smem_bytes<BoxT>();
+    const size_t smem = (size_t)warps * warp_smem_bytes<BoxT, ROWS>();
     // the attribute is per device: remembered per template instance and device ordinal
     static std::atomic<unsigned long long> configured{0};
     int dev = 0;
     SCB_CUDA(cudaGetDevice(&dev));
     const unsigned long long bit = 1ull << (dev & 63);
     if (!(configured.load(std::memory_order_acquire) & bit)) {
-        SCB_CUDA(cudaFuncSetAttribute(render_strips_kernel<OutT, BoxT, SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)(kMaxWarps * warp_smem_bytes<BoxT>())));
+        SCB_CUDA(cudaFuncSetAttribute(render_strips_kernel<OutT, BoxT, ROWS, SLOTS, COPY>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(kMaxWarps * warp_smem_bytes<BoxT, ROWS>())));
         configured.fetch_or(bit, std::memory_order_release);
     }
-    render_strips_kernel<OutT, BoxT, SLOTS><<<ctas, warps * 32, smem, s>>>(
+    render_strips_kernel<OutT, BoxT, ROWS, SLOTS, COPY><<<ctas, warps * 32, smem, s>>>(
         g, (const Unit *)w.pair_spot, w.edges, w.tile_start, w.next_tile, w.wmax_bits, n_spots, out, accumulate);
     return 0;
+}
+
+template <typename OutT, typename BoxT, int ROWS, int COPY>
+static int launch_render_slots(const Geo &g, const Workspace &w, int64_t n_spots, OutT *out, int accumulate,
+                               cudaStream_t s) {
+    return g.slots == 32 ? launch_render_as<OutT, BoxT, ROWS, 32, COPY>(g, w, n_spots, out, accumulate, s)
+                         : launch_render_as<OutT, BoxT, ROWS, 0, COPY>(g, w, n_spots, out, accumulate, s);
 }
 
 template <typename OutT>
 static int launch_render(const Geo &g, const Workspace &w, int64_t n_spots, OutT *out, int accumulate, int box_type,
                          cudaStream_t s) {
-    if (box_type == SCB_F32)
-        return g.slots == 32 ? launch_render_as<OutT, float, 32>(g, w, n_spots, out, accumulate, s)
-                             : launch_render_as<OutT, float, 0>(g, w, n_spots, out, accumulate, s);
-    return g.slots == 32 ? launch_render_as<OutT, double, 32>(g, w, n_spots, out, accumulate, s)
-                         : launch_render_as<OutT, double, 0>(g, w, n_spots, out, accumulate, s);
+    const RenderVariant v = render_variant();
+    if (box_type == SCB_F32) {
+        if (g.tile_h == 16)
+            return v.copy ? launch_render_slots<OutT, float, 16, 1>(g, w, n_spots, out, accumulate, s)
+                          : launch_render_slots<OutT, float, 16, 0>(g, w, n_spots, out, accumulate, s);
+        return v.copy ? launch_render_slots<OutT, float, 8, 1>(g, w, n_spots, out, accumulate, s)
+                      : launch_render_slots<OutT, float, 8, 0>(g, w, n_spots, out, accumulate, s);
+    }
+    return v.copy ? launch_render_slots<OutT, double, 8, 1>(g, w, n_spots, out, accumulate, s)
+                  : launch_render_slots<OutT, double, 8, 0>(g, w, n_spots, out, accumulate, s);
 }
 
 static int render_expected_strided(const scb_geometry *geom, int64_t n_spots, int frames, int64_t stride, const double *d_depth,

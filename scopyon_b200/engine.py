@@ -666,16 +666,29 @@ class DeviceEngine:
 
     def _lazy_plane(self):
         """A page-locked float32 (Nw, Nh) payload for one frame, or None when the caller already holds
-        ``LAZY_PINNED_BYTES`` of them (torch's caching host allocator recycles released ones)."""
-        import weakref
-        live = getattr(self, "_live_lazy", None)
-        if live is None:
-            live = self._live_lazy = weakref.WeakSet()
-        if (len(live) + 1) * self.n_w * self.n_h * 4 > LAZY_PINNED_BYTES:
+        ``LAZY_PINNED_BYTES`` of them.  Payloads are pooled: ``_recycle`` hands one back once neither the
+        frame nor any numpy view of it is alive, so a streaming consumer never pays for page-locking again."""
+        pool = self.__dict__.setdefault("_lazy_pool", dict(free=[], allocated=0))
+        if pool["free"]:
+            return pool["free"].pop()
+        if (pool["allocated"] + 1) * self.n_w * self.n_h * 4 > LAZY_PINNED_BYTES:
             return None
-        t = torch.empty((self.n_w, self.n_h), dtype=torch.float32, pin_memory=True)
-        live.add(t)
-        return t
+        pool["allocated"] += 1
+        return torch.empty((self.n_w, self.n_h), dtype=torch.float32, pin_memory=True)
+
+    def _lazy_view(self, tensor):
+        """numpy view of a pooled payload; the tensor returns to the pool when the view (and with it every
+        view derived from it: they keep it alive as their ``base``) has been collected."""
+        import weakref
+        array = tensor.numpy()
+        weakref.finalize(array, self._lazy_pool["free"].append, tensor)
+        return array
+
+    def _float64_wanted(self, f32):
+        """``widen`` callback of the HostPlanes this engine hands out: the caller asks for float64 arrays, so
+        the following frames are widened while they are in flight (see ``begin_frame``) instead of on demand."""
+        self._eager_float64 = True
+        return self.widen_host(f32)
 
     def _begin_frame(self, main, snapshots, frame_index, noise_seed, states, exposure_time, want_true_data,
                      want_expectation, snapshot_states, lazy=True):
@@ -712,9 +725,10 @@ class DeviceEngine:
         n_planes = 2 if want_expectation else 1
         payloads = None
         with _Trace(self, "host_alloc_planes"):
-            if self._large32 and lazy:
+            if self._large32 and lazy and not getattr(self, "_eager_float64", False):
                 payloads = [self._lazy_plane() for _ in range(n_planes)]
                 if any(p is None for p in payloads):
+                    self._lazy_pool["free"].extend(p for p in payloads if p is not None)
                     payloads = None
             if payloads is None:
                 hosts = [self._host_plane()[0] for _ in range(n_planes)]
@@ -793,7 +807,7 @@ class DeviceEngine:
         hosts = pending["hosts"]
         if pending["lazy"]:
             from .image import HostPlane
-            planes = [HostPlane(h.numpy(), widen=self.widen_host, keep=h) for h in hosts]
+            planes = [HostPlane(self._lazy_view(h), widen=self._float64_wanted) for h in hosts]
         else:
             planes = [h.numpy() for h in hosts]
         adc = planes[0]
@@ -817,6 +831,8 @@ class DeviceEngine:
         finally:
             for ticket in pending["tickets"]:
                 self.lib.scb_host_widen_wait(ticket)
+        if pending.get("lazy"):
+            self._lazy_pool["free"].extend(pending["hosts"])      # never handed out: back to the pool
 
     def __del__(self):
         # staging memory must outlive the widening jobs that read it

@@ -238,7 +238,10 @@ def test_poisson_inversion_never_returns_the_loop_bound():
     torch.cuda.synchronize()
     u = (wrd.astype(numpy.float64) + 0.5) / 2.0 ** 32
     want = scipy.stats.poisson.ppf(u, lam.astype(numpy.float64))
-    assert (out.cpu().numpy() != want).mean() < 5e-5
+    # the sampler's cumulative distribution is the exact one times 1 + 2.6e-6 (see detector.cu) plus fp32 rounding:
+    # a word within that distance of one of the <= 30 steps may land on the neighbouring count
+    assert (out.cpu().numpy() != want).mean() < 2e-4
+    assert abs(out.cpu().numpy() - want).max() <= 1
 
 
 @pytest.mark.parametrize("fpn", ["none", "column", "pixel"])
