@@ -275,6 +275,18 @@ int scb_render_expected_frames(const scb_geometry *geom, int64_t n_per_frame, in
                                int box_type, const double *d_inv_scale, const int32_t *d_slot_of_key,
                                void *d_out, int out_type, void *d_workspace, size_t workspace_bytes,
                                int32_t *d_errors, void *stream);
+/* The same with a visiting order: slot s of every frame's spot list shows particle d_order[s]
+ * (a permutation of 0 .. n_per_frame - 1, or NULL).  Images do not depend on it (integer accumulation);
+ * when it lists the particles tile by tile -- e.g. sorted by a coarse screen cell, refreshed every few
+ * blocks, molecules move about a pixel per frame -- the 32 spots of a warp share most of their strips and
+ * the census of the binning adds them with a tenth of the atomics. */
+int scb_render_expected_frames_ordered(const scb_geometry *geom, int64_t n_per_frame, int n_frames,
+                                       const int32_t *d_order, const double *d_depth, const double *d_x,
+                                       const double *d_y, const double *d_weight, const int64_t *d_sat,
+                                       const void *d_box, int box_type, const double *d_inv_scale,
+                                       const int32_t *d_slot_of_key, void *d_out, int out_type,
+                                       void *d_workspace, size_t workspace_bytes, int32_t *d_errors,
+                                       void *stream);
 
 /* Tensor-core variant of scb_render_expected for the separable Gaussian PSF
  * (fluorophore.type == 'Gaussian', _epifm.py:133-134): a 128 x 128 screen tile is the

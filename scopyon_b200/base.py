@@ -72,6 +72,18 @@ def _new_rows(n):
     return numpy.zeros((n, 5)).view(ParticleRows)
 
 
+class DeviceRows(object):
+    """``(N, 5)`` rows ``[depth, x, y, molecule id, p_state]`` on the GPU (``tensor``) with the molecule ids
+    as a host int64 array (``ids``): what ``__format_data`` makes of a ``sampling.DevicePoints`` snapshot."""
+
+    def __init__(self, tensor, ids):
+        self.tensor = tensor
+        self.ids = ids
+
+    def __len__(self):
+        return int(self.tensor.shape[0])
+
+
 def _project(points, pre):
     """3-D world coordinates -> (depth, x, y) in the camera frame (base.py:76-91)."""
     data = points * pre.scale - numpy.array(pre.origin)
@@ -112,6 +124,9 @@ class EPIFMSimulator(object):
     def __format_data(self, inputs):
         """Normalise one point array to ``(N, 5)`` rows ``[depth, x, y, molecule id, p_state]``
         (base.py:61-110)."""
+        from .sampling import DevicePoints
+        if isinstance(inputs, DevicePoints):
+            return self.__format_device(inputs)
         assert isinstance(inputs, numpy.ndarray)
         if inputs.ndim != 2:
             raise ValueError("The given 'inputs' has wrong dimension.")
@@ -132,14 +147,44 @@ class EPIFMSimulator(object):
         data.ids = numpy.ascontiguousarray(data[:, 3]).astype(numpy.int64)
         return data
 
+    def __format_device(self, inputs):
+        """``__format_data`` for a snapshot that lives on the GPU: the same row layout, built by tensor
+        operations on the device (base.py:61-110)."""
+        import torch
+        pre = self.__config.preprocessing
+        points = inputs.tensor
+        n, width = points.shape
+        data = torch.zeros((n, 5), dtype=torch.float64, device=points.device)
+        if width in (2, 4):
+            data[:, 1:3] = points[:, :2] * float(pre.scale)
+        elif width in (3, 5):
+            as_tensor = lambda v: torch.tensor(numpy.asarray(v, dtype=float), dtype=torch.float64, device=points.device)  # noqa: E731
+            shifted = points[:, :3] * float(pre.scale) - as_tensor(pre.origin)
+            unit_x, unit_y = numpy.asarray(pre.unit_x, dtype=float), numpy.asarray(pre.unit_y, dtype=float)
+            for column, axis in enumerate((numpy.cross(unit_x, unit_y), unit_x, unit_y)):
+                data[:, column] = shifted @ as_tensor(axis)
+        else:
+            raise ValueError("The given 'inputs' has wrong shape.")
+        ids = inputs.ids
+        if width in (2, 3):
+            data[:, 3] = torch.arange(n, dtype=torch.float64, device=points.device)
+            data[:, 4] = 1.0
+            ids = numpy.arange(n, dtype=numpy.int64)
+        else:
+            data[:, 3:5] = points[:, width - 2:]
+            if ids is None or len(ids) != n:
+                ids = points[:, width - 2].cpu().numpy().astype(numpy.int64)
+        return DeviceRows(data, ids)
+
     def __format_inputs(self, inputs):
-        if isinstance(inputs, numpy.ndarray):
+        from .sampling import DevicePoints
+        if isinstance(inputs, (numpy.ndarray, DevicePoints)):
             return ((0.0, self.__format_data(inputs)), )
         if isinstance(inputs, collections.abc.Iterable):
             data = []
             for elem in inputs:
                 if not (isinstance(elem, (tuple, list)) and len(elem) == 2
-                        and isinstance(elem[0], numbers.Real) and isinstance(elem[1], numpy.ndarray)):
+                        and isinstance(elem[0], numbers.Real) and isinstance(elem[1], (numpy.ndarray, DevicePoints))):
                     raise ValueError("The given 'inputs' has wrong type.")
                 rows = self.__format_data(elem[1])
                 # consecutive snapshots usually show the same molecules in the same order: they then

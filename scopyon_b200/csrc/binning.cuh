@@ -113,13 +113,21 @@ __device__ __forceinline__ int quick_run(int first, int last, double o, const Ge
 __device__ __forceinline__ int stripe_of(const Geo &g, int64_t spot) { return (int)(spot >> 5) & (g.stripes - 1); }
 
 // One thread per spot: footprint, depth key, tile census.
+//
+// Census.  Every (spot, tile) overlap takes `entries` places in its tile's list; the counter's old
+// value is the overlap's position (`ranks`, in the order the fill kernel walks a footprint's tiles), so
+// the fill needs no atomics.  The 32 spots of a warp vote before they count: overlaps with the same
+// tile (`__match_any_sync`) are added by one lane and share the returned base.  With `order` -- slot
+// s of the spot list reads particle order[s], a tile-major ordering the caller refreshes now and then
+// (molecules move a pixel or so per frame) -- the spots of a warp are neighbours on the screen and share
+// most of their tiles: a tenth of the atomics.  Without it the vote finds no partners and costs little.
 __global__ void __launch_bounds__(256)
 spot_prepare_kernel(Geo g, int64_t n, int64_t stride, const double *__restrict__ depth, const double *__restrict__ x,
                     const double *__restrict__ y, const double *__restrict__ weight,
                     const double *__restrict__ inv_scale, const int32_t *__restrict__ slot_of_key,
                     SpotRec *__restrict__ spots, int *__restrict__ tile_count,
                     unsigned long long *__restrict__ wmax_bits, int32_t *__restrict__ errors,
-                    int *__restrict__ ranks = nullptr, int rank_cap = 0) {
+                    int *__restrict__ ranks = nullptr, int rank_cap = 0, const int32_t *__restrict__ order = nullptr) {
     // grid: x over the spots of one frame, y over frames
     const int64_t in_frame = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int frame = blockIdx.y;
@@ -134,11 +142,14 @@ spot_prepare_kernel(Geo g, int64_t n, int64_t stride, const double *__restrict__
     rec.walk = 0;
     rec.row_run = rec.col_run = -1;
     double w_seen = 0.0;
+    bool counted = false;
     if (s < n_here) {
-        const double w = weight[s];
-        const double xi = __dsub_rn(x[s * stride], g.f1);
-        const double yi = __dsub_rn(y[s * stride], g.f2);
-        const double dz = depth ? fabs(__dsub_rn(depth[s * stride], g.f0)) : 0.0;
+        // the particle this slot shows: the same index of every frame of a block
+        const int64_t src = order ? (g.frames > 1 ? (int64_t)frame * g.spots_per_frame + order[in_frame] : order[in_frame]) : s;
+        const double w = weight[src];
+        const double xi = __dsub_rn(x[src * stride], g.f1);
+        const double yi = __dsub_rn(y[src * stride], g.f2);
+        const double dz = depth ? fabs(__dsub_rn(depth[src * stride], g.f0)) : 0.0;
         if (w > 0.0 && isfinite(xi) && isfinite(yi) && isfinite(dz)) {   // _epifm.py:217-218
             // depth key, _epifm.py:76-84
             int key;
@@ -171,33 +182,51 @@ spot_prepare_kernel(Geo g, int64_t n, int64_t stride, const double *__restrict__
                         rec.col_run = quick_run(rec.jmin, rec.jmax, rec.oy, g);
                     }
                     rec.walk = rec.row_run < 0 || rec.col_run < 0;
-                    // census: the counters exist in `stripes` copies (one per group of 32 spots,
-                    // round robin) so that the atomics of a frame spread over more L2 sectors
-                    int *count = tile_count + ((size_t)stripe_of(g, s) * g.frames + frame) * g.nti * g.ntj;
-                    const int t0 = rec.imin / g.tile_h, t1 = (rec.imax - 1) / g.tile_h;
-                    const int u0 = rec.jmin / g.tile_w, u1 = (rec.jmax - 1) / g.tile_w;
-                    // With `ranks` the census also hands every (spot, tile) its place in the tile's list
-                    // (the value the counter had), in the order the fill kernel walks the tiles: the
-                    // fill then needs no atomics of its own.
-                    int *my_rank = ranks ? ranks + (size_t)s * rank_cap : nullptr;
-                    int visited = 0;
-                    for (int tj = u0; tj <= u1; ++tj) {
-                        const int entries = overlap_entries(g, rec.jmin, rec.jmax, tj);
-                        for (int ti = t0; ti <= t1; ++ti) {
-                            if (my_rank) {
-                                const int r = atomicAdd(&count[ti * g.ntj + tj], entries);
-                                if (visited < rank_cap) my_rank[visited] = r;
-                                else atomicAdd(errors, 1);      // cannot happen: rank_cap bounds the tiles of a footprint
-                                ++visited;
-                            } else {
-                                atomicAdd(&count[ti * g.ntj + tj], entries);
-                            }
-                        }
-                    }
+                    counted = true;
                 }
             }
         }
         spots[s] = rec;
+    }
+    // ---- census (whole warps: the votes need every lane)
+    {
+        // the counters exist in `stripes` copies (one per group of 32 spots, round robin) so that the
+        // atomics of a frame spread over more L2 sectors; a warp's spots share their copy
+        int *count = tile_count + ((size_t)stripe_of(g, s) * g.frames + frame) * g.nti * g.ntj;
+        const int t0 = rec.imin / g.tile_h, t1 = counted ? (rec.imax - 1) / g.tile_h : t0 - 1;
+        const int u0 = rec.jmin / g.tile_w, u1 = counted ? (rec.jmax - 1) / g.tile_w : u0 - 1;
+        const int n_ti = t1 - t0 + 1;
+        const int mine = counted ? n_ti * (u1 - u0 + 1) : 0;
+        const int most = __reduce_max_sync(0xffffffffu, mine);
+        const unsigned lane = threadIdx.x & 31u, below = (1u << lane) - 1u;
+        int *my_rank = ranks ? ranks + (size_t)s * rank_cap : nullptr;
+        int ti = t0, tj = u0;                               // the fill kernel's walk: columns of tiles, rows inside
+        for (int k = 0; k < most; ++k) {                    // warp uniform
+            const bool have = k < mine;
+            const int tile = have ? ti * g.ntj + tj : -1 - (int)lane;         // lanes without a tile match nobody
+            const int entries = have ? overlap_entries(g, rec.jmin, rec.jmax, tj) : 0;
+            const unsigned peers = __match_any_sync(0xffffffffu, tile);
+            // entries of the partners below this lane and of all partners (entries < 8: three vote rounds)
+            const unsigned b0 = __ballot_sync(0xffffffffu, entries & 1), b1 = __ballot_sync(0xffffffffu, entries & 2),
+                           b2 = __ballot_sync(0xffffffffu, entries & 4);
+            const int before = __popc(b0 & peers & below) + 2 * __popc(b1 & peers & below) + 4 * __popc(b2 & peers & below);
+            const int total = __popc(b0 & peers) + 2 * __popc(b1 & peers) + 4 * __popc(b2 & peers);
+            const int leader = __ffs(peers) - 1;
+            int base = 0;
+            if (have && (int)lane == leader) {
+                if (my_rank) base = atomicAdd(&count[tile], total);
+                else atomicAdd(&count[tile], total);
+            }
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (have) {
+                if (entries >= 8) atomicAdd(errors, 1);     // cannot happen: scb_render_* refuse such geometries
+                if (my_rank) {
+                    if (k < rank_cap) my_rank[k] = base + before;
+                    else atomicAdd(errors, 1);              // cannot happen: rank_cap bounds the tiles of a footprint
+                }
+                if (++ti > t1) { ti = t0; ++tj; }
+            }
+        }
     }
     if (wmax_bits) {
         // largest weight: positive doubles order like their bit patterns, so an integer max

@@ -220,6 +220,19 @@ __device__ __forceinline__ void rows4_add(Acc *a, int rows_left, BoxT ws, const 
     }
 }
 
+template <typename BoxT, int ROWS, int ROUNDS>
+__device__ __forceinline__ void rounds_add(typename Mode<BoxT, ROWS>::Acc *a, const BoxT *st, int slots, int rows, BoxT ws) {
+    using M = Mode<BoxT, ROWS>;
+    BoxT box[ROUNDS][4];
+#pragma unroll
+    for (int r = 0; r < ROUNDS; ++r)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) box[r][k] = st[(r * 4 + k) * slots];
+#pragma unroll
+    for (int r = 0; r < ROUNDS; ++r)
+        rows4_add<typename M::Acc, BoxT, M::kCols>(a + r * 4 * M::kCols, rows - r * 4, ws, box[r]);
+}
+
 // Fast unit, consumer side: lane l reads its column of the staged box rows, four rows per round
 // (a unit has 1..ROWS rows; the round count is warp uniform).
 template <typename BoxT, int ROWS, int SLOTS>
@@ -250,12 +263,17 @@ __device__ __forceinline__ void unit_accumulate_fast(const Unit *meta, int u, in
     asm volatile("" : "+r"(rows));       // keep it one value: one compare per row below instead of two
     typename M::Acc *a = acc + acc_at + lane;
     const BoxT *st = stage + min(box_col + lane, slots - 1);   // idle lanes stay inside the row
-#pragma unroll 1
-    for (int r0 = 0; r0 < n_rows; r0 += 4) {                   // warp uniform
-        BoxT box[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) box[k] = st[(r0 + k) * slots];
-        rows4_add<typename M::Acc, BoxT, M::kCols>(a + r0 * M::kCols, rows - r0, ws, box);
+    // rounds of four rows, fully unrolled per round count (warp uniform): all loads of a unit are in flight
+    // before the first conversion
+    const int rounds = (n_rows + 3) >> 2;
+    if (rounds <= 1) {
+        rounds_add<BoxT, ROWS, 1>(a, st, slots, rows, ws);
+    } else if (rounds == 2 || ROWS == 8) {
+        rounds_add<BoxT, ROWS, 2>(a, st, slots, rows, ws);
+    } else if (rounds == 3) {
+        rounds_add<BoxT, ROWS, 3>(a, st, slots, rows, ws);
+    } else {
+        rounds_add<BoxT, ROWS, 4>(a, st, slots, rows, ws);
     }
 }
 
@@ -412,14 +430,13 @@ render_strips_kernel(Geo g, const Unit *__restrict__ units, const uint32_t *__re
                     if ((fast_mask >> u) & 1u) {
                         const char *src;
                         uint32_t bytes;
-                        if constexpr (sizeof(BoxT) == 4) {
+                        if constexpr (sizeof(BoxT) == 4) {     // the fetch moved the pointer behind the unpacked words
                             const uint2 where = *reinterpret_cast<const uint2 *>(&meta[u].erow);
                             src = reinterpret_cast<const char *>(((unsigned long long)where.y << 32) | where.x);
-                            bytes = (*reinterpret_cast<const uint32_t *>(&meta[u].src + 1) & 0xffu) * row_bytes;
                         } else {
                             src = static_cast<const char *>(meta[u].src);
-                            bytes = (meta[u].shape & 0xffu) * row_bytes;
                         }
+                        bytes = (meta[u].shape & 0xffu) * row_bytes;
                         char *dst = reinterpret_cast<char *>(ring + p_stage * kStageEntries);
                         for (uint32_t off = lane * 16u; off < bytes; off += 512u) cp_async16(dst + off, src + off);
                         if (++p_stage == kStages) p_stage = 0;
@@ -615,7 +632,8 @@ static int launch_render(const Geo &g, const Workspace &w, int64_t n_spots, OutT
                   : launch_render_slots<OutT, double, 8, 0>(g, w, n_spots, out, accumulate, s);
 }
 
-static int render_expected_strided(const scb_geometry *geom, int64_t n_spots, int frames, int64_t stride, const double *d_depth,
+static int render_expected_strided(const scb_geometry *geom, int64_t n_spots, int frames, int64_t stride,
+                                   const int32_t *d_order, const double *d_depth,
                                    const double *d_x, const double *d_y, const double *d_weight,
                                    const int64_t *d_sat, const void *d_box, int box_type, const double *d_inv_scale,
                                    const int32_t *d_slot_of_key, void *d_out, int out_type,
@@ -637,6 +655,8 @@ static int render_expected_strided(const scb_geometry *geom, int64_t n_spots, in
     Workspace w = carve(g, n_spots, d_workspace, sizeof(Unit), true);
     SCB_REQUIRE(workspace_bytes >= w.bytes, SCB_E_WORKSPACE, "scb_render_expected: workspace %zu < %zu",
                 workspace_bytes, w.bytes);
+    SCB_REQUIRE(g.tile_w / g.chunk < 8, SCB_E_UNSUPPORTED, "scb_render_expected: strips of %d columns in chunks of %d",
+                g.tile_w, g.chunk);     // the census votes on three bits of a (spot, strip) overlap's entry count
     SCB_REQUIRE((double)n_spots * 2.0 * w.edge_cap < 4294967296.0, SCB_E_UNSUPPORTED,
                 "scb_render_expected: %lld spots x %d pixel edges exceed the 32-bit edge index",
                 (long long)n_spots, 2 * w.edge_cap);
@@ -647,7 +667,7 @@ static int render_expected_strided(const scb_geometry *geom, int64_t n_spots, in
     if (n_spots > 0) {
         spot_prepare_kernel<<<dim3(scb_grid_for(n_spots / frames, 256), frames), 256, 0, s>>>(
             g, n_spots, stride, d_depth, d_x, d_y, d_weight, d_inv_scale, d_slot_of_key, w.spots, w.tile_count,
-            w.wmax_bits, d_errors, w.ranks, w.rank_cap);
+            w.wmax_bits, d_errors, w.ranks, w.rank_cap, d_order);
         dim3 egrid, eblock;
         edges_launch_shape(w.edge_cap, n_spots, egrid, eblock);
         spot_edges_kernel<<<egrid, eblock, 0, s>>>(g, n_spots, w.spots, w.edges, w.edge_cap);
@@ -678,7 +698,7 @@ extern "C" int scb_render_expected(const scb_geometry *geom, int64_t n_spots, co
                                    const int32_t *d_slot_of_key, void *d_out, int out_type,
                                    int accumulate, void *d_workspace, size_t workspace_bytes,
                                    int32_t *d_errors, void *stream) {
-    return render_expected_strided(geom, n_spots, 1, 1, d_depth, d_x, d_y, d_weight, d_sat, d_box, box_type, d_inv_scale,
+    return render_expected_strided(geom, n_spots, 1, 1, nullptr, d_depth, d_x, d_y, d_weight, d_sat, d_box, box_type, d_inv_scale,
                                    d_slot_of_key, d_out, out_type, accumulate, d_workspace, workspace_bytes, d_errors,
                                    stream);
 }
@@ -701,7 +721,7 @@ extern "C" int scb_render_expected_rows(const scb_geometry *geom, int64_t n, con
                                         int out_type, int accumulate, void *d_workspace, size_t workspace_bytes,
                                         int32_t *d_errors, void *stream) {
     SCB_REQUIRE(n == 0 || d_rows, SCB_E_NULL, "scb_render_expected_rows: NULL rows");
-    return render_expected_strided(geom, n, 1, 5, d_rows, d_rows + 1, d_rows + 2, d_weight, d_sat, d_box, box_type, d_inv_scale,
+    return render_expected_strided(geom, n, 1, 5, nullptr, d_rows, d_rows + 1, d_rows + 2, d_weight, d_sat, d_box, box_type, d_inv_scale,
                                    d_slot_of_key, d_out, out_type, accumulate, d_workspace, workspace_bytes, d_errors,
                                    stream);
 }
@@ -709,15 +729,28 @@ extern "C" int scb_render_expected_rows(const scb_geometry *geom, int64_t n, con
 // A block of movie frames in one call: frame f takes spots [f * n_per_frame, (f + 1) * n_per_frame)
 // of the arrays and image f of d_out.  Every kernel of the pipeline runs once for the whole block
 // (the binning kernels are latency bound, so a block costs little more than a frame).
+extern "C" int scb_render_expected_frames_ordered(const scb_geometry *geom, int64_t n_per_frame, int n_frames,
+                                                  const int32_t *d_order, const double *d_depth, const double *d_x,
+                                                  const double *d_y, const double *d_weight, const int64_t *d_sat,
+                                                  const void *d_box, int box_type, const double *d_inv_scale,
+                                                  const int32_t *d_slot_of_key, void *d_out, int out_type,
+                                                  void *d_workspace, size_t workspace_bytes, int32_t *d_errors,
+                                                  void *stream) {
+    SCB_REQUIRE(n_per_frame >= 0 && n_frames >= 1, SCB_E_INVALID, "scb_render_expected_frames: n=%lld frames=%d",
+                (long long)n_per_frame, n_frames);
+    SCB_REQUIRE(n_per_frame < ((int64_t)1 << 31), SCB_E_INVALID, "scb_render_expected_frames: n=%lld", (long long)n_per_frame);
+    return render_expected_strided(geom, n_per_frame * n_frames, n_frames, 1, d_order, d_depth, d_x, d_y, d_weight, d_sat,
+                                   d_box, box_type, d_inv_scale, d_slot_of_key, d_out, out_type, 0, d_workspace,
+                                   workspace_bytes, d_errors, stream);
+}
+
 extern "C" int scb_render_expected_frames(const scb_geometry *geom, int64_t n_per_frame, int n_frames,
                                           const double *d_depth, const double *d_x, const double *d_y,
                                           const double *d_weight, const int64_t *d_sat, const void *d_box,
                                           int box_type, const double *d_inv_scale, const int32_t *d_slot_of_key,
                                           void *d_out, int out_type, void *d_workspace, size_t workspace_bytes,
                                           int32_t *d_errors, void *stream) {
-    SCB_REQUIRE(n_per_frame >= 0 && n_frames >= 1, SCB_E_INVALID, "scb_render_expected_frames: n=%lld frames=%d",
-                (long long)n_per_frame, n_frames);
-    return render_expected_strided(geom, n_per_frame * n_frames, n_frames, 1, d_depth, d_x, d_y, d_weight, d_sat, d_box,
-                                   box_type, d_inv_scale, d_slot_of_key, d_out, out_type, 0, d_workspace,
-                                   workspace_bytes, d_errors, stream);
+    return scb_render_expected_frames_ordered(geom, n_per_frame, n_frames, nullptr, d_depth, d_x, d_y, d_weight, d_sat,
+                                              d_box, box_type, d_inv_scale, d_slot_of_key, d_out, out_type, d_workspace,
+                                              workspace_bytes, d_errors, stream);
 }

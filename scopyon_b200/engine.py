@@ -415,8 +415,16 @@ class DeviceEngine:
 
     # ------------------------------------------------------------------ states
     def new_budget_state(self, input_data, seed, initial=None):
-        ids = numpy.concatenate([numpy.asarray(p[:, 3], dtype=numpy.int64) for _, p in input_data]) \
-            if len(input_data) else numpy.zeros(0, dtype=numpy.int64)
+        def ids_of(p):
+            ids = getattr(p, "ids", None)
+            return ids if ids is not None and len(ids) == len(p) else numpy.asarray(numpy.asarray(p)[:, 3], dtype=numpy.int64)
+        columns, seen = [], set()
+        for _, p in input_data:
+            ids = ids_of(p)
+            if id(ids) not in seen:         # snapshots of one trajectory share their id column
+                seen.add(id(ids))
+                columns.append(ids)
+        ids = numpy.concatenate(columns) if columns else numpy.zeros(0, dtype=numpy.int64)
         return DeviceBudgetState(ids, seed, self.device, initial=initial)
 
     # ------------------------------------------------------------------ one frame
@@ -442,7 +450,11 @@ class DeviceEngine:
         stream = self._stream()
         focal = cfg.detector_focal_point
         true_dev, true_ids = None, None
-        rows_dev = torch.empty((total, 5), dtype=torch.float64, device=self.device)   # particle rows as given
+        on_device = [hasattr(p, "tensor") for _, p in snapshots]     # base.DeviceRows: the trajectory never left the GPU
+        lone = None
+        if len(snapshots) == 1 and on_device[0] and snapshots[0][1].tensor.device == self.device:
+            lone = snapshots[0][1].tensor                              # rendered where it lies
+        rows_dev = lone if lone is not None else torch.empty((total, 5), dtype=torch.float64, device=self.device)
         weight = torch.empty(total, dtype=torch.float64, device=self.device)
         self._stage_turn = (getattr(self, "_stage_turn", 0) + 1) % FRAMES_IN_FLIGHT   # this frame's staging area (see _h2d_stage)
         all_ids = self._ids_of(snapshots)
@@ -459,31 +471,46 @@ class DeviceEngine:
         keys = []
         offset = 0
         all_resident = self.tables.all_resident()
-        for (unit_time, particles), n in zip(snapshots, sizes):
+        for (unit_time, particles), n, resident in zip(snapshots, sizes, on_device):
             if n == 0:
                 continue
             ids = all_ids if n == total else all_ids[offset: offset + n]    # the cached object itself when it can be
             order, rounds, slots_dev = None, [(0, n)], None
             if table_ids is not None:
                 order, rounds, slots_dev, _ = self._molecule_slots(table_ids, ids)
-            # rows go up as they are: straight from the caller's array when that is page-locked
-            # (base.__format_data allocates it so), else through a pinned staging copy
-            host = None
-            if order is None and isinstance(particles, numpy.ndarray) and particles.dtype == numpy.float64 \
-                    and particles.flags.c_contiguous:
-                host = torch.from_numpy(particles.view(numpy.ndarray))
-                if not host.is_pinned():
-                    host = None
-            if host is None:
-                particles = numpy.asarray(particles, dtype=numpy.float64)
+            if resident:
+                source = particles.tensor
                 if order is not None:
-                    particles = particles[order]
-                host = self._h2d_stage(total)[offset: offset + n]
-                numpy.copyto(host.numpy(), particles)
-            rows_dev[offset: offset + n].copy_(host, non_blocking=True)
-            if not all_resident:
-                keys.append(depth_keys_of(numpy.asarray(particles)[:, 0] - focal[0], cfg.depth_cutoff,
-                                          self.geom.n_depth_keys))
+                    source = source[torch.from_numpy(order).to(self.device)]
+                    rows_dev = rows_dev if lone is None else torch.empty((total, 5), dtype=torch.float64, device=self.device)
+                    lone = None
+                if lone is None:
+                    rows_dev[offset: offset + n].copy_(source, non_blocking=True)
+                if not all_resident:
+                    depth = (source[:, 0] - float(focal[0])).abs()
+                    key = torch.clamp((depth / RESOLUTION).to(torch.int64), max=self.geom.n_depth_keys - 1)
+                    key = torch.where(depth < cfg.depth_cutoff + RESOLUTION, key,
+                                      torch.full_like(key, self.geom.n_depth_keys))
+                    keys.append(torch.unique(key).cpu().numpy())
+            else:
+                # rows go up as they are: straight from the caller's array when that is page-locked
+                # (base.__format_data allocates it so), else through a pinned staging copy
+                host = None
+                if order is None and isinstance(particles, numpy.ndarray) and particles.dtype == numpy.float64 \
+                        and particles.flags.c_contiguous:
+                    host = torch.from_numpy(particles.view(numpy.ndarray))
+                    if not host.is_pinned():
+                        host = None
+                if host is None:
+                    particles = numpy.asarray(particles, dtype=numpy.float64)
+                    if order is not None:
+                        particles = particles[order]
+                    host = self._h2d_stage(total)[offset: offset + n]
+                    numpy.copyto(host.numpy(), particles)
+                rows_dev[offset: offset + n].copy_(host, non_blocking=True)
+                if not all_resident:
+                    keys.append(depth_keys_of(numpy.asarray(particles)[:, 0] - focal[0], cfg.depth_cutoff,
+                                              self.geom.n_depth_keys))
             for lo, hi in rounds:
                 self._call(
                     "scb_emit_bleach_rows", states.seed if states is not None else 0, hi - lo,

@@ -88,6 +88,7 @@ class DeviceMovie:
         if self.budget is not None:
             self.budget.fill_(float("nan"))
         self.frame = 0
+        self.__dict__.pop("_order", None)
         if first_frame > 0:
             sigma_dxy = _native.vec3([self.sigma_xyd[2], self.sigma_xyd[0], self.sigma_xyd[1]])
             _native.check(eng.lib.scb_replay_frames(
@@ -268,11 +269,12 @@ class DeviceMovie:
             self._p(2), self._p(0), self._p(1), sigma_dxy, self.exposure, focal, ctypes.byref(eng.phys),
             _native.ptr(self.budget), _native.ptr(state[0]), _native.ptr(state[1]), _native.ptr(state[2]),
             _native.ptr(state[3]), stream), "scb_movie_frames")
-        _native.check(eng.lib.scb_render_expected_frames(
-            ctypes.byref(eng.geom), self.n, nf, _native.ptr(state[0]), _native.ptr(state[1]), _native.ptr(state[2]),
+        _native.check(eng.lib.scb_render_expected_frames_ordered(
+            ctypes.byref(eng.geom), self.n, nf, _native.ptr(self._visiting_order(state)),
+            _native.ptr(state[0]), _native.ptr(state[1]), _native.ptr(state[2]),
             _native.ptr(state[3]), _native.ptr(eng.sat), _native.ptr(eng.box), eng.box_type,
             _native.ptr(eng.inv_scale), _native.ptr(eng.slot_of_key), _native.ptr(photons), eng.elem_type,
-            _native.ptr(work), work.numel(), _native.ptr(eng.errors), stream), "scb_render_expected_frames")
+            _native.ptr(work), work.numel(), _native.ptr(eng.errors), stream), "scb_render_expected_frames_ordered")
         batched = (eng.dtype == torch.float32 and out.dtype == torch.float32 and out.is_contiguous()
                    and (eng.n_w * eng.n_h) % 4 == 0
                    and (self.configs.ADConverter_fpn_type != 'column' or eng.n_h % 4 == 0))
@@ -288,6 +290,26 @@ class DeviceMovie:
                 eng.detect(photons[f], self.frame + f, self.noise_seed, adc=out[f])
         self.weight = state[3, nf - 1]
         self.frame += nf
+
+    #: blocks rendered with one visiting order before it is refreshed (molecules move about a pixel per frame)
+    order_refresh_blocks = 8
+
+    def _visiting_order(self, state):
+        """Particle indices sorted by the coarse screen cell (32 x 32 pixels, row-major) of the first frame
+        of the block: neighbours in the spot list are then neighbours on the screen, which lets the census
+        of the binning add a warp's overlaps with a tenth of the atomics
+        (``scb_render_expected_frames_ordered``).  The images do not depend on it."""
+        cache = self.__dict__.setdefault("_order", dict(age=self.order_refresh_blocks, order=None))
+        if cache["order"] is None or cache["age"] >= self.order_refresh_blocks:
+            eng = self.engine
+            pl = float(self.configs.pixel_length)
+            focal = self.configs.detector_focal_point
+            row = ((state[1, 0] - float(focal[1])) / pl + eng.n_w * 0.5).clamp_(0, eng.n_w - 1).to(torch.int32) >> 5
+            col = ((state[2, 0] - float(focal[2])) / pl + eng.n_h * 0.5).clamp_(0, eng.n_h - 1).to(torch.int32) >> 5
+            cache["order"] = torch.argsort(row * ((eng.n_h + 31) >> 5) + col).to(torch.int32)
+            cache["age"] = 0
+        cache["age"] += 1
+        return cache["order"]
 
     def positions(self):
         """Current ``(N, 5)`` rows ``[depth, x, y, id, p_state]`` on the host (for parity checks)."""

@@ -19,7 +19,30 @@ from ._epifm import draw_seed
 
 _log = getLogger(__name__)
 
-__all__ = ["sample_inputs"]
+__all__ = ["sample_inputs", "DevicePoints"]
+
+
+class DevicePoints(object):
+    """One snapshot of a trajectory that stayed on the GPU: ``tensor`` is the ``(N, ndim + 2)`` float64
+    CUDA tensor of the rows ``[coordinates..., molecule id, p_state]`` that ``sample_inputs`` otherwise
+    returns as a numpy array, ``ids`` the molecule ids as a host int64 array (one object shared by all
+    snapshots of a trajectory).  ``form_image`` / ``generate_images`` accept it wherever they accept the
+    array: nothing is uploaded per frame.  (An extension: the reference keeps trajectories on the host.)"""
+
+    def __init__(self, tensor, ids):
+        assert tensor.dim() == 2 and tensor.is_cuda
+        self.tensor = tensor
+        self.ids = ids
+
+    ndim = 2
+    shape = property(lambda self: tuple(self.tensor.shape))
+
+    def __len__(self):
+        return int(self.tensor.shape[0])
+
+    def cpu(self):
+        """The snapshot as the numpy array the host path returns."""
+        return self.tensor.cpu().numpy()
 
 _CHUNK_BYTES = 1 << 30   # device staging for trajectories, copied back chunk by chunk
 
@@ -93,11 +116,14 @@ class DeviceParticles:
             None if upper is None else _pad3(upper), self._stream()), "scb_diffuse")
 
 
-def sample_inputs(t, *, N=None, conc=None, lower=None, upper=None, D=None, start=0, ndim=3, rng=None):
+def sample_inputs(t, *, N=None, conc=None, lower=None, upper=None, D=None, start=0, ndim=3, rng=None,
+                  device=False):
     """Generate the input data: a list of ``(time, points)`` with ``points`` of shape
     ``(N, ndim + 2)``, rows ``[coordinates..., molecule id, p_state = 1]``.
 
-    Args and return value as in the reference (``sampling.py:121-162``).
+    Args and return value as in the reference (``sampling.py:121-162``).  ``device=True`` (an extension)
+    leaves the snapshots on the GPU as ``DevicePoints`` -- the same numbers, never copied to the host --
+    which ``generate_images`` / ``form_image`` take in place of the arrays.
     """
     if rng is None:
         warnings.warn('A random number generator [rng] is not given.')
@@ -122,6 +148,8 @@ def sample_inputs(t, *, N=None, conc=None, lower=None, upper=None, D=None, start
     if N <= 0:
         empty = numpy.array([])
         return [(tk, empty.copy()) for tk in t]
+    if device and len(lower) > 3:
+        raise ValueError("device=True supports up to three axes")
 
     maxdim = len(lower)
     if D is None:
@@ -152,6 +180,23 @@ def sample_inputs(t, *, N=None, conc=None, lower=None, upper=None, D=None, start
     tcurrent = t[0]
     step_index = 0
     k = 0
+    if device:
+        ids = numpy.arange(start, start + N, dtype=numpy.int64)
+        tail = torch.from_numpy(template[:, maxdim:]).to(parts.device)          # (N, 2): id, p_state
+        for i in range(n_times):
+            tnext = t[i]
+            if tnext > tcurrent:
+                sigma = [0.0, 0.0, 0.0]
+                for dim in range(move_dim):
+                    sigma[dim] = float(numpy.sqrt(2 * D[dim] * (tnext - tcurrent)))
+                parts.step(seed, step_index, sigma)
+                step_index += 1
+                tcurrent = tnext
+            rows = torch.empty((N, maxdim + 2), dtype=torch.float64, device=parts.device)
+            rows[:, :dev_dim] = parts.coords[:dev_dim].t()
+            rows[:, maxdim:] = tail
+            inputs.append((float(t[i] if t[i] > t[0] else t[0]), DevicePoints(rows, ids)))
+        return inputs
     while k < n_times:
         m = min(chunk, n_times - k)
         stage = torch.empty((m, 3, N), dtype=torch.float64, device=parts.device)

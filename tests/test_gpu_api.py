@@ -235,3 +235,37 @@ default:
     full = first_frames(9, 9)
     assert len(short) == 2 and len(full) == 9
     assert numpy.array_equal(short[0], full[0]) and numpy.array_equal(short[1], full[1])
+
+
+def test_device_resident_trajectories_give_the_same_movie():
+    """sample_inputs(..., device=True) leaves the trajectory on the GPU (DevicePoints); generate_images and
+    form_image render it in place -- the same numbers as the host arrays, hence the same frames, budgets
+    and true_data, bit for bit."""
+    config = scopyon_b200.DefaultConfiguration()
+    config.update("""
+default:
+    magnification: 100
+    detector: {type: CMOS, image_size: [128, 96], pixel_length: {value: 6.5e-6, units: m}, QE: 0.73, exposure_time: 0.033}
+    effects: {photo_bleaching: {switch: true, half_life: {value: 0.1, units: s}}}
+""")
+    pl = 6.5e-8
+    t = numpy.arange(0, 6) * 0.033
+    kwargs = dict(N=300, lower=[-60 * pl, -45 * pl, 0.0], upper=[60 * pl, 45 * pl, 3e-7], D=2e-13, ndim=3)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        host = scopyon_b200.sample_inputs(t, rng=numpy.random.RandomState(21), **kwargs)
+        resident = scopyon_b200.sample_inputs(t, rng=numpy.random.RandomState(21), device=True, **kwargs)
+        assert all(numpy.array_equal(a[1], b[1].cpu()) and a[0] == b[0] for a, b in zip(host, resident))
+        movies = []
+        for inputs in (host, resident):
+            sim = scopyon_b200.create_simulator(config, rng=numpy.random.RandomState(4))
+            movies.append(list(sim.generate_images(inputs, num_frames=5, full_output=True)))
+        single = [scopyon_b200.form_image(inputs[2][1], config=config, rng=numpy.random.RandomState(6)).as_array()
+                  for inputs in (host, resident)]
+    for (img_a, info_a), (img_b, info_b) in zip(*movies):
+        assert numpy.array_equal(img_a.as_array(), img_b.as_array())
+        assert numpy.array_equal(info_a["expectation"], info_b["expectation"])
+        assert info_a["fluorescence_states"] == info_b["fluorescence_states"]
+        assert info_a["true_data"].keys() == info_b["true_data"].keys()
+        assert all(numpy.array_equal(info_a["true_data"][k], info_b["true_data"][k]) for k in info_a["true_data"])
+    assert numpy.array_equal(single[0], single[1]) and single[0].max() > 110
