@@ -110,7 +110,13 @@ __device__ __forceinline__ int quick_run(int first, int last, double o, const Ge
     return phase | (slot0 + 1) << 16;
 }
 
-__device__ __forceinline__ int stripe_of(const Geo &g, int64_t spot) { return (int)(spot >> 5) & (g.stripes - 1); }
+// Counter copy of a spot: one per group of 32 spots of its frame, round robin.  Counted inside the frame so
+// that the 32 lanes of a census warp (one frame, 32 consecutive in-frame indices) always share their copy,
+// whatever the number of spots per frame.
+__device__ __forceinline__ int stripe_of(const Geo &g, int64_t spot, int frame) {
+    const int64_t in_frame = g.frames > 1 ? spot - (int64_t)frame * g.spots_per_frame : spot;
+    return (int)(in_frame >> 5) & (g.stripes - 1);
+}
 
 // One thread per spot: footprint, depth key, tile census.
 //
@@ -192,7 +198,7 @@ spot_prepare_kernel(Geo g, int64_t n, int64_t stride, const double *__restrict__
     {
         // the counters exist in `stripes` copies (one per group of 32 spots, round robin) so that the
         // atomics of a frame spread over more L2 sectors; a warp's spots share their copy
-        int *count = tile_count + ((size_t)stripe_of(g, s) * g.frames + frame) * g.nti * g.ntj;
+        int *count = tile_count + ((size_t)stripe_of(g, s, frame) * g.frames + frame) * g.nti * g.ntj;
         const int t0 = rec.imin / g.tile_h, t1 = counted ? (rec.imax - 1) / g.tile_h : t0 - 1;
         const int u0 = rec.jmin / g.tile_w, u1 = counted ? (rec.jmax - 1) / g.tile_w : u0 - 1;
         const int n_ti = t1 - t0 + 1;
@@ -408,7 +414,7 @@ tile_fill_kernel(Geo g, int64_t n, const SpotRec *__restrict__ spots,
     const int imin = spots[s].imin, imax = spots[s].imax, jmin = spots[s].jmin, jmax = spots[s].jmax;
     const int t0 = imin / g.tile_h, t1 = (imax - 1) / g.tile_h;
     const int u0 = jmin / g.tile_w, u1 = (jmax - 1) / g.tile_w;
-    const int stripe = stripe_of(g, s);
+    const int stripe = stripe_of(g, s, 0);
     int *cursor = tile_cursor + (size_t)stripe * g.nti * g.ntj;
     for (int ti = t0; ti <= t1; ++ti)
         for (int tj = u0; tj <= u1; ++tj) {

@@ -124,7 +124,7 @@ strip_fill_kernel(Geo g, int64_t n, const SpotRec *__restrict__ spots, int edge_
                         (table_at + ((size_t)(rec.row_run & 0xffff) * g.modulus + (rec.col_run & 0xffff)) *
                                         (size_t)(g.slots * g.slots)) * (size_t)box_bytes;
     const uint32_t ebase = (uint32_t)s * 2u * (uint32_t)edge_cap;
-    const int stripe = stripe_of(g, s);
+    const int stripe = stripe_of(g, s, rec.frame);
     const int frame_tile0 = rec.frame * g.nti * g.ntj;     // first strip of the spot's frame
     const int *my_rank = ranks + (size_t)s * rank_cap;
     int visited = 0;
