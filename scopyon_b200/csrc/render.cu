@@ -30,6 +30,7 @@
 //     bitwise reproducible whatever order the work list was filled in.
 #include "binning.cuh"
 
+#include <cuda.h>      // CUtensorMap (types only: the encoder is looked up at run time)
 #include <atomic>
 #include <mutex>
 
@@ -196,6 +197,8 @@ __device__ __forceinline__ void unit_stage(const void *src, uint32_t bytes, void
 // box * weight -> accumulator LSBs, in the precision of the box table
 __device__ __forceinline__ long long to_fixed(double box, double ws) { return __double2ll_rn(__dmul_rn(box, ws)); }
 __device__ __forceinline__ int to_fixed(float box, float ws) { return __float2int_rn(__fmul_rn(box, ws)); }
+
+#include "render_reg.cuh"
 
 // Per-lane cp.async (LDGSTS) staging: the alternative to the TMA bulk copy.  A unit's rows are one
 // contiguous run of the block (<= 2 KB), so lane l copies the 16-byte pieces l, l + 32, ... of it: no
@@ -536,17 +539,31 @@ extern "C" int scb_profile_end(double *total_ms, int64_t *launches) {
 // Measured variants of the fp32 render, chosen once per process from the environment:
 //   SCB_RENDER_ROWS = 8 | 16   strip shape 8 x 128 or 16 x 64 pixels
 //   SCB_RENDER_COPY = tma | ldgsts   one TMA bulk copy per unit, or per-lane cp.async pieces
+//   SCB_RENDER_PATH = smem | tensor | ldg
+//       smem (default): render_strips_kernel, accumulators in shared memory, one TMA bulk copy per unit;
+//       tensor / ldg: the register-accumulator kernels of render_reg.cuh (one tensor-map TMA copy per unit / plain
+//       loads into registers).  All three give the same bits; round 2 measured 1.26 / 1.33 / 1.50 ms per 16-frame
+//       C4 block (profiles/render_variants_r2.md).
 struct RenderVariant {
-    int rows, copy;
+    int rows, copy, reg;
 };
-static RenderVariant render_variant() {
-    static const RenderVariant v = [] {
-        RenderVariant r = {kDefaultRows, kDefaultCopy};
-        if (const char *e = getenv("SCB_RENDER_ROWS")) r.rows = atoi(e) == 16 ? 16 : (atoi(e) == 8 ? 8 : r.rows);
-        if (const char *e = getenv("SCB_RENDER_COPY")) r.copy = e[0] == 'l' ? 1 : (e[0] == 't' ? 0 : r.copy);
-        return r;
-    }();
-    return v;
+static RenderVariant render_variant() {      // read at every call (a few getenv): tests flip the variables between calls
+    RenderVariant r = {kDefaultRows, kDefaultCopy, 0};
+    if (const char *e = getenv("SCB_RENDER_ROWS")) r.rows = atoi(e) == 16 ? 16 : (atoi(e) == 8 ? 8 : r.rows);
+    if (const char *e = getenv("SCB_RENDER_COPY")) r.copy = e[0] == 'l' ? 1 : (e[0] == 't' ? 0 : r.copy);
+    if (const char *e = getenv("SCB_RENDER_PATH")) r.reg = e[0] == 't' ? 2 : (e[0] == 'l' ? 1 : 0);
+    if (r.rows != 8 || r.copy != 0) r.reg = 0;        // strip shape and copy engine belong to the shared-memory kernel
+    return r;
+}
+
+static int forced_gather() {
+    const char *force = getenv("SCB_RENDER_FORCE_GATHER");
+    return force ? (force[0] == '1' ? 1 : (force[0] == '2' ? 2 : 0)) : 0;
+}
+
+// The register kernel takes every fp32 box table whose rows a tensor map can describe (strides in multiples of 16 bytes)
+static bool reg_path_for(bool have_box, int box_bytes, int slots) {
+    return render_variant().reg != 0 && have_box && box_bytes == 4 && slots % 4 == 0 && slots <= 1000;
 }
 
 static Geo strip_geo(const scb_geometry *geom, bool have_box, int box_bytes, int frames = 1, int64_t spots_per_frame = 0) {
@@ -558,11 +575,11 @@ static Geo strip_geo(const scb_geometry *geom, bool have_box, int box_bytes, int
     g.special_edges = 1;
     // with a box table whose block rows the TMA ring can hold (and copy: multiples of 16 bytes),
     // evenly spaced footprints never read their edges
-    g.quick_runs = have_box && g.slots <= kFastSlots && (g.slots * box_bytes) % 16 == 0;
+    g.quick_runs = reg_path_for(have_box, box_bytes, g.slots) ||
+                   (have_box && g.slots <= kFastSlots && (g.slots * box_bytes) % 16 == 0);
     // test hook: keep the table precision and accumulators but send every footprint down the SAT-corner path
-    if (const char *force = getenv("SCB_RENDER_FORCE_GATHER")) {
-        if (force[0] == '1') g.quick_runs = 0;
-    }
+    // ('1': of the shared-memory kernel, '2': of the kernel the tables would select)
+    if (forced_gather()) g.quick_runs = 0;
     return g;
 }
 
@@ -615,6 +632,55 @@ static int launch_render_slots(const Geo &g, const Workspace &w, int64_t n_spots
                                cudaStream_t s) {
     return g.slots == 32 ? launch_render_as<OutT, BoxT, ROWS, 32, COPY>(g, w, n_spots, out, accumulate, s)
                          : launch_render_as<OutT, BoxT, ROWS, 0, COPY>(g, w, n_spots, out, accumulate, s);
+}
+
+template <typename OutT, int WARPS, int CTAS, int STAGES>
+static int launch_render_reg_as(const CUtensorMap &box_map, const Geo &g, const Workspace &w, const int64_t *sat, OutT *out,
+                                int accumulate, cudaStream_t s) {
+    const int n_tiles = g.frames * g.nti * g.ntj;
+    // persistent grid: CTAS CTAs per SM, each warp pulls strips from a queue; small images get narrower CTAs
+    const int slots = CTAS * SCB_SM_COUNT;
+    int warps = (n_tiles + slots - 1) / slots;
+    warps = warps < 1 ? 1 : (warps > WARPS ? WARPS : warps);
+    int ctas = (n_tiles + warps - 1) / warps;
+    if (ctas > slots) ctas = slots;
+    const size_t smem = (size_t)warps * reg_warp_smem<STAGES>();
+    static std::atomic<unsigned long long> configured{0};
+    int dev = 0;
+    SCB_CUDA(cudaGetDevice(&dev));
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (!(configured.load(std::memory_order_acquire) & bit)) {
+        SCB_CUDA(cudaFuncSetAttribute(render_strips_reg_kernel<OutT, WARPS, CTAS, STAGES>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(WARPS * reg_warp_smem<STAGES>())));
+        configured.fetch_or(bit, std::memory_order_release);
+    }
+    render_strips_reg_kernel<OutT, WARPS, CTAS, STAGES><<<ctas, warps * 32, smem, s>>>(
+        box_map, g, (const RUnit *)w.pair_spot, w.spots, w.edges, w.edge_cap, sat, w.tile_start, w.next_tile, w.wmax_bits,
+        out, accumulate);
+    return 0;
+}
+
+template <typename OutT, int WARPS, int CTAS, int SLOTS, int DIST>
+static int launch_render_ldg_as(const Geo &g, const Workspace &w, const int64_t *sat, const float *box, OutT *out,
+                                int accumulate, cudaStream_t s) {
+    const int n_tiles = g.frames * g.nti * g.ntj;
+    const int slots = CTAS * SCB_SM_COUNT;
+    int warps = (n_tiles + slots - 1) / slots;
+    warps = warps < 1 ? 1 : (warps > WARPS ? WARPS : warps);
+    int ctas = (n_tiles + warps - 1) / warps;
+    if (ctas > slots) ctas = slots;
+    render_strips_ldg_kernel<OutT, WARPS, CTAS, SLOTS, DIST><<<ctas, warps * 32, (size_t)warps * kLdgWarpSmem, s>>>(
+        g, box, (const RUnit *)w.pair_spot, w.spots, w.edges, w.edge_cap, sat, w.tile_start, w.next_tile, w.wmax_bits, out,
+        accumulate);
+    return 0;
+}
+
+template <typename OutT>
+static int launch_render_reg(const CUtensorMap &box_map, const Geo &g, const Workspace &w, const int64_t *sat,
+                             const float *box, OutT *out, int accumulate, cudaStream_t s) {
+    if (render_variant().reg == 2) return launch_render_reg_as<OutT, 8, 3, 4>(box_map, g, w, sat, out, accumulate, s);
+    if (g.slots != 32) return launch_render_ldg_as<OutT, 8, 3, 0, 1>(g, w, sat, box, out, accumulate, s);
+    return launch_render_ldg_as<OutT, 8, 3, 32, 1>(g, w, sat, box, out, accumulate, s);
 }
 
 template <typename OutT>
@@ -673,10 +739,20 @@ static int render_expected_strided(const scb_geometry *geom, int64_t n_spots, in
         spot_edges_kernel<<<egrid, eblock, 0, s>>>(g, n_spots, w.spots, w.edges, w.edge_cap);
     }
     tile_scan_kernel<<<kScanCtas, 1024, 0, s>>>(n_tiles, g.stripes, w.tile_count, w.tile_start);
+    const bool reg_path = forced_gather() != 1 && reg_path_for(d_box != nullptr, box_bytes, g.slots);
+    CUtensorMap box_map;
+    if (reg_path && render_variant().reg == 2) {
+        rc = make_box_map(&box_map, d_box, g.slots, (long long)(g.n_depth_keys + 1) * g.modulus * g.modulus);
+        if (rc) return rc;
+    }
     if (n_spots > 0) {
-        strip_fill_kernel<<<scb_grid_for(n_spots, 256), 256, 0, s>>>(g, n_spots, w.spots, w.edge_cap, w.ranks, w.rank_cap,
-                                                                    d_sat, d_box, box_bytes, w.tile_start,
-                                                                    w.wmax_bits, (Unit *)w.pair_spot);
+        if (reg_path)
+            strip_fill_reg_kernel<<<scb_grid_for(n_spots, 256), 256, 0, s>>>(g, n_spots, w.spots, w.ranks, w.rank_cap,
+                                                                            w.tile_start, (RUnit *)w.pair_spot);
+        else
+            strip_fill_kernel<<<scb_grid_for(n_spots, 256), 256, 0, s>>>(g, n_spots, w.spots, w.edge_cap, w.ranks, w.rank_cap,
+                                                                        d_sat, d_box, box_bytes, w.tile_start,
+                                                                        w.wmax_bits, (Unit *)w.pair_spot);
     }
     int timed = -1;        // slot of this launch in the measurement hook's event pool
     if (g_profile.enabled) {
@@ -684,7 +760,10 @@ static int render_expected_strided(const scb_geometry *geom, int64_t n_spots, in
         if (g_profile.enabled && g_profile.used < g_profile.capacity) timed = g_profile.used++;
     }
     if (timed >= 0) cudaEventRecord(g_profile.start[timed], s);
-    if (out_type == SCB_F32) rc = launch_render<float>(g, w, n_spots, (float *)d_out, accumulate, box_type, s);
+    if (reg_path) {
+        if (out_type == SCB_F32) rc = launch_render_reg<float>(box_map, g, w, d_sat, (const float *)d_box, (float *)d_out, accumulate, s);
+        else rc = launch_render_reg<double>(box_map, g, w, d_sat, (const float *)d_box, (double *)d_out, accumulate, s);
+    } else if (out_type == SCB_F32) rc = launch_render<float>(g, w, n_spots, (float *)d_out, accumulate, box_type, s);
     else rc = launch_render<double>(g, w, n_spots, (double *)d_out, accumulate, box_type, s);
     if (timed >= 0) cudaEventRecord(g_profile.stop[timed], s);
     if (rc) return rc;

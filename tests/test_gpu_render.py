@@ -233,3 +233,54 @@ default:
     got32 = render(engine32, data, dtype=torch.float32)
     # 32-bit accumulators (box table present) or exact 64-bit ones (SAT only), fp32 output either way
     assert rel_err(got32.astype(numpy.float64), want) < (1e-6 if engine32.box is not None else 3e-7)
+
+
+@pytest.mark.parametrize("pixel_nm, magnification, reg_kernel", [
+    (65.0, 100, True),       # 32 slots per phase
+    (44.0, 100, True),       # 48 slots: wider than the shared-memory kernel's ring, the register kernels do not mind
+    (160.0, 100, True),      # 16 slots, 14-pixel footprints: the copy box overhangs the block on both axes (zero fill)
+    (100.0, 100, False),     # 22 slots: fp32 rows are no multiple of 16 bytes -> shared-memory kernel whatever is asked
+])
+def test_register_kernels_equal_shared_memory_kernel(pixel_nm, magnification, reg_kernel):
+    """fp32 mode: the register-accumulator kernels (SCB_RENDER_PATH=tensor: tensor-map TMA with zero-filled overhang;
+    =ldg: plain loads), their SAT-corner gather and the default shared-memory kernel give the same bits, on ragged
+    strips, clipped footprints, irregular footprints and a cluster."""
+    import os
+    yaml = """
+default:
+    detector: {type: CMOS, image_size: [150, 210], pixel_length: {value: %.9e, units: m}, exposure_time: 0.033}
+    magnification: %d
+""" % (pixel_nm * 1e-9 * magnification, magnification)
+    config, configs, params, engine = gpu_engine(yaml, precision="f32")
+    pl = configs.pixel_length
+    rng = numpy.random.RandomState(int(pixel_nm) + 1)
+    n = 1500
+    data = numpy.zeros((n, 5))
+    data[:, 0] = rng.uniform(0, 3, n).astype(int) * 150e-9
+    data[:, 1] = rng.uniform(-90 * pl, 90 * pl, n)                      # some footprints hang over the image border
+    data[:, 2] = rng.uniform(-120 * pl, 120 * pl, n)
+    data[:300, 1] = rng.normal(10 * pl, 1.5 * pl, 300)                  # a cluster: one long strip list
+    data[:300, 2] = rng.normal(-30 * pl, 1.5 * pl, 300)
+    data[300:360, 1:3] = numpy.round(data[300:360, 1:3] / pl) * pl      # exact pixel centres: irregular footprints
+    data[:, 3] = numpy.arange(n)
+    data[:, 4] = 1
+    engine.ensure_tables(numpy.unique(engine_keys(engine, configs, data)))
+    assert engine.box is not None and engine.box.dtype == torch.float32
+    from scopyon_b200 import _native
+    assert (_native.load().scb_psf_sat_slots(engine.geom.n_radial, engine.geom.sat_modulus) % 4 == 0) == reg_kernel
+    images = {}
+    for name, env in [("default", {}), ("tensor", {"SCB_RENDER_PATH": "tensor"}), ("ldg", {"SCB_RENDER_PATH": "ldg"}),
+                      ("tensor gather", {"SCB_RENDER_PATH": "tensor", "SCB_RENDER_FORCE_GATHER": "2"}),
+                      ("ldg gather", {"SCB_RENDER_PATH": "ldg", "SCB_RENDER_FORCE_GATHER": "2"}),
+                      ("shared gather", {"SCB_RENDER_FORCE_GATHER": "1"})]:
+        os.environ.update(env)
+        try:
+            images[name] = render(engine, data, dtype=torch.float32)
+        finally:
+            for k in env:
+                del os.environ[k]
+    assert images["default"].max() > 0
+    for name, image in images.items():
+        assert numpy.array_equal(image, images["default"]), name
+    exact = render(gpu_engine(yaml, precision="f64")[3], data)
+    assert rel_err(images["default"].astype(numpy.float64), exact) < 3e-6

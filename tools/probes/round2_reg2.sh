@@ -1,0 +1,11 @@
+set -x
+mkdir -p gpurun_out
+for v in "SCB_RENDER_REG=tensor SCB_RENDER_OCC=0" "SCB_RENDER_REG=tensor SCB_RENDER_OCC=5" "SCB_RENDER_REG=tensor SCB_RENDER_OCC=6" "SCB_RENDER_REG=tensor SCB_RENDER_OCC=7" "SCB_RENDER_PATH=smem"; do
+  f=$(echo $v | tr ' =' '__')
+  env $v python bench.py --resident-only --steps 4 > gpurun_out/r2d_bench_$f.json 2> gpurun_out/r2d_bench_$f.err
+  python - <<P
+import json
+d=json.loads(open("gpurun_out/r2d_bench_$f.json").read().strip().splitlines()[-1])
+print("VARIANT $v: frames/s %.0f render ms %.4f" % (d["value"], d["render_ms_per_launch"]))
+P
+done
