@@ -745,7 +745,11 @@ def run_e2e(args, config, movie, world, device):
     # host trajectory: positions of consecutive frames taken from the device movie
     inputs = []
     block = torch.empty((1, args.size, args.size), dtype=torch.float32, device=device)
-    for k in range(n_frames + 4):
+    # warm-up frames: PSF tables, buffers, and -- frames travel in blocks of engine.BLOCK_FRAMES with the next block
+    # enqueued while this one is handed out -- the page-locked payloads of three blocks
+    from scopyon_b200 import engine as engine_module
+    n_warm = max(4, 3 * engine_module.BLOCK_FRAMES)
+    for k in range(n_frames + n_warm):
         inputs.append((k * 0.033, movie.positions()[:, [1, 2, 0, 3, 4]]))   # (x, y, z, id, p_state) rows
         movie.render_block(block)
     import warnings
@@ -759,8 +763,8 @@ def run_e2e(args, config, movie, world, device):
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
             sim = scopyon_b200.create_simulator(config, rng=rng)
-            gen = sim.generate_images(source, num_frames=n_frames + 4)
-            for _ in range(4):                     # warm-up frames: build/attach PSF tables, allocate buffers --
+            gen = sim.generate_images(source, num_frames=n_frames + n_warm)
+            for _ in range(n_warm):                # warm-up frames: build/attach PSF tables, allocate buffers --
                 first = next(gen)                  # consumed like the timed ones, so one-off allocations of the
                 first.as_array(as_dtype)           # route this consumer takes happen here
             del first
@@ -785,7 +789,8 @@ def run_e2e(args, config, movie, world, device):
                         "Image.as_array(), exact); float64_value: Image.as_array() called on every frame "
                         "(widened by the host thread pool, scb_host_widen_*); device_inputs_value: as value, with the "
                         "trajectory resident on the GPU (sample_inputs(..., device=True): no per-frame upload)",
-        "frames_timed": n_frames, "per": "frame (one generate_images iteration)"})
+        "frames_timed": n_frames, "warmup_frames": n_warm, "frames_per_block": engine_module.BLOCK_FRAMES,
+        "per": "frame (one generate_images iteration; the engine renders blocks of frames_per_block frames)"})
     return out
 
 

@@ -275,6 +275,15 @@ int scb_render_expected_frames(const scb_geometry *geom, int64_t n_per_frame, in
                                int box_type, const double *d_inv_scale, const int32_t *d_slot_of_key,
                                void *d_out, int out_type, void *d_workspace, size_t workspace_bytes,
                                int32_t *d_errors, void *stream);
+/* The same on particle ROWS: frame f is the (n_per_frame, 5) float64 rows at d_rows + f * n_per_frame * 5
+ * (the snapshots of consecutive frames as EPIFMSimulator.__format_data makes them, base.py:61-110, uploaded
+ * back to back); d_weight[n_frames][n_per_frame] from scb_emit_bleach_rows.  generate_frames
+ * (_epifm.py:1017-1049) renders blocks of frames through it when every frame is one snapshot. */
+int scb_render_expected_rows_frames(const scb_geometry *geom, int64_t n_per_frame, int n_frames,
+                                    const double *d_rows, const double *d_weight, const int64_t *d_sat,
+                                    const void *d_box, int box_type, const double *d_inv_scale,
+                                    const int32_t *d_slot_of_key, void *d_out, int out_type,
+                                    void *d_workspace, size_t workspace_bytes, int32_t *d_errors, void *stream);
 /* The same with a visiting order: slot s of every frame's spot list shows particle d_order[s]
  * (a permutation of 0 .. n_per_frame - 1, or NULL).  Images do not depend on it (integer accumulation);
  * when it lists the particles tile by tile -- e.g. sorted by a coarse screen cell, refreshed every few

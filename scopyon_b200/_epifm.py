@@ -376,14 +376,42 @@ class _EPIFMSimulator:
                 infodict['fluorescence_states'] = budgets
             return camera, infodict
 
+        def begin_block(first, count):
+            """Frames ``first .. first + count - 1`` as one block when each of them is a single snapshot
+            (the engine may still decline: ragged snapshots, repeated ids), else None."""
+            frames, exposures = [], []
+            for frame_index in range(first, first + count):
+                windows, t, exposure = frame_windows(times, frame_index, start_time, exposure_time, self.configs)
+                if len(windows) != 1:
+                    return None
+                frames.append((windows[0][1], input_data[windows[0][0]][1]))
+                exposures.append(exposure)
+            return engine.begin_block(frames, first, noise_seed, states, exposures)
+
         from . import engine as engine_module
         in_flight = collections.deque()
+        block = engine_module.BLOCK_FRAMES if engine.block_route(full_output) else 1
+        next_frame = 0
+        single_until = 0        # frames below this index go one by one (their block was declined)
         try:
-            for frame_index in range(num_frames):
-                in_flight.append(begin(frame_index))
-                if len(in_flight) == engine_module.FRAMES_IN_FLIGHT:
-                    yield finish(in_flight.popleft())
-            while in_flight:
+            while next_frame < num_frames or in_flight:
+                # blocks: the next one is enqueued while the frames of this one are handed out; single frames:
+                # FRAMES_IN_FLIGHT - 1 frames of lookahead
+                while next_frame < num_frames:
+                    pending = None
+                    count = min(block, num_frames - next_frame)
+                    if count > 1 and next_frame >= single_until and engine.block_route(full_output):
+                        if len(in_flight) >= block:         # next block: as soon as this one's first frame is out
+                            break
+                        pending = begin_block(next_frame, count)
+                        if pending is None:
+                            single_until = next_frame + count
+                    if pending is None:
+                        if len(in_flight) >= engine_module.FRAMES_IN_FLIGHT:
+                            break
+                        pending = [begin(next_frame)]
+                    in_flight.extend(pending)
+                    next_frame += len(pending)
                 yield finish(in_flight.popleft())
         finally:
             # the caller stopped early (or a frame failed): nothing may still be writing into the

@@ -104,6 +104,9 @@ SIGNATURES = {
     "scb_render_expected_frames": (ctypes.c_int, [
         ctypes.POINTER(Geometry), ctypes.c_int64, ctypes.c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
         ctypes.c_int, c_ptr, c_ptr, c_ptr, ctypes.c_int, c_ptr, ctypes.c_size_t, c_ptr, c_ptr]),
+    "scb_render_expected_rows_frames": (ctypes.c_int, [
+        ctypes.POINTER(Geometry), ctypes.c_int64, ctypes.c_int, c_ptr, c_ptr, c_ptr, c_ptr,
+        ctypes.c_int, c_ptr, c_ptr, c_ptr, ctypes.c_int, c_ptr, ctypes.c_size_t, c_ptr, c_ptr]),
     "scb_render_expected_frames_ordered": (ctypes.c_int, [
         ctypes.POINTER(Geometry), ctypes.c_int64, ctypes.c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
         ctypes.c_int, c_ptr, c_ptr, c_ptr, ctypes.c_int, c_ptr, ctypes.c_size_t, c_ptr, c_ptr]),

@@ -235,7 +235,7 @@ spot_prepare_kernel(Geo g, int64_t n, int64_t stride, const double *__restrict__
         }
     }
     if (wmax_bits) {
-        // largest weight: positive doubles order like their bit patterns, so an integer max
+        // largest weight of the frame: positive doubles order like their bit patterns, so an integer max
         // is exact and order free; one atomic per warp
         unsigned long long bits = (unsigned long long)__double_as_longlong(w_seen);
 #pragma unroll
@@ -243,7 +243,7 @@ spot_prepare_kernel(Geo g, int64_t n, int64_t stride, const double *__restrict__
             const unsigned long long other = __shfl_xor_sync(0xffffffffu, bits, d);
             bits = other > bits ? other : bits;
         }
-        if ((threadIdx.x & 31) == 0 && bits != 0) atomicMax(wmax_bits, bits);
+        if ((threadIdx.x & 31) == 0 && bits != 0) atomicMax(wmax_bits + frame, bits);      // one slot per frame of the call
     }
 }
 
@@ -428,7 +428,7 @@ struct Workspace {
     uint32_t *edges;
     int edge_cap;            // edge slots per axis per spot
     int *tile_count, *tile_cursor, *tile_start;
-    unsigned long long *wmax_bits;   // bit pattern of the largest spot weight (cleared with the census)
+    unsigned long long *wmax_bits;   // [frames] bit pattern of the frame's largest spot weight (cleared with the census)
     int *next_tile;                  // dynamic tile queue of the persistent render kernel (cleared likewise)
     int *pair_spot;                  // list entries: spot indices (entry_bytes = 4) or render units
     int *ranks;                      // [n][rank_cap] list positions handed out by the census (render path)
@@ -506,8 +506,9 @@ Workspace carve(const Geo &g, int64_t n, void *base, size_t entry_bytes = sizeof
     w.edges = (uint32_t *)(p + off); off += align_up((size_t)(n > 0 ? n : 1) * 2 * w.edge_cap * sizeof(uint32_t));
     w.tile_count = (int *)(p + off); off += align_up(n_tiles * g.stripes * sizeof(int));
     w.tile_cursor = (int *)(p + off); off += align_up(n_tiles * g.stripes * sizeof(int));
+    // per frame, so that a frame's accumulator LSBs do not depend on the frames it shares a launch with
     w.wmax_bits = (unsigned long long *)(p + off);
-    w.next_tile = (int *)(p + off + 8); off += 256;
+    w.next_tile = (int *)(p + off + 8 * (size_t)g.frames); off += align_up(8 * (size_t)g.frames + 8);
     w.tile_start = (int *)(p + off); off += align_up((n_tiles * g.stripes + 1) * sizeof(int));
     w.pair_spot = (int *)(p + off); off += align_up((size_t)w.pair_capacity * entry_bytes);
     w.ranks = nullptr;

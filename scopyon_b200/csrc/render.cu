@@ -357,8 +357,7 @@ render_strips_kernel(Geo g, const Unit *__restrict__ units, const uint32_t *__re
     const int frame_tiles = g.nti * g.ntj, n_tiles = g.frames * frame_tiles;
     const int slots = SLOTS ? SLOTS : g.slots;
     const uint32_t row_bytes = (uint32_t)slots * (uint32_t)sizeof(BoxT);
-    const unsigned long long wmax = *wmax_bits;
-    const int call_shift = accumulator_shift(wmax, n_spots);      // 64-bit accumulators: one LSB per call
+    const int64_t frame_spots = g.frames > 1 ? g.spots_per_frame : n_spots;
 
     for (int i = lane; i < ROWS * kStripCols; i += 32) acc[i] = 0;
     for (int i = lane; i < kStages * kStageEntries; i += 32) ring[i] = (BoxT)0;   // rows past a unit's last are read (and dropped)
@@ -383,7 +382,11 @@ render_strips_kernel(Geo g, const Unit *__restrict__ units, const uint32_t *__re
         const int row0 = ti * ROWS, col0 = tj * kStripCols;
         OutT *image = out + (size_t)frame * g.n_w * g.n_h;
         const int seg_begin = tile_start[tile * g.stripes], seg_end = tile_start[(tile + 1) * g.stripes];
-        const int shift = sizeof(Acc) == 4 ? strip_shift(seg_end - seg_begin, wmax, g.box_peak) : call_shift;
+        // LSB per strip (32-bit accumulators) or per frame (64-bit), from the frame's own largest weight: a frame's
+        // bits do not depend on the frames it shares the launch with
+        const unsigned long long wmax = wmax_bits[frame];
+        const int shift = sizeof(Acc) == 4 ? strip_shift(seg_end - seg_begin, wmax, g.box_peak)
+                                           : accumulator_shift(wmax, frame_spots);
         const double scale = scalbn(1.0, shift), lsb = scalbn(1.0, -shift);
 
         for (int base = seg_begin; base < seg_end; base += kBatch) {
@@ -832,4 +835,21 @@ extern "C" int scb_render_expected_frames(const scb_geometry *geom, int64_t n_pe
     return scb_render_expected_frames_ordered(geom, n_per_frame, n_frames, nullptr, d_depth, d_x, d_y, d_weight, d_sat,
                                               d_box, box_type, d_inv_scale, d_slot_of_key, d_out, out_type, d_workspace,
                                               workspace_bytes, d_errors, stream);
+}
+
+// A block of frames given as particle ROWS: frame f is the (n_per_frame, 5) float64 rows at
+// d_rows + f * n_per_frame * 5 (the facade's snapshots of consecutive frames, uploaded back to back)
+extern "C" int scb_render_expected_rows_frames(const scb_geometry *geom, int64_t n_per_frame, int n_frames,
+                                               const double *d_rows, const double *d_weight, const int64_t *d_sat,
+                                               const void *d_box, int box_type, const double *d_inv_scale,
+                                               const int32_t *d_slot_of_key, void *d_out, int out_type,
+                                               void *d_workspace, size_t workspace_bytes, int32_t *d_errors,
+                                               void *stream) {
+    SCB_REQUIRE(n_per_frame >= 0 && n_frames >= 1, SCB_E_INVALID, "scb_render_expected_rows_frames: n=%lld frames=%d",
+                (long long)n_per_frame, n_frames);
+    SCB_REQUIRE(n_per_frame < ((int64_t)1 << 31), SCB_E_INVALID, "scb_render_expected_rows_frames: n=%lld", (long long)n_per_frame);
+    SCB_REQUIRE(n_per_frame == 0 || d_rows, SCB_E_NULL, "scb_render_expected_rows_frames: NULL rows");
+    return render_expected_strided(geom, n_per_frame * n_frames, n_frames, 5, nullptr, d_rows, d_rows + 1, d_rows + 2, d_weight,
+                                   d_sat, d_box, box_type, d_inv_scale, d_slot_of_key, d_out, out_type, 0, d_workspace,
+                                   workspace_bytes, d_errors, stream);
 }

@@ -167,7 +167,6 @@ render_strips_reg_kernel(const __grid_constant__ CUtensorMap box_map, Geo g, con
     unsigned long long *bars = reinterpret_cast<unsigned long long *>(meta + kRegBatch);
 
     const int frame_tiles = g.nti * g.ntj, n_tiles = g.frames * frame_tiles;
-    const unsigned long long wmax = *wmax_bits;
     const long long table_entries = (long long)g.modulus * g.modulus * g.slots * g.slots;
 
     if (lane == 0) {
@@ -192,7 +191,7 @@ render_strips_reg_kernel(const __grid_constant__ CUtensorMap box_map, Geo g, con
         const int ti = in_frame / g.ntj, tj = in_frame - ti * g.ntj;
         const int row0 = ti * 8, col0 = tj * 128;
         const int seg_begin = tile_start[tile * g.stripes], seg_end = tile_start[(tile + 1) * g.stripes];
-        const int shift = strip_shift(seg_end - seg_begin, wmax, g.box_peak);
+        const int shift = strip_shift(seg_end - seg_begin, wmax_bits[frame], g.box_peak);
         const double scale = scalbn(1.0, shift), lsb = scalbn(1.0, -shift);
 
         for (int base = seg_begin; base < seg_end; base += kRegBatch) {
@@ -313,7 +312,6 @@ render_strips_ldg_kernel(Geo g, const float *__restrict__ box, const RUnit *__re
     uint4 *meta = reinterpret_cast<uint4 *>(smem_raw + warp * kLdgWarpSmem);
 
     const int frame_tiles = g.nti * g.ntj, n_tiles = g.frames * frame_tiles;
-    const unsigned long long wmax = *wmax_bits;
     const long long table_entries = (long long)g.modulus * g.modulus * g.slots * g.slots;
     int acc[8][4];
 #pragma unroll
@@ -330,7 +328,7 @@ render_strips_ldg_kernel(Geo g, const float *__restrict__ box, const RUnit *__re
         const int ti = in_frame / g.ntj, tj = in_frame - ti * g.ntj;
         const int row0 = ti * 8, col0 = tj * 128;
         const int seg_begin = tile_start[tile * g.stripes], seg_end = tile_start[(tile + 1) * g.stripes];
-        const int shift = strip_shift(seg_end - seg_begin, wmax, g.box_peak);
+        const int shift = strip_shift(seg_end - seg_begin, wmax_bits[frame], g.box_peak);
         const double scale = scalbn(1.0, shift), lsb = scalbn(1.0, -shift);
 
         for (int base = seg_begin; base < seg_end; base += kRegBatch) {

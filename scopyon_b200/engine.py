@@ -49,6 +49,9 @@ FRAMES_IN_FLIGHT = 3
 # array materialised on demand) while fewer than this many bytes of such payloads are alive; a caller that
 # retains more frames than that gets eagerly widened float64 arrays in pageable memory instead.
 LAZY_PINNED_BYTES = 1 << 30
+#: frames ``generate_frames`` hands to the engine at once when every frame is one snapshot (``begin_block``): binning,
+#: rendering and the detector pass then run once per block instead of once per frame.  1 = frame by frame.
+BLOCK_FRAMES = int(os.environ.get("SCOPYON_B200_BLOCK_FRAMES", "8"))
 
 
 def walker_alias(values, weights):
@@ -818,6 +821,151 @@ class DeviceEngine:
                     true=true_host, budget=budget_host, states=states, done=done, errors=errors_host,
                     planes_done=planes_done, tickets=tickets,
                     exposure_time=exposure_time, want_expectation=want_expectation)
+
+    # ------------------------------------------------------------------ blocks of frames (generate_frames)
+    def block_route(self, want_full_output):
+        """Whether ``generate_frames`` may hand this engine several frames at once (``begin_block``): bare ADC
+        planes of large float32 frames -- the case where a movie is made of many frames of one snapshot each."""
+        return (BLOCK_FRAMES > 1 and not want_full_output and not self.gaussian_tc and self.dtype == torch.float32
+                and self.n_w * self.n_h >= HOST_WIDEN_MIN_PIXELS and not getattr(self, "_eager_float64", False)
+                and (self.n_w * self.n_h) % 4 == 0
+                and (self.configs.ADConverter_fpn_type != 'column' or self.n_h % 4 == 0))
+
+    def begin_block(self, frames, first_index, noise_seed, states, exposure_times):
+        """Enqueue ``len(frames)`` consecutive frames, each ONE snapshot ``(unit_time, particles)`` of the same
+        number of particles, as one block: the rows of all frames go up back to back, emission / bleaching runs
+        frame after frame (the budgets carry over), then binning, rendering and the detector pass run once for
+        the whole block (``scb_render_expected_rows_frames``, ``scb_detector_adc_frames``) and every frame is
+        downloaded into its own page-locked float32 payload.  Returns one handle per frame for ``finish_frame``
+        -- the frames are the ones ``begin_frame`` would have produced (same draws, same accumulator LSBs) -- or
+        None when the block must take the frame-by-frame route (ragged snapshots, repeated ids, no payloads)."""
+        nb = len(frames)
+        sizes = [len(p) for _, p in frames]
+        n = sizes[0]
+        if nb < 2 or n == 0 or any(m != n for m in sizes):
+            return None
+        slots_dev = None
+        if states is not None:
+            for snapshot in frames:
+                order, rounds, slots_dev, _ = self._molecule_slots(states.ids, self._ids_of([snapshot]))
+                if order is not None or len(rounds) != 1:
+                    return None
+        payloads = [self._lazy_plane() for _ in range(nb)]
+        if any(p is None for p in payloads):
+            self._lazy_pool["free"].extend(p for p in payloads if p is not None)
+            return None
+        with torch.cuda.device(self.device):
+            main = torch.cuda.current_stream(self.device)
+            self._frame_stream = ctypes.c_void_p(main.cuda_stream)
+            try:
+                with _Trace(self, "host_prepare"):
+                    return self._begin_block(main, frames, first_index, noise_seed, states, exposure_times, n, slots_dev,
+                                             payloads)
+            except Exception:
+                self._lazy_pool["free"].extend(payloads)
+                raise
+            finally:
+                self._frame_stream = None
+
+    def _begin_block(self, main, frames, first_index, noise_seed, states, exposure_times, n, slots_dev, payloads):
+        cfg = self.configs
+        nb = len(frames)
+        stream = self._stream()
+        focal = cfg.detector_focal_point
+        sets = self.__dict__.setdefault("_block_sets", [None, None])
+        turn = self._block_turn = (getattr(self, "_block_turn", 0) + 1) % 2
+        buf = sets[turn]
+        if buf is None or buf["nb"] < nb or buf["n"] < n:
+            need = self.lib.scb_render_frames_workspace_bytes(ctypes.byref(self.geom), n, BLOCK_FRAMES)
+            if buf is not None and buf["free"] is not None:
+                buf["free"].synchronize()
+            buf = sets[turn] = dict(
+                nb=BLOCK_FRAMES, n=n, free=None,
+                rows=torch.empty((BLOCK_FRAMES, n, 5), dtype=torch.float64, device=self.device),
+                weight=torch.empty((BLOCK_FRAMES, n), dtype=torch.float64, device=self.device),
+                photons=torch.empty((BLOCK_FRAMES, self.n_w, self.n_h), dtype=torch.float32, device=self.device),
+                adc=torch.empty((BLOCK_FRAMES, self.n_w, self.n_h), dtype=torch.float32, device=self.device),
+                work=torch.empty(int(need) + 256, dtype=torch.uint8, device=self.device),
+                det_work=torch.empty(BLOCK_FRAMES * self.lib.scb_detector_workspace_bytes(self.n_w, self.n_h),
+                                     dtype=torch.uint8, device=self.device),
+                stage=None)
+        if buf["free"] is not None:
+            main.wait_event(buf["free"])                 # the set's previous block has left the device
+        rows = buf["rows"][:nb, :n] if buf["n"] == n else None
+        if rows is None:        # fewer particles than the set was made for: a dense view of its memory
+            rows = buf["rows"].view(-1)[: nb * n * 5].view(nb, n, 5)
+        weight = buf["weight"].view(-1)[: nb * n].view(nb, n)
+        photons, adc = buf["photons"][:nb], buf["adc"][:nb]
+        keys = []
+        all_resident = self.tables.all_resident()
+        for k, (unit_time, particles) in enumerate(frames):
+            if hasattr(particles, "tensor"):             # base.DeviceRows: the trajectory never left the GPU
+                rows[k].copy_(particles.tensor, non_blocking=True)
+                if not all_resident:
+                    depth = (particles.tensor[:, 0] - float(focal[0])).abs()
+                    key = torch.clamp((depth / RESOLUTION).to(torch.int64), max=self.geom.n_depth_keys - 1)
+                    key = torch.where(depth < cfg.depth_cutoff + RESOLUTION, key,
+                                      torch.full_like(key, self.geom.n_depth_keys))
+                    keys.append(torch.unique(key).cpu().numpy())
+                continue
+            host = None
+            if isinstance(particles, numpy.ndarray) and particles.dtype == numpy.float64 and particles.flags.c_contiguous:
+                host = torch.from_numpy(particles.view(numpy.ndarray))
+                if not host.is_pinned():
+                    host = None
+            if host is None:                              # through the set's pinned staging area
+                if buf["stage"] is None or buf["stage"].shape[1] < n:
+                    buf["stage"] = torch.empty((BLOCK_FRAMES, n, 5), dtype=torch.float64, pin_memory=True)
+                host = buf["stage"][k, :n]
+                numpy.copyto(host.numpy(), numpy.asarray(particles, dtype=numpy.float64))
+            rows[k].copy_(host, non_blocking=True)
+            if not all_resident:
+                keys.append(depth_keys_of(numpy.asarray(particles)[:, 0] - focal[0], cfg.depth_cutoff,
+                                          self.geom.n_depth_keys))
+        if keys:
+            needed = numpy.unique(numpy.concatenate(keys))
+            if self.psf_type != _native.PSF_GAUSSIAN and (self.slot_host[needed] < 0).sum() > 128:
+                self.ensure_all_tables()
+            else:
+                self.ensure_tables(needed)
+        for k, (unit_time, _) in enumerate(frames):
+            self._call(
+                "scb_emit_bleach_rows", states.seed if states is not None else 0, n, _native.ptr(rows[k]),
+                None if slots_dev is None else _native.ptr(slots_dev), float(unit_time), float(focal[0]),
+                ctypes.byref(self.phys), None if states is None else _native.ptr(states.budget),
+                _native.ptr(weight[k]), None, stream)
+        self._call(
+            "scb_render_expected_rows_frames", ctypes.byref(self.geom), n, nb, _native.ptr(rows), _native.ptr(weight),
+            _native.ptr(self.sat), _native.ptr(self.box), self.box_type, _native.ptr(self.inv_scale),
+            _native.ptr(self.slot_of_key), _native.ptr(photons), _native.F32, _native.ptr(buf["work"]),
+            buf["work"].numel(), _native.ptr(self.errors), stream)
+        self._call(
+            "scb_detector_adc_frames", int(noise_seed), int(first_index), nb, ctypes.byref(self.det), self.n_w, self.n_h,
+            _native.F32, _native.ptr(photons), _native.ptr(self.offset), _native.ptr(self.alias),
+            0 if self.alias is None else int(self.alias.shape[0]), _native.ptr(adc), _native.ptr(buf["det_work"]),
+            buf["det_work"].numel(), stream)
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        with _Trace(self, "enqueue_d2h"):
+            ready = torch.cuda.Event()
+            ready.record(main)
+            self._copy_stream.wait_event(ready)
+            landed = []
+            with torch.cuda.stream(self._copy_stream):
+                for k, host in enumerate(payloads):
+                    host.copy_(adc[k], non_blocking=True)
+                    event = torch.cuda.Event()
+                    event.record(self._copy_stream)
+                    landed.append(event)
+            buf["free"] = landed[-1]
+        errors_host = torch.empty(1, dtype=torch.int32, pin_memory=True)
+        errors_host.copy_(self.errors, non_blocking=True)
+        self.errors.zero_()
+        done = torch.cuda.Event()
+        done.record(main)
+        return [dict(hosts=[payloads[k]], lazy=True, true=None, budget=None, states=states, done=done,
+                     errors=errors_host, planes_done=landed[k], tickets=[], exposure_time=exposure_times[k],
+                     want_expectation=False) for k in range(nb)]
 
     def finish_frame(self, pending):
         """Wait for a frame started by ``begin_frame``: ``(adc, expectation or None, true_data,

@@ -269,3 +269,39 @@ default:
         assert info_a["true_data"].keys() == info_b["true_data"].keys()
         assert all(numpy.array_equal(info_a["true_data"][k], info_b["true_data"][k]) for k in info_a["true_data"])
     assert numpy.array_equal(single[0], single[1]) and single[0].max() > 110
+
+
+@pytest.mark.parametrize("device_inputs", [False, True])
+def test_blocks_of_frames_equal_the_frame_by_frame_movie(device_inputs, monkeypatch):
+    """generate_images hands the engine blocks of BLOCK_FRAMES single-snapshot frames (one binning / render /
+    detector launch per block, engine.begin_block); the frames are those of the frame-by-frame route, bit for
+    bit -- TIRF illumination and bleaching, so weights differ from molecule to molecule and frame to frame, a
+    last block that is not full, and a frame of two snapshots (motion blur) in the middle that must go alone."""
+    from scopyon_b200 import engine as engine_module
+    config = scopyon_b200.DefaultConfiguration()
+    config.update("""
+default:
+    magnification: 100
+    detector: {type: CMOS, image_size: [1024, 1024], pixel_length: {value: 6.5e-6, units: m}, QE: 0.73, exposure_time: 0.033}
+    analog_to_digital_converter: {bit: 16, offset: 100, fullwell: 30000, type: column, count: 2.0}
+    effects: {photo_bleaching: {switch: true, half_life: {value: 0.3, units: s}}}
+""")
+    pl = 6.5e-8
+    t = list(numpy.arange(0, 23) * 0.033)
+    t.insert(12, 11.5 * 0.033)          # frame 11 sees two snapshots
+    kwargs = dict(N=600, lower=[-480 * pl, -480 * pl, 0.0], upper=[480 * pl, 480 * pl, 4e-7], D=3e-13, ndim=3)
+
+    def movie(block_frames):
+        monkeypatch.setattr(engine_module, "BLOCK_FRAMES", block_frames)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            inputs = scopyon_b200.sample_inputs(numpy.array(t), rng=numpy.random.RandomState(3), device=device_inputs,
+                                                **kwargs)
+            sim = scopyon_b200.create_simulator(config, rng=numpy.random.RandomState(8))
+            return [img.as_array(numpy.float32).copy() for img in sim.generate_images(inputs, num_frames=21)]
+
+    blocks, singles = movie(8), movie(1)
+    assert len(blocks) == 21 and blocks[0].shape == (1024, 1024)
+    for k, (a, b) in enumerate(zip(blocks, singles)):
+        assert numpy.array_equal(a, b), k
+    assert not numpy.array_equal(blocks[0], blocks[1]) and blocks[0].max() > 110

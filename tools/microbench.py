@@ -146,6 +146,55 @@ def bench_render():
                           "table_build_s": build_s, "errors": int(eng.errors.item())}))
 
 
+def bench_pitch():
+    """C4-shaped scenes (2048^2, 1e5 spots, 3-D) at pixel pitches with and without a whole number of table samples
+    per pixel: 65 nm takes the box-table / TMA path, 66.39 nm (the reference's default x241 on 16 um pixels) and
+    108.33 nm (x60 on 6.5 um) gather SAT corners.  SCB_GATHER_* select the measured gather variants."""
+    from bench import count_spot_pixel_evals
+    size, n = 2048, 100000
+    for label, pixel, mag in (("65 nm", 6.5e-6, 100), ("66.39 nm", 16e-6, 241), ("108.33 nm", 6.5e-6, 60)):
+        yaml = """
+default:
+    magnification: %d
+    light_source: {angle: {value: 0.0, units: radian}}
+    detector: {type: CMOS, image_size: [%d, %d], pixel_length: {value: %.9e, units: m}, QE: 0.73, exposure_time: 0.033}
+""" % (mag, size, size, pixel)
+        from scopyon_b200.engine import SatStore
+        SatStore.clear_shared()
+        torch.cuda.empty_cache()
+        configs, eng = engine_for(yaml)
+        pl = configs.pixel_length
+        rng = numpy.random.RandomState(1)
+        data = numpy.zeros((n, 5))
+        data[:, 1:3] = rng.uniform(-size * pl / 2, size * pl / 2, (n, 2))
+        data[:, 0] = rng.uniform(0, 1.5e-6, n)
+        data[:, 3] = numpy.arange(n)
+        data[:, 4] = 1
+        t0 = time.time()
+        eng.ensure_all_tables()
+        torch.cuda.synchronize()
+        build_s = time.time() - t0
+        soa = torch.from_numpy(numpy.ascontiguousarray(data[:, [0, 1, 2, 4]].T)).cuda()
+        w = torch.full((n,), 30.0, dtype=torch.float64, device="cuda")
+        out = torch.empty((size, size), dtype=torch.float32, device="cuda")
+        work = eng._render_workspace(n)
+
+        def go():
+            eng._call("scb_render_expected", ctypes.byref(eng.geom), n, _native.ptr(soa[0]), _native.ptr(soa[1]),
+                      _native.ptr(soa[2]), _native.ptr(w), _native.ptr(eng.sat), _native.ptr(eng.box), eng.box_type, _native.ptr(eng.inv_scale),
+                      _native.ptr(eng.slot_of_key), _native.ptr(out), _native.F32, 0, _native.ptr(work), work.numel(),
+                      _native.ptr(eng.errors), eng._stream())
+        ms, best = timed(go, iters=6, warm=2)
+        evals = count_spot_pixel_evals(data, size, pl)
+        print(json.dumps({"kernel": "scb_render_expected (prepare+scan+fill+render), one frame", "pixel": label, "size": size,
+                          "spots": n, "box_table": eng.box is not None, "ms": ms, "ms_best": best, "evals": evals,
+                          "evals/s": evals / (ms * 1e-3), "tables": eng.n_tables, "table_build_s": build_s,
+                          "sat_GB": 0 if eng.sat is None else eng.sat.numel() * 8 / 1e9,
+                          "variant": {k: v for k, v in os.environ.items() if k.startswith("SCB_")},
+                          "checksum": float(out.double().sum().item()), "errors": int(eng.errors.item())}))
+        del eng, soa, w, out, work
+
+
 def bench_gaussian():
     """BASELINE config 5: separable-Gaussian stress, 1e6 spots, 4096 x 4096."""
     from scopyon_b200.engine import SatStore
@@ -216,3 +265,5 @@ if __name__ == "__main__":
         bench_render()
     if "gaussian" in what:
         bench_gaussian()
+    if "pitch" in what:
+        bench_pitch()

@@ -36,7 +36,7 @@ with warnings.catch_warnings():
     prof.enable()
     total = 0.0
     for img in gen:
-        total += float(img.as_array()[0, 0])
+        total += float(img.as_array(numpy.float32)[0, 0])
     prof.disable()
     dt = time.perf_counter() - t0
 print("ms per frame (under cProfile): %.3f" % (dt / frames * 1e3))
