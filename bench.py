@@ -709,6 +709,10 @@ def run_weak(args):
                 "spot_pixel_evals_per_s": evals / (per_launch_ms * 1e-3), "ms_per_launch": per_launch_ms,
                 "frames_per_launch": frames_per_launch,
                 "share_of_step": render_ms / elapsed_ms,
+                # what keeps it below the HBM roofline: profiles/render_variants_r2.md
+                "limiter": "TMA request rate -- one bulk copy per unit, and an SM retires one copy per ~40-50 cycles "
+                           "whatever its size (tools/probes/tma_rate_probe.cu); issue slots 84 % busy, DRAM 57 % active "
+                           "(profiles/traffic_r2.json)",
             },
             "export": export, "host": host, "gather_ok": gather_ok, "spec_half_life": spec,
             "emitting_fraction": [emitting_start, emitting_end],
