@@ -31,6 +31,7 @@
 #include "binning.cuh"
 
 #include <cuda.h>      // CUtensorMap (types only: the encoder is looked up at run time)
+#include <string.h>
 #include <atomic>
 #include <mutex>
 
@@ -199,6 +200,7 @@ __device__ __forceinline__ long long to_fixed(double box, double ws) { return __
 __device__ __forceinline__ int to_fixed(float box, float ws) { return __float2int_rn(__fmul_rn(box, ws)); }
 
 #include "render_reg.cuh"
+#include "render_tile.cuh"
 
 // Per-lane cp.async (LDGSTS) staging: the alternative to the TMA bulk copy.  A unit's rows are one
 // contiguous run of the block (<= 2 KB), so lane l copies the 16-byte pieces l, l + 32, ... of it: no
@@ -554,7 +556,8 @@ static RenderVariant render_variant() {      // read at every call (a few getenv
     RenderVariant r = {kDefaultRows, kDefaultCopy, 0};
     if (const char *e = getenv("SCB_RENDER_ROWS")) r.rows = atoi(e) == 16 ? 16 : (atoi(e) == 8 ? 8 : r.rows);
     if (const char *e = getenv("SCB_RENDER_COPY")) r.copy = e[0] == 'l' ? 1 : (e[0] == 't' ? 0 : r.copy);
-    if (const char *e = getenv("SCB_RENDER_PATH")) r.reg = e[0] == 't' ? 2 : (e[0] == 'l' ? 1 : 0);
+    if (const char *e = getenv("SCB_RENDER_PATH"))
+        r.reg = !strcmp(e, "tile") ? 3 : (e[0] == 't' ? 2 : (e[0] == 'l' ? 1 : 0));
     if (r.rows != 8 || r.copy != 0) r.reg = 0;        // strip shape and copy engine belong to the shared-memory kernel
     return r;
 }
@@ -678,6 +681,34 @@ static int launch_render_ldg_as(const Geo &g, const Workspace &w, const int64_t 
     return 0;
 }
 
+template <typename OutT, int SLOTS, int CTAS>
+static int launch_render_tiles_as(const Geo &g, const Workspace &w, const int64_t *sat, const float *box, OutT *out,
+                                  int accumulate, cudaStream_t s) {
+    const int n_tiles = g.frames * g.nti * g.ntj;
+    int ctas = CTAS * SCB_SM_COUNT;
+    if (ctas > n_tiles) ctas = n_tiles;
+    static std::atomic<unsigned long long> configured{0};
+    int dev = 0;
+    SCB_CUDA(cudaGetDevice(&dev));
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (!(configured.load(std::memory_order_acquire) & bit)) {
+        SCB_CUDA(cudaFuncSetAttribute(render_tiles_kernel<OutT, SLOTS, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)kTileSmem));
+        configured.fetch_or(bit, std::memory_order_release);
+    }
+    render_tiles_kernel<OutT, SLOTS, CTAS><<<ctas, kTileWarps * 32, kTileSmem, s>>>(
+        g, box, (const TUnit *)w.pair_spot, w.spots, w.edges, w.edge_cap, sat, w.tile_start, w.next_tile, w.wmax_bits, out,
+        accumulate);
+    return 0;
+}
+
+template <typename OutT>
+static int launch_render_tiles(const Geo &g, const Workspace &w, const int64_t *sat, const float *box, OutT *out,
+                               int accumulate, cudaStream_t s) {
+    if (g.slots == 32) return launch_render_tiles_as<OutT, 32, 6>(g, w, sat, box, out, accumulate, s);
+    return launch_render_tiles_as<OutT, 0, 6>(g, w, sat, box, out, accumulate, s);
+}
+
 template <typename OutT>
 static int launch_render_reg(const CUtensorMap &box_map, const Geo &g, const Workspace &w, const int64_t *sat,
                              const float *box, OutT *out, int accumulate, cudaStream_t s) {
@@ -721,6 +752,18 @@ static int render_expected_strided(const scb_geometry *geom, int64_t n_spots, in
     SCB_REQUIRE(frames >= 1 && frames <= 4096 && n_spots % frames == 0, SCB_E_INVALID,
                 "scb_render_expected: %lld spots do not split into %d frames", (long long)n_spots, frames);
     Geo g = strip_geo(geom, d_box != nullptr, box_bytes, frames, n_spots / frames);
+    // the CTA-tile kernel (render_tile.cuh): 32 x 128 tiles, one list entry per (spot, tile, run of 32 columns)
+    const bool tile_path = render_variant().reg == 3 && forced_gather() != 1 && d_box && box_bytes == 4 &&
+                           g.slots <= 32 && g.slots % 4 == 0;
+    if (tile_path) {
+        const int quick = forced_gather() ? 0 : 1;
+        const double box_peak = g.box_peak;
+        g = make_geo(geom, kTileRows, kTileCols, kUnitCols, frames);
+        g.spots_per_frame = n_spots / frames;
+        g.box_peak = box_peak;
+        g.special_edges = 1;
+        g.quick_runs = quick;
+    }
     Workspace w = carve(g, n_spots, d_workspace, sizeof(Unit), true);
     SCB_REQUIRE(workspace_bytes >= w.bytes, SCB_E_WORKSPACE, "scb_render_expected: workspace %zu < %zu",
                 workspace_bytes, w.bytes);
@@ -742,14 +785,17 @@ static int render_expected_strided(const scb_geometry *geom, int64_t n_spots, in
         spot_edges_kernel<<<egrid, eblock, 0, s>>>(g, n_spots, w.spots, w.edges, w.edge_cap);
     }
     tile_scan_kernel<<<kScanCtas, 1024, 0, s>>>(n_tiles, g.stripes, w.tile_count, w.tile_start);
-    const bool reg_path = forced_gather() != 1 && reg_path_for(d_box != nullptr, box_bytes, g.slots);
+    const bool reg_path = !tile_path && forced_gather() != 1 && reg_path_for(d_box != nullptr, box_bytes, g.slots);
     CUtensorMap box_map;
     if (reg_path && render_variant().reg == 2) {
         rc = make_box_map(&box_map, d_box, g.slots, (long long)(g.n_depth_keys + 1) * g.modulus * g.modulus);
         if (rc) return rc;
     }
     if (n_spots > 0) {
-        if (reg_path)
+        if (tile_path)
+            tile_fill_units_kernel<<<scb_grid_for(n_spots, 256), 256, 0, s>>>(g, n_spots, w.spots, w.ranks, w.rank_cap,
+                                                                             w.tile_start, (TUnit *)w.pair_spot);
+        else if (reg_path)
             strip_fill_reg_kernel<<<scb_grid_for(n_spots, 256), 256, 0, s>>>(g, n_spots, w.spots, w.ranks, w.rank_cap,
                                                                             w.tile_start, (RUnit *)w.pair_spot);
         else
@@ -763,7 +809,10 @@ static int render_expected_strided(const scb_geometry *geom, int64_t n_spots, in
         if (g_profile.enabled && g_profile.used < g_profile.capacity) timed = g_profile.used++;
     }
     if (timed >= 0) cudaEventRecord(g_profile.start[timed], s);
-    if (reg_path) {
+    if (tile_path) {
+        if (out_type == SCB_F32) rc = launch_render_tiles<float>(g, w, d_sat, (const float *)d_box, (float *)d_out, accumulate, s);
+        else rc = launch_render_tiles<double>(g, w, d_sat, (const float *)d_box, (double *)d_out, accumulate, s);
+    } else if (reg_path) {
         if (out_type == SCB_F32) rc = launch_render_reg<float>(box_map, g, w, d_sat, (const float *)d_box, (float *)d_out, accumulate, s);
         else rc = launch_render_reg<double>(box_map, g, w, d_sat, (const float *)d_box, (double *)d_out, accumulate, s);
     } else if (out_type == SCB_F32) rc = launch_render<float>(g, w, n_spots, (float *)d_out, accumulate, box_type, s);

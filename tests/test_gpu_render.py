@@ -284,3 +284,15 @@ default:
         assert numpy.array_equal(image, images["default"]), name
     exact = render(gpu_engine(yaml, precision="f64")[3], data)
     assert rel_err(images["default"].astype(numpy.float64), exact) < 3e-6
+    # the CTA-tile kernel (32 x 128 tiles, one shared bulk copy per spot and tile) sets its accumulator LSB per tile:
+    # equal to the strip kernels to that LSB, and as close to the exact image as they are
+    for env in ({"SCB_RENDER_PATH": "tile"}, {"SCB_RENDER_PATH": "tile", "SCB_RENDER_FORCE_GATHER": "2"}):
+        os.environ.update(env)
+        try:
+            tiled = render(engine, data, dtype=torch.float32)
+        finally:
+            for k in env:
+                del os.environ[k]
+        assert rel_err(tiled.astype(numpy.float64), images["default"].astype(numpy.float64)) < 2e-6
+        assert rel_err(tiled.astype(numpy.float64), exact) < 3e-6
+        assert ((tiled > 0) == (images["default"] > 0)).all()
