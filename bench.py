@@ -224,11 +224,12 @@ def count_spot_pixel_evals(data, size, pl, sw=1e-9 * 1998):
 
 
 # --------------------------------------------------------------------------- CPU arm
-def cpu_sample(args, n_threads):
-    """Bounded sample of the workload on the host cores with the oracle port of the
-    reference algorithm: per-spot slice sums over the 1999^2 PSF table (one table per
-    integer-nm depth key, built on demand like the reference's cache) + per-pixel
-    Poisson / categorical / ADC detector loops.  Returns (frames_per_s, detail dict)."""
+def cpu_setup(args, n_threads):
+    """State of the CPU arm: the oracle port of the reference algorithm (per-spot slice sums over the 1999^2 PSF
+    table of the spot's integer-nm depth key + per-pixel Poisson / categorical / ADC detector loops) on a BOUNDED
+    SAMPLE of the workload -- `--cpu-sample-spots` of the molecules, placed like the workload's in x and y and on 16
+    depth keys spread over its depth range (the cost of a spot in the reference does not depend on its depth; 16
+    tables of 32 MB stay resident across steps the way the reference's PSF cache keeps them)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import c_oracle
     import epifm_oracle as orc
@@ -247,42 +248,56 @@ def cpu_sample(args, n_threads):
     lower, upper = box(args.size)
     n = args.cpu_sample_spots
     pts = numpy.stack([rng.uniform(lower[i], upper[i], n) for i in range(3)], axis=1)   # x, y, depth
-    t0 = time.perf_counter()
-    # Brownian step of the sample (sampling.py:116-118)
-    c_oracle.move_points(pts.copy(), numpy.sqrt(2 * D_COEFF * 0.033) * numpy.ones(3), 1)
-    t_move = time.perf_counter() - t0
-
+    levels = numpy.linspace(lower[2], upper[2], 16, endpoint=False) + 0.5e-9
+    pts[:, 2] = levels[numpy.arange(n) % 16]
     keys = _epifm.depth_keys_of(pts[:, 2], params["depth_cutoff"], geom.n_depth_keys)
     n_emit = numpy.array([orc.emitted(params, d, 0.033) for d in pts[:, 2]])
     weight = numpy.array([orc.spot_weight(params, e, 1.0) for e in n_emit])
-    t_table = t_render = 0.0
-    expected = numpy.zeros((args.size, args.size))
-    slot = numpy.full(geom.n_depth_keys + 1, -1, dtype=numpy.int32)
     uniq = numpy.unique(keys)
-    batch = 8                      # tables resident at once (8 x 32 MB); the reference caches them all
-    for b0 in range(0, len(uniq), batch):
-        group = uniq[b0: b0 + batch]
-        t0 = time.perf_counter()
-        tables = numpy.stack([c_oracle.table_from_radial(orc.radial_profile(
-            params, key * 1e-9 if key < geom.n_depth_keys else params["depth_cutoff"])) for key in group])
-        t_table += time.perf_counter() - t0
-        slot[:] = -1
-        slot[group] = numpy.arange(len(group))
-        sel = numpy.isin(keys, group)
-        t0 = time.perf_counter()
-        expected += c_oracle.render_bruteforce(geom, pts[sel, 2], pts[sel, 0], pts[sel, 1], weight[sel],
-                                               tables, slot, n_threads=n_threads)
-        t_render += time.perf_counter() - t0
+    t0 = time.perf_counter()
+    tables = numpy.stack([c_oracle.table_from_radial(orc.radial_profile(
+        params, key * 1e-9 if key < geom.n_depth_keys else params["depth_cutoff"])) for key in uniq])
+    t_table = time.perf_counter() - t0
+    slot = numpy.full(geom.n_depth_keys + 1, -1, dtype=numpy.int32)
+    slot[uniq] = numpy.arange(len(uniq))
     rn = _epifm.catalog_tables()["cmos_readout"]
+    return dict(c_oracle=c_oracle, params=params, geom=geom, pts=pts, weight=weight, tables=tables, slot=slot, rn=rn,
+                table_build_s=t_table, n_tables=int(len(uniq)), n=n, size=args.size, molecules=args.molecules)
+
+
+def cpu_step(state, n_threads):
+    """One step of the CPU arm: Brownian step, overlay and detector pass of the sample (one frame).
+    Returns (move_s, render_s, detector_s)."""
+    c_oracle, params, pts = state["c_oracle"], state["params"], state["pts"]
+    t0 = time.perf_counter()
+    c_oracle.move_points(pts.copy(), numpy.sqrt(2 * D_COEFF * 0.033) * numpy.ones(3), 1)     # sampling.py:116-118
+    t_move = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    expected = c_oracle.render_bruteforce(state["geom"], pts[:, 2], pts[:, 0], pts[:, 1], state["weight"],
+                                          state["tables"], state["slot"], n_threads=n_threads)
+    t_render = time.perf_counter() - t0
+    rn = state["rn"]
     t0 = time.perf_counter()
     c_oracle.detector_frame(expected, params["QE"], params["background_mean"], True, rn["electrons"], rn["weight"],
                             0.0, params["adc_fullwell"], params["adc_offset"], params["adc_bit"], 7, n_threads=n_threads)
     t_det = time.perf_counter() - t0
-    scale = args.molecules / float(n)
-    # PSF tables are a one-off per depth key in the reference (cache); a long movie touches all 1002
-    frame_s = (t_render + t_move) * scale + t_det
-    detail = dict(sample_spots=n, render_s=t_render, table_build_s=t_table, n_tables=int(len(numpy.unique(keys))),
-                  detector_s=t_det, move_s=t_move, frame_s_extrapolated=frame_s)
+    return t_move, t_render, t_det
+
+
+def cpu_extrapolate(state, t_move, t_render, t_det):
+    """Seconds per FULL frame from the sample's times: spot costs scale with the number of spots, the detector pass
+    already covers the whole frame; PSF tables are a one-off per depth key in the reference (cache) and are left out."""
+    scale = state["molecules"] / float(state["n"])
+    return (t_render + t_move) * scale + t_det
+
+
+def cpu_sample(args, n_threads):
+    """One step of the CPU arm (the GPU arm's `cpu_baseline` leg).  Returns (frames_per_s, detail dict)."""
+    state = cpu_setup(args, n_threads)
+    t_move, t_render, t_det = cpu_step(state, n_threads)
+    frame_s = cpu_extrapolate(state, t_move, t_render, t_det)
+    detail = dict(sample_spots=state["n"], render_s=t_render, table_build_s=state["table_build_s"],
+                  n_tables=state["n_tables"], detector_s=t_det, move_s=t_move, frame_s_extrapolated=frame_s)
     return 1.0 / frame_s, detail
 
 
@@ -353,24 +368,35 @@ def cpu_check_subprocess(args, payload_path):
 
 
 def run_reference(args):
+    """The reference arm: W untimed and EXACTLY K timed steps of the CPU port on the bounded sample (`cpu_setup`), all
+    host threads.  `ms_per_step` is the measured wall time of one sample step; `value` is the metric extrapolated from
+    the steps' times to the full workload (`cpu_extrapolate`), and says so."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     n_threads = os.cpu_count() or 1
-    for _ in range(max(args.warmup, 0) and 1):
-        cpu_sample(argparse.Namespace(**{**vars(args), "cpu_sample_spots": 32}), n_threads)
-    values, detail = [], None
     t0 = time.perf_counter()
-    for _ in range(max(1, min(args.steps, 3))):
-        v, detail = cpu_sample(args, n_threads)
-        values.append(v)
-    value = float(numpy.mean(values))
-    sample = ("{} of {} spots rendered by slice sums over per-depth 1999^2 tables + full {}^2 detector loop, "
-              "spot cost scaled linearly; PSF-table build ({:.2f} s for {} keys) excluded as one-off").format(
-                  detail["sample_spots"], args.molecules, args.size, detail["table_build_s"], detail["n_tables"])
+    state = cpu_setup(args, n_threads)
+    for _ in range(max(args.warmup, 0)):
+        cpu_step(state, n_threads)
+    times, walls = [], []
+    for _ in range(max(1, args.steps)):
+        w0 = time.perf_counter()
+        times.append(cpu_step(state, n_threads))
+        walls.append(time.perf_counter() - w0)
+    t_move, t_render, t_det = (float(numpy.mean([t[i] for t in times])) for i in range(3))
+    value = 1.0 / cpu_extrapolate(state, t_move, t_render, t_det)
+    sample = ("one step = one frame of {} of the {} spots (16 depth keys) rendered by slice sums over per-depth 1999^2 "
+              "tables + Brownian step + the full {}^2 detector loop; value = 1 / (spot seconds x {:.1f} + detector "
+              "seconds); PSF-table build ({:.2f} s for {} keys) is a one-off and not in the steps").format(
+                  state["n"], args.molecules, args.size, args.molecules / float(state["n"]), state["table_build_s"],
+                  state["n_tables"])
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / value,
+        "n_gpus": args.gpus, "steps": max(1, args.steps), "warmup": max(args.warmup, 0),
+        "ms_per_step": 1e3 * float(numpy.mean(walls)),
+        "extrapolated_ms_per_frame": 1e3 / value,
+        "step_seconds": {"brownian": t_move, "overlay": t_render, "detector": t_det},
         "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args),
         "cpu_baseline": {"value": value, "unit": "frames/s", "cores": n_threads, "kind": "port", "sample": sample},
