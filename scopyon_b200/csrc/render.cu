@@ -363,7 +363,7 @@ render_strips_kernel(Geo g, const Unit *__restrict__ units, const uint32_t *__re
 
     for (int i = lane; i < ROWS * kStripCols; i += 32) acc[i] = 0;
     for (int i = lane; i < kStages * kStageEntries; i += 32) ring[i] = (BoxT)0;   // rows past a unit's last are read (and dropped)
-    if (COPY == 0) {
+    if (COPY != 1) {
         if (lane == 0) {
             for (int st = 0; st < kStages; ++st) mbar_init(&bars[st], 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -372,7 +372,8 @@ render_strips_kernel(Geo g, const Unit *__restrict__ units, const uint32_t *__re
     }
     __syncwarp();
     int p_stage = 0, c_stage = 0;            // ring positions of the producer and the consumer (fast units only)
-    uint32_t c_parity = 0;
+    uint32_t c_parity = 0;                   // COPY 0: every stage completes one mbarrier phase per turn of the ring
+    uint32_t phases = 0;                     // COPY 2: bit s = phase of stage s's mbarrier (only its TMA units advance it)
 
     for (;;) {
         int tile = 0;
@@ -428,14 +429,20 @@ render_strips_kernel(Geo g, const Unit *__restrict__ units, const uint32_t *__re
             const uint32_t fast_mask = __ballot_sync(0xffffffffu, my_fast);
             __syncwarp();
 
+            // COPY 2 splits the units between the two engines -- even units of a batch by TMA bulk copy, odd ones by
+            // per-lane cp.async -- because neither is free: an SM retires one bulk copy per ~40-50 cycles whatever its
+            // size (tools/probes/tma_rate_probe.cu) and its issue costs ~37 instructions, while cp.async pieces cost
+            // shared-memory wavefronts the accumulators need too.
+            auto by_lanes = [&](int u) { return COPY == 1 || (COPY == 2 && (u & 1)); };
             auto stage_unit = [&](int u) {
-                if (COPY == 0) {
-                    if ((fast_mask >> u) & 1u) {          // warp uniform
-                        if (lane == u) unit_stage(my_src, my_bytes, ring + p_stage * kStageEntries, &bars[p_stage]);
-                        if (++p_stage == kStages) p_stage = 0;
-                    }
-                } else {
-                    if ((fast_mask >> u) & 1u) {
+                if ((fast_mask >> u) & 1u) {              // warp uniform
+                    if (!by_lanes(u)) {
+                        if (lane == u) {
+                            // the stage was last written by another lane's cp.async pieces (generic proxy)
+                            if (COPY == 2) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                            unit_stage(my_src, my_bytes, ring + p_stage * kStageEntries, &bars[p_stage]);
+                        }
+                    } else {
                         const char *src;
                         uint32_t bytes;
                         if constexpr (sizeof(BoxT) == 4) {     // the fetch moved the pointer behind the unpacked words
@@ -447,10 +454,10 @@ render_strips_kernel(Geo g, const Unit *__restrict__ units, const uint32_t *__re
                         bytes = (meta[u].shape & 0xffu) * row_bytes;
                         char *dst = reinterpret_cast<char *>(ring + p_stage * kStageEntries);
                         for (uint32_t off = lane * 16u; off < bytes; off += 512u) cp_async16(dst + off, src + off);
-                        if (++p_stage == kStages) p_stage = 0;
                     }
-                    cp_async_commit();                     // one group per unit, empty for gather units
+                    if (++p_stage == kStages) p_stage = 0;
                 }
+                if (COPY != 0) cp_async_commit();          // one group per unit, empty for TMA and gather units
             };
             for (int u = 0; u < min(nb, kStages - 1); ++u) stage_unit(u);
             for (int u = 0; u < nb; ++u) {
@@ -459,8 +466,13 @@ render_strips_kernel(Geo g, const Unit *__restrict__ units, const uint32_t *__re
                 __syncwarp();
                 if (u + kStages - 1 < nb) stage_unit(u + kStages - 1);
                 if ((fast_mask >> u) & 1u) {
-                    if (COPY == 0) {
-                        mbar_wait(&bars[c_stage], c_parity);
+                    if (!by_lanes(u)) {
+                        if (COPY == 2) {
+                            mbar_wait(&bars[c_stage], (phases >> c_stage) & 1u);
+                            phases ^= 1u << c_stage;
+                        } else {
+                            mbar_wait(&bars[c_stage], c_parity);
+                        }
                     } else {
                         // groups committed after unit u's: min(nb - 1 - u, 2)
                         const int ahead = min(nb - 1 - u, kStages - 1);
@@ -475,7 +487,7 @@ render_strips_kernel(Geo g, const Unit *__restrict__ units, const uint32_t *__re
                     unit_accumulate_gather<BoxT, ROWS>(meta, u, lane, acc, edges, scale);
                 }
             }
-            if (COPY == 1) cp_async_wait<0>();             // gather units at the end of a batch leave empty groups behind
+            if (COPY != 0) cp_async_wait<0>();             // TMA and gather units at the end of a batch leave empty groups behind
         }
 
         // ---- write the strip (coalesced rows) and clear the accumulators for the next one
@@ -555,10 +567,11 @@ struct RenderVariant {
 static RenderVariant render_variant() {      // read at every call (a few getenv): tests flip the variables between calls
     RenderVariant r = {kDefaultRows, kDefaultCopy, 0};
     if (const char *e = getenv("SCB_RENDER_ROWS")) r.rows = atoi(e) == 16 ? 16 : (atoi(e) == 8 ? 8 : r.rows);
-    if (const char *e = getenv("SCB_RENDER_COPY")) r.copy = e[0] == 'l' ? 1 : (e[0] == 't' ? 0 : r.copy);
+    if (const char *e = getenv("SCB_RENDER_COPY")) r.copy = e[0] == 'l' ? 1 : (e[0] == 'm' ? 2 : (e[0] == 't' ? 0 : r.copy));
     if (const char *e = getenv("SCB_RENDER_PATH"))
         r.reg = !strcmp(e, "tile") ? 3 : (e[0] == 't' ? 2 : (e[0] == 'l' ? 1 : 0));
     if (r.rows != 8 || r.copy != 0) r.reg = 0;        // strip shape and copy engine belong to the shared-memory kernel
+    if (r.rows != 8 && r.copy == 2) r.copy = 0;
     return r;
 }
 
@@ -725,11 +738,12 @@ static int launch_render(const Geo &g, const Workspace &w, int64_t n_spots, OutT
         if (g.tile_h == 16)
             return v.copy ? launch_render_slots<OutT, float, 16, 1>(g, w, n_spots, out, accumulate, s)
                           : launch_render_slots<OutT, float, 16, 0>(g, w, n_spots, out, accumulate, s);
+        if (v.copy == 2) return launch_render_slots<OutT, float, 8, 2>(g, w, n_spots, out, accumulate, s);
         return v.copy ? launch_render_slots<OutT, float, 8, 1>(g, w, n_spots, out, accumulate, s)
                       : launch_render_slots<OutT, float, 8, 0>(g, w, n_spots, out, accumulate, s);
     }
-    return v.copy ? launch_render_slots<OutT, double, 8, 1>(g, w, n_spots, out, accumulate, s)
-                  : launch_render_slots<OutT, double, 8, 0>(g, w, n_spots, out, accumulate, s);
+    return v.copy == 1 ? launch_render_slots<OutT, double, 8, 1>(g, w, n_spots, out, accumulate, s)
+                       : launch_render_slots<OutT, double, 8, 0>(g, w, n_spots, out, accumulate, s);
 }
 
 static int render_expected_strided(const scb_geometry *geom, int64_t n_spots, int frames, int64_t stride,
