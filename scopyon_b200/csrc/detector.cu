@@ -9,7 +9,8 @@
 // frame's noise does not depend on which GPU or launch produced it.
 //
 // Samplers (statistical parity, see tests/test_detector_gpu.py):
-//   Poisson(E)   E < 12: inversion by sequential search;  E >= 12: PTRS (Hoermann 1993)
+//   Poisson(E)   E < 12: inversion by sequential search;  E >= 12: PTRS (Hoermann 1993), its first trial in
+//                fp32 where the pixel is streamed (poisson_quick), the rest in the second pass
 //   EMCCD        n ~ Poisson(E);  S = rint(g * Gamma(n, 1)), redrawn while outside the
 //                reference's support [g*int(E-sigma)+, g*int(E+sigma)), sigma = 5 sqrt(E) + 10
 //                (the reference pmf is exactly this Poisson->Gamma mixture evaluated at
@@ -226,6 +227,81 @@ __device__ __forceinline__ double poisson_any(double lambda, uint32_t r, PixelRn
     return poisson_ptrs(lambda, rng);
 }
 
+// ---- bright pixels (12 <= E < kQuickLambda) without the second pass --------------------------------
+// The FIRST trial of PTRS is made in fp32 on the pixel's shot word where it is drawn: U from the word's top 24 bits
+// (as the inversion sampler uses them), the top 8 bits of V from its low 8.  The squeeze `us >= 0.07 && V <= vr`
+// accepts 86-92 % of the trials, and it can be decided from V's top bits alone whenever the whole interval they leave
+// lies below vr (and, for E < 256, from a conservative fp32 estimate of the exact acceptance bound when the squeeze
+// does not hold): then the count is final and the pixel never reaches the worklist.  Otherwise the second pass
+// CONTINUES that trial -- the same U and V, their remaining bits drawn from the pixel's overflow stream, the full
+// acceptance test in fp64 -- and goes on with fresh trials if it fails, so the sampler as a whole is PTRS with
+// nothing skipped or drawn twice.  Every operation is an explicit round-to-nearest intrinsic: the streaming kernel
+// and the generic kernel must reach the same decision and the same count.
+constexpr float kQuickLambda = 2048.0f;     // above it fp32 cannot place floor() reliably: second pass as before
+constexpr float kQuickFullTest = 256.0f;    // below it the exact acceptance test is estimated in fp32 as well
+__device__ __forceinline__ float __logf_rn(float x) { return logf(x); }   // (named like the pinned arithmetic around it)
+struct PtrsShape {
+    float b, a2, vr;        // b, 2 a, vr of Hoermann's algorithm for this lambda
+};
+__device__ __forceinline__ PtrsShape ptrs_shape(float lambda) {
+    PtrsShape s;
+    s.b = __fmaf_rn(2.53f, __fsqrt_rn(lambda), 0.931f);
+    s.a2 = __fmul_rn(2.0f, __fmaf_rn(0.02483f, s.b, -0.059f));
+    s.vr = __fsub_rn(0.9277f, __fdiv_rn(3.6224f, __fsub_rn(s.b, 2.0f)));
+    return s;
+}
+__device__ __forceinline__ bool poisson_quick(float lambda, uint32_t r, float &k) {
+    if (!(lambda >= kSmallLambda && lambda < kQuickLambda)) return false;
+    const PtrsShape s = ptrs_shape(lambda);
+    const float U = __fmaf_rn((float)(r >> 8) + 0.5f, 5.9604644775390625e-08f, -0.5f);     // centre of the 2^-24 cell
+    const float us = __fsub_rn(0.5f, fabsf(U));
+    const float v_top = (float)((r & 0xffu) + 1u) * 0.00390625f;                         // upper end of V's 2^-8 cell
+    k = floorf(__fadd_rn(__fmaf_rn(__fadd_rn(__fdiv_rn(s.a2, us), s.b), U, lambda), 0.43f));
+    if (us >= 0.07f && v_top <= s.vr) return true;
+    // Not in the squeeze.  For moderate lambda the exact test V <= T(k, us) is decided here as well when V's whole
+    // cell lies below an fp32 estimate of T taken 0.4 % low (the exponent below is good to ~1e-3 for lambda < 256);
+    // a cell that straddles T, a trial that fails and everything brighter go to the second pass, which evaluates
+    // the same trial in fp64.
+    if (!(lambda < kQuickFullTest) || k < 0.0f || us < 0.013f) return false;
+    const float a = __fmul_rn(0.5f, s.a2);
+    const float invalpha = __fadd_rn(1.1239f, __fdiv_rn(1.1328f, __fsub_rn(s.b, 3.4f)));
+    const float lhs = __fsub_rn(__logf_rn(invalpha), __logf_rn(__fadd_rn(__fdiv_rn(a, __fmul_rn(us, us)), s.b)));
+    const float rhs = __fsub_rn(__fmaf_rn(k, __logf_rn(lambda), -lambda), lgammaf(__fadd_rn(k, 1.0f)));
+    // accept iff log V + lhs <= rhs, i.e. V <= exp(rhs - lhs)
+    const float t_low = __fmul_rn(expf(__fsub_rn(rhs, lhs)), 0.996f);
+    return v_top <= t_low;
+}
+// Second pass for a pixel poisson_quick() declined: trial 1 on the same (U, V) refined by the overflow stream.
+__device__ __noinline__ double poisson_after_quick(double lambda, uint32_t r, PixelRng &rng) {
+    const double slam = sqrt(lambda);
+    const double b = 0.931 + 2.53 * slam;
+    const double a = -0.059 + 0.02483 * b;
+    const double invalpha = 1.1239 + 1.1328 / (b - 3.4);
+    const double vr = 0.9277 - 3.6224 / (b - 2.0);
+    const double loglam = log(lambda);
+    for (int trial = 0; trial < 1000; ++trial) {
+        double U, V;
+        if (trial == 0) {       // the cell of the first trial, position inside it from 32 + 32 fresh bits
+            U = ((double)(r >> 8) + (double)u01_open_low(rng.next())) * 5.9604644775390625e-08 - 0.5;
+            V = ((double)(r & 0xffu) + (double)u01_open_low(rng.next())) * 0.00390625;
+        } else {
+            U = u01_open_low_53(rng.next(), rng.next()) - 0.5;
+            V = u01_open_low_53(rng.next(), rng.next());
+        }
+        const double us = 0.5 - fabs(U);
+        const double k = floor((2.0 * a / us + b) * U + lambda + 0.43);
+        if (us >= 0.07 && V <= vr) return k;
+        if (k < 0.0 || (us < 0.013 && V > us)) continue;
+        if (log(V) + log(invalpha) - log(a / (us * us) + b) <= -lambda + k * loglam - lgamma(k + 1.0)) return k;
+    }
+    return floor(lambda);
+}
+// the count of a CCD / CMOS pixel in the second pass
+__device__ __forceinline__ double poisson_second_pass(double lambda, uint32_t r, PixelRng &rng) {
+    if (lambda >= (double)kSmallLambda && lambda < (double)kQuickLambda) return poisson_after_quick(lambda, r, rng);
+    return poisson_any(lambda, r, rng);
+}
+
 // Gamma(shape = n integer >= 1, scale = 1).
 __device__ __noinline__ double gamma_int(double n, PixelRng &rng) {
     if (n < 6.0) {
@@ -347,7 +423,10 @@ __device__ __forceinline__ PixelOut<T> detect_pixel(const DetArgs &a, const Alia
         // (S = 0 lies inside the reference's support whenever E < 12)
         const float n_small = poisson_small(fminf(lam, kSmallLambda), r_shot);
         o.sig = (T)n_small;
-        if (valid && (!(lam < kSmallLambda) || (DET == SCB_DET_EMCCD && n_small != 0.0f)))
+        float n_quick;
+        if (DET != SCB_DET_EMCCD && poisson_quick(lam, r_shot, n_quick))
+            o.sig = (T)n_quick;                                         // bright, first PTRS trial accepted in place
+        else if (valid && (!(lam < kSmallLambda) || (DET == SCB_DET_EMCCD && n_small != 0.0f)))
             a.slow_list[atomicAdd(a.slow_count, 1u)] = (uint32_t)pix;   // finished by detector_slow_kernel
     }
     if (a.in_noise) {
@@ -552,10 +631,18 @@ detector_fast_kernel(const __grid_constant__ DetArgs launch) {
         bool slow = valid && !(l0 < kSmallLambda && l1 < kSmallLambda && l2 < kSmallLambda && l3 < kSmallLambda);
         if (DET == SCB_DET_EMCCD) slow = slow || (valid && (k0 + k1) + (k2 + k3) != 0.0f);
         if (__any_sync(0xffffffffu, slow)) {
-            const bool s0 = slow && (!(l0 < kSmallLambda) || (DET == SCB_DET_EMCCD && k0 != 0.0f));
-            const bool s1 = slow && (!(l1 < kSmallLambda) || (DET == SCB_DET_EMCCD && k1 != 0.0f));
-            const bool s2 = slow && (!(l2 < kSmallLambda) || (DET == SCB_DET_EMCCD && k2 != 0.0f));
-            const bool s3 = slow && (!(l3 < kSmallLambda) || (DET == SCB_DET_EMCCD && k3 != 0.0f));
+            bool s0 = slow && (!(l0 < kSmallLambda) || (DET == SCB_DET_EMCCD && k0 != 0.0f));
+            bool s1 = slow && (!(l1 < kSmallLambda) || (DET == SCB_DET_EMCCD && k1 != 0.0f));
+            bool s2 = slow && (!(l2 < kSmallLambda) || (DET == SCB_DET_EMCCD && k2 != 0.0f));
+            bool s3 = slow && (!(l3 < kSmallLambda) || (DET == SCB_DET_EMCCD && k3 != 0.0f));
+            if (DET != SCB_DET_EMCCD) {
+                // bright pixels: the first PTRS trial here; only the ones it leaves undecided go to the second pass
+                float kq;
+                if (s0 && poisson_quick(l0, rs.x, kq)) { k0 = kq; s0 = false; }
+                if (s1 && poisson_quick(l1, rs.y, kq)) { k1 = kq; s1 = false; }
+                if (s2 && poisson_quick(l2, rs.z, kq)) { k2 = kq; s2 = false; }
+                if (s3 && poisson_quick(l3, rs.w, kq)) { k3 = kq; s3 = false; }
+            }
             const uint32_t b0 = __ballot_sync(0xffffffffu, s0), b1 = __ballot_sync(0xffffffffu, s1),
                            b2 = __ballot_sync(0xffffffffu, s2), b3 = __ballot_sync(0xffffffffu, s3);
             uint32_t base = 0;
@@ -627,7 +714,7 @@ detector_slow_kernel(const __grid_constant__ DetArgs launch) {
         PixelRng rng(a.seed, (uint64_t)pix, a.frame);
         double sig;
         if (DET == SCB_DET_EMCCD) sig = emccd_signal((double)ex, a.det.emgain, r_shot, rng);
-        else sig = poisson_any((double)ex, r_shot, rng);
+        else sig = poisson_second_pass((double)ex, r_shot, rng);
         T noi = (T)0;
         if (a.in_noise) {
             noi = ((const T *)a.in_noise)[pix];

@@ -79,9 +79,11 @@ default:
     assert numpy.array_equal(off, again.offset.cpu().numpy())               # same rng seed -> same map
 
 
-@pytest.mark.parametrize("lam", [0.0092, 0.7, 5.0, 11.9, 12.1, 80.0, 2500.0])
+@pytest.mark.parametrize("lam", [0.0092, 0.7, 5.0, 11.9, 12.1, 30.0, 80.0, 600.0, 2040.0, 2500.0])
 def test_poisson_shot_noise(lam):
-    """CCD/CMOS signal ~ Poisson(E) (_epifm.py:352,432): moments + KS on 49 152 pixels."""
+    """CCD/CMOS signal ~ Poisson(E) (_epifm.py:352,432): moments + KS on 49 152 pixels.  E < 12: inversion;
+    12 <= E < 2048: first PTRS trial in the streaming kernel, continued in the second pass when undecided;
+    beyond: PTRS in the second pass."""
     _, _, params, engine = gpu_engine(CCD, precision="f32")
     qe, bg = params["QE"], params["background_mean"]
     photons = torch.full((256, 192), lam / qe - bg, dtype=torch.float32, device=engine.device)
@@ -278,3 +280,31 @@ default:
     got = fast.cpu().numpy().astype(numpy.float64)
     assert abs(got - want).max() <= 4e-7 * want.max()           # a few fp32 ulps of the count
     assert got.max() == 2 ** 16 - 1 and got.min() >= 0 and (signal > 12).sum() > 500
+
+
+def test_bright_frame_poisson_on_a_million_pixels():
+    """A frame in which every pixel is bright (the first PTRS trial is made where the pixel is streamed and
+    86-92 % of the pixels never reach the second pass): a tighter KS than test_poisson_shot_noise, on 1 048 576
+    pixels per level, and the composite sampler's mean / variance / skewness."""
+    yaml = "default:\n    detector: {type: CMOS, image_size: [1024, 1024], QE: 0.73}\n"
+    _, _, params, engine = gpu_engine(yaml, precision="f32")
+    qe, bg = params["QE"], params["background_mean"]
+    for lam in (14.0, 57.3, 431.0):
+        photons = torch.full((1024, 1024), lam / qe - bg, dtype=torch.float32, device=engine.device)
+        _, expectation, sig, _ = run_detector(engine, photons, seed=5)
+        lam_eff = float(expectation.astype(float).mean())
+        n = sig.size
+        assert (sig == numpy.rint(sig)).all() and sig.min() >= 0
+        assert abs(sig.mean() - lam_eff) < 5 * numpy.sqrt(lam_eff / n)
+        assert abs(sig.var() / lam_eff - 1) < 5 * numpy.sqrt(2.0 / n) + 3 / (lam_eff * n) ** 0.5
+        skew = ((sig - sig.mean()) ** 3).mean() / sig.std() ** 3
+        assert abs(skew - lam_eff ** -0.5) < 5 * numpy.sqrt(6.0 / n)
+        ks = numpy.arange(0, int(sig.max()) + 2)
+        ecdf = numpy.searchsorted(numpy.sort(sig.ravel()), ks, side="right") / n
+        assert abs(ecdf - scipy.stats.poisson.cdf(ks, lam_eff)).max() < 1.63 / numpy.sqrt(n)   # alpha = 0.01
+        # the production path gives the same counts as the generic kernel that returned `sig`
+        fast = torch.empty_like(photons)
+        generic, _, _, _ = run_detector(engine, photons, seed=5)
+        engine.detect(photons, 0, 5, adc=fast)
+        torch.cuda.synchronize()
+        assert numpy.array_equal(fast.cpu().numpy(), generic)
