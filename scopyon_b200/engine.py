@@ -846,10 +846,12 @@ class DeviceEngine:
             return None
         slots_dev = None
         if states is not None:
+            slots_dev = []          # per frame: the frames of a movie usually share their ids (one cached device copy)
             for snapshot in frames:
-                order, rounds, slots_dev, _ = self._molecule_slots(states.ids, self._ids_of([snapshot]))
+                order, rounds, slots, _ = self._molecule_slots(states.ids, self._ids_of([snapshot]))
                 if order is not None or len(rounds) != 1:
                     return None
+                slots_dev.append(slots)
         payloads = [self._lazy_plane() for _ in range(nb)]
         if any(p is None for p in payloads):
             self._lazy_pool["free"].extend(p for p in payloads if p is not None)
@@ -931,7 +933,7 @@ class DeviceEngine:
         for k, (unit_time, _) in enumerate(frames):
             self._call(
                 "scb_emit_bleach_rows", states.seed if states is not None else 0, n, _native.ptr(rows[k]),
-                None if slots_dev is None else _native.ptr(slots_dev), float(unit_time), float(focal[0]),
+                None if slots_dev is None else _native.ptr(slots_dev[k]), float(unit_time), float(focal[0]),
                 ctypes.byref(self.phys), None if states is None else _native.ptr(states.budget),
                 _native.ptr(weight[k]), None, stream)
         self._call(

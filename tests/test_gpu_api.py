@@ -305,3 +305,42 @@ default:
     for k, (a, b) in enumerate(zip(blocks, singles)):
         assert numpy.array_equal(a, b), k
     assert not numpy.array_equal(blocks[0], blocks[1]) and blocks[0].max() > 110
+
+
+def test_blocks_of_frames_with_ids_that_change_from_frame_to_frame(monkeypatch):
+    """The molecules of a movie may be listed in a different order in every snapshot (rows carry their ids):
+    each frame of a block then needs its own row -> budget-slot map, and photobleaching must follow the
+    molecule, not the row.  Block route == frame-by-frame route, bit for bit."""
+    from scopyon_b200 import engine as engine_module
+    config = scopyon_b200.DefaultConfiguration()
+    config.update("""
+default:
+    magnification: 100
+    detector: {type: CMOS, image_size: [1024, 1024], pixel_length: {value: 6.5e-6, units: m}, QE: 0.73, exposure_time: 0.033}
+    effects: {photo_bleaching: {switch: true, half_life: {value: 0.2, units: s}}}
+""")
+    pl = 6.5e-8
+    rng = numpy.random.RandomState(17)
+    n = 500
+    base = numpy.zeros((n, 5))
+    base[:, 0] = rng.uniform(-450 * pl, 450 * pl, n)
+    base[:, 1] = rng.uniform(-450 * pl, 450 * pl, n)
+    base[:, 3] = numpy.arange(n)
+    base[:, 4] = 1.0
+    inputs = []
+    for k in range(12):
+        rows = base.copy()
+        rows[:, :2] += rng.normal(0, 2e-8, (n, 2))
+        inputs.append((k * 0.033, rows[rng.permutation(n)]))
+
+    def movie(block_frames):
+        monkeypatch.setattr(engine_module, "BLOCK_FRAMES", block_frames)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            sim = scopyon_b200.create_simulator(config, rng=numpy.random.RandomState(8))
+            return [img.as_array(numpy.float32).copy() for img in sim.generate_images(inputs, num_frames=11)]
+
+    blocks, singles = movie(8), movie(1)
+    for k, (a, b) in enumerate(zip(blocks, singles)):
+        assert numpy.array_equal(a, b), k
+    assert blocks[10].mean() < blocks[0].mean()          # the molecules bleach
