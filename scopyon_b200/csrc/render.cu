@@ -285,11 +285,29 @@ __device__ __forceinline__ void unit_accumulate_fast(const Unit *meta, int u, in
 // Gather unit: per-edge table offsets from `edges`, corners straight from global memory.  Neighbouring
 // lanes share a column edge (the right corners of lane l are the left corners of lane l + 1), so a lane
 // fetches its left corners only and takes the right ones from its neighbour by shuffle; the last active
-// lane fetches both.
+// lane fetches both.  The kernel is latency bound on this path (ncu at 66.39 nm pixels: 24 long-scoreboard stall
+// cycles per issued instruction, DRAM a third busy), so the loads are arranged in two dependent levels per unit
+// whatever its height: all edge offsets first (column edges by every lane, the unit's <= ROWS + 1 row edges by the
+// first lanes), then every corner of the unit at once.
+struct GatherEdges {
+    uint32_t left, right, my_row;
+};
+// level 1 of a gather unit: its edge offsets (column edges by every lane, row edge `lane` by the first lanes)
+__device__ __forceinline__ GatherEdges gather_edges(const Unit *meta, int u, int lane, const uint32_t *__restrict__ edges) {
+    const uint32_t shape = meta[u].shape;
+    const int n_rows = shape & 0xff, n_cols = (shape >> 8) & 0xff;
+    const uint32_t c = meta[u].ecol + (uint32_t)min(lane, n_cols - 1);   // idle lanes repeat the last column
+    GatherEdges e;
+    e.left = __ldg(edges + c);
+    e.right = __ldg(edges + c + 1);
+    e.my_row = __ldg(edges + meta[u].erow + (uint32_t)min(lane, n_rows));
+    return e;
+}
+
 template <typename BoxT, int ROWS>
 __device__ __forceinline__ void unit_accumulate_gather(const Unit *meta, int u, int lane,
-                                                       typename Mode<BoxT, ROWS>::Acc *acc,
-                                                       const uint32_t *__restrict__ edges, double scale) {
+                                                       typename Mode<BoxT, ROWS>::Acc *acc, const GatherEdges e,
+                                                       double scale) {
     using M = Mode<BoxT, ROWS>;
     BoxT ws;
     if constexpr (sizeof(BoxT) == 4) ws = *reinterpret_cast<const float *>(&meta[u].ws);   // scaled at fetch time
@@ -299,31 +317,31 @@ __device__ __forceinline__ void unit_accumulate_gather(const Unit *meta, int u, 
     const int rows = lane < n_cols ? n_rows : 0;
     typename M::Acc *a = acc + ((shape >> 16) & 0xff) * M::kCols + (shape >> 24) + lane;
     const long long *table = static_cast<const long long *>(meta[u].src);
-    const uint32_t c = meta[u].ecol + (uint32_t)min(lane, n_cols - 1);   // idle lanes repeat the last column
-    const uint32_t left = __ldg(edges + c), right = __ldg(edges + c + 1);
+    const uint32_t left = e.left, right = e.right;
     const bool last_lane = lane == n_cols - 1 || lane == 31;
-    const uint32_t erow = meta[u].erow;
-#pragma unroll 1
-    for (int r0 = 0; r0 < n_rows; r0 += 4) {                  // warp uniform; edges r0 .. r0 + 4
-        const uint32_t my_row = __ldg(edges + erow + (uint32_t)min(r0 + min(lane, 4), n_rows));
-        long long L[5], R[5];
+    // level 2: the corners on every row edge of the unit (edges past the unit's last repeat it: their rows are dropped)
+    long long L[ROWS + 1], own_right[ROWS + 1];
 #pragma unroll
-        for (int k = 0; k < 5; ++k) {
-            const uint32_t row = __shfl_sync(0xffffffffu, my_row, k);
-            L[k] = 0;
-            long long own_right = 0;
-            if (r0 + k <= n_rows) {                            // warp uniform
-                if (!((row | left) & kEdgeZero)) L[k] = __ldg(table + (row + left));
-                if (last_lane && !((row | right) & kEdgeZero)) own_right = __ldg(table + (row + right));
-            }
-            const long long from_neighbour = __shfl_down_sync(0xffffffffu, L[k], 1);
-            R[k] = last_lane ? own_right : from_neighbour;
+    for (int k = 0; k <= ROWS; ++k) {
+        const uint32_t row = __shfl_sync(0xffffffffu, e.my_row, k);
+        L[k] = 0;
+        own_right[k] = 0;
+        if (k <= n_rows) {                                     // warp uniform
+            if (!((row | left) & kEdgeZero)) L[k] = __ldg(table + (row + left));
+            if (last_lane && !((row | right) & kEdgeZero)) own_right[k] = __ldg(table + (row + right));
         }
-        BoxT box[4];
+    }
+    long long before = 0;
 #pragma unroll
-        for (int k = 0; k < 4; ++k)    // >= 0: the table is non-negative, edges are monotone; rounded as the box table is
-            box[k] = (BoxT)((R[k + 1] - L[k + 1]) - (R[k] - L[k]));
-        rows4_add<typename M::Acc, BoxT, M::kCols>(a + r0 * M::kCols, rows - r0, ws, box);
+    for (int k = 0; k <= ROWS; ++k) {
+        const long long from_neighbour = __shfl_down_sync(0xffffffffu, L[k], 1);
+        const long long here = (last_lane ? own_right[k] : from_neighbour) - L[k];
+        if (k > 0) {
+            // >= 0: the table is non-negative, edges are monotone; rounded as the box table is
+            const auto q = to_fixed((BoxT)(here - before), ws);
+            if (k - 1 < rows) a[(k - 1) * M::kCols] += q;
+        }
+        before = here;
     }
 }
 
@@ -484,7 +502,9 @@ render_strips_kernel(Geo g, const Unit *__restrict__ units, const uint32_t *__re
                     unit_accumulate_fast<BoxT, ROWS, SLOTS>(meta, u, lane, acc, ring + c_stage * kStageEntries, slots, scale);
                     if (++c_stage == kStages) { c_stage = 0; c_parity ^= 1u; }
                 } else {
-                    unit_accumulate_gather<BoxT, ROWS>(meta, u, lane, acc, edges, scale);
+                    // (requesting the next gather unit's edge offsets before this unit's corners was measured: no
+                    // gain at 66.39 nm, and the registers it holds cost the box-table path 2 %)
+                    unit_accumulate_gather<BoxT, ROWS>(meta, u, lane, acc, gather_edges(meta, u, lane, edges), scale);
                 }
             }
             if (COPY != 0) cp_async_wait<0>();             // TMA and gather units at the end of a batch leave empty groups behind
