@@ -1,7 +1,8 @@
 # Round-2 measurement pass on one B200 (run through gpurun); outputs under gpurun_out/, summaries go to profiles/.
 set -x
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3 > gpurun_out/r2f_tests.log
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3 > gpurun_out/r2f_tests.log
+timeout 300 python __graft_entry__.py --smoke > gpurun_out/r2f_smoke.log 2>&1; tail -2 gpurun_out/r2f_smoke.log
 python bench.py --steps 20 --warmup 5 > gpurun_out/r2f_bench_weak.json 2> gpurun_out/r2f_bench_weak.err
 python bench.py --scaling strong --movie-frames 10000 > gpurun_out/r2f_bench_strong.json 2> gpurun_out/r2f_bench_strong.err
 python bench.py --workload C5 > gpurun_out/r2f_bench_c5.json 2> gpurun_out/r2f_bench_c5.err
@@ -10,6 +11,6 @@ python bench.py --impl reference > gpurun_out/r2f_bench_reference.json 2> gpurun
 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2f_launches.csv python bench.py --steps 1 --warmup 1 --frames-per-step 16 --e2e-frames 8 --no-cpu-baseline > gpurun_out/r2f_launches.log 2>&1
 # full metrics of the four main kernels of the second 16-frame block
 ncu --set full --clock-control none --import-source on -k regex:'render_strips|detector_fast|strip_fill|spot_prepare' -s 4 -c 4 -f -o gpurun_out/r2f_block python bench.py --resident-only --steps 2 --warmup 1 --frames-per-step 16 > gpurun_out/r2f_block.log 2>&1
-python tools/microbench.py detector diffuse render > gpurun_out/r2f_microbench.jsonl 2>&1
+timeout 600 python tools/microbench.py detector diffuse render pitch > gpurun_out/r2f_microbench.jsonl 2>&1
 python tools/config_timings.py > gpurun_out/r2f_config_timings.jsonl 2>&1
 cat gpurun_out/r2f_tests.log gpurun_out/r2f_config_timings.jsonl
