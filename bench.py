@@ -723,7 +723,7 @@ def run_weak(args):
             "dtype": "f32 box tables and frames, 32-bit fixed-point accumulation per strip (edge arithmetic f64)",
             "data": "synthetic", "config": workload_config(args),
             "clocks": clocks, "e2e": e2e,
-            # per block of sixteen frames: movie_frames, spot_prepare, spot_edges, tile_scan, strip_fill,
+            # per launch group (frames_per_launch frames): movie_frames, spot_prepare, spot_edges, tile_scan, strip_fill,
             # render_strips, detector_fast, detector_slow
             "gpu_launches": int(8 * render_launches),
             "roofline": {
