@@ -63,12 +63,14 @@ constexpr int kFastSlots = 32;        // widest box-table block row the ring hol
 constexpr int kDefaultRows = 8;       // fp32 strip shape and copy engine unless the environment says otherwise
 constexpr int kDefaultCopy = 0;
 constexpr int kStages = 3;            // ring depth: the copy of unit u + 2 is issued while unit u is consumed
-template <typename BoxT, int ROWS> constexpr size_t warp_smem_bytes() {
-    return 4096 + kStages * ROWS * kFastSlots * sizeof(BoxT) + batch_units<ROWS>() * 32 + 32;
+// COPY 3 = a scene without box tables (every footprint gathers SAT corners): no ring, hence more warps per SM
+constexpr int kCopyNone = 3;
+template <typename BoxT, int ROWS, int COPY = 0> constexpr size_t warp_smem_bytes() {
+    return 4096 + (COPY == kCopyNone ? 0 : kStages * ROWS * kFastSlots * sizeof(BoxT)) + batch_units<ROWS>() * 32 + 32;
 }
 // CTAs per SM from the shared memory one warp needs (accumulators + ring + unit batch)
-template <typename BoxT, int ROWS> constexpr int ctas_per_sm() {
-    constexpr int fit = (int)(232448 / (kMaxWarps * warp_smem_bytes<BoxT, ROWS>() + 1024));
+template <typename BoxT, int ROWS, int COPY = 0> constexpr int ctas_per_sm() {
+    constexpr int fit = (int)(232448 / (kMaxWarps * warp_smem_bytes<BoxT, ROWS, COPY>() + 1024));
     return fit > 4 ? 4 : fit;
 }
 constexpr uint32_t kUnitFast = 0x80000000u;
@@ -357,7 +359,7 @@ static_assert(ctas_per_sm<double, 8>() * (kMaxWarps * warp_smem_bytes<double, 8>
 // COPY: 0 = TMA bulk copy per unit (issued by the lane that fetched the unit, completion on an mbarrier),
 //       1 = per-lane cp.async pieces (completion by cp.async group).
 template <typename OutT, typename BoxT, int ROWS, int SLOTS, int COPY>
-__global__ void __launch_bounds__(kMaxWarps * 32, ctas_per_sm<BoxT, ROWS>())
+__global__ void __launch_bounds__(kMaxWarps * 32, ctas_per_sm<BoxT, ROWS, COPY>())
 render_strips_kernel(Geo g, const Unit *__restrict__ units, const uint32_t *__restrict__ edges,
                      const int *__restrict__ tile_start, int *__restrict__ next_tile,
                      const unsigned long long *__restrict__ wmax_bits, int64_t n_spots,
@@ -372,10 +374,11 @@ render_strips_kernel(Geo g, const Unit *__restrict__ units, const uint32_t *__re
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // per-warp carve: accumulators | copy ring | unit batch | mbarriers
-    unsigned char *mine = smem_raw + warp * warp_smem_bytes<BoxT, ROWS>();
+    unsigned char *mine = smem_raw + warp * warp_smem_bytes<BoxT, ROWS, COPY>();
     Acc *acc = reinterpret_cast<Acc *>(mine);
     BoxT *ring = reinterpret_cast<BoxT *>(mine + kAccBytes);
-    Unit *meta = reinterpret_cast<Unit *>(mine + kAccBytes + kStages * kStageEntries * sizeof(BoxT));
+    constexpr size_t kRingBytes = COPY == kCopyNone ? 0 : kStages * kStageEntries * sizeof(BoxT);
+    Unit *meta = reinterpret_cast<Unit *>(mine + kAccBytes + kRingBytes);
     unsigned long long *bars = reinterpret_cast<unsigned long long *>(meta + kBatch);
 
     const int frame_tiles = g.nti * g.ntj, n_tiles = g.frames * frame_tiles;
@@ -384,8 +387,9 @@ render_strips_kernel(Geo g, const Unit *__restrict__ units, const uint32_t *__re
     const int64_t frame_spots = g.frames > 1 ? g.spots_per_frame : n_spots;
 
     for (int i = lane; i < ROWS * kStripCols; i += 32) acc[i] = 0;
-    for (int i = lane; i < kStages * kStageEntries; i += 32) ring[i] = (BoxT)0;   // rows past a unit's last are read (and dropped)
-    if (COPY != 1) {
+    if (COPY != kCopyNone)
+        for (int i = lane; i < kStages * kStageEntries; i += 32) ring[i] = (BoxT)0;   // rows past a unit's last are read (and dropped)
+    if (COPY != 1 && COPY != kCopyNone) {
         if (lane == 0) {
             for (int st = 0; st < kStages; ++st) mbar_init(&bars[st], 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -448,7 +452,7 @@ render_strips_kernel(Geo g, const Unit *__restrict__ units, const uint32_t *__re
                 dst[0] = head;
                 dst[1] = tail;
             }
-            const uint32_t fast_mask = __ballot_sync(0xffffffffu, my_fast);
+            const uint32_t fast_mask = COPY == kCopyNone ? 0u : __ballot_sync(0xffffffffu, my_fast);
             __syncwarp();
 
             // COPY 2 splits the units between the two engines -- even units of a batch by TMA bulk copy, odd ones by
@@ -479,7 +483,7 @@ render_strips_kernel(Geo g, const Unit *__restrict__ units, const uint32_t *__re
                     }
                     if (++p_stage == kStages) p_stage = 0;
                 }
-                if (COPY != 0) cp_async_commit();          // one group per unit, empty for TMA and gather units
+                if (COPY != 0 && COPY != kCopyNone) cp_async_commit();          // one group per unit, empty for TMA and gather units
             };
             for (int u = 0; u < min(nb, kStages - 1); ++u) stage_unit(u);
             for (int u = 0; u < nb; ++u) {
@@ -511,7 +515,7 @@ render_strips_kernel(Geo g, const Unit *__restrict__ units, const uint32_t *__re
                     unit_accumulate_gather<BoxT, ROWS>(meta, u, lane, acc, gather_edges(meta, u, lane, edges), scale);
                 }
             }
-            if (COPY != 0) cp_async_wait<0>();             // TMA and gather units at the end of a batch leave empty groups behind
+            if (COPY != 0 && COPY != kCopyNone) cp_async_wait<0>();     // TMA and gather units at the end of a batch leave empty groups behind
         }
 
         // ---- write the strip (coalesced rows) and clear the accumulators for the next one
@@ -648,12 +652,12 @@ static int launch_render_as(const Geo &g, const Workspace &w, int64_t n_spots, O
     const int n_tiles = g.frames * g.nti * g.ntj;
     // persistent grid: a few CTAs per SM, each warp pulls strips from a queue; small images get
     // narrower CTAs so that the strips still spread over all SMs
-    const int slots = ctas_per_sm<BoxT, ROWS>() * SCB_SM_COUNT;
+    const int slots = ctas_per_sm<BoxT, ROWS, COPY>() * SCB_SM_COUNT;
     int warps = (n_tiles + slots - 1) / slots;
     warps = warps < 1 ? 1 : (warps > kMaxWarps ? kMaxWarps : warps);
     int ctas = (n_tiles + warps - 1) / warps;
     if (ctas > slots) ctas = slots;
-    const size_t smem = (size_t)warps * warp_smem_bytes<BoxT, ROWS>();
+    const size_t smem = (size_t)warps * warp_smem_bytes<BoxT, ROWS, COPY>();
     // the attribute is per device: remembered per template instance and device ordinal
     static std::atomic<unsigned long long> configured{0};
     int dev = 0;
@@ -662,7 +666,7 @@ static int launch_render_as(const Geo &g, const Workspace &w, int64_t n_spots, O
     if (!(configured.load(std::memory_order_acquire) & bit)) {
         SCB_CUDA(cudaFuncSetAttribute(render_strips_kernel<OutT, BoxT, ROWS, SLOTS, COPY>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)(kMaxWarps * warp_smem_bytes<BoxT, ROWS>())));
+                                      (int)(kMaxWarps * warp_smem_bytes<BoxT, ROWS, COPY>())));
         configured.fetch_or(bit, std::memory_order_release);
     }
     render_strips_kernel<OutT, BoxT, ROWS, SLOTS, COPY><<<ctas, warps * 32, smem, s>>>(
@@ -758,6 +762,11 @@ template <typename OutT>
 static int launch_render(const Geo &g, const Workspace &w, int64_t n_spots, OutT *out, int accumulate, int box_type,
                          cudaStream_t s) {
     const RenderVariant v = render_variant();
+    // no footprint can take the box-table path (no table, or the test hook): the instance without a copy ring
+    if (!g.quick_runs && g.tile_h == 8) {
+        if (box_type == SCB_F32) return launch_render_as<OutT, float, 8, 0, kCopyNone>(g, w, n_spots, out, accumulate, s);
+        return launch_render_as<OutT, double, 8, 0, kCopyNone>(g, w, n_spots, out, accumulate, s);
+    }
     if (box_type == SCB_F32) {
         if (g.tile_h == 16)
             return v.copy ? launch_render_slots<OutT, float, 16, 1>(g, w, n_spots, out, accumulate, s)
