@@ -136,7 +136,8 @@ spot_prepare_kernel(Geo g, int64_t n, int64_t stride, const double *__restrict__
                     const double *__restrict__ inv_scale, const int32_t *__restrict__ slot_of_key,
                     SpotRec *__restrict__ spots, int *__restrict__ tile_count,
                     unsigned long long *__restrict__ wmax_bits, int32_t *__restrict__ errors,
-                    int *__restrict__ ranks = nullptr, int rank_cap = 0, const int32_t *__restrict__ order = nullptr) {
+                    int *__restrict__ ranks = nullptr, int rank_cap = 0, const int32_t *__restrict__ order = nullptr,
+                    int *__restrict__ walk_list = nullptr, unsigned *__restrict__ walk_count = nullptr) {
     // grid: x over the spots of one frame, y over frames
     const int64_t in_frame = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int frame = blockIdx.y;
@@ -237,6 +238,18 @@ spot_prepare_kernel(Geo g, int64_t n, int64_t stride, const double *__restrict__
             }
         }
     }
+    if (walk_list) {
+        // footprints whose edges must be walked (spot_edges_kernel) are listed, one atomic per warp: with box
+        // tables they are rare, and the edge kernel then reads a short list instead of every spot record
+        const unsigned walks = __ballot_sync(0xffffffffu, counted && rec.walk != 0);
+        if (walks) {
+            const unsigned lane = threadIdx.x & 31u;
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(walk_count, (unsigned)__popc(walks));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if ((walks >> lane) & 1u) walk_list[base + __popc(walks & ((1u << lane) - 1u))] = (int)s;
+        }
+    }
     if (wmax_bits) {
         // largest weight of the frame: positive doubles order like their bit patterns, so an integer max
         // is exact and order free; one atomic per warp
@@ -261,12 +274,8 @@ spot_prepare_kernel(Geo g, int64_t n, int64_t stride, const double *__restrict__
 // special_edges == 0 the plain sample index is stored instead (Gaussian tensor-core path).
 constexpr uint32_t kEdgeZero = 0x80000000u;
 
-__global__ void __launch_bounds__(128)
-spot_edges_kernel(Geo g, int64_t n, SpotRec *__restrict__ spots, uint32_t *__restrict__ edges, int edge_cap) {
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t s = t >> 1;
-    const int axis = (int)(t & 1);
-    if (s >= n) return;
+__device__ __forceinline__ void spot_edges_of(const Geo &g, int64_t s, int axis, SpotRec *__restrict__ spots,
+                                              uint32_t *__restrict__ edges, int edge_cap) {
     const SpotRec rec = spots[s];
     if (rec.slot < 0 || !rec.walk) return;
     const int first = axis ? rec.jmin : rec.imin, last = axis ? rec.jmax : rec.imax;
@@ -313,6 +322,16 @@ spot_edges_kernel(Geo g, int64_t n, SpotRec *__restrict__ spots, uint32_t *__res
     }
     const int run = regular ? (run_phase | (run_slot0 + 1) << 16) : -1;
     if (axis) spots[s].col_run = run; else spots[s].row_run = run;
+}
+
+__global__ void __launch_bounds__(128)
+spot_edges_kernel(Geo g, int64_t n, SpotRec *__restrict__ spots, uint32_t *__restrict__ edges, int edge_cap,
+                  const int *__restrict__ walk_list = nullptr, const unsigned *__restrict__ walk_count = nullptr) {
+    // with a list (written by spot_prepare_kernel): a grid-stride loop over its (spot, axis) pairs; without: one
+    // thread per (spot, axis) of all spots
+    const int64_t pairs = walk_list ? 2 * (int64_t)*walk_count : 2 * n;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < pairs; t += (int64_t)gridDim.x * blockDim.x)
+        spot_edges_of(g, walk_list ? walk_list[t >> 1] : (t >> 1), (int)(t & 1), spots, edges, edge_cap);
 }
 
 // launch shape of spot_edges_kernel
@@ -436,6 +455,8 @@ struct Workspace {
     int *pair_spot;                  // list entries: spot indices (entry_bytes = 4) or render units
     int *ranks;                      // [n][rank_cap] list positions handed out by the census (render path)
     int rank_cap;
+    int *walk_list;                  // spots whose edges must be walked (render path)
+    unsigned *walk_count;            // its length (cleared with the census)
     size_t bytes;
     int64_t pair_capacity;
 };
@@ -511,14 +532,17 @@ Workspace carve(const Geo &g, int64_t n, void *base, size_t entry_bytes = sizeof
     w.tile_cursor = (int *)(p + off); off += align_up(n_tiles * g.stripes * sizeof(int));
     // per frame, so that a frame's accumulator LSBs do not depend on the frames it shares a launch with
     w.wmax_bits = (unsigned long long *)(p + off);
-    w.next_tile = (int *)(p + off + 8 * (size_t)g.frames); off += align_up(8 * (size_t)g.frames + 8);
+    w.next_tile = (int *)(p + off + 8 * (size_t)g.frames);
+    w.walk_count = (unsigned *)(p + off + 8 * (size_t)g.frames + 4); off += align_up(8 * (size_t)g.frames + 8);
     w.tile_start = (int *)(p + off); off += align_up((n_tiles * g.stripes + 1) * sizeof(int));
     w.pair_spot = (int *)(p + off); off += align_up((size_t)w.pair_capacity * entry_bytes);
     w.ranks = nullptr;
     w.rank_cap = 0;
+    w.walk_list = nullptr;
     if (with_ranks) {
         w.rank_cap = tiles_per_spot_bound(g);
         w.ranks = (int *)(p + off); off += align_up((size_t)(n > 0 ? n : 1) * w.rank_cap * sizeof(int));
+        w.walk_list = (int *)(p + off); off += align_up((size_t)(n > 0 ? n : 1) * sizeof(int));
     }
     w.bytes = off;
     return w;

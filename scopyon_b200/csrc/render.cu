@@ -826,10 +826,13 @@ static int render_expected_strided(const scb_geometry *geom, int64_t n_spots, in
     if (n_spots > 0) {
         spot_prepare_kernel<<<dim3(scb_grid_for(n_spots / frames, 256), frames), 256, 0, s>>>(
             g, n_spots, stride, d_depth, d_x, d_y, d_weight, d_inv_scale, d_slot_of_key, w.spots, w.tile_count,
-            w.wmax_bits, d_errors, w.ranks, w.rank_cap, d_order);
+            w.wmax_bits, d_errors, w.ranks, w.rank_cap, d_order, w.walk_list, w.walk_count);
+        // the edge kernel walks the listed footprints only: a grid-stride loop over the list, sized for the device
         dim3 egrid, eblock;
         edges_launch_shape(w.edge_cap, n_spots, egrid, eblock);
-        spot_edges_kernel<<<egrid, eblock, 0, s>>>(g, n_spots, w.spots, w.edges, w.edge_cap);
+        const unsigned cap = (unsigned)(SCB_SM_COUNT * 16);
+        if (egrid.x > cap) egrid.x = cap;
+        spot_edges_kernel<<<egrid, eblock, 0, s>>>(g, n_spots, w.spots, w.edges, w.edge_cap, w.walk_list, w.walk_count);
     }
     tile_scan_kernel<<<kScanCtas, 1024, 0, s>>>(n_tiles, g.stripes, w.tile_count, w.tile_start);
     const bool reg_path = !tile_path && forced_gather() != 1 && reg_path_for(d_box != nullptr, box_bytes, g.slots);
