@@ -173,7 +173,7 @@ __device__ __forceinline__ void box_muller(uint32_t r0, uint32_t r1, float &n0, 
 // the last row / column, so the clamped closing edge of a footprint is simply the next slot.
 // All corners a footprint needs are then one dense (rows+1) x (cols+1) rectangle of one
 // B x B block -- contiguous B*8-byte rows that a TMA bulk copy moves as they are.  B is a
-// multiple of 16 (128-byte lines) unless that would waste more than a quarter of the table.
+// multiple of 16 (128-byte lines) unless that would waste more than a quarter of the table,
 struct SatLayout {
     int modulus, slots, side;
     __host__ __device__ long long block_entries() const { return (long long)slots * slots; }
@@ -185,8 +185,9 @@ static inline SatLayout scb_sat_layout(int n_radial, int modulus) {
     L.modulus = modulus < 1 ? 1 : modulus;
     L.side = 2 * (n_radial - 1) + 1;
     const int used = (L.side + 1 + L.modulus - 1) / L.modulus;
-    const int b16 = (used + 1 + 15) & ~15, b2 = (used + 1 + 1) & ~1;
-    L.slots = (b16 * 4 <= (used + 1) * 5) ? b16 : b2;
+    // ... else a multiple of 4: rows of fp32 box values stay multiples of 16 bytes, which every copy engine needs
+    const int b16 = (used + 1 + 15) & ~15, b4 = (used + 1 + 3) & ~3;
+    L.slots = (b16 * 4 <= (used + 1) * 5) ? b16 : b4;
     return L;
 }
 

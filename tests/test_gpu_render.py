@@ -193,7 +193,8 @@ def test_motion_blur_sums_snapshots():
 @pytest.mark.parametrize("pixel_nm, magnification", [
     (44.0, 100),      # 48 slots per phase: wider than the TMA ring -> every footprint gathers SAT corners
     (65.0, 100),      # 32 slots: the box-table / TMA path at its compile-time width
-    (100.0, 100),     # 22 slots: box-table path at run-time width (fp64 rows are 16-byte multiples, fp32 rows are not)
+    (100.0, 100),     # 24 slots: box-table path at run-time width, in fp32 too (slots are a multiple of four)
+    (130.0, 100),     # 20 slots
     (160.0, 100),     # 16 slots, 14-pixel footprints: mostly idle lanes
     (250.0, 40),      # 10 slots, 9-pixel footprints
     (66.39, 241),     # default magnification: no whole number of samples per pixel, SAT path only
@@ -239,7 +240,7 @@ default:
     (65.0, 100, True),       # 32 slots per phase
     (44.0, 100, True),       # 48 slots: wider than the shared-memory kernel's ring, the register kernels do not mind
     (160.0, 100, True),      # 16 slots, 14-pixel footprints: the copy box overhangs the block on both axes (zero fill)
-    (100.0, 100, False),     # 22 slots: fp32 rows are no multiple of 16 bytes -> shared-memory kernel whatever is asked
+    (100.0, 100, True),      # 24 slots at run-time width
 ])
 def test_register_kernels_equal_shared_memory_kernel(pixel_nm, magnification, reg_kernel):
     """fp32 mode: the register-accumulator kernels (SCB_RENDER_PATH=tensor: tensor-map TMA with zero-filled overhang;
