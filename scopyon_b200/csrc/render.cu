@@ -610,7 +610,10 @@ static int forced_gather() {
 
 // The register kernel takes every fp32 box table whose rows a tensor map can describe (strides in multiples of 16 bytes)
 static bool reg_path_for(bool have_box, int box_bytes, int slots) {
-    return render_variant().reg != 0 && have_box && box_bytes == 4 && slots % 4 == 0 && slots <= 1000;
+    if (!(have_box && box_bytes == 4 && slots % 4 == 0 && slots <= 1000)) return false;
+    // asked for, or the only kernels that can: block rows wider than the shared-memory kernel's ring (small pixels,
+    // e.g. 50 nm: 48 slots) would otherwise send every footprint down the SAT-corner gather
+    return render_variant().reg != 0 || slots > kFastSlots;
 }
 
 static Geo strip_geo(const scb_geometry *geom, bool have_box, int box_bytes, int frames = 1, int64_t spots_per_frame = 0) {

@@ -152,8 +152,8 @@ def bench_pitch():
     108.33 nm (x60 on 6.5 um) gather SAT corners.  SCB_GATHER_* select the measured gather variants."""
     from bench import count_spot_pixel_evals
     size, n = 2048, 100000
-    for label, pixel, mag in (("65 nm", 6.5e-6, 100), ("100 nm", 6.5e-6, 65), ("66.39 nm", 16e-6, 241),
-                              ("108.33 nm", 6.5e-6, 60)):
+    for label, pixel, mag in (("65 nm", 6.5e-6, 100), ("100 nm", 6.5e-6, 65), ("50 nm", 6.5e-6, 130),
+                              ("66.39 nm", 16e-6, 241), ("108.33 nm", 6.5e-6, 60)):
         yaml = """
 default:
     magnification: %d
