@@ -826,10 +826,13 @@ class DeviceEngine:
     def block_route(self, want_full_output):
         """Whether ``generate_frames`` may hand this engine several frames at once (``begin_block``): bare ADC
         planes of large float32 frames -- the case where a movie is made of many frames of one snapshot each."""
-        return (BLOCK_FRAMES > 1 and not want_full_output and not self.gaussian_tc and self.dtype == torch.float32
-                and self.n_w * self.n_h >= HOST_WIDEN_MIN_PIXELS and not getattr(self, "_eager_float64", False)
+        if not (BLOCK_FRAMES > 1 and not want_full_output and not self.gaussian_tc and self.dtype == torch.float32
                 and (self.n_w * self.n_h) % 4 == 0
-                and (self.configs.ADConverter_fpn_type != 'column' or self.n_h % 4 == 0))
+                and (self.configs.ADConverter_fpn_type != 'column' or self.n_h % 4 == 0)):
+            return False
+        # large frames: float32 payloads (not once the caller asks for float64 arrays: those are widened by host
+        # threads frame by frame); small frames: widened on the device, float64 arrays as ever
+        return self.n_w * self.n_h < HOST_WIDEN_MIN_PIXELS or not getattr(self, "_eager_float64", False)
 
     def begin_block(self, frames, first_index, noise_seed, states, exposure_times):
         """Enqueue ``len(frames)`` consecutive frames, each ONE snapshot ``(unit_time, particles)`` of the same
@@ -852,10 +855,14 @@ class DeviceEngine:
                 if order is not None or len(rounds) != 1:
                     return None
                 slots_dev.append(slots)
-        payloads = [self._lazy_plane() for _ in range(nb)]
-        if any(p is None for p in payloads):
-            self._lazy_pool["free"].extend(p for p in payloads if p is not None)
-            return None
+        small = self.n_w * self.n_h < HOST_WIDEN_MIN_PIXELS
+        if small:
+            payloads = [self._host_plane()[0] for _ in range(nb)]       # float64 arrays, widened on the device
+        else:
+            payloads = [self._lazy_plane() for _ in range(nb)]
+            if any(p is None for p in payloads):
+                self._lazy_pool["free"].extend(p for p in payloads if p is not None)
+                return None
         with torch.cuda.device(self.device):
             main = torch.cuda.current_stream(self.device)
             self._frame_stream = ctypes.c_void_p(main.cuda_stream)
@@ -864,7 +871,8 @@ class DeviceEngine:
                     return self._begin_block(main, frames, first_index, noise_seed, states, exposure_times, n, slots_dev,
                                              payloads)
             except Exception:
-                self._lazy_pool["free"].extend(payloads)
+                if not small:
+                    self._lazy_pool["free"].extend(payloads)
                 raise
             finally:
                 self._frame_stream = None
@@ -890,7 +898,7 @@ class DeviceEngine:
                 work=torch.empty(int(need) + 256, dtype=torch.uint8, device=self.device),
                 det_work=torch.empty(BLOCK_FRAMES * self.lib.scb_detector_workspace_bytes(self.n_w, self.n_h),
                                      dtype=torch.uint8, device=self.device),
-                stage=None)
+                adc64=None, stage=None)
         if buf["free"] is not None:
             main.wait_event(buf["free"])                 # the set's previous block has left the device
         rows = buf["rows"][:nb, :n] if buf["n"] == n else None
@@ -948,6 +956,13 @@ class DeviceEngine:
             buf["det_work"].numel(), stream)
         if getattr(self, "_copy_stream", None) is None:
             self._copy_stream = torch.cuda.Stream(device=self.device)
+        lazy = payloads[0].dtype == torch.float32
+        source = adc
+        if not lazy:                # small frames leave the device as float64 (exact widening, one launch per block)
+            if buf["adc64"] is None:
+                buf["adc64"] = torch.empty((BLOCK_FRAMES, self.n_w, self.n_h), dtype=torch.float64, device=self.device)
+            source = buf["adc64"][:nb]
+            source.copy_(adc)
         with _Trace(self, "enqueue_d2h"):
             ready = torch.cuda.Event()
             ready.record(main)
@@ -955,7 +970,7 @@ class DeviceEngine:
             landed = []
             with torch.cuda.stream(self._copy_stream):
                 for k, host in enumerate(payloads):
-                    host.copy_(adc[k], non_blocking=True)
+                    host.copy_(source[k], non_blocking=True)
                     event = torch.cuda.Event()
                     event.record(self._copy_stream)
                     landed.append(event)
@@ -965,7 +980,7 @@ class DeviceEngine:
         self.errors.zero_()
         done = torch.cuda.Event()
         done.record(main)
-        return [dict(hosts=[payloads[k]], lazy=True, true=None, budget=None, states=states, done=done,
+        return [dict(hosts=[payloads[k]], lazy=lazy, true=None, budget=None, states=states, done=done,
                      errors=errors_host, planes_done=landed[k], tickets=[], exposure_time=exposure_times[k],
                      want_expectation=False) for k in range(nb)]
 
