@@ -434,6 +434,8 @@ render_strips_kernel(Geo g, const Unit *__restrict__ units, const uint32_t *__re
                 my_src = reinterpret_cast<const void *>(((unsigned long long)head.w << 32) | head.z);
                 my_bytes = (tail.z & 0xffu) * row_bytes;
                 my_fast = (tail.w & kUnitFast) != 0;
+                // (an L2 prefetch of the unit's rows here, up to a batch before its copy is issued, was measured: 4.5 %
+                // slower -- the kernel has no issue slots to spare and does not wait for memory)
                 if constexpr (sizeof(BoxT) == 4) {
                     // fp32 mode: the fetching lane forms the unit's weight in accumulator LSBs once (the same
                     // double product and conversion the 32 consumer lanes would each repeat) and, for a
