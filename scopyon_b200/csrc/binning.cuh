@@ -6,6 +6,7 @@
 #pragma once
 #include "scb_common.cuh"
 #include <cooperative_groups.h>
+#include <climits>
 
 namespace {
 
@@ -110,12 +111,13 @@ __device__ __forceinline__ int quick_run(int first, int last, double o, const Ge
     return phase | (slot0 + 1) << 16;
 }
 
-// Counter copy of a spot: one per group of 32 spots of its frame, round robin.  Counted inside the frame so
-// that the 32 lanes of a census warp (one frame, 32 consecutive in-frame indices) always share their copy,
+// Counter copy of a spot: one per group of 256 spots of its frame, round robin.  Counted inside the frame so
+// that the threads of a census CTA (one frame, 256 consecutive in-frame indices) always share their copy,
 // whatever the number of spots per frame.
+constexpr int kCensusThreads = 256;
 __device__ __forceinline__ int stripe_of(const Geo &g, int64_t spot, int frame) {
     const int64_t in_frame = g.frames > 1 ? spot - (int64_t)frame * g.spots_per_frame : spot;
-    return (int)(in_frame >> 5) & (g.stripes - 1);
+    return (int)(in_frame >> 8) & (g.stripes - 1);
 }
 
 // One thread per spot: footprint, depth key, tile census.
@@ -127,17 +129,20 @@ __device__ __forceinline__ int stripe_of(const Geo &g, int64_t spot, int frame) 
 // s of the spot list reads particle order[s], a tile-major ordering the caller refreshes now and then
 // (molecules move a pixel or so per frame) -- the spots of a warp are neighbours on the screen and share
 // most of their tiles: a tenth of the atomics.  Without it the vote finds no partners and costs little.
+constexpr int kLocalStrips = 4096;     // strip counters of a CTA's shared-memory census (a 2048 x 2048 frame has 4096 strips)
+constexpr int kLocalRanks = 16;        // strips per footprint it can hold (the rest: global atomics)
 #ifndef SCB_PREPARE_CTAS
-#define SCB_PREPARE_CTAS 6     // 40 registers, 48 warps per SM (measured: 3 % off the kernel)
+#define SCB_PREPARE_CTAS 5     // 48 registers, no spills, 40 warps per SM (6: 40 registers with spills, 1 % slower)
 #endif
-__global__ void __launch_bounds__(256, SCB_PREPARE_CTAS)
+template <int CTAS, bool LOCAL>      // CTAs per SM; LOCAL: the shared-memory census is compiled in
+__global__ void __launch_bounds__(256, CTAS)
 spot_prepare_kernel(Geo g, int64_t n, int64_t stride, const double *__restrict__ depth, const double *__restrict__ x,
                     const double *__restrict__ y, const double *__restrict__ weight,
                     const double *__restrict__ inv_scale, const int32_t *__restrict__ slot_of_key,
                     SpotRec *__restrict__ spots, int *__restrict__ tile_count,
                     unsigned long long *__restrict__ wmax_bits, int32_t *__restrict__ errors,
-                    int *__restrict__ ranks = nullptr, int rank_cap = 0, const int32_t *__restrict__ order = nullptr,
-                    int *__restrict__ walk_list = nullptr, unsigned *__restrict__ walk_count = nullptr) {
+                    int *__restrict__ ranks, int rank_cap, const int32_t *__restrict__ order,
+                    int *__restrict__ walk_list, unsigned *__restrict__ walk_count) {
     // grid: x over the spots of one frame, y over frames
     const int64_t in_frame = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int frame = blockIdx.y;
@@ -198,10 +203,74 @@ spot_prepare_kernel(Geo g, int64_t n, int64_t stride, const double *__restrict__
         }
         spots[s] = rec;
     }
-    // ---- census (whole warps: the votes need every lane)
-    {
-        // the counters exist in `stripes` copies (one per group of 32 spots, round robin) so that the
-        // atomics of a frame spread over more L2 sectors; a warp's spots share their copy
+    // ---- census, first choice: per CTA in shared memory.  The strips the CTA's 256 spots touch lie in a box of
+    // strips (a few dozen when the caller hands the spots over in screen order, a whole 2048 x 2048 frame at
+    // most); the overlaps are counted there with shared-memory atomics, whose old values are the positions inside
+    // the CTA's share of each list, and one global atomic per (CTA, touched strip) -- all of them in flight at
+    // once, nobody waits for a chain of them -- turns the shares into list positions.
+    bool census_done = false;
+    if (LOCAL && ranks != nullptr && rank_cap <= kLocalRanks) {  // CTA uniform
+        __shared__ int s_count[kLocalStrips];
+        __shared__ unsigned short s_local[kLocalRanks * kCensusThreads];
+        __shared__ int s_box[4];
+        const int tid = threadIdx.x;
+        if (tid == 0) { s_box[0] = INT_MAX; s_box[1] = -1; s_box[2] = INT_MAX; s_box[3] = -1; }
+        __syncthreads();
+        const int t0 = rec.imin / g.tile_h, t1 = (rec.imax - 1) / g.tile_h;
+        const int u0 = rec.jmin / g.tile_w, u1 = (rec.jmax - 1) / g.tile_w;
+        {
+            const int lo_i = __reduce_min_sync(0xffffffffu, counted ? t0 : INT_MAX);
+            const int hi_i = __reduce_max_sync(0xffffffffu, counted ? t1 : -1);
+            const int lo_j = __reduce_min_sync(0xffffffffu, counted ? u0 : INT_MAX);
+            const int hi_j = __reduce_max_sync(0xffffffffu, counted ? u1 : -1);
+            if ((tid & 31) == 0 && hi_i >= 0) {
+                atomicMin(&s_box[0], lo_i); atomicMax(&s_box[1], hi_i);
+                atomicMin(&s_box[2], lo_j); atomicMax(&s_box[3], hi_j);
+            }
+        }
+        __syncthreads();
+        const int bi0 = s_box[0], bi1 = s_box[1], bj0 = s_box[2], bj1 = s_box[3];
+        const int span_j = bj1 - bj0 + 1;
+        const int cells = bi1 >= bi0 ? (bi1 - bi0 + 1) * span_j : 0;
+        if (cells <= kLocalStrips) {                                // CTA uniform
+            census_done = true;
+            for (int c = tid; c < cells; c += kCensusThreads) s_count[c] = 0;
+            __syncthreads();
+            if (counted) {
+                int k = 0;
+                for (int tj = u0; tj <= u1; ++tj) {                 // the fill kernel's walk: columns of strips, rows inside
+                    const int entries = overlap_entries(g, rec.jmin, rec.jmax, tj);
+                    if (entries >= 8) atomicAdd(errors, 1);         // cannot happen: scb_render_* refuse such geometries
+                    for (int ti = t0; ti <= t1; ++ti, ++k) {
+                        const int at = atomicAdd(&s_count[(ti - bi0) * span_j + (tj - bj0)], entries);
+                        if (k < rank_cap) s_local[k * kCensusThreads + tid] = (unsigned short)at;
+                    }
+                }
+                if (k > rank_cap) atomicAdd(errors, 1);             // cannot happen: rank_cap bounds the strips of a footprint
+            }
+            __syncthreads();
+            int *count = tile_count + ((size_t)stripe_of(g, s, frame) * g.frames + frame) * g.nti * g.ntj;
+            for (int c = tid; c < cells; c += kCensusThreads) {
+                const int mine = s_count[c];
+                if (mine > 0) {
+                    const int ci = c / span_j;
+                    s_count[c] = atomicAdd(&count[(bi0 + ci) * g.ntj + bj0 + (c - ci * span_j)], mine);
+                }
+            }
+            __syncthreads();
+            if (counted) {
+                int *my_rank = ranks + (size_t)s * rank_cap;
+                int k = 0;
+                for (int tj = u0; tj <= u1; ++tj)
+                    for (int ti = t0; ti <= t1 && k < rank_cap; ++ti, ++k)
+                        my_rank[k] = s_count[(ti - bi0) * span_j + (tj - bj0)] + (int)s_local[k * kCensusThreads + tid];
+            }
+        }
+    }
+    // ---- census, otherwise (no list positions wanted, or strips spread too far): global atomics, warps vote first
+    if (!census_done) {
+        // the counters exist in `stripes` copies (one per group of 256 spots, round robin) so that the
+        // atomics of a frame spread over more L2 sectors; a CTA's spots share their copy
         int *count = tile_count + ((size_t)stripe_of(g, s, frame) * g.frames + frame) * g.nti * g.ntj;
         const int t0 = rec.imin / g.tile_h, t1 = counted ? (rec.imax - 1) / g.tile_h : t0 - 1;
         const int u0 = rec.jmin / g.tile_w, u1 = counted ? (rec.jmax - 1) / g.tile_w : u0 - 1;

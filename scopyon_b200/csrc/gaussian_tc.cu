@@ -330,8 +330,9 @@ extern "C" int scb_render_gaussian_tc(const scb_geometry *geom, int64_t n_spots,
     SCB_CUDA(cudaMemsetAsync(w.tile_count, 0, (size_t)((char *)w.tile_start - (char *)w.tile_count), s));
     if (n_spots > 0) {
         // depth plays no role for the Gaussian (depth-independent PSF): x doubles as a dummy depth
-        spot_prepare_kernel<<<scb_grid_for(n_spots, 256), 256, 0, s>>>(
-            g, n_spots, 1, nullptr, d_x, d_y, d_weight, nullptr, nullptr, w.spots, w.tile_count, nullptr, d_errors);
+        spot_prepare_kernel<SCB_PREPARE_CTAS, false><<<scb_grid_for(n_spots, 256), 256, 0, s>>>(
+            g, n_spots, 1, nullptr, d_x, d_y, d_weight, nullptr, nullptr, w.spots, w.tile_count, nullptr, d_errors,
+            nullptr, 0, nullptr, nullptr, nullptr);
         dim3 egrid, eblock;
         edges_launch_shape(w.edge_cap, n_spots, egrid, eblock);
         spot_edges_kernel<<<egrid, eblock, 0, s>>>(g, n_spots, w.spots, w.edges, w.edge_cap);

@@ -37,7 +37,7 @@
 #include <mutex>
 
 #ifndef SCB_FILL_CTAS
-#define SCB_FILL_CTAS 4        // 64 registers: 32 warps per SM for a kernel that waits on loads (2: 110 registers, 1.7 % slower)
+#define SCB_FILL_CTAS 3        // 80 registers, 24 warps per SM: the ten list positions a footprint needs are all in flight at once
 #endif
 
 namespace {
@@ -112,7 +112,8 @@ __device__ __forceinline__ int strip_shift(int n_units, unsigned long long wmax_
 
 // One thread per spot: write the spot's units into the strips' list segments, at the places the
 // census handed out (`ranks`, in the same tile order) -- no atomics here.
-__global__ void __launch_bounds__(256, SCB_FILL_CTAS)
+template <int CTAS, int kFillAhead>
+__global__ void __launch_bounds__(256, CTAS)
 strip_fill_kernel(Geo g, int64_t n, const SpotRec *__restrict__ spots, int edge_cap,
                   const int *__restrict__ ranks, int rank_cap,
                   const int64_t *__restrict__ sat, const void *__restrict__ box_table, int box_bytes,
@@ -136,35 +137,59 @@ strip_fill_kernel(Geo g, int64_t n, const SpotRec *__restrict__ spots, int edge_
     const int stripe = stripe_of(g, s, rec.frame);
     const int frame_tile0 = rec.frame * g.nti * g.ntj;     // first strip of the spot's frame
     const int *my_rank = ranks + (size_t)s * rank_cap;
-    int visited = 0;
     const int t0 = rec.imin / g.tile_h, t1 = (rec.imax - 1) / g.tile_h;
     const int u0 = rec.jmin / g.tile_w, u1 = (rec.jmax - 1) / g.tile_w;
-    for (int tj = u0; tj <= u1; ++tj) {
-        const int c_lo = max(rec.jmin, tj * g.tile_w), c_hi = min(rec.jmax, (tj + 1) * g.tile_w);
-        const int entries = (c_hi - c_lo + g.chunk - 1) / g.chunk;
-        for (int ti = t0; ti <= t1; ++ti) {
-            const int r_lo = max(rec.imin, ti * g.tile_h), r_hi = min(rec.imax, (ti + 1) * g.tile_h);
-            const int tile = frame_tile0 + ti * g.ntj + tj;
-            Unit *dst = units + tile_start[tile * g.stripes + stripe] + __ldg(my_rank + visited);
-            ++visited;
-            const int rows = r_hi - r_lo;
-            u.erow = ebase + (uint32_t)(r_lo - rec.imin);
-            const int first_box_row = row_slot0 + (r_lo - rec.imin) + 1;
-            for (int q = 0; q < entries; ++q) {
-                const int c = c_lo + q * g.chunk;
-                u.ecol = ebase + (uint32_t)(edge_cap + c - rec.jmin);
-                u.shape = (uint32_t)rows | (uint32_t)min(g.chunk, c_hi - c) << 8 |
-                          (uint32_t)(r_lo - ti * g.tile_h) << 16 | (uint32_t)(c - tj * g.tile_w) << 24;
-                if (fast) {
-                    u.src = block + (size_t)first_box_row * g.slots * (size_t)box_bytes;
-                    u.extra = kUnitFast | (uint32_t)(col_slot0 + (c - rec.jmin) + 1);
-                } else {
-                    u.src = sat + table_at;
-                    u.extra = 0;
-                }
-                dst[q] = u;
+    const int n_ti = t1 - t0 + 1, n_strips = n_ti * (u1 - u0 + 1);
+    // the list positions of the footprint's first kFillAhead strips (all of them for ~31-row footprints) are
+    // requested before the first unit is written: one round of load latency per spot instead of one per strip
+    int pos[kFillAhead > 0 ? kFillAhead : 1];
+    if (kFillAhead > 0) {
+        int ci = 0, cj = 0;
+#pragma unroll
+        for (int k = 0; k < kFillAhead; ++k) {
+            pos[k] = 0;
+            if (k < n_strips) {
+                const int tile = frame_tile0 + (t0 + ci) * g.ntj + (u0 + cj);
+                pos[k] = tile_start[tile * g.stripes + stripe] + __ldg(my_rank + k);
+                if (++ci == n_ti) { ci = 0; ++cj; }
             }
         }
+    }
+    auto emit = [&](int ti, int tj, Unit *dst) {
+        const int c_lo = max(rec.jmin, tj * g.tile_w), c_hi = min(rec.jmax, (tj + 1) * g.tile_w);
+        const int entries = (c_hi - c_lo + g.chunk - 1) / g.chunk;
+        const int r_lo = max(rec.imin, ti * g.tile_h), r_hi = min(rec.imax, (ti + 1) * g.tile_h);
+        const int rows = r_hi - r_lo;
+        u.erow = ebase + (uint32_t)(r_lo - rec.imin);
+        const int first_box_row = row_slot0 + (r_lo - rec.imin) + 1;
+        for (int q = 0; q < entries; ++q) {
+            const int c = c_lo + q * g.chunk;
+            u.ecol = ebase + (uint32_t)(edge_cap + c - rec.jmin);
+            u.shape = (uint32_t)rows | (uint32_t)min(g.chunk, c_hi - c) << 8 |
+                      (uint32_t)(r_lo - ti * g.tile_h) << 16 | (uint32_t)(c - tj * g.tile_w) << 24;
+            if (fast) {
+                u.src = block + (size_t)first_box_row * g.slots * (size_t)box_bytes;
+                u.extra = kUnitFast | (uint32_t)(col_slot0 + (c - rec.jmin) + 1);
+            } else {
+                u.src = sat + table_at;
+                u.extra = 0;
+            }
+            dst[q] = u;
+        }
+    };
+    // the census' walk: columns of strips, rows inside
+    int ci = 0, cj = 0;
+#pragma unroll
+    for (int k = 0; k < kFillAhead; ++k) {
+        if (k < n_strips) {
+            emit(t0 + ci, u0 + cj, units + pos[k]);
+            if (++ci == n_ti) { ci = 0; ++cj; }
+        }
+    }
+    for (int k = kFillAhead; k < n_strips; ++k) {
+        const int tile = frame_tile0 + (t0 + ci) * g.ntj + (u0 + cj);
+        emit(t0 + ci, u0 + cj, units + tile_start[tile * g.stripes + stripe] + __ldg(my_rank + k));
+        if (++ci == n_ti) { ci = 0; ++cj; }
     }
 }
 
@@ -839,7 +864,11 @@ static int render_expected_strided(const scb_geometry *geom, int64_t n_spots, in
     // census, cursors, weight maximum and the strip queue are adjacent 256-aligned blocks: clear them all
     SCB_CUDA(cudaMemsetAsync(w.tile_count, 0, (size_t)((char *)w.tile_start - (char *)w.tile_count), s));
     if (n_spots > 0) {
-        spot_prepare_kernel<<<dim3(scb_grid_for(n_spots / frames, 256), frames), 256, 0, s>>>(
+        // SCB_PREPARE_CENSUS=global: the census by global atomics only (the measured alternative)
+        const char *census = getenv("SCB_PREPARE_CENSUS");
+        auto prepare = census && census[0] == 'g' ? spot_prepare_kernel<6, false>
+                                                  : spot_prepare_kernel<SCB_PREPARE_CTAS, true>;
+        prepare<<<dim3(scb_grid_for(n_spots / frames, 256), frames), 256, 0, s>>>(
             g, n_spots, stride, d_depth, d_x, d_y, d_weight, d_inv_scale, d_slot_of_key, w.spots, w.tile_count,
             w.wmax_bits, d_errors, w.ranks, w.rank_cap, d_order, w.walk_list, w.walk_count);
         // the edge kernel walks the listed footprints only: a grid-stride loop over the list, sized for the device
@@ -863,10 +892,14 @@ static int render_expected_strided(const scb_geometry *geom, int64_t n_spots, in
         else if (reg_path)
             strip_fill_reg_kernel<<<scb_grid_for(n_spots, 256), 256, 0, s>>>(g, n_spots, w.spots, w.ranks, w.rank_cap,
                                                                             w.tile_start, (RUnit *)w.pair_spot);
-        else
-            strip_fill_kernel<<<scb_grid_for(n_spots, 256), 256, 0, s>>>(g, n_spots, w.spots, w.edge_cap, w.ranks, w.rank_cap,
-                                                                        d_sat, d_box, box_bytes, w.tile_start,
-                                                                        w.wmax_bits, (Unit *)w.pair_spot);
+        else {
+            // SCB_FILL_VARIANT=old: list positions loaded strip by strip (the measured alternative: 119 vs 112 us per
+            // 16-frame C4 block; with 4 / 2 CTAs per SM the up-front requests take 124 / 135 us)
+            const char *fv = getenv("SCB_FILL_VARIANT");
+            auto fill = fv && fv[0] == 'o' ? strip_fill_kernel<4, 0> : strip_fill_kernel<SCB_FILL_CTAS, 10>;
+            fill<<<scb_grid_for(n_spots, 256), 256, 0, s>>>(g, n_spots, w.spots, w.edge_cap, w.ranks, w.rank_cap, d_sat, d_box,
+                                                            box_bytes, w.tile_start, w.wmax_bits, (Unit *)w.pair_spot);
+        }
     }
     int timed = -1;        // slot of this launch in the measurement hook's event pool
     if (g_profile.enabled) {
