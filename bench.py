@@ -605,14 +605,14 @@ def timed_blocks(movie, block, steps, lib, world):
 def traffic_record(args):
     """DRAM bytes per launch of the render kernel from the committed `ncu --set full` capture."""
     if args.molecules != 100000 or args.size != 2048:
-        return None, None
+        return None, None, None
     for name in ("traffic_r2.json", "traffic_r1.json"):
         path = os.path.join(ROOT, "profiles", name)
         if os.path.exists(path):
             for kernel, entry in json.load(open(path)).items():
                 if kernel.startswith("render_strips_kernel<float"):
-                    return entry.get("dram_bytes_per_launch"), "profiles/" + name
-    return None, None
+                    return entry.get("dram_bytes_per_launch"), "profiles/" + name, entry.get("frames_per_launch")
+    return None, None, None
 
 
 # --------------------------------------------------------------------------- GPU arm: weak scaling (default)
@@ -708,7 +708,11 @@ def run_weak(args):
         per_launch_ms = render_ms / max(1, render_launches)
         frames_per_launch = K * F / max(1, render_launches)      # render_block renders several frames per launch
         evals *= frames_per_launch
-        traffic, traffic_source = traffic_record(args)
+        # the capture is one launch of `captured_frames` frames; the timed launches hold frames_per_launch: per launch, like `achieved`
+        traffic, traffic_source, captured_frames = traffic_record(args)
+        if traffic is not None and captured_frames:
+            traffic = traffic * frames_per_launch / captured_frames
+            traffic_source += " (%d-frame launch, scaled to %g frames per launch)" % (captured_frames, frames_per_launch)
         # algorithmic bytes: one box-table value per spot-pixel eval -- 4 bytes with
         # the fp32 tables that fp32 frames use, 8 with fp64 tables
         bytes_per_eval = 4.0 if movie.engine.box is not None and movie.engine.box.dtype == torch.float32 else 8.0
@@ -737,7 +741,7 @@ def run_weak(args):
                 "share_of_step": render_ms / elapsed_ms,
                 # what keeps it below the HBM roofline: profiles/render_variants_r2.md
                 "limiter": "TMA request rate -- one bulk copy per unit, and an SM retires one copy per ~40-50 cycles "
-                           "whatever its size (tools/probes/tma_rate_probe.cu); issue slots 84 % busy, DRAM 57 % active "
+                           "whatever its size (tools/probes/tma_rate_probe.cu); issue slots 82 % busy, DRAM 57 % active "
                            "(profiles/traffic_r2.json)",
             },
             "export": export, "host": host, "gather_ok": gather_ok, "spec_half_life": spec,
