@@ -297,3 +297,50 @@ default:
         assert rel_err(tiled.astype(numpy.float64), images["default"].astype(numpy.float64)) < 2e-6
         assert rel_err(tiled.astype(numpy.float64), exact) < 3e-6
         assert ((tiled > 0) == (images["default"] > 0)).all()
+
+
+@pytest.mark.parametrize("size, pixel_nm, n, why", [
+    ((150, 210), 65.0, 1500, "a few dozen strips: the shared-memory census"),
+    ((64, 8192), 65.0, 4000, "512 strips in one row of the box, scattered spots: shared memory, every counter touched"),
+    ((4104, 1100), 65.0, 3000, "513 x 9 strips > 4096 counters: the global-atomic census takes over"),
+    ((300, 300), 20.0, 600, "101-row footprints over more than 16 strips each: the global-atomic census"),
+], ids=["small", "wide", "tall", "fine-pitch"])
+def test_census_paths_give_the_same_image(size, pixel_nm, n, why):
+    """spot_prepare counts a CTA's (spot, strip) overlaps in shared memory when the strips it touches fit 4096
+    counters and its footprints 16 strips each, with global atomics otherwise (SCB_PREPARE_CENSUS=global forces
+    that); strip_fill requests its list positions up front (SCB_FILL_VARIANT=old: strip by strip).  The lists
+    come out in different orders; the image is the same, bit for bit (fixed-point accumulation)."""
+    import os
+    yaml = """
+default:
+    detector: {type: CMOS, image_size: [%d, %d], pixel_length: {value: %.9e, units: m}, exposure_time: 0.033}
+    magnification: 100
+""" % (size[0], size[1], pixel_nm * 1e-7)
+    config, configs, params, engine = gpu_engine(yaml, precision="f32")
+    pl = configs.pixel_length
+    rng = numpy.random.RandomState(n)
+    data = numpy.zeros((n, 5))
+    data[:, 0] = rng.uniform(0, 3, n).astype(int) * 150e-9
+    data[:, 1] = rng.uniform(-0.55 * size[0] * pl, 0.55 * size[0] * pl, n)      # some footprints hang over the border
+    data[:, 2] = rng.uniform(-0.55 * size[1] * pl, 0.55 * size[1] * pl, n)
+    data[: n // 5, 1] = rng.normal(0.1 * size[0] * pl, 1.5 * pl, n // 5)        # a cluster: one long strip list
+    data[: n // 5, 2] = rng.normal(-0.2 * size[1] * pl, 1.5 * pl, n // 5)
+    data[:, 3] = numpy.arange(n)
+    data[:, 4] = 1
+    engine.ensure_tables(numpy.unique(engine_keys(engine, configs, data)))
+    images = {}
+    for name, env in [("default", {}), ("global census", {"SCB_PREPARE_CENSUS": "global"}),
+                      ("fill strip by strip", {"SCB_FILL_VARIANT": "old"}),
+                      ("both", {"SCB_PREPARE_CENSUS": "global", "SCB_FILL_VARIANT": "old"})]:
+        os.environ.update(env)
+        try:
+            images[name] = render(engine, data, dtype=torch.float32)
+        finally:
+            for k in env:
+                del os.environ[k]
+    assert images["default"].max() > 0, why
+    for name, image in images.items():
+        assert numpy.array_equal(image, images["default"]), (name, why)
+    # and the list lengths add up: the image carries every spot's photons that fall inside the frame
+    exact = render(gpu_engine(yaml, precision="f64")[3], data)
+    assert rel_err(images["default"].astype(numpy.float64), exact) < 3e-6
