@@ -66,8 +66,9 @@ constexpr int kDefaultCopy = 0;
 constexpr int kStages = 3;            // ring depth: the copy of unit u + 2 is issued while unit u is consumed
 // COPY 3 = a scene without box tables (every footprint gathers SAT corners): no ring, hence more warps per SM
 constexpr int kCopyNone = 3;
+constexpr int kStageTail = 16;        // bytes behind a ring stage: its mbarrier (the stage's address gives both)
 template <typename BoxT, int ROWS, int COPY = 0> constexpr size_t warp_smem_bytes() {
-    return 4096 + (COPY == kCopyNone ? 0 : kStages * ROWS * kFastSlots * sizeof(BoxT)) + batch_units<ROWS>() * 32 + 32;
+    return 4096 + (COPY == kCopyNone ? 0 : kStages * (ROWS * kFastSlots * sizeof(BoxT) + kStageTail)) + batch_units<ROWS>() * 32 + 32;
 }
 // CTAs per SM from the shared memory one warp needs (accumulators + ring + unit batch)
 template <typename BoxT, int ROWS, int COPY = 0> constexpr int ctas_per_sm() {
@@ -225,6 +226,25 @@ __device__ __forceinline__ void tma_row(void *dst, const void *src, uint32_t byt
 __device__ __forceinline__ void unit_stage(const void *src, uint32_t bytes, void *stage, void *bar) {
     mbar_expect_tx(bar, bytes);
     tma_row(stage, src, bytes, bar);
+}
+
+// the same by shared-memory address (the barrier sits right behind its stage)
+__device__ __forceinline__ void unit_stage_at(const void *src, uint32_t bytes, uint32_t stage_s, uint32_t bar_s) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(stage_s),
+                 "l"(src), "r"(bytes), "r"(bar_s)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait_at(uint32_t bar_s, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(bar_s), "r"(parity) : "memory");
 }
 
 // box * weight -> accumulator LSBs, in the precision of the box table
@@ -404,9 +424,14 @@ render_strips_kernel(Geo g, const Unit *__restrict__ units, const uint32_t *__re
     unsigned char *mine = smem_raw + warp * warp_smem_bytes<BoxT, ROWS, COPY>();
     Acc *acc = reinterpret_cast<Acc *>(mine);
     BoxT *ring = reinterpret_cast<BoxT *>(mine + kAccBytes);
-    constexpr size_t kRingBytes = COPY == kCopyNone ? 0 : kStages * kStageEntries * sizeof(BoxT);
+    // a stage = its box rows, then 16 bytes holding its mbarrier: stage and barrier share one address register
+    constexpr int kStageStride = kStageEntries + kStageTail / (int)sizeof(BoxT);          // in table entries
+    constexpr uint32_t kStageBytes = kStageEntries * sizeof(BoxT), kStrideBytes = kStageBytes + kStageTail;
+    constexpr size_t kRingBytes = COPY == kCopyNone ? 0 : kStages * (size_t)kStrideBytes;
     Unit *meta = reinterpret_cast<Unit *>(mine + kAccBytes + kRingBytes);
-    unsigned long long *bars = reinterpret_cast<unsigned long long *>(meta + kBatch);
+    auto stage_of = [&](int st) { return ring + st * kStageStride; };
+    auto bar_of = [&](int st) { return reinterpret_cast<unsigned long long *>(ring + st * kStageStride + kStageEntries); };
+    const uint32_t ring_s = smem_addr(ring);
 
     const int frame_tiles = g.nti * g.ntj, n_tiles = g.frames * frame_tiles;
     const int slots = SLOTS ? SLOTS : g.slots;
@@ -414,11 +439,13 @@ render_strips_kernel(Geo g, const Unit *__restrict__ units, const uint32_t *__re
     const int64_t frame_spots = g.frames > 1 ? g.spots_per_frame : n_spots;
 
     for (int i = lane; i < ROWS * kStripCols; i += 32) acc[i] = 0;
-    if (COPY != kCopyNone)
-        for (int i = lane; i < kStages * kStageEntries; i += 32) ring[i] = (BoxT)0;   // rows past a unit's last are read (and dropped)
+    if (COPY != kCopyNone) {
+        for (int i = lane; i < kStages * kStageStride; i += 32) ring[i] = (BoxT)0;   // rows past a unit's last are read (and dropped)
+        __syncwarp();                                                                // ... before the barriers inside are set up
+    }
     if (COPY != 1 && COPY != kCopyNone) {
         if (lane == 0) {
-            for (int st = 0; st < kStages; ++st) mbar_init(&bars[st], 1);
+            for (int st = 0; st < kStages; ++st) mbar_init(bar_of(st), 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // zeroed ring visible to the async proxy
@@ -426,6 +453,10 @@ render_strips_kernel(Geo g, const Unit *__restrict__ units, const uint32_t *__re
     __syncwarp();
     int p_stage = 0, c_stage = 0;            // ring positions of the producer and the consumer (fast units only)
     uint32_t c_parity = 0;                   // COPY 0: every stage completes one mbarrier phase per turn of the ring
+    // COPY 0 walks the ring by address: c_at = shared address of the consumer's stage (the producer's destinations
+    // are worked out per lane when a batch is fetched: the ring is drained at every batch boundary, so the batch's
+    // k-th box-table unit lands k stages behind c_at)
+    uint32_t c_at = ring_s;
     uint32_t phases = 0;                     // COPY 2: bit s = phase of stage s's mbarrier (only its TMA units advance it)
 
     for (;;) {
@@ -483,6 +514,13 @@ render_strips_kernel(Geo g, const Unit *__restrict__ units, const uint32_t *__re
             }
             const uint32_t fast_mask = COPY == kCopyNone ? 0u : __ballot_sync(0xffffffffu, my_fast);
             __syncwarp();
+            uint32_t my_dst = 0;             // COPY 0: shared address of the stage this lane's unit is copied into
+            if constexpr (COPY == 0) {
+                uint32_t turn = (uint32_t)__popc(fast_mask & ((1u << lane) - 1u)) + (c_at - ring_s) / kStrideBytes;
+                turn -= (turn * 43u >> 7) * 3u;                            // mod 3 (turn < 35)
+                static_assert(kStages == 3, "ring arithmetic");
+                my_dst = ring_s + turn * kStrideBytes;
+            }
 
             // COPY 2 splits the units between the two engines -- even units of a batch by TMA bulk copy, odd ones by
             // per-lane cp.async -- because neither is free: an SM retires one bulk copy per ~40-50 cycles whatever its
@@ -496,10 +534,12 @@ render_strips_kernel(Geo g, const Unit *__restrict__ units, const uint32_t *__re
             auto stage_unit = [&](int u) {
                 if (is_fast(u)) {                          // warp uniform
                     if (!by_lanes(u)) {
-                        if (lane == u) {
+                        if constexpr (COPY == 0) {
+                            if (lane == u) unit_stage_at(my_src, my_bytes, my_dst, my_dst + kStageBytes);
+                        } else if (lane == u) {
                             // the stage was last written by another lane's cp.async pieces (generic proxy)
                             if (COPY == 2) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                            unit_stage(my_src, my_bytes, ring + p_stage * kStageEntries, &bars[p_stage]);
+                            unit_stage(my_src, my_bytes, stage_of(p_stage), bar_of(p_stage));
                         }
                     } else {
                         const char *src;
@@ -511,10 +551,10 @@ render_strips_kernel(Geo g, const Unit *__restrict__ units, const uint32_t *__re
                             src = static_cast<const char *>(meta[u].src);
                         }
                         bytes = (meta[u].shape & 0xffu) * row_bytes;
-                        char *dst = reinterpret_cast<char *>(ring + p_stage * kStageEntries);
+                        char *dst = reinterpret_cast<char *>(stage_of(p_stage));
                         for (uint32_t off = lane * 16u; off < bytes; off += 512u) cp_async16(dst + off, src + off);
                     }
-                    if (++p_stage == kStages) p_stage = 0;
+                    if (COPY != 0 && ++p_stage == kStages) p_stage = 0;
                 }
                 if (COPY != 0 && COPY != kCopyNone) cp_async_commit();          // one group per unit, empty for TMA and gather units
             };
@@ -527,10 +567,10 @@ render_strips_kernel(Geo g, const Unit *__restrict__ units, const uint32_t *__re
                 if (is_fast(u)) {
                     if (!by_lanes(u)) {
                         if (COPY == 2) {
-                            mbar_wait(&bars[c_stage], (phases >> c_stage) & 1u);
+                            mbar_wait(bar_of(c_stage), (phases >> c_stage) & 1u);
                             phases ^= 1u << c_stage;
                         } else {
-                            mbar_wait(&bars[c_stage], c_parity);
+                            mbar_wait_at(c_at + kStageBytes, c_parity);
                         }
                     } else {
                         // groups committed after unit u's: min(nb - 1 - u, 2)
@@ -540,8 +580,15 @@ render_strips_kernel(Geo g, const Unit *__restrict__ units, const uint32_t *__re
                         else cp_async_wait<0>();
                         __syncwarp();                      // the other lanes' pieces have landed too
                     }
-                    unit_accumulate_fast<BoxT, ROWS, SLOTS>(meta, u, lane, acc, ring + c_stage * kStageEntries, slots, scale);
-                    if (++c_stage == kStages) { c_stage = 0; c_parity ^= 1u; }
+                    if constexpr (COPY == 0) {
+                        unit_accumulate_fast<BoxT, ROWS, SLOTS>(meta, u, lane, acc,
+                                                                ring + (c_at - ring_s) / (uint32_t)sizeof(BoxT), slots, scale);
+                        c_at += kStrideBytes;
+                        if (c_at == ring_s + kStages * kStrideBytes) { c_at = ring_s; c_parity ^= 1u; }
+                    } else {
+                        unit_accumulate_fast<BoxT, ROWS, SLOTS>(meta, u, lane, acc, stage_of(c_stage), slots, scale);
+                        if (++c_stage == kStages) { c_stage = 0; c_parity ^= 1u; }
+                    }
                 } else {
                     // (requesting the next gather unit's edge offsets before this unit's corners was measured: no
                     // gain at 66.39 nm, and the registers it holds cost the box-table path 2 %)
