@@ -740,9 +740,11 @@ def run_weak(args):
                 "frames_per_launch": frames_per_launch,
                 "share_of_step": render_ms / elapsed_ms,
                 # what keeps it below the HBM roofline: profiles/render_variants_r2.md
-                "limiter": "TMA request rate -- one bulk copy per unit, and an SM retires one copy per ~40-50 cycles "
-                           "whatever its size (tools/probes/tma_rate_probe.cu); issue slots 82 % busy, DRAM 57 % active "
-                           "(profiles/traffic_r2.json)",
+                "limiter": "co-limited: shared-memory wavefronts 83 % of peak (box load, accumulator load and store per pixel "
+                           "row, the copies' writes), issue slots 82 %, and the TMA unit's request rate -- one bulk copy per unit "
+                           "at 36 cycles per unit per SM, where back-to-back bulk copies alone retire one per 40-50 cycles whatever "
+                           "their size (tools/probes/tma_rate_probe.cu); DRAM 57 % active (profiles/traffic_r2.json, "
+                           "profiles/ncu_block_r2_summary.csv)",
             },
             "export": export, "host": host, "gather_ok": gather_ok, "spec_half_life": spec,
             "emitting_fraction": [emitting_start, emitting_end],
