@@ -344,3 +344,47 @@ default:
     # and the list lengths add up: the image carries every spot's photons that fall inside the frame
     exact = render(gpu_engine(yaml, precision="f64")[3], data)
     assert rel_err(images["default"].astype(numpy.float64), exact) < 3e-6
+
+
+def test_copy_engine_and_strip_shape_variants():
+    """The measured variants of the shared-memory kernel -- per-lane cp.async instead of the TMA bulk copy
+    (SCB_RENDER_COPY=ldgsts), units split between the two engines (=mix), 16 x 64 strips (SCB_RENDER_ROWS=16) --
+    share its ring layout (a stage's mbarrier sits behind its rows).  Same strips: the same bits; other strips:
+    another accumulator LSB per strip, equal to that LSB."""
+    import os
+    yaml = """
+default:
+    detector: {type: CMOS, image_size: [150, 210], pixel_length: {value: 6.5e-6, units: m}, exposure_time: 0.033}
+    magnification: 100
+"""
+    config, configs, params, engine = gpu_engine(yaml, precision="f32")
+    pl = configs.pixel_length
+    rng = numpy.random.RandomState(11)
+    n = 1500
+    data = numpy.zeros((n, 5))
+    data[:, 0] = rng.uniform(0, 3, n).astype(int) * 150e-9
+    data[:, 1] = rng.uniform(-90 * pl, 90 * pl, n)
+    data[:, 2] = rng.uniform(-120 * pl, 120 * pl, n)
+    data[:300, 1] = rng.normal(10 * pl, 1.5 * pl, 300)
+    data[:300, 2] = rng.normal(-30 * pl, 1.5 * pl, 300)
+    data[300:360, 1:3] = numpy.round(data[300:360, 1:3] / pl) * pl      # exact pixel centres: irregular footprints
+    data[:, 3] = numpy.arange(n)
+    data[:, 4] = 1
+    engine.ensure_tables(numpy.unique(engine_keys(engine, configs, data)))
+
+    def image(env):
+        os.environ.update(env)
+        try:
+            return render(engine, data, dtype=torch.float32)
+        finally:
+            for k in env:
+                del os.environ[k]
+
+    default = image({})
+    assert default.max() > 0
+    for env in ({"SCB_RENDER_COPY": "ldgsts"}, {"SCB_RENDER_COPY": "mix"}):
+        assert numpy.array_equal(image(env), default), env
+    for env in ({"SCB_RENDER_ROWS": "16"}, {"SCB_RENDER_ROWS": "16", "SCB_RENDER_COPY": "ldgsts"}):
+        tall = image(env)
+        assert rel_err(tall.astype(numpy.float64), default.astype(numpy.float64)) < 2e-6, env
+        assert ((tall > 0) == (default > 0)).all(), env
