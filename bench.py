@@ -514,7 +514,7 @@ def export_rate(movie, fmt, frames, world, device):
     def sink(first, block):
         touched[0] += float(block[0, 0, 0])      # the consumer reads from every delivered block
 
-    movie.stream_frames(2 * movie.frames_per_launch, fmt=fmt, sink=sink)     # buffers, pinned ring
+    movie.stream_frames(2 * movie.export_block_frames, fmt=fmt, sink=sink)     # buffers, pinned ring
     barrier(world)
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     start.record()
@@ -859,7 +859,7 @@ def run_strong(args):
     def one_pass(fmt):
         for _ in range(max(1, min(args.warmup, 2))):          # buffers, pinned ring, clocks
             movie.reset(first_frame=0)
-            movie.stream_frames(4 * movie.frames_per_launch, fmt=fmt, sink=sink)
+            movie.stream_frames(4 * movie.export_block_frames, fmt=fmt, sink=sink)
         barrier(world)
         a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         t_wall = time.perf_counter()
@@ -887,7 +887,7 @@ def run_strong(args):
             headline = (rate, ms, replay)
     clocks = sampler.stop()
     # device-resident rate of the same partition (no export), for comparison
-    block = torch.empty((movie.frames_per_launch * 8, args.size, args.size), dtype=torch.float32, device=device)
+    block = torch.empty((movie.frames_per_launch * 4, args.size, args.size), dtype=torch.float32, device=device)
     movie.reset(first_frame=first)
     ms_res, _, launches, _ = timed_blocks(movie, block, max(1, args.steps), lib, world)
     ms_res = max_over_ranks(ms_res, world, device)
@@ -896,14 +896,15 @@ def run_strong(args):
     gather_ok = gather_check(args, world, rank, device)
     if rank == 0:
         rate, ms, replay = headline
-        n_blocks = (last - first + movie.frames_per_launch - 1) // movie.frames_per_launch
+        n_blocks = (last - first + movie.export_block_frames - 1) // movie.export_block_frames
         line = {
             "metric": METRIC, "value": rate, "unit": "frames/s", "n_gpus": world, "steps": 1, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32 box tables and frames, 32-bit fixed-point accumulation per strip (edge arithmetic f64)",
             "data": "synthetic", "config": workload_config(args), "clocks": clocks,
             "step": "the whole movie: every rank replays its prefix, renders its frame block and streams every "
-                    "finished 16-frame block to page-locked host memory ({}); max over ranks".format(args.export),
+                    "finished {}-frame block to page-locked host memory ({}); max over ranks".format(
+                        movie.export_block_frames, args.export),
             "replay_ms": replay, "export": rates, "device_resident_frames_per_s": resident,
             "e2e": {"value": rate, "unit": "frames/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": int(T * args.size * args.size * {"f32": 4, "u16": 2, "u8": 1}[args.export]),

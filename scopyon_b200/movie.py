@@ -126,9 +126,12 @@ class DeviceMovie:
     #: frames binned and rendered per launch by ``render_block`` (the binning kernels are
     #: latency bound and the render kernel balances better over more strips: 16 frames per
     #: launch run 1.45x faster than 16 single frames, 32 another 3 % faster, 64 another 1.3 %;
-    #: about 150 MB of scratch per frame at C4 and, when frames are exported, three page-locked
-    #: host blocks of that many frames)
-    frames_per_launch = 32
+    #: about 150 MB of scratch per frame at C4)
+    frames_per_launch = 64
+    #: frames per block of ``stream_frames`` (one launch group and one download each; three page-locked
+    #: host blocks of that many frames: a shorter block keeps the first frame's latency and the pinned
+    #: memory down, and the exported rates sit at the host bound either way)
+    export_block_frames = 32
 
     def render_block(self, out):
         """Fill ``out`` (device tensor (B, Nw, Nh)) with the next B frames.  Bit-identical to B
@@ -155,11 +158,11 @@ class DeviceMovie:
         """Buffers of ``stream_frames``: two device blocks (one renders while the other leaves the
         device), their converted copies for the integer formats, ``ring`` page-locked host blocks."""
         eng = self.engine
-        key = (fmt, int(ring), self.frames_per_launch)
+        key = (fmt, int(ring), self.export_block_frames)
         plans = self.__dict__.setdefault("_export_plans", {})
         plan = plans.get(key)
         if plan is None:
-            nb = self.frames_per_launch
+            nb = self.export_block_frames
             shape = (nb, eng.n_w, eng.n_h)
             wire = {"f32": torch.float32, "u16": torch.uint16, "u8": torch.uint8}[fmt]
             plan = plans[key] = dict(
@@ -171,7 +174,7 @@ class DeviceMovie:
 
     def stream_frames(self, num_frames, fmt="f32", sink=None, limits=None, ring=3):
         """Render the next ``num_frames`` frames and stream every finished block of
-        ``frames_per_launch`` frames to page-locked host memory -- the data plane of a sharded movie
+        ``export_block_frames`` frames to page-locked host memory -- the data plane of a sharded movie
         (the reference yields every frame to its caller, ``_epifm.py:1045-1049``; a rank of a
         frame-block partition exports its own block range, nothing is gathered on one GPU).
 
@@ -188,7 +191,7 @@ class DeviceMovie:
         if eng.dtype != torch.float32:
             raise ValueError("stream_frames exports the float32 pipeline's frames (precision='f32')")
         ring = max(2, int(ring))
-        nb = self.frames_per_launch
+        nb = self.export_block_frames
         lib = eng.lib
         with torch.cuda.device(eng.device):
             plan = self._export_plan(fmt, ring)

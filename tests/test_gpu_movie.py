@@ -146,7 +146,7 @@ def test_stream_frames_exports_the_movie_block_by_block(frames_per_launch, tmp_p
 
     def collect(fmt, **kwargs):
         _, movie = make_movie("0.0", "true")
-        movie.frames_per_launch = frames_per_launch
+        movie.export_block_frames = frames_per_launch
         got, firsts = [], []
 
         def sink(first, block):
@@ -167,7 +167,7 @@ def test_stream_frames_exports_the_movie_block_by_block(frames_per_launch, tmp_p
     assert u8.dtype == numpy.uint8 and numpy.array_equal(u8, want)
     # a second call continues the movie where the first stopped
     _, movie = make_movie("0.0", "true")
-    movie.frames_per_launch = frames_per_launch
+    movie.export_block_frames = frames_per_launch
     parts = []
     movie.stream_frames(10, sink=lambda first, block: parts.append(block.copy()))
     movie.stream_frames(n_frames - 10, sink=lambda first, block: parts.append(block.copy()))
