@@ -297,6 +297,24 @@ int scb_render_expected_frames_ordered(const scb_geometry *geom, int64_t n_per_f
                                        void *d_workspace, size_t workspace_bytes, int32_t *d_errors,
                                        void *stream);
 
+/* The same for consecutive blocks of one movie: the binning in one pass.  scb_render_expected_frames_ordered counts the
+ * (spot, strip) overlaps, scans the counts into list segments and fills the lists in a second pass over the spots.
+ * When the workspace still holds the LIST PLAN a previous call left behind -- every strip's room, a quarter above
+ * what that block's census counted: molecules move about a pixel per frame -- the census, the hand-out of list
+ * positions and the writing of the units need no scan between them (plan_mode bit 0: use the plan in the workspace;
+ * bit 1: leave a plan behind for the next call).  The caller sets bit 0 only when the previous call on this workspace
+ * had bit 1 set and the same geometry, n_per_frame and n_frames; a unit beyond its strip's room goes to a short
+ * overflow list the render also reads, so the images never depend on the plan: they are those of
+ * scb_render_expected_frames_ordered, bit for bit.  More than 65536 overflowing units are counted in d_errors (the
+ * caller renders that block again with plan_mode 0 or 2). */
+int scb_render_expected_frames_planned(const scb_geometry *geom, int64_t n_per_frame, int n_frames,
+                                       const int32_t *d_order, const double *d_depth, const double *d_x,
+                                       const double *d_y, const double *d_weight, const int64_t *d_sat,
+                                       const void *d_box, int box_type, const double *d_inv_scale,
+                                       const int32_t *d_slot_of_key, void *d_out, int out_type,
+                                       void *d_workspace, size_t workspace_bytes, int32_t *d_errors,
+                                       int plan_mode, void *stream);
+
 /* Tensor-core variant of scb_render_expected for the separable Gaussian PSF
  * (fluorophore.type == 'Gaussian', _epifm.py:133-134): a 128 x 128 screen tile is the
  * contraction D[i][j] = sum_s (w_s Ex_s(i)) Ey_s(j) over the spots binned to it, issued as

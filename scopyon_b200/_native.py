@@ -110,6 +110,9 @@ SIGNATURES = {
     "scb_render_expected_frames_ordered": (ctypes.c_int, [
         ctypes.POINTER(Geometry), ctypes.c_int64, ctypes.c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
         ctypes.c_int, c_ptr, c_ptr, c_ptr, ctypes.c_int, c_ptr, ctypes.c_size_t, c_ptr, c_ptr]),
+    "scb_render_expected_frames_planned": (ctypes.c_int, [
+        ctypes.POINTER(Geometry), ctypes.c_int64, ctypes.c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
+        ctypes.c_int, c_ptr, c_ptr, c_ptr, ctypes.c_int, c_ptr, ctypes.c_size_t, c_ptr, ctypes.c_int, c_ptr]),
     "scb_gaussian_tc_workspace_bytes": (ctypes.c_size_t, [ctypes.POINTER(Geometry), ctypes.c_int64]),
     "scb_render_gaussian_tc": (ctypes.c_int, [
         ctypes.POINTER(Geometry), ctypes.c_int64, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, ctypes.c_int, ctypes.c_int,

@@ -120,35 +120,14 @@ __device__ __forceinline__ int stripe_of(const Geo &g, int64_t spot, int frame) 
     return (int)(in_frame >> 8) & (g.stripes - 1);
 }
 
-// One thread per spot: footprint, depth key, tile census.
-//
-// Census.  Every (spot, tile) overlap takes `entries` places in its tile's list; the counter's old
-// value is the overlap's position (`ranks`, in the order the fill kernel walks a footprint's tiles), so
-// the fill needs no atomics.  The 32 spots of a warp vote before they count: overlaps with the same
-// tile (`__match_any_sync`) are added by one lane and share the returned base.  With `order` -- slot
-// s of the spot list reads particle order[s], a tile-major ordering the caller refreshes now and then
-// (molecules move a pixel or so per frame) -- the spots of a warp are neighbours on the screen and share
-// most of their tiles: a tenth of the atomics.  Without it the vote finds no partners and costs little.
-constexpr int kLocalStrips = 4096;     // strip counters of a CTA's shared-memory census (a 2048 x 2048 frame has 4096 strips)
-constexpr int kLocalRanks = 16;        // strips per footprint it can hold (the rest: global atomics)
-#ifndef SCB_PREPARE_CTAS
-#define SCB_PREPARE_CTAS 5     // 48 registers, no spills, 40 warps per SM (6: 40 registers with spills, 1 % slower)
-#endif
-template <int CTAS, bool LOCAL>      // CTAs per SM; LOCAL: the shared-memory census is compiled in
-__global__ void __launch_bounds__(256, CTAS)
-spot_prepare_kernel(Geo g, int64_t n, int64_t stride, const double *__restrict__ depth, const double *__restrict__ x,
-                    const double *__restrict__ y, const double *__restrict__ weight,
-                    const double *__restrict__ inv_scale, const int32_t *__restrict__ slot_of_key,
-                    SpotRec *__restrict__ spots, int *__restrict__ tile_count,
-                    unsigned long long *__restrict__ wmax_bits, int32_t *__restrict__ errors,
-                    int *__restrict__ ranks, int rank_cap, const int32_t *__restrict__ order,
-                    int *__restrict__ walk_list, unsigned *__restrict__ walk_count) {
-    // grid: x over the spots of one frame, y over frames
-    const int64_t in_frame = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int frame = blockIdx.y;
-    const int64_t s = g.frames > 1 ? (int64_t)frame * g.spots_per_frame + in_frame : in_frame;
-    const int64_t n_here = g.frames > 1 ? ((int64_t)(frame + 1) * g.spots_per_frame < n ? (int64_t)(frame + 1) * g.spots_per_frame : n) : n;
-    SpotRec rec;
+// The record of spot s (its footprint, depth table, weight, regular runs); true when it touches the image.
+// _epifm.py:217-218, 76-84, 233-235, 255-257
+__device__ __forceinline__ bool spot_record(const Geo &g, int64_t s, int64_t n_here, int64_t in_frame, int frame, int64_t stride,
+                                            const double *__restrict__ depth, const double *__restrict__ x,
+                                            const double *__restrict__ y, const double *__restrict__ weight,
+                                            const double *__restrict__ inv_scale, const int32_t *__restrict__ slot_of_key,
+                                            const int32_t *__restrict__ order, int32_t *__restrict__ errors, SpotRec &rec,
+                                            double &w_seen) {
     rec.slot = -1;
     rec.frame = frame;
     rec.pad = 0;
@@ -156,7 +135,7 @@ spot_prepare_kernel(Geo g, int64_t n, int64_t stride, const double *__restrict__
     rec.ox = rec.oy = rec.w = 0.0;
     rec.walk = 0;
     rec.row_run = rec.col_run = -1;
-    double w_seen = 0.0;
+    w_seen = 0.0;
     bool counted = false;
     if (s < n_here) {
         // the particle this slot shows: the same index of every frame of a block
@@ -201,8 +180,43 @@ spot_prepare_kernel(Geo g, int64_t n, int64_t stride, const double *__restrict__
                 }
             }
         }
-        spots[s] = rec;
     }
+    return counted;
+}
+
+// One thread per spot: footprint, depth key, tile census.
+//
+// Census.  Every (spot, tile) overlap takes `entries` places in its tile's list; the counter's old
+// value is the overlap's position (`ranks`, in the order the fill kernel walks a footprint's tiles), so
+// the fill needs no atomics.  The 32 spots of a warp vote before they count: overlaps with the same
+// tile (`__match_any_sync`) are added by one lane and share the returned base.  With `order` -- slot
+// s of the spot list reads particle order[s], a tile-major ordering the caller refreshes now and then
+// (molecules move a pixel or so per frame) -- the spots of a warp are neighbours on the screen and share
+// most of their tiles: a tenth of the atomics.  Without it the vote finds no partners and costs little.
+constexpr int kLocalStrips = 4096;     // strip counters of a CTA's shared-memory census (a 2048 x 2048 frame has 4096 strips)
+constexpr int kLocalRanks = 16;        // strips per footprint it can hold (the rest: global atomics)
+#ifndef SCB_PREPARE_CTAS
+#define SCB_PREPARE_CTAS 5     // 48 registers, no spills, 40 warps per SM (6: 40 registers with spills, 1 % slower)
+#endif
+template <int CTAS, bool LOCAL>      // CTAs per SM; LOCAL: the shared-memory census is compiled in
+__global__ void __launch_bounds__(256, CTAS)
+spot_prepare_kernel(Geo g, int64_t n, int64_t stride, const double *__restrict__ depth, const double *__restrict__ x,
+                    const double *__restrict__ y, const double *__restrict__ weight,
+                    const double *__restrict__ inv_scale, const int32_t *__restrict__ slot_of_key,
+                    SpotRec *__restrict__ spots, int *__restrict__ tile_count,
+                    unsigned long long *__restrict__ wmax_bits, int32_t *__restrict__ errors,
+                    int *__restrict__ ranks, int rank_cap, const int32_t *__restrict__ order,
+                    int *__restrict__ walk_list, unsigned *__restrict__ walk_count) {
+    // grid: x over the spots of one frame, y over frames
+    const int64_t in_frame = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int frame = blockIdx.y;
+    const int64_t s = g.frames > 1 ? (int64_t)frame * g.spots_per_frame + in_frame : in_frame;
+    const int64_t n_here = g.frames > 1 ? ((int64_t)(frame + 1) * g.spots_per_frame < n ? (int64_t)(frame + 1) * g.spots_per_frame : n) : n;
+    SpotRec rec;
+    double w_seen = 0.0;
+    const bool counted = spot_record(g, s, n_here, in_frame, frame, stride, depth, x, y, weight, inv_scale, slot_of_key,
+                                     order, errors, rec, w_seen);
+    if (s < n_here) spots[s] = rec;
     // ---- census, first choice: per CTA in shared memory.  The strips the CTA's 256 spots touch lie in a box of
     // strips (a few dozen when the caller hands the spots over in screen order, a whole 2048 x 2048 frame at
     // most); the overlaps are counted there with shared-memory atomics, whose old values are the positions inside
@@ -418,8 +432,14 @@ inline void edges_launch_shape(int edge_cap, int64_t n, dim3 &grid, dim3 &block)
 // CTAs before it through distributed shared memory -- one launch, no global round trip.
 constexpr int kScanCtas = 8;
 
+// PLAN: the scan of every list's ROOM instead of its length -- a quarter more than the census counted plus 32 units --
+// for a following block of frames whose lists are filled while they are counted (render.cu)
+template <bool PLAN>
 __global__ void __cluster_dims__(kScanCtas, 1, 1) __launch_bounds__(1024)
-tile_scan_kernel(int n_tiles, int stripes, const int *__restrict__ tile_count, int *__restrict__ tile_start) {
+tile_scan_kernel(int n_tiles, int stripes, const int *__restrict__ tile_count, int *__restrict__ tile_start,
+                 int tight = 0) {
+    // tight (a test hook): half of what was counted, so that units overflow
+    auto room = [tight](int c) { return PLAN ? (tight ? c >> 1 : c + (c >> 2) + 32) : c; };
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     __shared__ int warp_tot[32];
@@ -437,7 +457,7 @@ tile_scan_kernel(int n_tiles, int stripes, const int *__restrict__ tile_count, i
 #pragma unroll
     for (int r = 0; r < kScanRounds; ++r) {
         const int j = first + r * 1024 + threadIdx.x;
-        held[r] = (r < rounds && j < n) ? tile_count[(size_t)(j & mask) * n_tiles + (j >> shift)] : 0;
+        held[r] = (r < rounds && j < n) ? room(tile_count[(size_t)(j & mask) * n_tiles + (j >> shift)]) : 0;
     }
     // CTA total first (one block reduction), so that every CTA knows its offset before it writes
     int mine = 0;
@@ -445,7 +465,7 @@ tile_scan_kernel(int n_tiles, int stripes, const int *__restrict__ tile_count, i
     for (int r = 0; r < kScanRounds; ++r) mine += held[r];
     for (int r = kScanRounds; r < rounds; ++r) {
         const int j = first + r * 1024 + threadIdx.x;
-        if (j < n) mine += tile_count[(size_t)(j & mask) * n_tiles + (j >> shift)];
+        if (j < n) mine += room(tile_count[(size_t)(j & mask) * n_tiles + (j >> shift)]);
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, d);
@@ -487,7 +507,7 @@ tile_scan_kernel(int n_tiles, int stripes, const int *__restrict__ tile_count, i
         if (r < rounds) scan_round(r, held[r]);
     for (int r = kScanRounds; r < rounds; ++r) {
         const int j = first + r * 1024 + threadIdx.x;
-        scan_round(r, j < n ? tile_count[(size_t)(j & mask) * n_tiles + (j >> shift)] : 0);
+        scan_round(r, j < n ? room(tile_count[(size_t)(j & mask) * n_tiles + (j >> shift)]) : 0);
     }
     cluster.sync();      // keep cta_total alive until every CTA has read it
 }
@@ -514,6 +534,8 @@ tile_fill_kernel(Geo g, int64_t n, const SpotRec *__restrict__ spots,
         }
 }
 
+constexpr int kOverflowCap = 65536;    // units a planned block render may put aside (more: an error, the caller renders the block again unplanned)
+
 struct Workspace {
     SpotRec *spots;
     uint32_t *edges;
@@ -526,6 +548,13 @@ struct Workspace {
     int rank_cap;
     int *walk_list;                  // spots whose edges must be walked (render path)
     unsigned *walk_count;            // its length (cleared with the census)
+    // capacity plan of a block render (render.cu: spot_bin_fused_kernel): where every strip's list starts when the
+    // lists are filled in the same pass that counts them -- sized from the previous block's census, kept in the
+    // workspace from call to call -- and the units that did not fit their strip's room
+    int *plan_base;                  // [n_tiles + 1]
+    unsigned *overflow_count;        // cleared with the census
+    int *overflow_tile;              // [kOverflowCap]
+    void *overflow_units;            // [kOverflowCap] render units
     size_t bytes;
     int64_t pair_capacity;
 };
@@ -602,13 +631,20 @@ Workspace carve(const Geo &g, int64_t n, void *base, size_t entry_bytes = sizeof
     // per frame, so that a frame's accumulator LSBs do not depend on the frames it shares a launch with
     w.wmax_bits = (unsigned long long *)(p + off);
     w.next_tile = (int *)(p + off + 8 * (size_t)g.frames);
-    w.walk_count = (unsigned *)(p + off + 8 * (size_t)g.frames + 4); off += align_up(8 * (size_t)g.frames + 8);
+    w.walk_count = (unsigned *)(p + off + 8 * (size_t)g.frames + 4);
+    w.overflow_count = (unsigned *)(p + off + 8 * (size_t)g.frames + 8); off += align_up(8 * (size_t)g.frames + 16);
     w.tile_start = (int *)(p + off); off += align_up((n_tiles * g.stripes + 1) * sizeof(int));
     w.pair_spot = (int *)(p + off); off += align_up((size_t)w.pair_capacity * entry_bytes);
     w.ranks = nullptr;
     w.rank_cap = 0;
     w.walk_list = nullptr;
+    w.plan_base = nullptr;
+    w.overflow_tile = nullptr;
+    w.overflow_units = nullptr;
     if (with_ranks) {
+        w.plan_base = (int *)(p + off); off += align_up((n_tiles + 1) * sizeof(int));
+        w.overflow_tile = (int *)(p + off); off += align_up((size_t)kOverflowCap * sizeof(int));
+        w.overflow_units = (void *)(p + off); off += align_up((size_t)kOverflowCap * entry_bytes);
         w.rank_cap = tiles_per_spot_bound(g);
         w.ranks = (int *)(p + off); off += align_up((size_t)(n > 0 ? n : 1) * w.rank_cap * sizeof(int));
         w.walk_list = (int *)(p + off); off += align_up((size_t)(n > 0 ? n : 1) * sizeof(int));

@@ -337,7 +337,7 @@ extern "C" int scb_render_gaussian_tc(const scb_geometry *geom, int64_t n_spots,
         edges_launch_shape(w.edge_cap, n_spots, egrid, eblock);
         spot_edges_kernel<<<egrid, eblock, 0, s>>>(g, n_spots, w.spots, w.edges, w.edge_cap);
     }
-    tile_scan_kernel<<<kScanCtas, 1024, 0, s>>>(n_tiles, g.stripes, w.tile_count, w.tile_start);
+    tile_scan_kernel<false><<<kScanCtas, 1024, 0, s>>>(n_tiles, g.stripes, w.tile_count, w.tile_start);
     if (n_spots > 0) {
         tile_fill_kernel<<<scb_grid_for(n_spots, 256), 256, 0, s>>>(g, n_spots, w.spots, w.tile_start, w.tile_cursor,
                                                                    w.pair_spot);

@@ -194,6 +194,218 @@ strip_fill_kernel(Geo g, int64_t n, const SpotRec *__restrict__ spots, int edge_
     }
 }
 
+// ---- binning of a block of frames in ONE pass ------------------------------------------------------------------
+// When the strips' list regions are laid out beforehand -- `plan_base`, the scan of every list's room, sized a quarter
+// above what the previous block's census counted (tile_scan_kernel<true>; molecules move about a pixel per frame) --
+// the census, the hand-out of list positions and the writing of the units need no scan between them: this kernel is
+// spot_prepare_kernel and strip_fill_kernel in one, without the spot records (kept only for footprints whose edges
+// must be walked), the rank table and the second pass over the spots.  A CTA counts its 256 spots' overlaps in shared
+// memory, claims its share of every touched strip's list with one global atomic (the counter's old value is the share's
+// offset) and its threads write their units there.  A unit beyond its strip's room -- the plan is a forecast -- goes to
+// a short overflow list the render kernel also reads; the image does not depend on where a unit was listed.
+constexpr int kFusedStrips = 1024;     // strip counters of a CTA (more: its spots claim their places one by one)
+struct ListPlan {
+    const int *base;                   // [n_tiles + 1] start of every strip's list region; NULL: lists are tile_start's
+    const int *count;                  // [n_tiles] units counted per strip (the census)
+    long long capacity;                // units the list buffer holds
+    unsigned *overflow_count;
+    int *overflow_tile;
+    Unit *overflow_units;
+};
+
+// the units of one spot: what strip_fill_kernel writes, for a footprint whose record is still in registers
+struct UnitMaker {
+    Unit u;
+    bool fast;
+    int row_slot0, col_slot0;
+    const char *block;
+    const int64_t *table;
+    uint32_t ebase;
+    __device__ __forceinline__ UnitMaker(const Geo &g, const SpotRec &rec, int64_t s, int edge_cap, const int64_t *sat,
+                                         const void *box_table, int box_bytes) {
+        u.ws = rec.w;
+        const size_t table_at = (size_t)rec.slot * ((size_t)g.modulus * g.modulus * g.slots * g.slots);
+        fast = g.quick_runs && rec.row_run >= 0 && rec.col_run >= 0;
+        row_slot0 = (rec.row_run >> 16) - 1;
+        col_slot0 = (rec.col_run >> 16) - 1;
+        block = static_cast<const char *>(box_table) +
+                (table_at + ((size_t)(rec.row_run & 0xffff) * g.modulus + (rec.col_run & 0xffff)) * (size_t)(g.slots * g.slots)) *
+                    (size_t)box_bytes;
+        table = sat + table_at;
+        ebase = (uint32_t)s * 2u * (uint32_t)edge_cap;
+    }
+    // chunk q of the overlap with strip (ti, tj)
+    __device__ __forceinline__ const Unit &make(const Geo &g, const SpotRec &rec, int ti, int tj, int q, int edge_cap, int box_bytes) {
+        const int c_lo = max(rec.jmin, tj * g.tile_w), c_hi = min(rec.jmax, (tj + 1) * g.tile_w);
+        const int r_lo = max(rec.imin, ti * g.tile_h), r_hi = min(rec.imax, (ti + 1) * g.tile_h);
+        const int c = c_lo + q * g.chunk;
+        u.erow = ebase + (uint32_t)(r_lo - rec.imin);
+        u.ecol = ebase + (uint32_t)(edge_cap + c - rec.jmin);
+        u.shape = (uint32_t)(r_hi - r_lo) | (uint32_t)min(g.chunk, c_hi - c) << 8 | (uint32_t)(r_lo - ti * g.tile_h) << 16 |
+                  (uint32_t)(c - tj * g.tile_w) << 24;
+        if (fast) {
+            u.src = block + (size_t)(row_slot0 + (r_lo - rec.imin) + 1) * g.slots * (size_t)box_bytes;
+            u.extra = kUnitFast | (uint32_t)(col_slot0 + (c - rec.jmin) + 1);
+        } else {
+            u.src = table;
+            u.extra = 0;
+        }
+        return u;
+    }
+};
+
+__global__ void __launch_bounds__(256, 4)
+spot_bin_fused_kernel(Geo g, int64_t n, int64_t stride, const double *__restrict__ depth, const double *__restrict__ x,
+                      const double *__restrict__ y, const double *__restrict__ weight,
+                      const double *__restrict__ inv_scale, const int32_t *__restrict__ slot_of_key,
+                      SpotRec *__restrict__ spots, int *__restrict__ tile_count,
+                      unsigned long long *__restrict__ wmax_bits, int32_t *__restrict__ errors,
+                      const int32_t *__restrict__ order, int *__restrict__ walk_list, unsigned *__restrict__ walk_count,
+                      int edge_cap, const int64_t *__restrict__ sat, const void *__restrict__ box_table, int box_bytes,
+                      Unit *__restrict__ units, ListPlan plan) {
+    __shared__ int s_count[kFusedStrips];          // overlaps counted per strip of the CTA's box, then the share's offset
+    __shared__ int s_base[kFusedStrips];           // start of the strip's list
+    __shared__ int s_room[kFusedStrips];           // units it holds
+    __shared__ int s_box[4];
+    const int tid = threadIdx.x;
+    const int64_t in_frame = (int64_t)blockIdx.x * blockDim.x + tid;
+    const int frame = blockIdx.y;
+    const int64_t s = (int64_t)frame * g.spots_per_frame + in_frame;
+    const int64_t n_here = (int64_t)(frame + 1) * g.spots_per_frame < n ? (int64_t)(frame + 1) * g.spots_per_frame : n;
+    SpotRec rec;
+    double w_seen = 0.0;
+    const bool counted = spot_record(g, s, n_here, in_frame, frame, stride, depth, x, y, weight, inv_scale, slot_of_key, order,
+                                     errors, rec, w_seen);
+    if (counted && rec.walk) spots[s] = rec;       // read (and completed) by spot_edges_kernel only
+
+    if (tid == 0) { s_box[0] = INT_MAX; s_box[1] = -1; s_box[2] = INT_MAX; s_box[3] = -1; }
+    __syncthreads();
+    const int t0 = rec.imin / g.tile_h, t1 = (rec.imax - 1) / g.tile_h;
+    const int u0 = rec.jmin / g.tile_w, u1 = (rec.jmax - 1) / g.tile_w;
+    {
+        const int lo_i = __reduce_min_sync(0xffffffffu, counted ? t0 : INT_MAX);
+        const int hi_i = __reduce_max_sync(0xffffffffu, counted ? t1 : -1);
+        const int lo_j = __reduce_min_sync(0xffffffffu, counted ? u0 : INT_MAX);
+        const int hi_j = __reduce_max_sync(0xffffffffu, counted ? u1 : -1);
+        if ((tid & 31) == 0 && hi_i >= 0) {
+            atomicMin(&s_box[0], lo_i); atomicMax(&s_box[1], hi_i);
+            atomicMin(&s_box[2], lo_j); atomicMax(&s_box[3], hi_j);
+        }
+    }
+    __syncthreads();
+    const int bi0 = s_box[0], bi1 = s_box[1], bj0 = s_box[2], bj1 = s_box[3];
+    const int span_j = bj1 - bj0 + 1;
+    const int cells = bi1 >= bi0 ? (bi1 - bi0 + 1) * span_j : 0;
+    const bool local = cells <= kFusedStrips;                          // CTA uniform
+    const int frame_tile0 = frame * g.nti * g.ntj;
+    int *count = tile_count + frame_tile0;
+    UnitMaker maker(g, rec, s, edge_cap, sat, box_table, box_bytes);
+    // a unit's place: `at` in the list of `tile` (which starts at `base` and holds `room`), or the overflow list
+    auto put = [&](int tile, int base, int room, int at, const Unit &u) {
+        if (at < room && (long long)base + at < plan.capacity) {
+            units[base + at] = u;
+        } else {
+            const unsigned o = atomicAdd(plan.overflow_count, 1u);
+            if (o < (unsigned)kOverflowCap) {
+                plan.overflow_tile[o] = tile;
+                plan.overflow_units[o] = u;
+            } else {
+                atomicAdd(errors, 1);
+            }
+        }
+    };
+    if (local) {
+        for (int c = tid; c < cells; c += kCensusThreads) s_count[c] = 0;
+        __syncthreads();
+        // pass 1: count; the counter's old value is the overlap's place inside the CTA's share (kept packed, 16 bits
+        // each, in registers for the first kFusedKeep strips of the footprint; the rest claim their places directly)
+        unsigned long long keep0 = 0, keep1 = 0, keep2 = 0;
+        if (counted) {
+            int k = 0;
+            for (int tj = u0; tj <= u1; ++tj) {
+                const int entries = overlap_entries(g, rec.jmin, rec.jmax, tj);
+                for (int ti = t0; ti <= t1; ++ti, ++k) {
+                    if (k < 12) {
+                        const unsigned long long at = (unsigned)atomicAdd(&s_count[(ti - bi0) * span_j + (tj - bj0)], entries);
+                        if (k < 4) keep0 |= at << (16 * k);
+                        else if (k < 8) keep1 |= at << (16 * (k - 4));
+                        else keep2 |= at << (16 * (k - 8));
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        for (int c = tid; c < cells; c += kCensusThreads) {
+            const int mine = s_count[c];
+            if (mine > 0) {
+                const int ci = c / span_j;
+                const int tile = (bi0 + ci) * g.ntj + bj0 + (c - ci * span_j);
+                s_count[c] = atomicAdd(&count[tile], mine);
+                const int b = plan.base[frame_tile0 + tile];
+                s_base[c] = b;
+                s_room[c] = plan.base[frame_tile0 + tile + 1] - b;
+            }
+        }
+        __syncthreads();
+        if (counted) {
+            int k = 0;
+            for (int tj = u0; tj <= u1; ++tj) {
+                const int entries = overlap_entries(g, rec.jmin, rec.jmax, tj);
+                for (int ti = t0; ti <= t1; ++ti, ++k) {
+                    const int tile = ti * g.ntj + tj;
+                    int base, room, at;
+                    if (k < 12) {
+                        const int c = (ti - bi0) * span_j + (tj - bj0);
+                        const unsigned long long word = k < 4 ? keep0 >> (16 * k) : (k < 8 ? keep1 >> (16 * (k - 4)) : keep2 >> (16 * (k - 8)));
+                        base = s_base[c];
+                        room = s_room[c];
+                        at = s_count[c] + (int)(word & 0xffffu);
+                    } else {
+                        base = plan.base[frame_tile0 + tile];
+                        room = plan.base[frame_tile0 + tile + 1] - base;
+                        at = atomicAdd(&count[tile], entries);
+                    }
+                    for (int q = 0; q < entries; ++q)
+                        put(frame_tile0 + tile, base, room, at + q, maker.make(g, rec, ti, tj, q, edge_cap, box_bytes));
+                }
+            }
+        }
+    } else if (counted) {
+        // the CTA's strips spread too far for its counters: every overlap claims its place with its own atomic
+        for (int tj = u0; tj <= u1; ++tj) {
+            const int entries = overlap_entries(g, rec.jmin, rec.jmax, tj);
+            for (int ti = t0; ti <= t1; ++ti) {
+                const int tile = ti * g.ntj + tj;
+                const int base = plan.base[frame_tile0 + tile];
+                const int room = plan.base[frame_tile0 + tile + 1] - base;
+                const int at = atomicAdd(&count[tile], entries);
+                for (int q = 0; q < entries; ++q)
+                    put(frame_tile0 + tile, base, room, at + q, maker.make(g, rec, ti, tj, q, edge_cap, box_bytes));
+            }
+        }
+    }
+    // footprints whose edges must be walked are listed (as in spot_prepare_kernel)
+    {
+        const unsigned walks = __ballot_sync(0xffffffffu, counted && rec.walk != 0);
+        if (walks) {
+            const unsigned lane = tid & 31u;
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(walk_count, (unsigned)__popc(walks));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if ((walks >> lane) & 1u) walk_list[base + __popc(walks & ((1u << lane) - 1u))] = (int)s;
+        }
+    }
+    {
+        unsigned long long bits = (unsigned long long)__double_as_longlong(w_seen);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, bits, d);
+            bits = other > bits ? other : bits;
+        }
+        if ((tid & 31) == 0 && bits != 0) atomicMax(wmax_bits + frame, bits);
+    }
+}
+
 // ---- mbarrier / TMA helpers ------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -449,7 +661,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, ctas_per_sm<BoxT, ROWS, COPY>(
 render_strips_kernel(Geo g, const Unit *__restrict__ units, const uint32_t *__restrict__ edges,
                      const int *__restrict__ tile_start, int *__restrict__ next_tile,
                      const unsigned long long *__restrict__ wmax_bits, int64_t n_spots,
-                     OutT *__restrict__ out, int accumulate) {
+                     OutT *__restrict__ out, int accumulate, ListPlan plan) {
     using M = Mode<BoxT, ROWS>;
     using Acc = typename M::Acc;
     constexpr int kStripCols = M::kCols;
@@ -507,14 +719,29 @@ render_strips_kernel(Geo g, const Unit *__restrict__ units, const uint32_t *__re
         const int ti = in_frame / g.ntj, tj = in_frame - ti * g.ntj;
         const int row0 = ti * ROWS, col0 = tj * kStripCols;
         OutT *image = out + (size_t)frame * g.n_w * g.n_h;
-        const int seg_begin = tile_start[tile * g.stripes], seg_end = tile_start[(tile + 1) * g.stripes];
+        // the strip's list: a segment of the scanned lists, or -- planned block renders -- the filled part of the
+        // region the plan gave it, followed by the units of the overflow list that belong to it
+        int seg_begin, seg_end, n_units;
+        if (plan.base) {
+            seg_begin = plan.base[tile];
+            const long long room = min((long long)plan.base[tile + 1], plan.capacity) - seg_begin;
+            n_units = plan.count[tile];
+            seg_end = seg_begin + (int)max(0ll, min((long long)n_units, room));
+        } else {
+            seg_begin = tile_start[tile * g.stripes];
+            seg_end = tile_start[(tile + 1) * g.stripes];
+            n_units = seg_end - seg_begin;
+        }
         // LSB per strip (32-bit accumulators) or per frame (64-bit), from the frame's own largest weight: a frame's
         // bits do not depend on the frames it shares the launch with
         const unsigned long long wmax = wmax_bits[frame];
-        const int shift = sizeof(Acc) == 4 ? strip_shift(seg_end - seg_begin, wmax, g.box_peak)
+        const int shift = sizeof(Acc) == 4 ? strip_shift(n_units, wmax, g.box_peak)
                                            : accumulator_shift(wmax, frame_spots);
         const double scale = scalbn(1.0, shift), lsb = scalbn(1.0, -shift);
 
+        const Unit *list = units;
+        unsigned overflow_at = 0;                  // overflow entries looked at so far
+        for (;;) {
         for (int base = seg_begin; base < seg_end; base += kBatch) {
             const int nb = min(kBatch, seg_end - base);
             __syncwarp();
@@ -524,7 +751,7 @@ render_strips_kernel(Geo g, const Unit *__restrict__ units, const uint32_t *__re
             uint32_t my_bytes = 0;
             bool my_fast = false;
             if (lane < nb) {
-                const uint4 *src = reinterpret_cast<const uint4 *>(units + base + lane);
+                const uint4 *src = reinterpret_cast<const uint4 *>(list + base + lane);
                 uint4 *dst = reinterpret_cast<uint4 *>(meta + lane);
                 uint4 head = __ldg(src);                                    // {ws, src}
                 uint4 tail = __ldg(src + 1);                                // {erow, ecol, shape, extra}
@@ -639,6 +866,22 @@ render_strips_kernel(Geo g, const Unit *__restrict__ units, const uint32_t *__re
             if (COPY != kCopyNone && fast_mask == whole) run_batch(std::true_type());
             else run_batch(std::false_type());
             if (COPY != 0 && COPY != kCopyNone) cp_async_wait<0>();     // TMA and gather units at the end of a batch leave empty groups behind
+        }
+        // the next unit of the overflow list that belongs to this strip, if any (the list is empty unless the plan
+        // fell short somewhere)
+        if (!plan.base) break;
+        const unsigned n_over = min(*plan.overflow_count, (unsigned)kOverflowCap);
+        int found = -1;
+        while (overflow_at < n_over && found < 0) {
+            const unsigned i = overflow_at + lane;
+            const unsigned hits = __ballot_sync(0xffffffffu, i < n_over && plan.overflow_tile[i] == tile);
+            if (hits) found = (int)overflow_at + __ffs(hits) - 1;
+            overflow_at = hits ? (unsigned)found + 1u : overflow_at + 32u;
+        }
+        if (found < 0) break;
+        list = plan.overflow_units;
+        seg_begin = found;
+        seg_end = found + 1;
         }
 
         // ---- write the strip (coalesced rows) and clear the accumulators for the next one
@@ -774,7 +1017,7 @@ extern "C" size_t scb_render_frames_workspace_bytes(const scb_geometry *geom, in
 
 template <typename OutT, typename BoxT, int ROWS, int SLOTS, int COPY>
 static int launch_render_as(const Geo &g, const Workspace &w, int64_t n_spots, OutT *out, int accumulate,
-                            cudaStream_t s) {
+                            cudaStream_t s, const ListPlan &plan) {
     const int n_tiles = g.frames * g.nti * g.ntj;
     // persistent grid: a few CTAs per SM, each warp pulls strips from a queue; small images get
     // narrower CTAs so that the strips still spread over all SMs
@@ -796,15 +1039,15 @@ static int launch_render_as(const Geo &g, const Workspace &w, int64_t n_spots, O
         configured.fetch_or(bit, std::memory_order_release);
     }
     render_strips_kernel<OutT, BoxT, ROWS, SLOTS, COPY><<<ctas, warps * 32, smem, s>>>(
-        g, (const Unit *)w.pair_spot, w.edges, w.tile_start, w.next_tile, w.wmax_bits, n_spots, out, accumulate);
+        g, (const Unit *)w.pair_spot, w.edges, w.tile_start, w.next_tile, w.wmax_bits, n_spots, out, accumulate, plan);
     return 0;
 }
 
 template <typename OutT, typename BoxT, int ROWS, int COPY>
 static int launch_render_slots(const Geo &g, const Workspace &w, int64_t n_spots, OutT *out, int accumulate,
-                               cudaStream_t s) {
-    return g.slots == 32 ? launch_render_as<OutT, BoxT, ROWS, 32, COPY>(g, w, n_spots, out, accumulate, s)
-                         : launch_render_as<OutT, BoxT, ROWS, 0, COPY>(g, w, n_spots, out, accumulate, s);
+                               cudaStream_t s, const ListPlan &plan) {
+    return g.slots == 32 ? launch_render_as<OutT, BoxT, ROWS, 32, COPY>(g, w, n_spots, out, accumulate, s, plan)
+                         : launch_render_as<OutT, BoxT, ROWS, 0, COPY>(g, w, n_spots, out, accumulate, s, plan);
 }
 
 template <typename OutT, int WARPS, int CTAS, int STAGES>
@@ -886,23 +1129,23 @@ static int launch_render_reg(const CUtensorMap &box_map, const Geo &g, const Wor
 
 template <typename OutT>
 static int launch_render(const Geo &g, const Workspace &w, int64_t n_spots, OutT *out, int accumulate, int box_type,
-                         cudaStream_t s) {
+                         cudaStream_t s, const ListPlan &plan) {
     const RenderVariant v = render_variant();
     // no footprint can take the box-table path (no table, or the test hook): the instance without a copy ring
     if (!g.quick_runs && g.tile_h == 8) {
-        if (box_type == SCB_F32) return launch_render_as<OutT, float, 8, 0, kCopyNone>(g, w, n_spots, out, accumulate, s);
-        return launch_render_as<OutT, double, 8, 0, kCopyNone>(g, w, n_spots, out, accumulate, s);
+        if (box_type == SCB_F32) return launch_render_as<OutT, float, 8, 0, kCopyNone>(g, w, n_spots, out, accumulate, s, plan);
+        return launch_render_as<OutT, double, 8, 0, kCopyNone>(g, w, n_spots, out, accumulate, s, plan);
     }
     if (box_type == SCB_F32) {
         if (g.tile_h == 16)
-            return v.copy ? launch_render_slots<OutT, float, 16, 1>(g, w, n_spots, out, accumulate, s)
-                          : launch_render_slots<OutT, float, 16, 0>(g, w, n_spots, out, accumulate, s);
-        if (v.copy == 2) return launch_render_slots<OutT, float, 8, 2>(g, w, n_spots, out, accumulate, s);
-        return v.copy ? launch_render_slots<OutT, float, 8, 1>(g, w, n_spots, out, accumulate, s)
-                      : launch_render_slots<OutT, float, 8, 0>(g, w, n_spots, out, accumulate, s);
+            return v.copy ? launch_render_slots<OutT, float, 16, 1>(g, w, n_spots, out, accumulate, s, plan)
+                          : launch_render_slots<OutT, float, 16, 0>(g, w, n_spots, out, accumulate, s, plan);
+        if (v.copy == 2) return launch_render_slots<OutT, float, 8, 2>(g, w, n_spots, out, accumulate, s, plan);
+        return v.copy ? launch_render_slots<OutT, float, 8, 1>(g, w, n_spots, out, accumulate, s, plan)
+                      : launch_render_slots<OutT, float, 8, 0>(g, w, n_spots, out, accumulate, s, plan);
     }
-    return v.copy == 1 ? launch_render_slots<OutT, double, 8, 1>(g, w, n_spots, out, accumulate, s)
-                       : launch_render_slots<OutT, double, 8, 0>(g, w, n_spots, out, accumulate, s);
+    return v.copy == 1 ? launch_render_slots<OutT, double, 8, 1>(g, w, n_spots, out, accumulate, s, plan)
+                       : launch_render_slots<OutT, double, 8, 0>(g, w, n_spots, out, accumulate, s, plan);
 }
 
 static int render_expected_strided(const scb_geometry *geom, int64_t n_spots, int frames, int64_t stride,
@@ -911,7 +1154,7 @@ static int render_expected_strided(const scb_geometry *geom, int64_t n_spots, in
                                    const int64_t *d_sat, const void *d_box, int box_type, const double *d_inv_scale,
                                    const int32_t *d_slot_of_key, void *d_out, int out_type,
                                    int accumulate, void *d_workspace, size_t workspace_bytes,
-                                   int32_t *d_errors, void *stream) {
+                                   int32_t *d_errors, void *stream, int plan_mode = 0) {
     int rc = check_geometry(geom);
     if (rc) return rc;
     SCB_REQUIRE(n_spots >= 0 && n_spots < (int64_t)1 << 30, SCB_E_INVALID, "n_spots=%lld", (long long)n_spots);
@@ -925,6 +1168,7 @@ static int render_expected_strided(const scb_geometry *geom, int64_t n_spots, in
     SCB_REQUIRE(frames >= 1 && frames <= 4096 && n_spots % frames == 0, SCB_E_INVALID,
                 "scb_render_expected: %lld spots do not split into %d frames", (long long)n_spots, frames);
     Geo g = strip_geo(geom, d_box != nullptr, box_bytes, frames, n_spots / frames);
+    if (plan_mode != 0 && frames > 1) g.stripes = 1;      // list plans index one counter per strip
     // the CTA-tile kernel (render_tile.cuh): 32 x 128 tiles, one list entry per (spot, tile, run of 32 columns)
     const bool tile_path = render_variant().reg == 3 && forced_gather() != 1 && d_box && box_bytes == 4 &&
                            g.slots <= 32 && g.slots % 4 == 0;
@@ -949,6 +1193,24 @@ static int render_expected_strided(const scb_geometry *geom, int64_t n_spots, in
     const int n_tiles = g.frames * g.nti * g.ntj;
     // census, cursors, weight maximum and the strip queue are adjacent 256-aligned blocks: clear them all
     SCB_CUDA(cudaMemsetAsync(w.tile_count, 0, (size_t)((char *)w.tile_start - (char *)w.tile_count), s));
+    const bool reg_path = !tile_path && forced_gather() != 1 && reg_path_for(d_box != nullptr, box_bytes, g.slots);
+    // A planned block render (plan_mode bit 0: the workspace holds the list plan the previous call left behind for the
+    // same geometry, spots and frames) counts, places and writes the units in one pass; bit 1 leaves a plan behind.
+    // Only the shared-memory kernel's units are written that way.
+    const bool can_plan = !tile_path && !reg_path && frames > 1 && g.stripes == 1 && w.plan_base != nullptr && n_spots > 0;
+    const bool planned = can_plan && (plan_mode & 1);
+    ListPlan plan = {nullptr, w.tile_count, w.pair_capacity, w.overflow_count, w.overflow_tile, (Unit *)w.overflow_units};
+    if (planned) plan.base = w.plan_base;
+    if (planned) {
+        spot_bin_fused_kernel<<<dim3(scb_grid_for(n_spots / frames, 256), frames), 256, 0, s>>>(
+            g, n_spots, stride, d_depth, d_x, d_y, d_weight, d_inv_scale, d_slot_of_key, w.spots, w.tile_count, w.wmax_bits,
+            d_errors, d_order, w.walk_list, w.walk_count, w.edge_cap, d_sat, d_box, box_bytes, (Unit *)w.pair_spot, plan);
+        dim3 egrid, eblock;
+        edges_launch_shape(w.edge_cap, n_spots, egrid, eblock);
+        const unsigned cap = (unsigned)(SCB_SM_COUNT * 16);
+        if (egrid.x > cap) egrid.x = cap;
+        spot_edges_kernel<<<egrid, eblock, 0, s>>>(g, n_spots, w.spots, w.edges, w.edge_cap, w.walk_list, w.walk_count);
+    } else {
     if (n_spots > 0) {
         // SCB_PREPARE_CENSUS=global: the census by global atomics only (the measured alternative)
         const char *census = getenv("SCB_PREPARE_CENSUS");
@@ -964,14 +1226,14 @@ static int render_expected_strided(const scb_geometry *geom, int64_t n_spots, in
         if (egrid.x > cap) egrid.x = cap;
         spot_edges_kernel<<<egrid, eblock, 0, s>>>(g, n_spots, w.spots, w.edges, w.edge_cap, w.walk_list, w.walk_count);
     }
-    tile_scan_kernel<<<kScanCtas, 1024, 0, s>>>(n_tiles, g.stripes, w.tile_count, w.tile_start);
-    const bool reg_path = !tile_path && forced_gather() != 1 && reg_path_for(d_box != nullptr, box_bytes, g.slots);
+    tile_scan_kernel<false><<<kScanCtas, 1024, 0, s>>>(n_tiles, g.stripes, w.tile_count, w.tile_start);
+    }
     CUtensorMap box_map;
     if (reg_path && render_variant().reg == 2) {
         rc = make_box_map(&box_map, d_box, g.slots, (long long)(g.n_depth_keys + 1) * g.modulus * g.modulus);
         if (rc) return rc;
     }
-    if (n_spots > 0) {
+    if (n_spots > 0 && !planned) {
         if (tile_path)
             tile_fill_units_kernel<<<scb_grid_for(n_spots, 256), 256, 0, s>>>(g, n_spots, w.spots, w.ranks, w.rank_cap,
                                                                              w.tile_start, (TUnit *)w.pair_spot);
@@ -999,10 +1261,15 @@ static int render_expected_strided(const scb_geometry *geom, int64_t n_spots, in
     } else if (reg_path) {
         if (out_type == SCB_F32) rc = launch_render_reg<float>(box_map, g, w, d_sat, (const float *)d_box, (float *)d_out, accumulate, s);
         else rc = launch_render_reg<double>(box_map, g, w, d_sat, (const float *)d_box, (double *)d_out, accumulate, s);
-    } else if (out_type == SCB_F32) rc = launch_render<float>(g, w, n_spots, (float *)d_out, accumulate, box_type, s);
-    else rc = launch_render<double>(g, w, n_spots, (double *)d_out, accumulate, box_type, s);
+    } else if (out_type == SCB_F32) rc = launch_render<float>(g, w, n_spots, (float *)d_out, accumulate, box_type, s, plan);
+    else rc = launch_render<double>(g, w, n_spots, (double *)d_out, accumulate, box_type, s, plan);
     if (timed >= 0) cudaEventRecord(g_profile.stop[timed], s);
     if (rc) return rc;
+    // the plan for the next block of the same shape: every list's room from this block's census
+    if (can_plan && (plan_mode & 2)) {
+        const char *tight = getenv("SCB_PLAN_TIGHT");       // test hook: plans that are too small
+        tile_scan_kernel<true><<<kScanCtas, 1024, 0, s>>>(n_tiles, 1, w.tile_count, w.plan_base, tight && tight[0] == '1');
+    }
     SCB_CUDA_LAUNCH_CHECK("scb_render_expected");
     return 0;
 }
@@ -1057,6 +1324,22 @@ extern "C" int scb_render_expected_frames_ordered(const scb_geometry *geom, int6
     return render_expected_strided(geom, n_per_frame * n_frames, n_frames, 1, d_order, d_depth, d_x, d_y, d_weight, d_sat,
                                    d_box, box_type, d_inv_scale, d_slot_of_key, d_out, out_type, 0, d_workspace,
                                    workspace_bytes, d_errors, stream);
+}
+
+extern "C" int scb_render_expected_frames_planned(const scb_geometry *geom, int64_t n_per_frame, int n_frames,
+                                                  const int32_t *d_order, const double *d_depth, const double *d_x,
+                                                  const double *d_y, const double *d_weight, const int64_t *d_sat,
+                                                  const void *d_box, int box_type, const double *d_inv_scale,
+                                                  const int32_t *d_slot_of_key, void *d_out, int out_type,
+                                                  void *d_workspace, size_t workspace_bytes, int32_t *d_errors,
+                                                  int plan_mode, void *stream) {
+    SCB_REQUIRE(n_per_frame >= 0 && n_frames >= 1, SCB_E_INVALID, "scb_render_expected_frames_planned: n=%lld frames=%d",
+                (long long)n_per_frame, n_frames);
+    SCB_REQUIRE(n_per_frame < ((int64_t)1 << 31), SCB_E_INVALID, "scb_render_expected_frames_planned: n=%lld", (long long)n_per_frame);
+    SCB_REQUIRE(plan_mode >= 0 && plan_mode <= 3, SCB_E_INVALID, "scb_render_expected_frames_planned: plan_mode=%d", plan_mode);
+    return render_expected_strided(geom, n_per_frame * n_frames, n_frames, 1, d_order, d_depth, d_x, d_y, d_weight, d_sat,
+                                   d_box, box_type, d_inv_scale, d_slot_of_key, d_out, out_type, 0, d_workspace,
+                                   workspace_bytes, d_errors, stream, plan_mode);
 }
 
 extern "C" int scb_render_expected_frames(const scb_geometry *geom, int64_t n_per_frame, int n_frames,

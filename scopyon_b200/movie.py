@@ -12,6 +12,7 @@ and then renders its own block.  No collective sits inside the per-frame compute
 only used to gather finished frames (``gather_frames``).
 """
 import ctypes
+import os
 
 import numpy
 
@@ -274,12 +275,20 @@ class DeviceMovie:
             self._p(2), self._p(0), self._p(1), sigma_dxy, self.exposure, focal, ctypes.byref(eng.phys),
             _native.ptr(self.budget), _native.ptr(state[0]), _native.ptr(state[1]), _native.ptr(state[2]),
             _native.ptr(state[3]), stream), "scb_movie_frames")
-        _native.check(eng.lib.scb_render_expected_frames_ordered(
+        # consecutive blocks of the same shape: the binning of this block runs in one pass over the list plan the
+        # previous block left in the workspace (bit 0), and leaves one for the next (bit 1); the images are the same
+        plan_key = (nf, work.data_ptr(), self.frame)
+        plan_mode = 0
+        if self.plan_blocks:
+            plan_mode = 2 | (1 if cache.get("plan") == plan_key else 0)
+        _native.check(eng.lib.scb_render_expected_frames_planned(
             ctypes.byref(eng.geom), self.n, nf, _native.ptr(self._visiting_order(state)),
             _native.ptr(state[0]), _native.ptr(state[1]), _native.ptr(state[2]),
             _native.ptr(state[3]), _native.ptr(eng.sat), _native.ptr(eng.box), eng.box_type,
             _native.ptr(eng.inv_scale), _native.ptr(eng.slot_of_key), _native.ptr(photons), eng.elem_type,
-            _native.ptr(work), work.numel(), _native.ptr(eng.errors), stream), "scb_render_expected_frames_ordered")
+            _native.ptr(work), work.numel(), _native.ptr(eng.errors), plan_mode, stream),
+            "scb_render_expected_frames_planned")
+        cache["plan"] = (nf, work.data_ptr(), self.frame + nf) if plan_mode & 2 else None
         batched = (eng.dtype == torch.float32 and out.dtype == torch.float32 and out.is_contiguous()
                    and (eng.n_w * eng.n_h) % 4 == 0
                    and (self.configs.ADConverter_fpn_type != 'column' or eng.n_h % 4 == 0))
@@ -298,6 +307,9 @@ class DeviceMovie:
 
     #: blocks rendered with one visiting order before it is refreshed (molecules move about a pixel per frame)
     order_refresh_blocks = 8
+    #: consecutive blocks bin their spots in one pass over a list plan taken from the previous block's census
+    #: (``scb_render_expected_frames_planned``; SCOPYON_B200_PLAN=0 turns it off: count, scan, fill)
+    plan_blocks = os.environ.get("SCOPYON_B200_PLAN", "1") != "0"
 
     def _visiting_order(self, state):
         """Particle indices sorted by the coarse screen cell (32 x 32 pixels, row-major) of the first frame

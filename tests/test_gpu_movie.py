@@ -193,3 +193,31 @@ def test_frames_to_u16():
         torch.cuda.synchronize()
         want = numpy.rint(numpy.clip(numpy.nan_to_num(stack.astype(numpy.float64), nan=0.0), 0, 65535)).astype(numpy.uint16)
         assert numpy.array_equal(out.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("tight", [False, True], ids=["plan", "tight-plan"])
+def test_planned_blocks_equal_unplanned_blocks(tight):
+    """Consecutive blocks of a movie bin their spots in one pass over the list plan the previous block left behind
+    (scb_render_expected_frames_planned); a plan that is too small (the test hook halves every list's room) sends
+    units to the overflow list.  Either way the frames are those of the count / scan / fill pipeline, bit for bit."""
+    import os
+    n_frames, nf = 40, 8
+
+    def movie_frames(plan):
+        _, movie = make_movie("0.0", "true", n=3000)
+        movie.plan_blocks = plan
+        movie.frames_per_launch = nf
+        frames = torch.empty((n_frames, 96, 80), dtype=torch.float32, device=movie.engine.device)
+        movie.render_block(frames)
+        torch.cuda.synchronize()
+        assert int(movie.engine.errors.item()) == 0
+        return frames.cpu().numpy()
+
+    want = movie_frames(False)
+    if tight:
+        os.environ["SCB_PLAN_TIGHT"] = "1"
+    try:
+        got = movie_frames(True)
+    finally:
+        os.environ.pop("SCB_PLAN_TIGHT", None)
+    assert want.max() > 0 and numpy.array_equal(got, want)
