@@ -31,6 +31,7 @@ struct Geo {
     int frames;         // images rendered by one call (a block of movie frames); strips of frame f follow those of f - 1
     int64_t spots_per_frame;
     int tile_h, tile_w; // screen tile in pixels (8 x 128: SAT render strips, 128 x 128: Gaussian tensor-core render)
+    int th_shift, tw_shift, chunk_shift;   // their logarithms (and the chunk's) when they are powers of two, else -1
     int chunk;          // >0: a (spot, tile) pair is listed once per `chunk` columns of the overlap
     int stripes;        // copies of the per-tile counters (power of two): spreads the census atomics
     uint32_t modulus_magic;   // ceil(2^32 / modulus): b / modulus == umulhi(b, magic) for b < 2^16
@@ -70,8 +71,12 @@ __device__ __forceinline__ int edge_index(int i, int i_first, int i_last, double
 __device__ __forceinline__ int overlap_entries(const Geo &g, int jmin, int jmax, int tj) {
     if (g.chunk <= 0) return 1;
     const int c_lo = max(jmin, tj * g.tile_w), c_hi = min(jmax, (tj + 1) * g.tile_w);
+    if (g.chunk_shift >= 0) return (c_hi - c_lo + g.chunk - 1) >> g.chunk_shift;
     return (c_hi - c_lo + g.chunk - 1) / g.chunk;
 }
+// first / last strip row and column of a footprint: non-negative pixel indices over the tile size
+__device__ __forceinline__ int strip_row_of(const Geo &g, int i) { return g.th_shift >= 0 ? i >> g.th_shift : i / g.tile_h; }
+__device__ __forceinline__ int strip_col_of(const Geo &g, int j) { return g.tw_shift >= 0 ? j >> g.tw_shift : j / g.tile_w; }
 
 // Unclamped ceil((i*pl - o)/res) when it is safely away from a rounding decision (|distance to
 // an integer| > 1e-9 samples, far above the ~1e-12 the evaluation order can move it); false otherwise.
@@ -566,6 +571,8 @@ Geo make_geo(const scb_geometry *geom, int tile_h, int tile_w, int chunk = 0, in
     g.special_edges = 0;
     g.quick_runs = 0;
     g.tile_h = tile_h; g.tile_w = tile_w; g.chunk = chunk;
+    auto log2_of = [](int v) { int k = 0; while (v > 1 && !(v & 1)) { v >>= 1; ++k; } return v == 1 ? k : -1; };
+    g.th_shift = log2_of(tile_h); g.tw_shift = log2_of(tile_w); g.chunk_shift = chunk > 0 ? log2_of(chunk) : -1;
     g.n_w = geom->n_w; g.n_h = geom->n_h;
     g.frames = frames < 1 ? 1 : frames; g.spots_per_frame = 0;
     g.box_peak = 1.0;
