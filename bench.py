@@ -727,9 +727,9 @@ def run_weak(args):
             "dtype": "f32 box tables and frames, 32-bit fixed-point accumulation per strip (edge arithmetic f64)",
             "data": "synthetic", "config": workload_config(args),
             "clocks": clocks, "e2e": e2e,
-            # per launch group (frames_per_launch frames): movie_frames, spot_prepare, spot_edges, tile_scan, strip_fill,
-            # render_strips, detector_fast, detector_slow
-            "gpu_launches": int(8 * render_launches),
+            # per launch group (frames_per_launch frames) of a planned block: movie_frames, spot_bin_fused, spot_edges,
+            # render_strips, tile_scan (the next block's list plan), detector_fast, detector_slow
+            "gpu_launches": int(7 * render_launches),
             "roofline": {
                 "kernel": "render_strips_kernel<float>", "bound": "hbm", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_source,
@@ -910,7 +910,7 @@ def run_strong(args):
                     "d2h_bytes_per_step": int(T * args.size * args.size * {"f32": 4, "u16": 2, "u8": 1}[args.export]),
                     "note": "device-resident trajectory (DeviceMovie API); every frame leaves the GPU inside the timed region"},
             "host": host, "gather_ok": gather_ok,
-            "gpu_launches": int(world * n_blocks * 8), "setup_s": setup_s,
+            "gpu_launches": int(world * n_blocks * (7 if args.export == "f32" else 8)), "setup_s": setup_s,
         }
         if rates["f32"]["value"] and host.get("frames_per_s_at_pcie_f32"):
             line["export"]["f32"]["frac_of_pcie_bound"] = rates["f32"]["value"] / host["frames_per_s_at_pcie_f32"]
