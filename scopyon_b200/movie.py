@@ -251,6 +251,7 @@ class DeviceMovie:
                     deliver(k - (ring - 1))
             for k in sorted(in_flight):
                 deliver(k)
+            self._raise_device_errors(wait=True)
         return delivered
 
     def _render_frames(self, out):
@@ -275,6 +276,7 @@ class DeviceMovie:
             self._p(2), self._p(0), self._p(1), sigma_dxy, self.exposure, focal, ctypes.byref(eng.phys),
             _native.ptr(self.budget), _native.ptr(state[0]), _native.ptr(state[1]), _native.ptr(state[2]),
             _native.ptr(state[3]), stream), "scb_movie_frames")
+        self._raise_device_errors(wait=False)
         # consecutive blocks of the same shape: the binning of this block runs in one pass over the list plan the
         # previous block left in the workspace (bit 0), and leaves one for the next (bit 1); the images are the same
         plan_key = (nf, work.data_ptr(), self.frame)
@@ -289,6 +291,14 @@ class DeviceMovie:
             _native.ptr(work), work.numel(), _native.ptr(eng.errors), plan_mode, stream),
             "scb_render_expected_frames_planned")
         cache["plan"] = (nf, work.data_ptr(), self.frame + nf) if plan_mode & 2 else None
+        if plan_mode & 1:
+            # a plan that fell short by more than the overflow list holds is counted in the engine's error word:
+            # fetched without waiting, looked at when the next block is enqueued (or by check_errors())
+            seen = self.__dict__.setdefault("_errors_seen", dict(
+                host=torch.zeros(1, dtype=torch.int32).pin_memory(), event=torch.cuda.Event()))
+            seen["host"].copy_(eng.errors.reshape(-1)[:1], non_blocking=True)
+            seen["event"].record(torch.cuda.current_stream(eng.device))
+            seen["pending"] = True
         batched = (eng.dtype == torch.float32 and out.dtype == torch.float32 and out.is_contiguous()
                    and (eng.n_w * eng.n_h) % 4 == 0
                    and (self.configs.ADConverter_fpn_type != 'column' or eng.n_h % 4 == 0))
@@ -304,6 +314,25 @@ class DeviceMovie:
                 eng.detect(photons[f], self.frame + f, self.noise_seed, adc=out[f])
         self.weight = state[3, nf - 1]
         self.frame += nf
+
+    def _raise_device_errors(self, wait):
+        seen = self.__dict__.get("_errors_seen")
+        if not seen or not seen.get("pending"):
+            return
+        if wait:
+            seen["event"].synchronize()
+        elif not seen["event"].query():
+            return
+        seen["pending"] = False
+        if int(seen["host"][0]) > 0:
+            raise RuntimeError("scopyon_b200: {} device-side errors while rendering a planned block (a list plan fell "
+                               "short by more than the overflow list holds): render again with plan_blocks = False"
+                               .format(int(seen["host"][0])))
+
+    def check_errors(self):
+        """Wait for the blocks enqueued so far and raise if the device counted an error in one of them."""
+        with torch.cuda.device(self.engine.device):
+            self._raise_device_errors(wait=True)
 
     #: blocks rendered with one visiting order before it is refreshed (molecules move about a pixel per frame)
     order_refresh_blocks = 8

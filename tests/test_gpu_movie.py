@@ -221,3 +221,22 @@ def test_planned_blocks_equal_unplanned_blocks(tight):
     finally:
         os.environ.pop("SCB_PLAN_TIGHT", None)
     assert want.max() > 0 and numpy.array_equal(got, want)
+
+
+def test_a_plan_that_falls_short_by_too_much_is_reported():
+    """More units beyond their strips' room than the overflow list holds (65 536): the device counts them and the
+    movie raises -- at the next block, or when asked (check_errors) -- instead of handing out frames with spots missing."""
+    import os
+    _, movie = make_movie("0.0", "false", n=12000)
+    movie.frames_per_launch = 8
+    frames = torch.empty((16, 96, 80), dtype=torch.float32, device=movie.engine.device)
+    os.environ["SCB_PLAN_TIGHT"] = "1"
+    try:
+        movie.render_block(frames[:8])          # first block: count / scan / fill, leaves a plan of half the room
+        movie.check_errors()
+        movie.render_block(frames[8:])          # ~ 3e5 units, half of them beyond their strip's room
+        with pytest.raises(RuntimeError, match="planned block"):
+            movie.check_errors()
+    finally:
+        os.environ.pop("SCB_PLAN_TIGHT", None)
+        movie.engine.errors.zero_()
