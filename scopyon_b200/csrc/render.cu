@@ -204,6 +204,7 @@ strip_fill_kernel(Geo g, int64_t n, const SpotRec *__restrict__ spots, int edge_
 // offset) and its threads write their units there.  A unit beyond its strip's room -- the plan is a forecast -- goes to
 // a short overflow list the render kernel also reads; the image does not depend on where a unit was listed.
 constexpr int kFusedStrips = 1024;     // strip counters of a CTA (more: its spots claim their places one by one)
+constexpr int kFusedKeep = 12;         // strips of a footprint whose places inside the CTA's shares are kept (three packed words)
 struct ListPlan {
     const int *base;                   // [n_tiles + 1] start of every strip's list region; NULL: lists are tile_start's
     const int *count;                  // [n_tiles] units counted per strip (the census)
@@ -326,7 +327,7 @@ spot_bin_fused_kernel(Geo g, int64_t n, int64_t stride, const double *__restrict
             for (int tj = u0; tj <= u1; ++tj) {
                 const int entries = overlap_entries(g, rec.jmin, rec.jmax, tj);
                 for (int ti = t0; ti <= t1; ++ti, ++k) {
-                    if (k < 12) {
+                    if (k < kFusedKeep) {
                         const unsigned long long at = (unsigned)atomicAdd(&s_count[(ti - bi0) * span_j + (tj - bj0)], entries);
                         if (k < 4) keep0 |= at << (16 * k);
                         else if (k < 8) keep1 |= at << (16 * (k - 4));
@@ -355,7 +356,7 @@ spot_bin_fused_kernel(Geo g, int64_t n, int64_t stride, const double *__restrict
                 for (int ti = t0; ti <= t1; ++ti, ++k) {
                     const int tile = ti * g.ntj + tj;
                     int base, room, at;
-                    if (k < 12) {
+                    if (k < kFusedKeep) {
                         const int c = (ti - bi0) * span_j + (tj - bj0);
                         const unsigned long long word = k < 4 ? keep0 >> (16 * k) : (k < 8 ? keep1 >> (16 * (k - 4)) : keep2 >> (16 * (k - 8)));
                         base = s_base[c];
