@@ -208,7 +208,7 @@ constexpr int kFusedKeep = 12;         // strips of a footprint whose places ins
 struct ListPlan {
     const int *base;                   // [n_tiles + 1] start of every strip's list region; NULL: lists are tile_start's
     const int *count;                  // [n_tiles] units counted per strip (the census)
-    long long capacity;                // units the list buffer holds
+    int capacity;                      // units the list buffer holds (clamped to INT_MAX: list positions are 32-bit)
     unsigned *overflow_count;
     int *overflow_tile;
     Unit *overflow_units;
@@ -304,7 +304,7 @@ spot_bin_fused_kernel(Geo g, int64_t n, int64_t stride, const double *__restrict
     UnitMaker maker(g, rec, s, edge_cap, sat, box_table, box_bytes);
     // a unit's place: `at` in the list of `tile` (which starts at `base` and holds `room`), or the overflow list
     auto put = [&](int tile, int base, int room, int at, const Unit &u) {
-        if (at < room && (long long)base + at < plan.capacity) {
+        if (at < room && at < plan.capacity - base) {
             units[base + at] = u;
         } else {
             const unsigned o = atomicAdd(plan.overflow_count, 1u);
@@ -726,9 +726,9 @@ render_strips_kernel(Geo g, const Unit *__restrict__ units, const uint32_t *__re
         int seg_begin, seg_end, n_units;
         if (plan.base) {
             seg_begin = plan.base[tile];
-            const long long room = min((long long)plan.base[tile + 1], plan.capacity) - seg_begin;
+            const int room = min(plan.base[tile + 1], plan.capacity) - seg_begin;
             n_units = plan.count[tile];
-            seg_end = seg_begin + (int)max(0ll, min((long long)n_units, room));
+            seg_end = seg_begin + max(0, min(n_units, room));
         } else {
             seg_begin = tile_start[tile * g.stripes];
             seg_end = tile_start[(tile + 1) * g.stripes];
@@ -743,6 +743,7 @@ render_strips_kernel(Geo g, const Unit *__restrict__ units, const uint32_t *__re
 
         const Unit *list = units;
         unsigned overflow_at = 0;                  // overflow entries looked at so far
+        int missing = n_units - (seg_end - seg_begin);     // units of this strip that sit in the overflow list
         for (;;) {
         for (int base = seg_begin; base < seg_end; base += kBatch) {
             const int nb = min(kBatch, seg_end - base);
@@ -871,7 +872,8 @@ render_strips_kernel(Geo g, const Unit *__restrict__ units, const uint32_t *__re
         }
         // the next unit of the overflow list that belongs to this strip, if any (the list is empty unless the plan
         // fell short somewhere)
-        if (!plan.base) break;
+        if (!plan.base || missing <= 0) break;     // (a strip whose plan held looks at nothing: only the strips that
+        --missing;                                 // overflowed search the list, and stop at their last unit)
         const unsigned n_over = min(*plan.overflow_count, (unsigned)kOverflowCap);
         int found = -1;
         while (overflow_at < n_over && found < 0) {
@@ -1201,7 +1203,8 @@ static int render_expected_strided(const scb_geometry *geom, int64_t n_spots, in
     // Only the shared-memory kernel's units are written that way.
     const bool can_plan = !tile_path && !reg_path && frames > 1 && g.stripes == 1 && w.plan_base != nullptr && n_spots > 0;
     const bool planned = can_plan && (plan_mode & 1);
-    ListPlan plan = {nullptr, w.tile_count, w.pair_capacity, w.overflow_count, w.overflow_tile, (Unit *)w.overflow_units};
+    ListPlan plan = {nullptr, w.tile_count, (int)(w.pair_capacity < INT_MAX ? w.pair_capacity : INT_MAX), w.overflow_count,
+                     w.overflow_tile, (Unit *)w.overflow_units};
     if (planned) plan.base = w.plan_base;
     if (planned) {
         // 4 CTAs per SM (64 registers); measured: 3 (72 registers) -1.5 %, 5 (48 registers, spills) -2 % on the C4 step
