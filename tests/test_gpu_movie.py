@@ -22,9 +22,11 @@ default:
 """
 
 
-def make_movie(angle, bleaching, n=400, seed=11, precision="f32"):
+def make_movie(angle, bleaching, n=400, seed=11, precision="f32", pixel_length=None):
     config = scopyon_b200.DefaultConfiguration()
     config.update(YAML % (angle, bleaching))
+    if pixel_length is not None:
+        config.default.detector.pixel_length = pixel_length
     pl = 6.5e-8
     lower, upper = [-48 * pl, -40 * pl, 0.0], [48 * pl, 40 * pl, 1.3e-6]
     return config, DeviceMovie(config, n, lower, upper, 2e-13, seed, precision=precision)
@@ -195,8 +197,9 @@ def test_frames_to_u16():
         assert numpy.array_equal(out.cpu().numpy(), want)
 
 
+@pytest.mark.parametrize("pixel_length", [None, 6.639e-6], ids=["box-tables", "sat-corners"])
 @pytest.mark.parametrize("tight", [False, True], ids=["plan", "tight-plan"])
-def test_planned_blocks_equal_unplanned_blocks(tight):
+def test_planned_blocks_equal_unplanned_blocks(tight, pixel_length):
     """Consecutive blocks of a movie bin their spots in one pass over the list plan the previous block left behind
     (scb_render_expected_frames_planned); a plan that is too small (the test hook halves every list's room) sends
     units to the overflow list.  Either way the frames are those of the count / scan / fill pipeline, bit for bit."""
@@ -204,7 +207,7 @@ def test_planned_blocks_equal_unplanned_blocks(tight):
     n_frames, nf = 40, 8
 
     def movie_frames(plan):
-        _, movie = make_movie("0.0", "true", n=3000)
+        _, movie = make_movie("0.0", "true", n=3000, pixel_length=pixel_length)     # 66.39 nm: every footprint walks its edges
         movie.plan_blocks = plan
         movie.frames_per_launch = nf
         frames = torch.empty((n_frames, 96, 80), dtype=torch.float32, device=movie.engine.device)
